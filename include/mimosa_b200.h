@@ -1,0 +1,196 @@
+/* mimosa_b200.h — C ABI of the B200-native LiDAR geometric-factor path (scan-to-map point-to-plane ICP).
+ *
+ * Drop-in boundary for ntnu-arl/mimosa's  lidar::Geometric -> ICPFactor -> IncrementalVoxelMapPCL  path.
+ * Every entry point names the reference interface it replaces (paths relative to the mimosa repo).
+ * Plain pointers and sizes only; every call returns an int status (0 = MB_OK); no exception and no
+ * CUDA/torch type crosses this boundary.  All host buffers are caller-owned.  There is NO CPU fallback:
+ * without a usable sm_100 device mb_init() fails with MB_ERR_NO_DEVICE.
+ *
+ * Threading: handles are thread-compatible — one caller at a time per handle, different handles may be
+ * used concurrently (ICPFactor::linearize is `const` but mutates per-point caches,
+ * mimosa/include/mimosa/lidar/geometric_factor.hpp:79-116; instances are serialised by graph_mutex_,
+ * mimosa/src/graph/manager.cpp:574).
+ */
+#ifndef MIMOSA_B200_H_
+#define MIMOSA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_API __attribute__((visibility("default")))
+
+enum mb_status {
+  MB_OK = 0,
+  MB_ERR_INVALID_ARG = 1,
+  MB_ERR_NO_DEVICE = 2,   /* no CUDA device / not sm_100: the product never falls back to the CPU */
+  MB_ERR_CUDA = 3,        /* a CUDA runtime call failed; see mb_last_error() */
+  MB_ERR_UNSUPPORTED = 4, /* project_on_degneneracy=true, binary factor, k>MB_MAX_K, coordinate out of range */
+  MB_ERR_NCCL = 5,
+  MB_ERR_CAPACITY = 6
+};
+
+/* Per-point state of ICPFactor::RejectStatus, mimosa/include/mimosa/lidar/geometric_factor.hpp:35-46. */
+enum mb_reject_status {
+  MB_UNPROCESSED = 0,
+  MB_INSUFFICIENT_CORRES_POINTS = 1,
+  MB_CORRES_MAX_DIST = 2,
+  MB_EIGEN_SOLVER_FAIL = 3,
+  MB_MIN_EIGEN_VALUE_LOW = 4,
+  MB_LINE = 5,
+  MB_CORRES_PLANE_INVALID = 6,
+  MB_MAX_ERROR = 7,
+  MB_VALID = 8
+};
+
+#define MB_MAX_K 8         /* num_corres_points supported by the device path (reference default 5) */
+#define MB_POINT_STRIDE 32 /* sizeof(mimosa::lidar::Point), mimosa/include/mimosa/lidar/point.hpp:18-39 */
+
+/* mimosa::lidar::RegistrationConfig, mimosa/include/mimosa/lidar/geometric_config.hpp:17-33.
+ * Same fields, same order, reals kept as float (they are promoted to double where the reference
+ * promotes them: geometric_factor.hpp:283,299,333-339). */
+typedef struct mb_icp_config {
+  float source_voxel_grid_filter_leaf_size;
+  float source_voxel_grid_min_dist_in_voxel;
+  float target_ivox_map_leaf_size;
+  float target_ivox_map_min_dist_in_voxel;
+  uint64_t num_corres_points;
+  float max_corres_distance;
+  float plane_validity_distance;
+  float lidar_point_noise_std_dev;
+  int32_t use_huber;
+  float huber_threshold;
+  int32_t reg_4_dof;
+  int32_t project_on_degneneracy; /* must be 0 (every shipped config); 1 -> MB_ERR_UNSUPPORTED */
+  float degen_thresh_rot;
+  float degen_thresh_trans;
+} mb_icp_config;
+
+/* What ICPFactor::linearize hands to GTSAM plus what Geometric::getFactors reads back from the factor:
+ *   HessianFactor(key, G = H, g, f)               geometric_factor.hpp:559-560
+ *   getLocalizabilities()                          geometric_factor.hpp:52-62  (used at geometric.cpp:208-228)
+ *   getDegenInfo()                                 geometric_factor.hpp:64-70
+ *   status histogram                               geometric.cpp:280-323 (LidarGeometricDebug.msg:11-19)
+ *   getLinearizeCount()                            geometric_factor.hpp:72
+ * Matrices are row-major; column j of an eigenvector matrix belongs to eigenvalue j (ascending). */
+typedef struct mb_linearization {
+  double H[36];
+  double g[6]; /* = -J^T e */
+  double f;    /* = sum e^2 */
+  int64_t counts[9];
+  double loc_trans_comp[3], loc_rot_comp[3], loc_trans_final[3], loc_rot_final[3];
+  double eigvec_trans[9], eigvec_rot[9];
+  double degen_rot[3], degen_trans[3], degen_eigvec_rot[9], degen_eigvec_trans[9];
+  int32_t linearize_count;
+  int32_t n_searched; /* points that redid data association in this call (telemetry, not in the reference) */
+} mb_linearization;
+
+/* One iteration of the stand-alone Gauss-Newton harness (stands in for ISAM2's update(),
+ * mimosa/src/graph/manager.cpp:585-588):  delta = (H + lambda I)^-1 g,  T <- T * Pose3::Expmap(delta). */
+typedef struct mb_icp_trace {
+  double H[36], g[6], f, delta[6];
+  double R[9], t[3]; /* pose after this iteration's retract */
+  int64_t counts[9];
+  int32_t n_searched;
+  int32_t solve_ok;
+} mb_icp_trace;
+
+typedef struct mb_ctx mb_ctx;
+typedef struct mb_map mb_map;
+typedef struct mb_factor mb_factor;
+
+/* ---- context ---------------------------------------------------------------------------------------
+ * One context per process and GPU (one process per GPU; `device` is the CUDA ordinal, normally
+ * LOCAL_RANK).  Replaces nothing in the reference (it has no device) — the analogue of constructing
+ * lidar::Geometric, mimosa/src/lidar/geometric.cpp:13-45. */
+MB_API int mb_init(int device, mb_ctx** out);
+MB_API int mb_shutdown(mb_ctx* ctx);
+MB_API const char* mb_last_error(void);
+MB_API int mb_version(void);
+/* Synchronise the context's stream. */
+MB_API int mb_sync(mb_ctx* ctx);
+/* CUDA-event timer on the context's stream (device time of everything enqueued between the calls). */
+MB_API int mb_timer_begin(mb_ctx* ctx);
+MB_API int mb_timer_end(mb_ctx* ctx, float* ms);
+/* Number of kernel launches this context has issued since creation (bench.py's gpu_launches). */
+MB_API int mb_launch_count(mb_ctx* ctx, uint64_t* out);
+/* Write `bytes` of device memory (L2 flush between timed iterations). */
+MB_API int mb_flush_l2(mb_ctx* ctx, size_t bytes);
+
+/* Multi-GPU: scan blocks are sharded across ranks, the map is replicated, and the packed normal equations
+ * are all-reduced once per iteration (new in this implementation; the reference is single-process).
+ * mb_comm_unique_id fills a 128-byte NCCL id on rank 0; the caller ships it to the other ranks
+ * (torch.distributed / MPI / anything) and every rank calls mb_comm_init. */
+MB_API int mb_comm_unique_id(void* id128);
+MB_API int mb_comm_init(mb_ctx* ctx, int rank, int world, const void* id128);
+
+/* ---- map: mimosa::lidar::IncrementalVoxelMapPCL over gtsam_points::iVox ------------------------------
+ * mb_map_create   <- IncrementalVoxelMapPCL(leaf) + set_lru_horizon + set_neighbor_voxel_mode +
+ *                    voxel_insertion_setting().set_min_dist_in_cell,  mimosa/src/lidar/geometric.cpp:23-28
+ * mb_map_insert   <- IncrementalVoxelMapPCL::insert, mimosa/src/lidar/incremental_voxel_map.cpp:19-24
+ *                    (xyz = first three floats of each record; stride 12 for packed V3F as at
+ *                    geometric.cpp:487-495, 32 for lidar::Point)
+ * mb_map_snapshot <- the deep copy-constructor, incremental_voxel_map.hpp:34-43, used at geometric.cpp:494
+ * mb_map_knn      <- IncrementalVoxelMapPCL::knn_search, incremental_voxel_map.cpp:26-32
+ *                    (idx = (voxel_id << 32) | point_id, d2 ascending, ok = found == k)
+ * mb_map_points   <- iVox::point(i), geometric_factor.hpp:184
+ * mb_map_download <- IncrementalVoxelMapPCL::getCloud, incremental_voxel_map.cpp:34-38 (plus voxel layout)
+ * mb_map_upload   <- restore of a downloaded map (no reference analogue; the reference cannot checkpoint) */
+MB_API int mb_map_create(mb_ctx* ctx, float leaf, float min_dist, int cap, int nbr_mode, uint64_t lru_horizon,
+                         mb_map** out);
+MB_API int mb_map_release(mb_map* map);
+MB_API int mb_map_insert(mb_map* map, const float* xyz, size_t n, size_t stride_bytes);
+MB_API int mb_map_snapshot(mb_map* map, mb_map** out);
+MB_API int mb_map_size(mb_map* map, size_t* n_voxels, size_t* n_points, uint64_t* lru_counter);
+MB_API int mb_map_knn(mb_map* map, const double* q, size_t nq, int k, uint64_t* idx, double* d2, uint8_t* ok);
+MB_API int mb_map_points(mb_map* map, const uint64_t* idx, size_t n, double* xyz);
+/* coords n_vox*3 i32, counts n_vox i32, lru n_vox u32 (may be NULL), pts n_vox*cap*3 f32 (zero padded). */
+MB_API int mb_map_download(mb_map* map, int32_t* coords, int32_t* counts, uint32_t* lru, float* pts);
+MB_API int mb_map_upload(mb_map* map, const int32_t* coords, const int32_t* counts, const uint32_t* lru,
+                         const float* pts, size_t n_vox, uint64_t lru_counter);
+/* Device-resident k-NN over `nq` queries already in HBM (float64 xyz triples uploaded once with
+ * mb_map_knn_stage); runs only the search kernel, results stay on the device.  For roofline timing. */
+MB_API int mb_map_knn_stage(mb_map* map, const double* q, size_t nq, int k);
+MB_API int mb_map_knn_staged_run(mb_map* map);
+MB_API int mb_map_knn_staged_fetch(mb_map* map, uint64_t* idx, double* d2, uint8_t* ok);
+
+/* ---- factor: mimosa::lidar::ICPFactor (unary) -------------------------------------------------------
+ * mb_factor_create     <- ICPFactor(key, ivox_target, cloud_source, config) + commonConstructor,
+ *                         geometric_factor.hpp:119-156.  The scan is copied (H2D); the map handle is
+ *                         retained (shared_ptr semantics) and must not be inserted into while a factor
+ *                         references it — take mb_map_snapshot first, as geometric.cpp:494 does.
+ *                         [shard_begin, shard_end) selects this rank's block of the scan (0, n for one GPU).
+ * mb_factor_linearize  <- ICPFactor::linearize(values), geometric_factor.hpp:231-562, with
+ *                         R,t = values.at<Pose3>(X(key)) (row-major R) and gravity_unit =
+ *                         values.at<Unit3>(G(0)).unitVector() (read unconditionally at :257)
+ * mb_factor_download_state <- getStatuses / getCorresMeansTarget / getCorresNormalsTarget,
+ *                         geometric_factor.hpp:48-50 (+ the DA anchor and localizability vectors, :79-106)
+ * mb_icp_run           <- the smoother's repeated update(), mimosa/src/graph/manager.cpp:585-588,
+ *                         as a device-resident Gauss-Newton loop (see mb_icp_trace) */
+MB_API int mb_factor_create(mb_ctx* ctx, mb_map* map, const void* pts, size_t n, size_t stride_bytes,
+                            const mb_icp_config* cfg, size_t shard_begin, size_t shard_end, mb_factor** out);
+MB_API int mb_factor_release(mb_factor* f);
+MB_API int mb_factor_reset(mb_factor* f); /* back to the freshly constructed state */
+MB_API int mb_factor_linearize(mb_factor* f, const double R[9], const double t[3], const double gravity_unit[3],
+                               mb_linearization* out);
+/* Arrays cover this rank's shard only (shard_end - shard_begin points); any pointer may be NULL. */
+MB_API int mb_factor_download_state(mb_factor* f, uint8_t* status, double* p_da, double* mean, double* normal,
+                                    double* loc_rot, double* loc_trans, uint64_t* knn_idx);
+/* R,t updated in place; trace may be NULL or hold `iters` entries. */
+MB_API int mb_icp_run(mb_factor* f, double R[9], double t[3], int iters, double lambda, mb_icp_trace* trace);
+/* Debug/ablation switches: bit0 = disable the data-association cache ("forced" search every call). */
+MB_API int mb_factor_set_flags(mb_factor* f, uint32_t flags);
+
+/* ---- scan preparation ("next" rows of the scope table) ----------------------------------------------
+ * mb_downsample <- Geometric::downsample, mimosa/src/lidar/geometric.cpp:55-126 (greedy per-voxel thinning,
+ *                  output = kept input indices in voxel-creation order then in-voxel order). */
+MB_API int mb_downsample(mb_ctx* ctx, const float* xyz, size_t n, size_t stride_bytes, float leaf, size_t cap,
+                         float min_dist, uint32_t* out_idx, size_t* n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIMOSA_B200_H_ */

@@ -1,0 +1,161 @@
+"""ctypes binding of libmimosa_b200.so (the C ABI declared in include/mimosa_b200.h).
+
+This is plumbing for the Python tests / bench; C++ callers include the header directly.  There is no
+fallback: if the library is missing, or the machine has no sm_100 GPU, loading / mb_init raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmimosa_b200.so")
+
+MB_OK = 0
+MB_ERR_INVALID_ARG = 1
+MB_ERR_NO_DEVICE = 2
+MB_ERR_CUDA = 3
+MB_ERR_UNSUPPORTED = 4
+MB_ERR_NCCL = 5
+MB_ERR_CAPACITY = 6
+MB_MAX_K = 8
+MB_POINT_STRIDE = 32
+
+STATUS_NAMES = [
+    "Unprocessed",
+    "InsufficientCorresPoints",
+    "CorresMaxDist",
+    "EigenSolverFail",
+    "MinEigenValueLow",
+    "Line",
+    "CorresPlaneInvalid",
+    "MaxError",
+    "Valid",
+]
+
+
+class IcpConfig(C.Structure):
+    """mb_icp_config == mimosa::lidar::RegistrationConfig (geometric_config.hpp:17-33)."""
+
+    _fields_ = [
+        ("source_voxel_grid_filter_leaf_size", C.c_float),
+        ("source_voxel_grid_min_dist_in_voxel", C.c_float),
+        ("target_ivox_map_leaf_size", C.c_float),
+        ("target_ivox_map_min_dist_in_voxel", C.c_float),
+        ("num_corres_points", C.c_uint64),
+        ("max_corres_distance", C.c_float),
+        ("plane_validity_distance", C.c_float),
+        ("lidar_point_noise_std_dev", C.c_float),
+        ("use_huber", C.c_int32),
+        ("huber_threshold", C.c_float),
+        ("reg_4_dof", C.c_int32),
+        ("project_on_degneneracy", C.c_int32),
+        ("degen_thresh_rot", C.c_float),
+        ("degen_thresh_trans", C.c_float),
+    ]
+
+
+class Linearization(C.Structure):
+    _fields_ = [
+        ("H", C.c_double * 36),
+        ("g", C.c_double * 6),
+        ("f", C.c_double),
+        ("counts", C.c_int64 * 9),
+        ("loc_trans_comp", C.c_double * 3),
+        ("loc_rot_comp", C.c_double * 3),
+        ("loc_trans_final", C.c_double * 3),
+        ("loc_rot_final", C.c_double * 3),
+        ("eigvec_trans", C.c_double * 9),
+        ("eigvec_rot", C.c_double * 9),
+        ("degen_rot", C.c_double * 3),
+        ("degen_trans", C.c_double * 3),
+        ("degen_eigvec_rot", C.c_double * 9),
+        ("degen_eigvec_trans", C.c_double * 9),
+        ("linearize_count", C.c_int32),
+        ("n_searched", C.c_int32),
+    ]
+
+
+class IcpTrace(C.Structure):
+    _fields_ = [
+        ("H", C.c_double * 36),
+        ("g", C.c_double * 6),
+        ("f", C.c_double),
+        ("delta", C.c_double * 6),
+        ("R", C.c_double * 9),
+        ("t", C.c_double * 3),
+        ("counts", C.c_int64 * 9),
+        ("n_searched", C.c_int32),
+        ("solve_ok", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/mimosa_b200.h declares.
+_P = C.c_void_p
+_SZ = C.c_size_t
+SIGNATURES = {
+    "mb_init": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "mb_shutdown": (C.c_int, [_P]),
+    "mb_last_error": (C.c_char_p, []),
+    "mb_version": (C.c_int, []),
+    "mb_sync": (C.c_int, [_P]),
+    "mb_timer_begin": (C.c_int, [_P]),
+    "mb_timer_end": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "mb_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "mb_flush_l2": (C.c_int, [_P, _SZ]),
+    "mb_comm_unique_id": (C.c_int, [_P]),
+    "mb_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "mb_map_create": (C.c_int, [_P, C.c_float, C.c_float, C.c_int, C.c_int, C.c_uint64, C.POINTER(_P)]),
+    "mb_map_release": (C.c_int, [_P]),
+    "mb_map_insert": (C.c_int, [_P, _P, _SZ, _SZ]),
+    "mb_map_snapshot": (C.c_int, [_P, C.POINTER(_P)]),
+    "mb_map_size": (C.c_int, [_P, C.POINTER(_SZ), C.POINTER(_SZ), C.POINTER(C.c_uint64)]),
+    "mb_map_knn": (C.c_int, [_P, _P, _SZ, C.c_int, _P, _P, _P]),
+    "mb_map_points": (C.c_int, [_P, _P, _SZ, _P]),
+    "mb_map_download": (C.c_int, [_P, _P, _P, _P, _P]),
+    "mb_map_upload": (C.c_int, [_P, _P, _P, _P, _P, _SZ, C.c_uint64]),
+    "mb_map_knn_stage": (C.c_int, [_P, _P, _SZ, C.c_int]),
+    "mb_map_knn_staged_run": (C.c_int, [_P]),
+    "mb_map_knn_staged_fetch": (C.c_int, [_P, _P, _P, _P]),
+    "mb_factor_create": (C.c_int, [_P, _P, _P, _SZ, _SZ, C.POINTER(IcpConfig), _SZ, _SZ, C.POINTER(_P)]),
+    "mb_factor_release": (C.c_int, [_P]),
+    "mb_factor_reset": (C.c_int, [_P]),
+    "mb_factor_linearize": (C.c_int, [_P, _P, _P, _P, C.POINTER(Linearization)]),
+    "mb_factor_download_state": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    "mb_icp_run": (C.c_int, [_P, _P, _P, C.c_int, C.c_double, _P]),
+    "mb_factor_set_flags": (C.c_int, [_P, C.c_uint32]),
+    "mb_downsample": (C.c_int, [_P, _P, _SZ, _SZ, C.c_float, _SZ, C.c_float, _P, C.POINTER(_SZ)]),
+}
+
+
+class MimosaError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"mimosa_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library and bind every symbol.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  mimosa_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code: int) -> None:
+    if code != MB_OK:
+        raise MimosaError(code, load().mb_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,150 @@
+// Context, error reporting, timing and communicator plumbing of libmimosa_b200.so.
+#include <mutex>
+
+#include "mb_internal.cuh"
+
+namespace mb {
+namespace {
+thread_local std::string g_last_error;
+}
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+
+namespace {
+__global__ void k_fill(uint4* p, size_t n, unsigned v) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = make_uint4(v, v, v, v);
+}
+}  // namespace
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" {
+
+const char* mb_last_error(void) { return g_last_error.c_str(); }
+int mb_version(void) { return 100; }
+
+int mb_init(int device, mb_ctx** out) {
+  MB_REQUIRE(out, "null out");
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0) {
+    set_error("mb_init: no CUDA device (%s); this library has no CPU path", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    return MB_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n_dev) {
+    set_error("mb_init: device %d outside [0, %d)", device, n_dev);
+    return MB_ERR_INVALID_ARG;
+  }
+  cudaDeviceProp prop;
+  MB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("mb_init: device %d is sm_%d%d; this build carries sm_100a code only", device, prop.major, prop.minor);
+    return MB_ERR_NO_DEVICE;
+  }
+  MB_CUDA(cudaSetDevice(device));
+  mb_ctx* c = new mb_ctx;
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  MB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  MB_CUDA(cudaEventCreate(&c->ev0));
+  MB_CUDA(cudaEventCreate(&c->ev1));
+  *out = c;
+  return MB_OK;
+}
+
+int mb_shutdown(mb_ctx* c) {
+  if (!c) return MB_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->comm) ncclCommDestroy(c->comm);
+  cudaFree(c->flush_buf);
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return MB_OK;
+}
+
+int mb_sync(mb_ctx* c) {
+  MB_REQUIRE(c, "null ctx");
+  MB_CUDA(cudaSetDevice(c->device));
+  MB_CUDA(cudaStreamSynchronize(c->stream));
+  return MB_OK;
+}
+
+int mb_timer_begin(mb_ctx* c) {
+  MB_REQUIRE(c, "null ctx");
+  MB_CUDA(cudaSetDevice(c->device));
+  MB_CUDA(cudaEventRecord(c->ev0, c->stream));
+  return MB_OK;
+}
+
+int mb_timer_end(mb_ctx* c, float* ms) {
+  MB_REQUIRE(c && ms, "null argument");
+  MB_CUDA(cudaSetDevice(c->device));
+  MB_CUDA(cudaEventRecord(c->ev1, c->stream));
+  MB_CUDA(cudaEventSynchronize(c->ev1));
+  MB_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return MB_OK;
+}
+
+int mb_launch_count(mb_ctx* c, uint64_t* out) {
+  MB_REQUIRE(c && out, "null argument");
+  *out = c->launches;
+  return MB_OK;
+}
+
+int mb_flush_l2(mb_ctx* c, size_t bytes) {
+  MB_REQUIRE(c, "null ctx");
+  MB_CUDA(cudaSetDevice(c->device));
+  bytes = (bytes + 15) & ~(size_t)15;
+  if (bytes > c->flush_bytes) {
+    MB_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->flush_buf) MB_CUDA(cudaFree(c->flush_buf));
+    c->flush_buf = nullptr;
+    c->flush_bytes = 0;
+    MB_CUDA(cudaMalloc(&c->flush_buf, bytes));
+    c->flush_bytes = bytes;
+  }
+  static unsigned tick = 0;
+  k_fill<<<c->sm_count * 4, 256, 0, c->stream>>>((uint4*)c->flush_buf, bytes / 16, ++tick);
+  ++c->launches;
+  MB_CUDA(cudaGetLastError());
+  return MB_OK;
+}
+
+int mb_comm_unique_id(void* id128) {
+  MB_REQUIRE(id128, "null id");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+  ncclUniqueId id;
+  MB_NCCL(ncclGetUniqueId(&id));
+  std::memcpy(id128, &id, sizeof(id));
+  return MB_OK;
+}
+
+int mb_comm_init(mb_ctx* c, int rank, int world, const void* id128) {
+  MB_REQUIRE(c && id128, "null argument");
+  MB_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank/world");
+  MB_CUDA(cudaSetDevice(c->device));
+  if (c->comm) {
+    ncclCommDestroy(c->comm);
+    c->comm = nullptr;
+  }
+  c->rank = rank;
+  c->world = world;
+  if (world == 1) return MB_OK;
+  ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof(id));
+  MB_NCCL(ncclCommInitRank(&c->comm, world, id, rank));
+  return MB_OK;
+}
+
+}  // extern "C"

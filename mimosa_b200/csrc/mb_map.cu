@@ -1,0 +1,902 @@
+// Device-resident incremental hashed voxel map: build (sort + per-voxel greedy insert), LRU eviction,
+// snapshot, restricted k-NN.  See mb_map.cuh for the layout and include/mimosa_b200.h for the reference
+// interfaces each entry point replaces.
+//
+// Insert reproduces the reference's *sequential* semantics (gtsam_points::IncrementalVoxelMap::insert as
+// used at mimosa/src/lidar/geometric.cpp:495; the per-voxel rule is restated in-tree at
+// mimosa/include/mimosa/lidar/utils.hpp:260-278) on a parallel machine:
+//   * points only interact inside one voxel, so a STABLE radix sort by voxel key turns the input into one
+//     run per voxel with the input order preserved inside the run;
+//   * voxel ids are creation order = order of each new voxel's first point in the input, recovered with a
+//     flag-and-scan over the original positions;
+//   * one warp walks each run in order applying "full? -> reject; any stored point closer than min_dist?
+//     -> reject; else append" with the stored points spread over the lanes.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <vector>
+
+#include "mb_map.cuh"
+
+namespace mb {
+
+namespace {
+
+constexpr int kCoordBias = 1 << 20;
+
+__device__ __forceinline__ uint64_t pack_key(int x, int y, int z) {
+  return ((uint64_t)(uint32_t)(x + kCoordBias) << 42) | ((uint64_t)(uint32_t)(y + kCoordBias) << 21) |
+         (uint64_t)(uint32_t)(z + kCoordBias);
+}
+__device__ __forceinline__ int3 unpack_key(uint64_t k) {
+  return make_int3((int)((k >> 42) & 0x1fffff) - kCoordBias, (int)((k >> 21) & 0x1fffff) - kCoordBias,
+                   (int)(k & 0x1fffff) - kCoordBias);
+}
+
+__global__ void k_make_keys(const unsigned char* __restrict__ raw, size_t n, size_t stride, double inv_leaf,
+                            uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int* __restrict__ err) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* f = (const float*)(raw + i * stride);
+  const int cx = fast_floor((double)f[0] * inv_leaf), cy = fast_floor((double)f[1] * inv_leaf),
+            cz = fast_floor((double)f[2] * inv_leaf);
+  if (abs(cx) >= kCoordBias || abs(cy) >= kCoordBias || abs(cz) >= kCoordBias || !isfinite(f[0]) ||
+      !isfinite(f[1]) || !isfinite(f[2]))
+    *err = 1;
+  keys[i] = pack_key(cx, cy, cz);
+  vals[i] = (uint32_t)i;
+}
+
+__global__ void k_mark_heads(const uint64_t* __restrict__ keys, size_t n, uint32_t* __restrict__ head) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+
+__global__ void k_run_starts(const uint32_t* __restrict__ head, const uint32_t* __restrict__ run_id, size_t n,
+                             uint32_t* __restrict__ run_start) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (head[i]) run_start[run_id[i]] = (uint32_t)i;
+  if (i == n - 1) run_start[run_id[i] + 1] = (uint32_t)n;
+}
+
+// counters[0] = number of runs, counters[1] = number of new voxels
+__global__ void k_count2(const uint32_t* __restrict__ a_flag, const uint32_t* __restrict__ a_scan,
+                         const uint32_t* __restrict__ b_flag, const uint32_t* __restrict__ b_scan, size_t n,
+                         uint32_t* __restrict__ counters) {
+  if (a_flag) counters[0] = a_flag[n - 1] + a_scan[n - 1];
+  if (b_flag) counters[1] = b_flag[n - 1] + b_scan[n - 1];
+}
+
+__global__ void k_lookup_runs(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                              const uint32_t* __restrict__ run_start, uint32_t n_runs, const int4* __restrict__ table,
+                              uint32_t mask, uint32_t* __restrict__ run_packed, uint32_t* __restrict__ new_flag) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_runs) return;
+  const uint32_t s = run_start[r];
+  const int3 c = unpack_key(keys[s]);
+  const uint32_t p = table_find(table, mask, c.x, c.y, c.z);
+  run_packed[r] = p;
+  if (p == kEmpty) new_flag[vals[s]] = 1u;  // stable sort: the run's first element is its earliest input point
+}
+
+__device__ __forceinline__ uint32_t table_claim(int4* table, uint32_t mask, int x, int y, int z, uint32_t packed) {
+  uint32_t h = hash_coord(x, y, z) & mask;
+  while (true) {
+    const unsigned old = atomicCAS((unsigned*)&table[h].w, kEmpty, packed);
+    if (old == kEmpty) {
+      table[h].x = x;
+      table[h].y = y;
+      table[h].z = z;
+      return h;
+    }
+    h = (h + 1) & mask;
+  }
+}
+
+__global__ void k_create_voxels(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                const uint32_t* __restrict__ run_start, uint32_t n_runs,
+                                const uint32_t* __restrict__ run_packed, const uint32_t* __restrict__ new_rank,
+                                uint32_t base_id, int lru, int4* __restrict__ table, uint32_t mask,
+                                int4* __restrict__ info, int32_t* __restrict__ count, uint32_t* __restrict__ epos,
+                                uint32_t* __restrict__ run_slot) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_runs) return;
+  const uint32_t p = run_packed[r];
+  if (p != kEmpty) {
+    run_slot[r] = p >> kCountBits;
+    return;
+  }
+  const uint32_t s = run_start[r];
+  const int3 c = unpack_key(keys[s]);
+  const uint32_t id = base_id + new_rank[vals[s]];
+  info[id] = make_int4(c.x, c.y, c.z, lru);
+  count[id] = 0;
+  epos[id] = table_claim(table, mask, c.x, c.y, c.z, id << kCountBits);
+  run_slot[r] = id;
+}
+
+// One warp per run.  Lane q holds stored point q of the voxel (as doubles).
+__global__ void k_insert_runs(const unsigned char* __restrict__ raw, size_t stride, const uint32_t* __restrict__ vals,
+                              const uint32_t* __restrict__ run_start, uint32_t n_runs,
+                              const uint32_t* __restrict__ run_slot, int cap, double min_sq, int lru,
+                              float4* __restrict__ pts, int4* __restrict__ info, int32_t* __restrict__ count,
+                              const uint32_t* __restrict__ epos, int4* __restrict__ table) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_runs; r += warps) {
+    const uint32_t slot = run_slot[r];
+    int c = count[slot];
+    double mx = 0, my = 0, mz = 0;
+    if (lane < c) {
+      const float4 p = pts[(size_t)slot * cap + lane];
+      mx = p.x;
+      my = p.y;
+      mz = p.z;
+    }
+    const uint32_t t1 = run_start[r + 1];
+    for (uint32_t t = run_start[r]; t < t1 && c < cap; ++t) {
+      const float* f = (const float*)(raw + (size_t)vals[t] * stride);
+      const float fx = f[0], fy = f[1], fz = f[2];
+      const bool close = lane < c && sqdist4(mx, my, mz, (double)fx, (double)fy, (double)fz) < min_sq;
+      if (__any_sync(kFull, close)) continue;
+      if (lane == c) {
+        mx = fx;
+        my = fy;
+        mz = fz;
+        pts[(size_t)slot * cap + c] = make_float4(fx, fy, fz, 0.f);
+      }
+      ++c;
+    }
+    if (lane == 0) {
+      count[slot] = c;
+      info[slot].w = lru;
+      table[epos[slot]].w = (int)((slot << kCountBits) | (uint32_t)c);
+    }
+  }
+}
+
+__global__ void k_rehash(const int4* __restrict__ info, const int32_t* __restrict__ count, uint32_t n_vox,
+                         int4* __restrict__ table, uint32_t mask, uint32_t* __restrict__ epos) {
+  const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n_vox) return;
+  const int4 c = info[id];
+  epos[id] = table_claim(table, mask, c.x, c.y, c.z, (id << kCountBits) | (uint32_t)count[id]);
+}
+
+__global__ void k_flag_keep(const int4* __restrict__ info, uint32_t n_vox, long long horizon, long long counter,
+                            uint32_t* __restrict__ keep) {
+  const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n_vox) return;
+  keep[id] = ((long long)info[id].w + horizon < counter) ? 0u : 1u;
+}
+
+// One warp per surviving voxel moves its bucket to the compacted id.
+__global__ void k_compact(const uint32_t* __restrict__ keep, const uint32_t* __restrict__ new_id, uint32_t n_vox,
+                          int cap, const float4* __restrict__ pts, const int4* __restrict__ info,
+                          const int32_t* __restrict__ count, float4* __restrict__ pts2, int4* __restrict__ info2,
+                          int32_t* __restrict__ count2) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; id < n_vox; id += warps) {
+    if (!keep[id]) continue;
+    const uint32_t d = new_id[id];
+    if (lane < cap) pts2[(size_t)d * cap + lane] = pts[(size_t)id * cap + lane];
+    if (lane == 0) {
+      info2[d] = info[id];
+      count2[d] = count[id];
+    }
+  }
+}
+
+// ---- Geometric::downsample (mimosa/src/lidar/geometric.cpp:55-126) ----------------------------------
+__global__ void k_ds_mark(const uint32_t* __restrict__ vals, const uint32_t* __restrict__ run_start, uint32_t n_runs,
+                          uint32_t* __restrict__ first_flag) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_runs) first_flag[vals[run_start[r]]] = 1u;
+}
+
+// One warp per run (= per voxel of the one-shot grid).  FlatContainerMinimal::add (lidar/utils.hpp:260-278):
+// full -> reject, any kept point with (kept - p).squaredNorm() < min_sq -> reject, else keep.
+__global__ void k_ds_runs(const unsigned char* __restrict__ raw, size_t stride, const uint32_t* __restrict__ vals,
+                          const uint32_t* __restrict__ run_start, uint32_t n_runs,
+                          const uint32_t* __restrict__ first_rank, int cap, double min_sq,
+                          uint32_t* __restrict__ kept, uint32_t* __restrict__ kept_count) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_runs; r += warps) {
+    const uint32_t t0 = run_start[r], t1 = run_start[r + 1];
+    const uint32_t vox = first_rank[vals[t0]];
+    int c = 0;
+    double mx = 0, my = 0, mz = 0;
+    for (uint32_t t = t0; t < t1 && c < cap; ++t) {
+      const uint32_t i = vals[t];
+      const float* f = (const float*)(raw + (size_t)i * stride);
+      const d3 p = mk3((double)f[0], (double)f[1], (double)f[2]);
+      const bool close = lane < c && sqnorm3(sub3(mk3(mx, my, mz), p)) < min_sq;
+      if (__any_sync(kFull, close)) continue;
+      if (lane == c) {
+        mx = p.x;
+        my = p.y;
+        mz = p.z;
+        kept[(size_t)vox * cap + c] = i;
+      }
+      ++c;
+    }
+    if (lane == 0) kept_count[vox] = (uint32_t)c;
+  }
+}
+
+__global__ void k_ds_scatter(const uint32_t* __restrict__ kept, const uint32_t* __restrict__ kept_count,
+                             const uint32_t* __restrict__ offset, uint32_t n_vox, int cap, uint32_t* __restrict__ out) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t v = t / cap, j = t % cap;
+  if (v >= n_vox || j >= kept_count[v]) return;
+  out[offset[v] + j] = kept[(size_t)v * cap + j];
+}
+
+constexpr int kKnnWarps = 8;
+
+// Standalone restricted k-NN: one warp per query, warp-strided over the query list.
+__global__ void __launch_bounds__(kKnnWarps * 32)
+    k_knn(MapView mv, const double* __restrict__ q, size_t nq, int k, uint64_t* __restrict__ idx,
+          double* __restrict__ d2, uint8_t* __restrict__ ok) {
+  __shared__ int8_t s_off[32 * 3];
+  __shared__ uint32_t s_vox_all[kKnnWarps][32];
+  if (threadIdx.x < kMaxNbr * 3) s_off[threadIdx.x] = mv.off[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* s_vox = s_vox_all[warp];
+  const size_t stride = (size_t)gridDim.x * kKnnWarps;
+  for (size_t i = (size_t)blockIdx.x * kKnnWarps + warp; i < nq; i += stride) {
+    const double qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
+    KnnOut o;
+    knn_warp(mv, s_off, s_vox, qx, qy, qz, k, lane, o);
+    if (lane < k) {
+      uint64_t g = ~0ull;
+      double d = DBL_MAX;
+      if (o.seq != 0xffffffffu) {
+        float4 p;
+        g = knn_fetch(mv, s_vox, o.seq, p);
+        d = o.d2;
+      }
+      idx[i * k + lane] = g;
+      d2[i * k + lane] = d;
+    }
+    if (lane == 0) ok[i] = o.found == k;
+  }
+}
+
+__global__ void k_gather_points(const float4* __restrict__ pts, int cap, const uint64_t* __restrict__ idx, size_t n,
+                                double* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t g = idx[i];
+  const float4 p = pts[(size_t)(g >> 32) * cap + (size_t)(g & 0xffffffffull)];
+  out[3 * i] = p.x;
+  out[3 * i + 1] = p.y;
+  out[3 * i + 2] = p.z;
+}
+
+__global__ void k_sum_counts(const int32_t* __restrict__ count, uint32_t n_vox, unsigned long long* __restrict__ out) {
+  unsigned long long local = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vox; i += gridDim.x * blockDim.x) local += count[i];
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(kFull, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
+}
+
+inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// Bump allocator over the map's scratch buffer.
+struct Bump {
+  char* base;
+  size_t off = 0, cap;
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = (T*)(base + off);
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+int ensure_scratch(mb_map* m, size_t bytes) {
+  if (bytes <= m->scratch_bytes) return MB_OK;
+  MB_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  if (m->scratch) MB_CUDA(cudaFree(m->scratch));
+  m->scratch = nullptr;
+  m->scratch_bytes = 0;
+  MB_CUDA(cudaMalloc(&m->scratch, bytes));
+  m->scratch_bytes = bytes;
+  return MB_OK;
+}
+
+int rebuild_table(mb_map* m, size_t want_table) {
+  cudaStream_t st = m->ctx->stream;
+  if (want_table != m->table_cap) {
+    MB_CUDA(cudaStreamSynchronize(st));
+    if (m->table) MB_CUDA(cudaFree(m->table));
+    m->table = nullptr;
+    MB_CUDA(cudaMalloc(&m->table, want_table * sizeof(int4)));
+    m->table_cap = want_table;
+  }
+  MB_CUDA(cudaMemsetAsync(m->table, 0xff, m->table_cap * sizeof(int4), st));
+  if (m->n_vox) {
+    k_rehash<<<blocks_for(m->n_vox, 256), 256, 0, st>>>(m->info, m->count, (uint32_t)m->n_vox, m->table,
+                                                        (uint32_t)(m->table_cap - 1), m->epos);
+    ++m->ctx->launches;
+    MB_CUDA(cudaGetLastError());
+  }
+  return MB_OK;
+}
+
+}  // namespace
+
+int map_reserve(mb_map* m, size_t want_vox) {
+  cudaStream_t st = m->ctx->stream;
+  if (want_vox >= (1u << (32 - kCountBits)) - 1) {
+    set_error("map_reserve: %zu voxels exceed the %d-bit voxel id space", want_vox, 32 - kCountBits);
+    return MB_ERR_CAPACITY;
+  }
+  if (want_vox > m->cap_vox) {
+    size_t new_cap = std::max<size_t>(want_vox, m->cap_vox + m->cap_vox / 2);
+    new_cap = std::max<size_t>(new_cap, 4096);
+    float4* pts2 = nullptr;
+    int4* info2 = nullptr;
+    int32_t* count2 = nullptr;
+    uint32_t* epos2 = nullptr;
+    MB_CUDA(cudaMalloc(&pts2, new_cap * m->cap * sizeof(float4)));
+    MB_CUDA(cudaMalloc(&info2, new_cap * sizeof(int4)));
+    MB_CUDA(cudaMalloc(&count2, new_cap * sizeof(int32_t)));
+    MB_CUDA(cudaMalloc(&epos2, new_cap * sizeof(uint32_t)));
+    if (m->n_vox) {
+      MB_CUDA(cudaMemcpyAsync(pts2, m->pts, m->n_vox * m->cap * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+      MB_CUDA(cudaMemcpyAsync(info2, m->info, m->n_vox * sizeof(int4), cudaMemcpyDeviceToDevice, st));
+      MB_CUDA(cudaMemcpyAsync(count2, m->count, m->n_vox * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+      MB_CUDA(cudaMemcpyAsync(epos2, m->epos, m->n_vox * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    }
+    MB_CUDA(cudaStreamSynchronize(st));
+    if (m->pts) cudaFree(m->pts);
+    if (m->info) cudaFree(m->info);
+    if (m->count) cudaFree(m->count);
+    if (m->epos) cudaFree(m->epos);
+    m->pts = pts2;
+    m->info = info2;
+    m->count = count2;
+    m->epos = epos2;
+    m->cap_vox = new_cap;
+  }
+  size_t want_table = 1024;
+  while (want_table < 2 * m->cap_vox) want_table <<= 1;
+  if (want_table > m->table_cap) MB_TRY(rebuild_table(m, want_table));
+  return MB_OK;
+}
+
+int launch_knn(mb_map* m, const double* d_q, size_t nq, int k, uint64_t* d_idx, double* d_d2, uint8_t* d_ok) {
+  if (nq == 0) return MB_OK;
+  const size_t want = (nq + kKnnWarps - 1) / kKnnWarps;
+  const unsigned grid = (unsigned)std::min<size_t>(want, (size_t)m->ctx->sm_count * 8);
+  k_knn<<<grid, kKnnWarps * 32, 0, m->ctx->stream>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
+  ++m->ctx->launches;
+  MB_CUDA(cudaGetLastError());
+  return MB_OK;
+}
+
+}  // namespace mb
+
+using namespace mb;
+
+// ---- C ABI ------------------------------------------------------------------------------------------
+extern "C" {
+
+int mb_map_create(mb_ctx* ctx, float leaf, float min_dist, int cap, int nbr_mode, uint64_t lru_horizon,
+                  mb_map** out) {
+  MB_REQUIRE(ctx && out, "null argument");
+  MB_REQUIRE(leaf > 0.f && min_dist >= 0.f, "leaf must be > 0 and min_dist >= 0");
+  MB_REQUIRE(nbr_mode == 1 || nbr_mode == 7 || nbr_mode == 19 || nbr_mode == 27,
+             "neighbor_voxel_mode must be 1, 7, 19 or 27 (geometric_config.cpp:84-89)");
+  if (cap < 1 || cap >= (1 << kCountBits)) {
+    set_error("mb_map_create: cap %d outside [1, %d]", cap, (1 << kCountBits) - 1);
+    return MB_ERR_UNSUPPORTED;
+  }
+  MB_CUDA(cudaSetDevice(ctx->device));
+  mb_map* m = new mb_map;
+  m->ctx = ctx;
+  m->leaf = (double)leaf;
+  m->inv_leaf = 1.0 / (double)leaf;
+  m->min_sq_dist = (double)min_dist * (double)min_dist;
+  m->cap = cap;
+  m->nbr_mode = nbr_mode;
+  m->lru_horizon = lru_horizon;
+  int n = 0;
+  auto push = [&](int i, int j, int k) {
+    m->off[3 * n] = (int8_t)i;
+    m->off[3 * n + 1] = (int8_t)j;
+    m->off[3 * n + 2] = (int8_t)k;
+    ++n;
+  };
+  if (nbr_mode == 1) {
+    push(0, 0, 0);
+  } else if (nbr_mode == 7) {
+    push(0, 0, 0);
+    push(1, 0, 0);
+    push(-1, 0, 0);
+    push(0, 1, 0);
+    push(0, -1, 0);
+    push(0, 0, 1);
+    push(0, 0, -1);
+  } else {
+    for (int i = -1; i <= 1; ++i)
+      for (int j = -1; j <= 1; ++j)
+        for (int k = -1; k <= 1; ++k) {
+          if (nbr_mode == 19 && i != 0 && j != 0 && k != 0) continue;
+          push(i, j, k);
+        }
+  }
+  m->n_off = n;
+  int s = map_reserve(m, 4096);
+  if (s != MB_OK) {
+    delete m;
+    return s;
+  }
+  *out = m;
+  return MB_OK;
+}
+
+int mb_map_release(mb_map* m) {
+  if (!m) return MB_OK;
+  if (m->refs.fetch_sub(1) > 1) return MB_OK;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  cudaFree(m->pts);
+  cudaFree(m->info);
+  cudaFree(m->count);
+  cudaFree(m->epos);
+  cudaFree(m->table);
+  cudaFree(m->scratch);
+  cudaFree(m->q_dev);
+  cudaFree(m->q_idx);
+  cudaFree(m->q_d2);
+  cudaFree(m->q_ok);
+  delete m;
+  return MB_OK;
+}
+
+int mb_map_snapshot(mb_map* m, mb_map** out) {
+  MB_REQUIRE(m && out, "null argument");
+  MB_CUDA(cudaSetDevice(m->ctx->device));
+  mb_map* s = new mb_map;
+  s->ctx = m->ctx;
+  s->leaf = m->leaf;
+  s->inv_leaf = m->inv_leaf;
+  s->min_sq_dist = m->min_sq_dist;
+  s->cap = m->cap;
+  s->nbr_mode = m->nbr_mode;
+  s->n_off = m->n_off;
+  std::memcpy(s->off, m->off, sizeof(m->off));
+  s->lru_horizon = m->lru_horizon;
+  s->lru_counter = m->lru_counter;
+  int st = map_reserve(s, std::max<size_t>(m->n_vox, 4096));
+  if (st != MB_OK) {
+    mb_map_release(s);
+    return st;
+  }
+  cudaStream_t stream = m->ctx->stream;
+  if (m->n_vox) {
+    MB_CUDA(cudaMemcpyAsync(s->pts, m->pts, m->n_vox * m->cap * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+    MB_CUDA(cudaMemcpyAsync(s->info, m->info, m->n_vox * sizeof(int4), cudaMemcpyDeviceToDevice, stream));
+    MB_CUDA(cudaMemcpyAsync(s->count, m->count, m->n_vox * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+  }
+  s->n_vox = m->n_vox;
+  st = rebuild_table(s, s->table_cap);
+  if (st != MB_OK) {
+    mb_map_release(s);
+    return st;
+  }
+  *out = s;
+  return MB_OK;
+}
+
+int mb_map_size(mb_map* m, size_t* n_voxels, size_t* n_points, uint64_t* lru_counter) {
+  MB_REQUIRE(m, "null map");
+  MB_CUDA(cudaSetDevice(m->ctx->device));
+  if (n_voxels) *n_voxels = m->n_vox;
+  if (lru_counter) *lru_counter = m->lru_counter;
+  if (n_points) {
+    *n_points = 0;
+    if (m->n_vox) {
+      cudaStream_t st = m->ctx->stream;
+      MB_TRY(ensure_scratch(m, 1024));
+      unsigned long long* d_sum = (unsigned long long*)m->scratch;
+      MB_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(unsigned long long), st));
+      k_sum_counts<<<std::min<unsigned>(blocks_for(m->n_vox, 256), 1024u), 256, 0, st>>>(m->count, (uint32_t)m->n_vox,
+                                                                                         d_sum);
+      ++m->ctx->launches;
+      unsigned long long h = 0;
+      MB_CUDA(cudaMemcpyAsync(&h, d_sum, sizeof(h), cudaMemcpyDeviceToHost, st));
+      MB_CUDA(cudaStreamSynchronize(st));
+      *n_points = (size_t)h;
+    }
+  }
+  return MB_OK;
+}
+
+int mb_map_insert(mb_map* m, const float* xyz, size_t n, size_t stride_bytes) {
+  MB_REQUIRE(m, "null map");
+  MB_REQUIRE(n == 0 || xyz, "null points");
+  MB_REQUIRE(stride_bytes >= 12 && stride_bytes % 4 == 0, "stride must be >= 12 and a multiple of 4");
+  MB_REQUIRE(n < 0xffffffffull, "too many points in one insert");
+  MB_REQUIRE(m->refs.load() == 1, "map is referenced by a factor: insert into a snapshot (geometric.cpp:494)");
+  MB_CUDA(cudaSetDevice(m->ctx->device));
+  cudaStream_t st = m->ctx->stream;
+  mb_ctx* ctx = m->ctx;
+  if (n > 0) {
+    size_t sort_temp = 0, scan_temp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_temp, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)n, 0, 63, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_temp, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, st);
+    const size_t temp_bytes = std::max(sort_temp, scan_temp);
+    const size_t need = n * stride_bytes + n * (16 + 8 + 4 * 7) + temp_bytes + 256 * 16 + 1024;
+    MB_TRY(ensure_scratch(m, need));
+    Bump b{(char*)m->scratch, 0, m->scratch_bytes};
+    unsigned char* raw = b.take<unsigned char>(n * stride_bytes);
+    uint64_t* keys = b.take<uint64_t>(n);
+    uint64_t* keys_s = b.take<uint64_t>(n);
+    uint32_t* vals = b.take<uint32_t>(n);
+    uint32_t* vals_s = b.take<uint32_t>(n);
+    uint32_t* head = b.take<uint32_t>(n);
+    uint32_t* run_id = b.take<uint32_t>(n);
+    uint32_t* run_start = b.take<uint32_t>(n + 1);
+    uint32_t* run_packed = b.take<uint32_t>(n);
+    uint32_t* run_slot = b.take<uint32_t>(n);
+    uint32_t* new_flag = b.take<uint32_t>(n);
+    uint32_t* new_rank = b.take<uint32_t>(n);
+    uint32_t* counters = b.take<uint32_t>(4);
+    int* err = b.take<int>(1);
+    void* temp = b.take<unsigned char>(temp_bytes);
+
+    MB_CUDA(cudaMemcpyAsync(raw, xyz, n * stride_bytes, cudaMemcpyHostToDevice, st));
+    MB_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
+    MB_CUDA(cudaMemsetAsync(new_flag, 0, n * sizeof(uint32_t), st));
+    k_make_keys<<<blocks_for(n, 256), 256, 0, st>>>(raw, n, stride_bytes, m->inv_leaf, keys, vals, err);
+    size_t tb = temp_bytes;
+    MB_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, keys, keys_s, vals, vals_s, (int)n, 0, 63, st));
+    k_mark_heads<<<blocks_for(n, 256), 256, 0, st>>>(keys_s, n, head);
+    tb = temp_bytes;
+    MB_CUDA(cub::DeviceScan::ExclusiveSum(temp, tb, head, run_id, (int)n, st));
+    k_run_starts<<<blocks_for(n, 256), 256, 0, st>>>(head, run_id, n, run_start);
+    k_count2<<<1, 1, 0, st>>>(head, run_id, nullptr, nullptr, n, counters);
+    ctx->launches += 4 + 6;  // own kernels + (approximate) CUB passes
+    uint32_t h_counters[2] = {0, 0};
+    int h_err = 0;
+    MB_CUDA(cudaMemcpyAsync(h_counters, counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaMemcpyAsync(&h_err, err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    if (h_err) {
+      set_error("mb_map_insert: non-finite point or voxel coordinate outside +-2^20");
+      return MB_ERR_UNSUPPORTED;
+    }
+    const uint32_t n_runs = h_counters[0];
+    k_lookup_runs<<<blocks_for(n_runs, 256), 256, 0, st>>>(keys_s, vals_s, run_start, n_runs, m->table,
+                                                           (uint32_t)(m->table_cap - 1), run_packed, new_flag);
+    tb = temp_bytes;
+    MB_CUDA(cub::DeviceScan::ExclusiveSum(temp, tb, new_flag, new_rank, (int)n, st));
+    k_count2<<<1, 1, 0, st>>>(nullptr, nullptr, new_flag, new_rank, n, counters);
+    ctx->launches += 2 + 2;
+    MB_CUDA(cudaMemcpyAsync(h_counters, counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    const uint32_t n_new = h_counters[1];
+    MB_TRY(map_reserve(m, m->n_vox + n_new));  // may rebuild the table; existing ids are unchanged
+    k_create_voxels<<<blocks_for(n_runs, 256), 256, 0, st>>>(keys_s, vals_s, run_start, n_runs, run_packed, new_rank,
+                                                             (uint32_t)m->n_vox, (int)m->lru_counter, m->table,
+                                                             (uint32_t)(m->table_cap - 1), m->info, m->count, m->epos,
+                                                             run_slot);
+    m->n_vox += n_new;
+    const unsigned grid = (unsigned)std::min<size_t>(((size_t)n_runs + 7) / 8, (size_t)ctx->sm_count * 16);
+    k_insert_runs<<<grid, 256, 0, st>>>(raw, stride_bytes, vals_s, run_start, n_runs, run_slot, m->cap,
+                                        m->min_sq_dist, (int)m->lru_counter, m->pts, m->info, m->count, m->epos,
+                                        m->table);
+    ctx->launches += 2;
+    MB_CUDA(cudaGetLastError());
+  }
+  // LRU bookkeeping (every lru_clear_cycle = 10 inserts): drop voxels with lru + horizon < counter.
+  ++m->lru_counter;
+  if (m->lru_counter % 10 == 0 && m->n_vox > 0) {
+    size_t scan_temp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_temp, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)m->n_vox, st);
+    // scratch is free again here (the insert kernels above are ordered before us on the stream), but
+    // ensure_scratch may reallocate, which synchronises first.
+    MB_TRY(ensure_scratch(m, m->n_vox * 8 + scan_temp + 4096));
+    Bump b{(char*)m->scratch, 0, m->scratch_bytes};
+    uint32_t* keep = b.take<uint32_t>(m->n_vox);
+    uint32_t* new_id = b.take<uint32_t>(m->n_vox);
+    uint32_t* counters = b.take<uint32_t>(4);
+    void* temp = b.take<unsigned char>(scan_temp);
+    k_flag_keep<<<blocks_for(m->n_vox, 256), 256, 0, st>>>(m->info, (uint32_t)m->n_vox, (long long)m->lru_horizon,
+                                                           (long long)m->lru_counter, keep);
+    MB_CUDA(cub::DeviceScan::ExclusiveSum(temp, scan_temp, keep, new_id, (int)m->n_vox, st));
+    k_count2<<<1, 1, 0, st>>>(keep, new_id, nullptr, nullptr, m->n_vox, counters);
+    ctx->launches += 4;
+    uint32_t n_keep = 0;
+    MB_CUDA(cudaMemcpyAsync(&n_keep, counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    if (n_keep < m->n_vox) {
+      float4* pts2 = nullptr;
+      int4* info2 = nullptr;
+      int32_t* count2 = nullptr;
+      MB_CUDA(cudaMalloc(&pts2, m->cap_vox * m->cap * sizeof(float4)));
+      MB_CUDA(cudaMalloc(&info2, m->cap_vox * sizeof(int4)));
+      MB_CUDA(cudaMalloc(&count2, m->cap_vox * sizeof(int32_t)));
+      const unsigned grid = (unsigned)std::min<size_t>((m->n_vox + 7) / 8, (size_t)ctx->sm_count * 16);
+      k_compact<<<grid, 256, 0, st>>>(keep, new_id, (uint32_t)m->n_vox, m->cap, m->pts, m->info, m->count, pts2, info2,
+                                      count2);
+      ++ctx->launches;
+      MB_CUDA(cudaStreamSynchronize(st));
+      cudaFree(m->pts);
+      cudaFree(m->info);
+      cudaFree(m->count);
+      m->pts = pts2;
+      m->info = info2;
+      m->count = count2;
+      m->n_vox = n_keep;
+      MB_TRY(rebuild_table(m, m->table_cap));
+    }
+  }
+  MB_CUDA(cudaStreamSynchronize(st));
+  return MB_OK;
+}
+
+int mb_map_download(mb_map* m, int32_t* coords, int32_t* counts, uint32_t* lru, float* pts) {
+  MB_REQUIRE(m, "null map");
+  MB_CUDA(cudaSetDevice(m->ctx->device));
+  cudaStream_t st = m->ctx->stream;
+  const size_t nv = m->n_vox;
+  if (nv == 0) return MB_OK;
+  std::vector<int4> info(nv);
+  MB_CUDA(cudaMemcpyAsync(info.data(), m->info, nv * sizeof(int4), cudaMemcpyDeviceToHost, st));
+  if (counts) MB_CUDA(cudaMemcpyAsync(counts, m->count, nv * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  std::vector<float4> hp;
+  if (pts) {
+    hp.resize(nv * m->cap);
+    MB_CUDA(cudaMemcpyAsync(hp.data(), m->pts, nv * m->cap * sizeof(float4), cudaMemcpyDeviceToHost, st));
+  }
+  std::vector<int32_t> hc;
+  if (pts && !counts) {
+    hc.resize(nv);
+    MB_CUDA(cudaMemcpyAsync(hc.data(), m->count, nv * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  }
+  MB_CUDA(cudaStreamSynchronize(st));
+  const int32_t* cnt = counts ? counts : hc.data();
+  for (size_t v = 0; v < nv; ++v) {
+    if (coords) {
+      coords[3 * v] = info[v].x;
+      coords[3 * v + 1] = info[v].y;
+      coords[3 * v + 2] = info[v].z;
+    }
+    if (lru) lru[v] = (uint32_t)info[v].w;
+    if (pts)
+      for (int j = 0; j < m->cap; ++j) {
+        float* f = pts + (v * m->cap + j) * 3;
+        if (j < cnt[v]) {
+          const float4 p = hp[v * m->cap + j];
+          f[0] = p.x;
+          f[1] = p.y;
+          f[2] = p.z;
+        } else {
+          f[0] = f[1] = f[2] = 0.f;
+        }
+      }
+  }
+  return MB_OK;
+}
+
+int mb_map_upload(mb_map* m, const int32_t* coords, const int32_t* counts, const uint32_t* lru, const float* pts,
+                  size_t n_vox, uint64_t lru_counter) {
+  MB_REQUIRE(m && (n_vox == 0 || (coords && counts && pts)), "null argument");
+  MB_REQUIRE(m->refs.load() == 1, "map is referenced by a factor");
+  MB_CUDA(cudaSetDevice(m->ctx->device));
+  cudaStream_t st = m->ctx->stream;
+  m->n_vox = 0;
+  MB_TRY(map_reserve(m, std::max<size_t>(n_vox, 4096)));
+  std::vector<int4> info(n_vox);
+  std::vector<float4> hp(n_vox * m->cap, make_float4(0.f, 0.f, 0.f, 0.f));
+  for (size_t v = 0; v < n_vox; ++v) {
+    MB_REQUIRE(counts[v] >= 0 && counts[v] <= m->cap, "voxel count outside [0, cap]");
+    info[v] = make_int4(coords[3 * v], coords[3 * v + 1], coords[3 * v + 2], lru ? (int)lru[v] : 0);
+    for (int j = 0; j < counts[v]; ++j) {
+      const float* f = pts + (v * m->cap + j) * 3;
+      hp[v * m->cap + j] = make_float4(f[0], f[1], f[2], 0.f);
+    }
+  }
+  if (n_vox) {
+    MB_CUDA(cudaMemcpyAsync(m->info, info.data(), n_vox * sizeof(int4), cudaMemcpyHostToDevice, st));
+    MB_CUDA(cudaMemcpyAsync(m->count, counts, n_vox * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    MB_CUDA(cudaMemcpyAsync(m->pts, hp.data(), n_vox * m->cap * sizeof(float4), cudaMemcpyHostToDevice, st));
+  }
+  m->n_vox = n_vox;
+  m->lru_counter = lru_counter;
+  MB_TRY(rebuild_table(m, m->table_cap));
+  MB_CUDA(cudaStreamSynchronize(st));
+  return MB_OK;
+}
+
+static int stage_buffers(mb_map* m, size_t nq, int k) {
+  if (nq > m->q_cap || k != m->q_k) {
+    MB_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    cudaFree(m->q_dev);
+    cudaFree(m->q_idx);
+    cudaFree(m->q_d2);
+    cudaFree(m->q_ok);
+    m->q_dev = nullptr;
+    m->q_idx = nullptr;
+    m->q_d2 = nullptr;
+    m->q_ok = nullptr;
+    m->q_cap = 0;
+    MB_CUDA(cudaMalloc(&m->q_dev, nq * 3 * sizeof(double)));
+    MB_CUDA(cudaMalloc(&m->q_idx, nq * k * sizeof(uint64_t)));
+    MB_CUDA(cudaMalloc(&m->q_d2, nq * k * sizeof(double)));
+    MB_CUDA(cudaMalloc(&m->q_ok, nq));
+    m->q_cap = nq;
+    m->q_k = k;
+  }
+  m->q_n = nq;
+  return MB_OK;
+}
+
+int mb_map_knn_stage(mb_map* m, const double* q, size_t nq, int k) {
+  MB_REQUIRE(m && q && nq > 0, "null argument");
+  if (k < 1 || k > MB_MAX_K) {
+    set_error("mb_map_knn: k=%d outside [1, %d]", k, MB_MAX_K);
+    return MB_ERR_UNSUPPORTED;
+  }
+  MB_CUDA(cudaSetDevice(m->ctx->device));
+  MB_TRY(stage_buffers(m, nq, k));
+  MB_CUDA(cudaMemcpyAsync(m->q_dev, q, nq * 3 * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
+  MB_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  return MB_OK;
+}
+
+int mb_map_knn_staged_run(mb_map* m) {
+  MB_REQUIRE(m && m->q_n > 0, "nothing staged");
+  MB_CUDA(cudaSetDevice(m->ctx->device));
+  return launch_knn(m, m->q_dev, m->q_n, m->q_k, m->q_idx, m->q_d2, m->q_ok);
+}
+
+int mb_map_knn_staged_fetch(mb_map* m, uint64_t* idx, double* d2, uint8_t* ok) {
+  MB_REQUIRE(m && m->q_n > 0, "nothing staged");
+  MB_CUDA(cudaSetDevice(m->ctx->device));
+  cudaStream_t st = m->ctx->stream;
+  if (idx) MB_CUDA(cudaMemcpyAsync(idx, m->q_idx, m->q_n * m->q_k * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  if (d2) MB_CUDA(cudaMemcpyAsync(d2, m->q_d2, m->q_n * m->q_k * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (ok) MB_CUDA(cudaMemcpyAsync(ok, m->q_ok, m->q_n, cudaMemcpyDeviceToHost, st));
+  MB_CUDA(cudaStreamSynchronize(st));
+  return MB_OK;
+}
+
+int mb_map_knn(mb_map* m, const double* q, size_t nq, int k, uint64_t* idx, double* d2, uint8_t* ok) {
+  if (nq == 0) return MB_OK;
+  MB_TRY(mb_map_knn_stage(m, q, nq, k));
+  MB_TRY(mb_map_knn_staged_run(m));
+  return mb_map_knn_staged_fetch(m, idx, d2, ok);
+}
+
+int mb_map_points(mb_map* m, const uint64_t* idx, size_t n, double* xyz) {
+  MB_REQUIRE(m && (n == 0 || (idx && xyz)), "null argument");
+  if (n == 0) return MB_OK;
+  MB_CUDA(cudaSetDevice(m->ctx->device));
+  cudaStream_t st = m->ctx->stream;
+  // validate on the host against a copy of the counts (indices come from the caller)
+  std::vector<int32_t> cnt(m->n_vox);
+  if (m->n_vox) MB_CUDA(cudaMemcpyAsync(cnt.data(), m->count, m->n_vox * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  MB_CUDA(cudaStreamSynchronize(st));
+  for (size_t i = 0; i < n; ++i) {
+    const uint64_t v = idx[i] >> 32, j = idx[i] & 0xffffffffull;
+    MB_REQUIRE(v < m->n_vox && (int64_t)j < cnt[v], "point index out of range");
+  }
+  MB_TRY(ensure_scratch(m, n * (sizeof(uint64_t) + 3 * sizeof(double)) + 1024));
+  Bump b{(char*)m->scratch, 0, m->scratch_bytes};
+  uint64_t* d_idx = b.take<uint64_t>(n);
+  double* d_out = b.take<double>(3 * n);
+  MB_CUDA(cudaMemcpyAsync(d_idx, idx, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  k_gather_points<<<blocks_for(n, 256), 256, 0, st>>>(m->pts, m->cap, d_idx, n, d_out);
+  ++m->ctx->launches;
+  MB_CUDA(cudaMemcpyAsync(xyz, d_out, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  MB_CUDA(cudaStreamSynchronize(st));
+  return MB_OK;
+}
+
+// Scratch for mb_downsample lives in the context-free path: allocate per call (scan-sized, a few MB).
+int mb_downsample(mb_ctx* ctx, const float* xyz, size_t n, size_t stride_bytes, float leaf, size_t cap,
+                  float min_dist, uint32_t* out_idx, size_t* n_out) {
+  MB_REQUIRE(ctx && n_out && (n == 0 || (xyz && out_idx)), "null argument");
+  MB_REQUIRE(stride_bytes >= 12 && stride_bytes % 4 == 0, "stride must be >= 12 and a multiple of 4");
+  MB_REQUIRE(leaf > 0.f && min_dist >= 0.f, "leaf must be > 0 and min_dist >= 0");
+  MB_REQUIRE(n < 0x7fffffffull, "too many points");
+  if (cap < 1 || cap > 32) {
+    set_error("mb_downsample: cap %zu outside [1, 32]", cap);
+    return MB_ERR_UNSUPPORTED;
+  }
+  *n_out = 0;
+  if (n == 0) return MB_OK;
+  MB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const double inv_leaf = 1.0 / (double)leaf;
+  const double min_sq = (double)min_dist * (double)min_dist;
+  size_t sort_temp = 0, scan_temp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_temp, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, (int)n, 0, 63, st);
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_temp, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, st);
+  const size_t temp_bytes = std::max(sort_temp, scan_temp);
+  const size_t bytes = n * stride_bytes + n * (16 + 8 + 4 * 8) + n * cap * 4 + temp_bytes + 256 * 20;
+  void* scratch = nullptr;
+  MB_CUDA(cudaMalloc(&scratch, bytes));
+  struct Free {
+    void* p;
+    cudaStream_t s;
+    ~Free() {
+      cudaStreamSynchronize(s);
+      cudaFree(p);
+    }
+  } guard{scratch, st};
+  Bump b{(char*)scratch, 0, bytes};
+  unsigned char* raw = b.take<unsigned char>(n * stride_bytes);
+  uint64_t* keys = b.take<uint64_t>(n);
+  uint64_t* keys_s = b.take<uint64_t>(n);
+  uint32_t* vals = b.take<uint32_t>(n);
+  uint32_t* vals_s = b.take<uint32_t>(n);
+  uint32_t* head = b.take<uint32_t>(n);
+  uint32_t* run_id = b.take<uint32_t>(n);
+  uint32_t* run_start = b.take<uint32_t>(n + 1);
+  uint32_t* first_flag = b.take<uint32_t>(n);
+  uint32_t* first_rank = b.take<uint32_t>(n);
+  uint32_t* kept_count = b.take<uint32_t>(n);
+  uint32_t* offset = b.take<uint32_t>(n);
+  uint32_t* out_d = b.take<uint32_t>(n);
+  uint32_t* kept = b.take<uint32_t>(n * cap);
+  uint32_t* counters = b.take<uint32_t>(4);
+  int* err = b.take<int>(1);
+  void* temp = b.take<unsigned char>(temp_bytes);
+
+  MB_CUDA(cudaMemcpyAsync(raw, xyz, n * stride_bytes, cudaMemcpyHostToDevice, st));
+  MB_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
+  MB_CUDA(cudaMemsetAsync(first_flag, 0, n * sizeof(uint32_t), st));
+  k_make_keys<<<blocks_for(n, 256), 256, 0, st>>>(raw, n, stride_bytes, inv_leaf, keys, vals, err);
+  size_t tb = temp_bytes;
+  MB_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, keys, keys_s, vals, vals_s, (int)n, 0, 63, st));
+  k_mark_heads<<<blocks_for(n, 256), 256, 0, st>>>(keys_s, n, head);
+  tb = temp_bytes;
+  MB_CUDA(cub::DeviceScan::ExclusiveSum(temp, tb, head, run_id, (int)n, st));
+  k_run_starts<<<blocks_for(n, 256), 256, 0, st>>>(head, run_id, n, run_start);
+  k_count2<<<1, 1, 0, st>>>(head, run_id, nullptr, nullptr, n, counters);
+  uint32_t n_runs = 0;
+  int h_err = 0;
+  MB_CUDA(cudaMemcpyAsync(&n_runs, counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  MB_CUDA(cudaMemcpyAsync(&h_err, err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MB_CUDA(cudaStreamSynchronize(st));
+  if (h_err) {
+    set_error("mb_downsample: non-finite point or voxel coordinate outside +-2^20");
+    return MB_ERR_UNSUPPORTED;
+  }
+  k_ds_mark<<<blocks_for(n_runs, 256), 256, 0, st>>>(vals_s, run_start, n_runs, first_flag);
+  tb = temp_bytes;
+  MB_CUDA(cub::DeviceScan::ExclusiveSum(temp, tb, first_flag, first_rank, (int)n, st));
+  const unsigned grid = (unsigned)std::min<size_t>(((size_t)n_runs + 7) / 8, (size_t)ctx->sm_count * 16);
+  k_ds_runs<<<grid, 256, 0, st>>>(raw, stride_bytes, vals_s, run_start, n_runs, first_rank, (int)cap, min_sq, kept,
+                                  kept_count);
+  tb = temp_bytes;
+  MB_CUDA(cub::DeviceScan::ExclusiveSum(temp, tb, kept_count, offset, (int)n_runs, st));
+  k_count2<<<1, 1, 0, st>>>(kept_count, offset, nullptr, nullptr, n_runs, counters);
+  k_ds_scatter<<<blocks_for((size_t)n_runs * cap, 256), 256, 0, st>>>(kept, kept_count, offset, n_runs, (int)cap, out_d);
+  ctx->launches += 9 + 10;
+  uint32_t total = 0;
+  MB_CUDA(cudaMemcpyAsync(&total, counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  MB_CUDA(cudaStreamSynchronize(st));
+  MB_CUDA(cudaMemcpyAsync(out_idx, out_d, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  MB_CUDA(cudaStreamSynchronize(st));
+  *n_out = total;
+  MB_CUDA(cudaGetLastError());
+  return MB_OK;
+}
+
+}  // extern "C"

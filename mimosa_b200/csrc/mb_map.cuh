@@ -1,0 +1,60 @@
+// Device-resident incremental hashed voxel map (internal header).
+//
+// Replaces gtsam_points::iVox behind mimosa::lidar::IncrementalVoxelMapPCL
+// (mimosa/include/mimosa/lidar/incremental_voxel_map.hpp:22-51).  Layout in HBM, all indexed by the
+// voxel id (= creation order, compacted on LRU eviction, exactly the reference's flat-vector index so
+// that (voxel_id << 32) | point_id reproduces the reference's global point index):
+//   pts    float4[cap_vox * cap]   320-byte buckets (cap = 20), xyz stored as f32 — lossless, the reference
+//                                  ingests V3F (mimosa/src/lidar/geometric.cpp:487-492)
+//   info   int4  [cap_vox]         {cx, cy, cz, lru}
+//   count  int32 [cap_vox]
+//   epos   uint32[cap_vox]         position of the voxel's entry in `table`
+//   table  int4  [table_cap]       open-addressing hash {cx, cy, cz, (id << 5) | count}, load <= 0.5
+#pragma once
+#include "mb_internal.cuh"
+
+struct mb_map {
+  mb_ctx* ctx = nullptr;
+  std::atomic<int> refs{1};
+  // parameters
+  double leaf = 1.0, inv_leaf = 1.0, min_sq_dist = 0.0;
+  int cap = 20, nbr_mode = 7, n_off = 7;
+  int8_t off[mb::kMaxNbr * 3] = {0};
+  uint64_t lru_horizon = 100, lru_counter = 0;
+  // storage
+  size_t cap_vox = 0, n_vox = 0, table_cap = 0;
+  float4* pts = nullptr;
+  int4* info = nullptr;
+  int32_t* count = nullptr;
+  uint32_t* epos = nullptr;
+  int4* table = nullptr;
+  unsigned long long* d_npts = nullptr;  // device counter of stored points
+  // staged k-NN (roofline timing)
+  double* q_dev = nullptr;
+  size_t q_n = 0, q_cap = 0;
+  int q_k = 0;
+  uint64_t* q_idx = nullptr;
+  double* q_d2 = nullptr;
+  uint8_t* q_ok = nullptr;
+  // scratch reused across inserts
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+
+  mb::MapView view() const {
+    mb::MapView v;
+    v.table = table;
+    v.table_mask = (uint32_t)(table_cap - 1);
+    v.pts = pts;
+    v.cap = cap;
+    v.n_off = n_off;
+    v.inv_leaf = inv_leaf;
+    std::memcpy(v.off, off, sizeof(off));
+    return v;
+  }
+};
+
+namespace mb {
+int map_reserve(mb_map* m, size_t want_vox);
+// Launch the standalone search kernel over device-resident queries (nq x 3 doubles).
+int launch_knn(mb_map* m, const double* d_q, size_t nq, int k, uint64_t* d_idx, double* d_d2, uint8_t* d_ok);
+}  // namespace mb

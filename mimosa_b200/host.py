@@ -1,0 +1,328 @@
+"""Python mirror of the reference's C++ interface for the LiDAR geometric-factor path, over the C ABI.
+
+Names follow the reference so parity tests read like tests of mimosa itself:
+
+* ``RegistrationConfig``     mimosa/include/mimosa/lidar/geometric_config.hpp:17-33
+* ``IncrementalVoxelMap``    mimosa::lidar::IncrementalVoxelMapPCL, incremental_voxel_map.hpp:22-51
+* ``ICPFactor``              mimosa::lidar::ICPFactor (unary), geometric_factor.hpp:25-563
+
+The production host language is C++ (see mimosa_b200/host/ for the header-only C++ mirror); this module exists
+because the test and benchmark harness of this repository is Python.  All compute happens in
+libmimosa_b200.so on the GPU; numpy is used for argument marshalling only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+from .capi import IcpConfig, IcpTrace, Linearization, check
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+@dataclass
+class RegistrationConfig:
+    """Defaults are the struct defaults of geometric_config.hpp:17-33."""
+
+    source_voxel_grid_filter_leaf_size: float = 0.5
+    source_voxel_grid_min_dist_in_voxel: float = 0.1
+    target_ivox_map_leaf_size: float = 0.5
+    target_ivox_map_min_dist_in_voxel: float = 0.1
+    num_corres_points: int = 5
+    max_corres_distance: float = 2.24
+    plane_validity_distance: float = 0.04
+    lidar_point_noise_std_dev: float = 0.02
+    use_huber: bool = True
+    huber_threshold: float = 1.345
+    reg_4_dof: bool = False
+    project_on_degneneracy: bool = True
+    degen_thresh_rot: float = 10.0
+    degen_thresh_trans: float = 15.0
+
+    def to_c(self) -> IcpConfig:
+        return IcpConfig(
+            self.source_voxel_grid_filter_leaf_size,
+            self.source_voxel_grid_min_dist_in_voxel,
+            self.target_ivox_map_leaf_size,
+            self.target_ivox_map_min_dist_in_voxel,
+            int(self.num_corres_points),
+            self.max_corres_distance,
+            self.plane_validity_distance,
+            self.lidar_point_noise_std_dev,
+            int(self.use_huber),
+            self.huber_threshold,
+            int(self.reg_4_dof),
+            int(self.project_on_degneneracy),
+            self.degen_thresh_rot,
+            self.degen_thresh_trans,
+        )
+
+
+def hornbill_config() -> RegistrationConfig:
+    """mimosa/config/hornbill/params.yaml:86-102 (also magpie / lapwing / parrot / euroc)."""
+    return RegistrationConfig(
+        source_voxel_grid_filter_leaf_size=1.0,
+        source_voxel_grid_min_dist_in_voxel=0.2,
+        target_ivox_map_leaf_size=1.0,
+        target_ivox_map_min_dist_in_voxel=0.2,
+        num_corres_points=5,
+        max_corres_distance=1.0,
+        plane_validity_distance=0.07,
+        lidar_point_noise_std_dev=0.07,
+        use_huber=True,
+        huber_threshold=1.345,
+        reg_4_dof=False,
+        project_on_degneneracy=False,
+        degen_thresh_rot=0.0,
+        degen_thresh_trans=40.0,
+    )
+
+
+HORNBILL_MAP = dict(leaf=1.0, min_dist=0.2, cap=20, nbr_mode=19, lru_horizon=1000)
+
+
+class Context:
+    """One per process and GPU (mb_init)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = capi.load()
+        h = C.c_void_p()
+        check(self.lib.mb_init(device, C.byref(h)))
+        self.h = h
+        self.device = device
+        self.rank, self.world = 0, 1
+
+    def close(self):
+        if self.h:
+            self.lib.mb_shutdown(self.h)
+            self.h = None
+
+    def sync(self):
+        check(self.lib.mb_sync(self.h))
+
+    def timer_begin(self):
+        check(self.lib.mb_timer_begin(self.h))
+
+    def timer_end(self) -> float:
+        ms = C.c_float()
+        check(self.lib.mb_timer_end(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self) -> int:
+        v = C.c_uint64()
+        check(self.lib.mb_launch_count(self.h, C.byref(v)))
+        return int(v.value)
+
+    def flush_l2(self, nbytes: int = 256 << 20):
+        check(self.lib.mb_flush_l2(self.h, nbytes))
+
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        check(self.lib.mb_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, rank: int, world: int, uid: bytes):
+        buf = C.create_string_buffer(uid, 128)
+        check(self.lib.mb_comm_init(self.h, rank, world, buf))
+        self.rank, self.world = rank, world
+
+    def downsample(self, xyz: np.ndarray, leaf: float, cap: int, min_dist: float) -> np.ndarray:
+        """Geometric::downsample (geometric.cpp:55-126): indices of the kept points, reference order."""
+        pts = np.ascontiguousarray(xyz, dtype=np.float32)
+        n, stride = pts.shape[0], pts.strides[0]
+        out = np.empty(n, dtype=np.uint32)
+        n_out = C.c_size_t()
+        check(self.lib.mb_downsample(self.h, _ptr(pts), n, stride, leaf, cap, min_dist, _ptr(out), C.byref(n_out)))
+        return out[: n_out.value].copy()
+
+
+class IncrementalVoxelMap:
+    """IncrementalVoxelMapPCL: insert / knn_search / getCloud / copy (snapshot)."""
+
+    def __init__(self, ctx: Context, leaf: float, min_dist: float = 0.1, cap: int = 20, nbr_mode: int = 7,
+                 lru_horizon: int = 100, _handle=None):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.leaf, self.min_dist, self.cap, self.nbr_mode, self.lru_horizon = leaf, min_dist, cap, nbr_mode, lru_horizon
+        if _handle is None:
+            h = C.c_void_p()
+            check(self.lib.mb_map_create(ctx.h, leaf, min_dist, cap, nbr_mode, lru_horizon, C.byref(h)))
+            _handle = h
+        self.h = _handle
+
+    def release(self):
+        if self.h:
+            self.lib.mb_map_release(self.h)
+            self.h = None
+
+    def insert(self, xyz: np.ndarray):
+        """xyz: (n, >=3) float32 rows; only the first three columns are read (stride honoured)."""
+        pts = np.ascontiguousarray(xyz, dtype=np.float32)
+        check(self.lib.mb_map_insert(self.h, _ptr(pts), pts.shape[0], pts.strides[0] if pts.shape[0] else 12))
+
+    def snapshot(self) -> "IncrementalVoxelMap":
+        """The deep copy mimosa makes before every insert (geometric.cpp:494)."""
+        h = C.c_void_p()
+        check(self.lib.mb_map_snapshot(self.h, C.byref(h)))
+        return IncrementalVoxelMap(self.ctx, self.leaf, self.min_dist, self.cap, self.nbr_mode, self.lru_horizon, h)
+
+    def size(self):
+        nv, npts, lru = C.c_size_t(), C.c_size_t(), C.c_uint64()
+        check(self.lib.mb_map_size(self.h, C.byref(nv), C.byref(npts), C.byref(lru)))
+        return int(nv.value), int(npts.value), int(lru.value)
+
+    def knn_search(self, q: np.ndarray, k: int):
+        """Returns (idx (nq,k) uint64, d2 (nq,k) float64, ok (nq,) bool) — ok == (found == k)."""
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, 3)
+        nq = q.shape[0]
+        idx = np.empty((nq, k), dtype=np.uint64)
+        d2 = np.empty((nq, k), dtype=np.float64)
+        ok = np.empty(nq, dtype=np.uint8)
+        check(self.lib.mb_map_knn(self.h, _ptr(q), nq, k, _ptr(idx), _ptr(d2), _ptr(ok)))
+        return idx, d2, ok.astype(bool)
+
+    def knn_stage(self, q: np.ndarray, k: int):
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, 3)
+        self._staged = (q.shape[0], k)
+        check(self.lib.mb_map_knn_stage(self.h, _ptr(q), q.shape[0], k))
+
+    def knn_staged_run(self):
+        check(self.lib.mb_map_knn_staged_run(self.h))
+
+    def knn_staged_fetch(self):
+        nq, k = self._staged
+        idx = np.empty((nq, k), dtype=np.uint64)
+        d2 = np.empty((nq, k), dtype=np.float64)
+        ok = np.empty(nq, dtype=np.uint8)
+        check(self.lib.mb_map_knn_staged_fetch(self.h, _ptr(idx), _ptr(d2), _ptr(ok)))
+        return idx, d2, ok.astype(bool)
+
+    def points(self, idx: np.ndarray) -> np.ndarray:
+        """iVox::point(i) for global indices (voxel_id << 32) | point_id."""
+        idx = np.ascontiguousarray(idx, dtype=np.uint64).ravel()
+        out = np.empty((idx.size, 3), dtype=np.float64)
+        check(self.lib.mb_map_points(self.h, _ptr(idx), idx.size, _ptr(out)))
+        return out
+
+    def download(self):
+        """(coords (nv,3) i32, counts (nv,) i32, lru (nv,) u32, pts (nv,cap,3) f32, lru_counter)."""
+        nv, _, lru_counter = self.size()
+        coords = np.zeros((nv, 3), dtype=np.int32)
+        counts = np.zeros(nv, dtype=np.int32)
+        lru = np.zeros(nv, dtype=np.uint32)
+        pts = np.zeros((nv, self.cap, 3), dtype=np.float32)
+        check(self.lib.mb_map_download(self.h, _ptr(coords), _ptr(counts), _ptr(lru), _ptr(pts)))
+        return coords, counts, lru, pts, lru_counter
+
+    def upload(self, coords, counts, lru, pts, lru_counter: int = 0):
+        coords = np.ascontiguousarray(coords, dtype=np.int32)
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        lru = None if lru is None else np.ascontiguousarray(lru, dtype=np.uint32)
+        pts = np.ascontiguousarray(pts, dtype=np.float32)
+        check(self.lib.mb_map_upload(self.h, _ptr(coords), _ptr(counts), _ptr(lru), _ptr(pts), coords.shape[0], lru_counter))
+
+    def get_cloud(self) -> np.ndarray:
+        """IncrementalVoxelMapPCL::getCloud: all stored points, voxel order then in-voxel order."""
+        _, counts, _, pts, _ = self.download()
+        keep = np.arange(self.cap)[None, :] < counts[:, None]
+        return pts[keep]
+
+
+class ICPFactor:
+    """Unary scan-to-map ICP factor.  `scan` is (n, >=3) float32 (xyz first), e.g. (n, 8) lidar::Point rows."""
+
+    def __init__(self, ctx: Context, target: IncrementalVoxelMap, scan: np.ndarray, config: RegistrationConfig,
+                 shard=None):
+        self.ctx, self.lib, self.target, self.config = ctx, ctx.lib, target, config
+        pts = np.ascontiguousarray(scan, dtype=np.float32)
+        n = pts.shape[0]
+        begin, end = (0, n) if shard is None else shard
+        self.n_total, self.begin, self.end = n, begin, end
+        self.k = int(config.num_corres_points)
+        h = C.c_void_p()
+        cfg = config.to_c()
+        check(self.lib.mb_factor_create(ctx.h, target.h, _ptr(pts), n, pts.strides[0] if n else 12, C.byref(cfg),
+                                        begin, end, C.byref(h)))
+        self.h = h
+        self.last = None
+
+    @property
+    def n(self):
+        return self.end - self.begin
+
+    def release(self):
+        if self.h:
+            self.lib.mb_factor_release(self.h)
+            self.h = None
+
+    def reset(self):
+        check(self.lib.mb_factor_reset(self.h))
+
+    def set_flags(self, forced_search: bool = False, cuda_graph: bool = False):
+        check(self.lib.mb_factor_set_flags(self.h, (1 if forced_search else 0) | (2 if cuda_graph else 0)))
+
+    def linearize(self, R, t, gravity_unit=(0.0, 0.0, -1.0)) -> Linearization:
+        R = np.ascontiguousarray(R, dtype=np.float64).reshape(9)
+        t = np.ascontiguousarray(t, dtype=np.float64).reshape(3)
+        g = np.ascontiguousarray(gravity_unit, dtype=np.float64).reshape(3)
+        out = Linearization()
+        check(self.lib.mb_factor_linearize(self.h, _ptr(R), _ptr(t), _ptr(g), C.byref(out)))
+        self.last = out
+        return out
+
+    def download_state(self, knn: bool = True):
+        n = self.n
+        st = np.empty(n, dtype=np.uint8)
+        arrs = [np.empty((n, 3), dtype=np.float64) for _ in range(5)]
+        idx = np.empty((n, self.k), dtype=np.uint64) if knn else None
+        check(self.lib.mb_factor_download_state(self.h, _ptr(st), *[_ptr(a) for a in arrs], _ptr(idx)))
+        return dict(status=st, p_da=arrs[0], mean=arrs[1], normal=arrs[2], loc_rot=arrs[3], loc_trans=arrs[4], knn_idx=idx)
+
+    # accessors named after geometric_factor.hpp:48-72
+    def get_statuses(self):
+        return self.download_state(knn=False)["status"]
+
+    def get_corres_means_target(self):
+        return self.download_state(knn=False)["mean"]
+
+    def get_corres_normals_target(self):
+        return self.download_state(knn=False)["normal"]
+
+    def get_localizabilities(self):
+        L = self.last
+        a = lambda x, shape=None: np.array(x, dtype=np.float64).reshape(shape) if shape else np.array(x, dtype=np.float64)
+        return (a(L.loc_trans_comp), a(L.loc_rot_comp), a(L.loc_trans_final), a(L.loc_rot_final),
+                a(L.eigvec_trans, (3, 3)), a(L.eigvec_rot, (3, 3)))
+
+    def get_linearize_count(self):
+        return 0 if self.last is None else int(self.last.linearize_count)
+
+    def icp_run(self, R, t, iters: int, lam: float = 0.0, want_trace: bool = True):
+        """Device-resident Gauss-Newton loop; returns (R, t, trace list)."""
+        R = np.array(R, dtype=np.float64).reshape(9).copy()
+        t = np.array(t, dtype=np.float64).reshape(3).copy()
+        trace = (IcpTrace * iters)() if (want_trace and iters) else None
+        check(self.lib.mb_icp_run(self.h, _ptr(R), _ptr(t), iters, lam, trace))
+        return R.reshape(3, 3), t, (list(trace) if trace is not None else [])
+
+
+def degeneracy_flags(L: Linearization, config: RegistrationConfig):
+    """Geometric::getFactors' consumer of the localizabilities (geometric.cpp:218-228)."""
+    ev = np.zeros((6, 6))
+    ev[:3, :3] = np.array(L.eigvec_rot).reshape(3, 3)
+    ev[3:, 3:] = np.array(L.eigvec_trans).reshape(3, 3)
+    d = np.zeros(6)
+    d[:3] = np.array(L.loc_rot_comp) < config.degen_thresh_rot
+    d[3:] = np.array(L.loc_trans_comp) < config.degen_thresh_trans
+    return ev, d
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous block of the scan owned by `rank` (ceil(n/world) points per rank)."""
+    per = (n + world - 1) // world
+    b = min(n, rank * per)
+    return b, min(n, b + per)
