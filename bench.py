@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""bench.py — ICP iterations/s of the LiDAR geometric-factor path (BASELINE.json's metric).
+
+Workload (config C4 of BASELINE.json, also used at N = 1): a synthetic 131 072-point OS0-128-style scan
+registered against a ~10 M-point hashed voxel map, 20 Gauss-Newton iterations per scan, hornbill parameters
+(mimosa/config/hornbill/params.yaml:86-102).  One "step" = one scan = 20 ICP iterations (each = one
+ICPFactor::linearize + 6x6 solve + SE(3) retract, data-association cache semantics on, as in the reference).
+
+  value     device-resident loop (mb_icp_run, CUDA graph), scan + map already in HBM; per-step CUDA-event times
+  e2e       the reference-facing call sequence with HOST buffers: ICPFactor(scan) [H2D], then 20 x
+            { linearize(pose) -> H, g, f [D2H] ; 6x6 solve + retract on the host } — what mimosa's
+            Geometric::getFactors + the smoother's update() loop would drive
+  roofline  the restricted k-NN kernel alone on a "spread" query set (131 072 queries over the whole 10 M-pt
+            map, working set >> L2), algorithmic bytes / CUDA-event time vs the measured HBM copy bandwidth
+  cpu_baseline  the CPU oracle (port of the reference path) on the box's host cores, same inputs
+
+`--impl reference` times the CPU oracle only (no GPU code on that path).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tools")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+ITERS = 20
+LAMBDA = 0.0
+N_SCAN = 131072
+MAP_POINTS = 10_000_000
+MAP_HALF_EXTENT = 500.0
+K_NN = 5
+METRIC = "icp_iterations_per_sec"
+UNIT = "iterations/s"
+WORKLOAD = "C4: 131072-pt OS0-128 scan vs 10M-pt voxel map, 20 ICP iters/scan, hornbill params"
+if os.environ.get("MB_BENCH_SMALL"):  # development dry-runs only; the workload string says so
+    N_SCAN, MAP_POINTS, MAP_HALF_EXTENT = 20000, 300_000, 100.0
+    WORKLOAD = "DEV-SMALL (not the benchmark config): 20000-pt scan vs 300k-pt map"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_inputs():
+    """Deterministic inputs shared by every arm: the chunk sequence fed to the map and the scan."""
+    import synth
+
+    rng = synth.rng_for(4)
+    R_true, t_true = synth.rot_from_rpy(0.0, 0.0, 0.3), np.array([1.0, -1.0, 0.2])
+    scan = synth.make_scan(R_true, t_true, N_SCAN, rng)
+    R0, t0 = synth.perturbed_start(R_true, t_true)
+    return rng, scan, R0, t0, R_true, t_true
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.rows, self.proc, self.device = [], None, device
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.device)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nme, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- algorithmic bytes of one k-NN launch ----------------------------------------------------
+def knn_algorithmic_bytes(q: np.ndarray, coords: np.ndarray, counts: np.ndarray, k: int, nbr_mode: int = 19, leaf: float = 1.0):
+    """Compulsory bytes: every query (24 B) read once, every DISTINCT probed hash entry (16 B) once, every
+    DISTINCT occupied neighbour bucket's stored points (count x 16 B) once, results written once
+    (k x (8 + 8) + 1 B per query)."""
+    offs = np.array([(i, j, kk) for i in (-1, 0, 1) for j in (-1, 0, 1) for kk in (-1, 0, 1)
+                     if nbr_mode == 27 or not (i and j and kk)], dtype=np.int64)
+    c = np.floor(q / leaf).astype(np.int64)
+    bias = 1 << 20
+    pack = lambda a: ((a[..., 0] + bias) << 42) | ((a[..., 1] + bias) << 21) | (a[..., 2] + bias)
+    probed = np.unique(pack(c[:, None, :] + offs[None, :, :]).ravel())
+    mkeys = pack(coords.astype(np.int64))
+    order = np.argsort(mkeys)
+    pos = np.searchsorted(mkeys[order], probed)
+    pos[pos >= mkeys.size] = mkeys.size - 1
+    hit = mkeys[order][pos] == probed
+    bucket_bytes = int(counts[order][pos[hit]].astype(np.int64).sum()) * 16
+    nq = q.shape[0]
+    total = nq * 24 + probed.size * 16 + bucket_bytes + nq * (k * 16 + 1)
+    return total, {"queries": nq, "distinct_probed_coords": int(probed.size), "distinct_buckets": int(hit.sum()),
+                   "bucket_bytes": bucket_bytes}
+
+
+def host_gn_step(L, R, t, lam):
+    """The harness' stand-in for ISAM2 on the e2e path: delta = (H + lam I)^-1 g, T <- T Exp(delta) (numpy)."""
+    import synth
+
+    H = np.array(L.H).reshape(6, 6)
+    g = np.array(L.g)
+    try:
+        d = np.linalg.solve(H + lam * np.eye(6), g)
+    except np.linalg.LinAlgError:
+        return R, t
+    dR, dt = synth.expmap_se3(d)
+    return R @ dR, R @ dt + t
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle (port of the reference's ICPFactor / iVox path) on the host cores."""
+    if rank != 0:
+        return
+    import oracle_py as orc
+    import synth
+    from mimosa_b200.host import HORNBILL_MAP, hornbill_config
+
+    orc.build()
+    rng, scan, R0, t0, _, _ = make_inputs()
+    t_build = time.time()
+    mo = orc.IVoxRef(**HORNBILL_MAP)
+    synth.build_map(mo.insert, MAP_POINTS, MAP_HALF_EXTENT, rng, size_fn=lambda: mo.size()[1])
+    log(f"[reference] oracle map built: {mo.size()} in {time.time() - t_build:.1f}s")
+    cores = orc.max_threads()
+    f = orc.IcpFactorRef(mo, scan, hornbill_config())
+
+    def step(nt):
+        f.reset()
+        return f.icp_run(R0, t0, ITERS, LAMBDA, n_threads=nt)[3]
+
+    for _ in range(args.warmup):
+        step(cores)
+    secs = [step(cores) for _ in range(args.steps)]
+    total = float(np.sum(secs))
+    value = ITERS * args.steps / total
+    faithful = ITERS / min(step(4) for _ in range(3))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "iters_per_step": ITERS, "map_points": mo.size()[1], "map_voxels": mo.size()[0],
+                   "scan_points": int(scan.shape[0])},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full scans x {ITERS} iterations, OpenMP {cores} threads "
+                                   f"(the reference hard-codes 4: {faithful:.1f} it/s at 4 threads)",
+                         "faithful_4_threads": faithful},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--profile-knn", action="store_true", help="only build inputs and run a few k-NN launches (for ncu)")
+    ap.add_argument("--profile-icp", action="store_true", help="only build inputs and run two ICP steps (for ncu)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if not (args.profile_knn or args.profile_icp) else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch  # first: maps torch's bundled NCCL before libmimosa_b200.so asks for libnccl.so.2
+    import torch.distributed as dist
+
+    import synth
+    from mimosa_b200 import HORNBILL_MAP, Context, ICPFactor, IncrementalVoxelMap, hornbill_config, shard_range
+    from mimosa_b200.capi import Linearization
+
+    if world > 1:
+        dist.init_process_group(backend="gloo", rank=rank, world_size=world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    ctx = Context(local_rank)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(ctx.comm_unique_id()), dtype=torch.uint8).clone()
+        dist.broadcast(uid, src=0)
+        ctx.comm_init(rank, world, bytes(uid.numpy().tobytes()))
+
+    # ---- inputs (every rank builds the identical replicated map) -----------------------------------------
+    t_setup = time.time()
+    rng, scan, R0, t0, R_true, t_true = make_inputs()
+    mg = IncrementalVoxelMap(ctx, **HORNBILL_MAP)
+    synth.build_map(mg.insert, MAP_POINTS, MAP_HALF_EXTENT, rng, size_fn=lambda: mg.size()[1])
+    n_vox, n_pts, _ = mg.size()
+    log(f"[rank {rank}] map: {n_vox} voxels, {n_pts} points; scan {scan.shape}; setup {time.time() - t_setup:.1f}s")
+    cfg = hornbill_config()
+    shard = shard_range(scan.shape[0], rank, world)
+
+    if args.profile_knn or args.profile_icp:
+        if args.profile_knn:
+            cloud = mg.get_cloud()
+            q = synth.spread_queries(cloud, N_SCAN, synth.rng_for(40))
+            mg.knn_stage(q, K_NN)
+            for _ in range(max(args.steps, 1)):
+                ctx.flush_l2()
+                mg.knn_staged_run()
+            ctx.sync()
+        if args.profile_icp:
+            f = ICPFactor(ctx, mg, scan, cfg, shard)
+            for _ in range(max(args.steps, 1)):
+                f.reset()
+                ctx.flush_l2()
+                f.icp_run(R0, t0, ITERS, LAMBDA, want_trace=False)
+        return
+
+    # ---- value: device-resident ICP loop ---------------------------------------------------------------
+    f = ICPFactor(ctx, mg, scan, cfg, shard)
+    f.set_flags(cuda_graph=not args.no_graph)
+
+    def dev_step():
+        f.reset()
+        ctx.flush_l2()
+        ctx.sync()
+        barrier()
+        ctx.timer_begin()
+        R, t, _ = f.icp_run(R0, t0, ITERS, LAMBDA, want_trace=False)
+        return ctx.timer_end(), R, t
+
+    for _ in range(args.warmup):
+        dev_step()
+    launches0 = ctx.launch_count()
+    flush_launches = 0
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        step_ms = []
+        for _ in range(args.steps):
+            ms, R, t = dev_step()
+            step_ms.append(ms)
+            flush_launches += 1
+        ctx.sync()
+        barrier()
+        # ---- e2e: reference-facing calls with host buffers -------------------------------------------------
+        e2e_secs = []
+        lin_bytes = 0
+        for s in range(args.warmup + args.steps):
+            ctx.flush_l2()
+            ctx.sync()
+            barrier()
+            t_a = time.perf_counter()
+            fe = ICPFactor(ctx, mg, scan, cfg, shard)  # H2D: this rank's block of the scan
+            Re, te = R0, t0
+            for _ in range(ITERS):
+                L = fe.linearize(Re, te)  # H2D pose, D2H normal equations
+                Re, te = host_gn_step(L, Re, te, LAMBDA)
+            ctx.sync()
+            t_b = time.perf_counter()
+            fe.release()
+            if s >= args.warmup:
+                e2e_secs.append(t_b - t_a)
+    launches = ctx.launch_count() - launches0
+
+    total_ms = float(np.sum(step_ms))
+    e2e_total = float(np.sum(e2e_secs))
+    if world > 1:
+        tt = torch.tensor([total_ms, e2e_total], dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms, e2e_total = float(tt[0]), float(tt[1])
+    value = ITERS * args.steps / (total_ms * 1e-3)
+    e2e_value = ITERS * args.steps / e2e_total
+    pose_err = float(np.abs(np.asarray(t) - t_true).max())
+    n_shard = shard[1] - shard[0]
+    h2d = ((n_shard + 31) // 32 * 32) * 16 + ITERS * 15 * 8
+    import ctypes as C
+
+    d2h = ITERS * (C.sizeof(Linearization) + 6 * 8)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "iters_per_step": ITERS, "map_points": n_pts, "map_voxels": n_vox,
+                   "scan_points": int(scan.shape[0]), "parallelism": f"scan-block shard x{world}, map replicated, "
+                   "40-double NCCL allreduce/iter" if world > 1 else "1 GPU",
+                   "l2": "flushed (256 MiB write) before every timed step, outside the event bracket",
+                   "cuda_graph": not args.no_graph, "final_pose_err_m": pose_err},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1e3 * e2e_total / args.steps,
+                "what": "mb_factor_create(host scan) + 20 x [mb_factor_linearize(host pose) -> host H,g,f + host 6x6 solve/retract]"},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+    }
+
+    if rank == 0 and world == 1:
+        # ---- roofline: the restricted k-NN kernel, spread regime ---------------------------------------
+        coords, counts, _, pts, lru_counter = mg.download()
+        cloud = pts[np.arange(pts.shape[1])[None, :] < counts[:, None]]
+        q = synth.spread_queries(cloud, N_SCAN, synth.rng_for(40))
+        bytes_alg, parts = knn_algorithmic_bytes(q, coords, counts, K_NN)
+        mg.knn_stage(q, K_NN)
+        for _ in range(3):
+            ctx.flush_l2()
+            mg.knn_staged_run()
+        knn_ms = []
+        for _ in range(10):
+            ctx.flush_l2()
+            ctx.sync()
+            ctx.timer_begin()
+            mg.knn_staged_run()
+            knn_ms.append(ctx.timer_end())
+        t_knn = float(np.mean(knn_ms)) * 1e-3
+        peak, peak_src = peaks()
+        achieved = bytes_alg / t_knn / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("k_knn_dram_bytes_per_launch")
+        line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": traffic, "kernel": "k_knn (restricted 19-voxel k-NN, k=5), spread queries over the "
+                            "whole map, L2 flushed before every launch", "algorithmic_bytes": int(bytes_alg),
+                            "us_per_launch": t_knn * 1e6, "us_min": float(np.min(knn_ms)) * 1e3, "peak_source": peak_src,
+                            "queries_per_s": N_SCAN / t_knn, **parts}
+        # local regime for context: the scan's own first-iteration queries (working set << L2)
+        q_loc = scan[:, :3].astype(np.float64) @ R0.T + t0
+        b_loc, _ = knn_algorithmic_bytes(q_loc, coords, counts, K_NN)
+        mg.knn_stage(q_loc, K_NN)
+        loc_ms = []
+        for _ in range(8):
+            ctx.flush_l2()
+            ctx.sync()
+            ctx.timer_begin()
+            mg.knn_staged_run()
+            loc_ms.append(ctx.timer_end())
+        line["roofline"]["local_regime"] = {"us_per_launch": float(np.mean(loc_ms[3:])) * 1e3, "algorithmic_bytes": int(b_loc),
+                                            "achieved_gbs": b_loc / (float(np.mean(loc_ms[3:])) * 1e-3) / 1e9}
+
+        # ---- cpu_baseline: the oracle on the host cores, same map + scan ----------------------------------
+        if not args.no_cpu_baseline:
+            import oracle_py as orc
+
+            orc.build()
+            mo = orc.IVoxRef(**HORNBILL_MAP)
+            mo.load_raw(coords, counts, None, pts, lru_counter)
+            fo = orc.IcpFactorRef(mo, scan, cfg)
+            cores = orc.max_threads()
+
+            def cpu_step(nt):
+                fo.reset()
+                return fo.icp_run(R0, t0, ITERS, LAMBDA, n_threads=nt)
+
+            cpu_step(cores)
+            reps, spent, best_all = 0, 0.0, 1e30
+            while reps < 3 or (spent < 10.0 and reps < 40):
+                Rc, tc, _, secs = cpu_step(cores)
+                spent += secs
+                best_all = min(best_all, secs)
+                reps += 1
+            best4 = min(cpu_step(4)[3] for _ in range(3))
+            line["cpu_baseline"] = {
+                "value": ITERS * reps / spent, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{reps} full scans x {ITERS} iterations of the same workload (oracle, OpenMP {cores} threads)",
+                "best_all_cores": ITERS / best_all, "faithful_4_threads": ITERS / best4,
+                "pose_agrees_with_gpu": bool(np.abs(np.asarray(tc) - np.asarray(t)).max() < 1e-6)}
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    f.release()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

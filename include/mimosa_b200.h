@@ -110,6 +110,9 @@ MB_API int mb_init(int device, mb_ctx** out);
 MB_API int mb_shutdown(mb_ctx* ctx);
 MB_API const char* mb_last_error(void);
 MB_API int mb_version(void);
+/* sizeof of the ABI structs as compiled (0: mb_icp_config, 1: mb_linearization, 2: mb_icp_trace) so a foreign
+ * binding can verify its layout. */
+MB_API size_t mb_sizeof(int which);
 /* Synchronise the context's stream. */
 MB_API int mb_sync(mb_ctx* ctx);
 /* CUDA-event timer on the context's stream (device time of everything enqueued between the calls). */

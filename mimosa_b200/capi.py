@@ -98,6 +98,7 @@ SIGNATURES = {
     "mb_shutdown": (C.c_int, [_P]),
     "mb_last_error": (C.c_char_p, []),
     "mb_version": (C.c_int, []),
+    "mb_sizeof": (C.c_size_t, [C.c_int]),
     "mb_sync": (C.c_int, [_P]),
     "mb_timer_begin": (C.c_int, [_P]),
     "mb_timer_end": (C.c_int, [_P, C.POINTER(C.c_float)]),
@@ -147,11 +148,20 @@ def load() -> C.CDLL:
             f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a).  mimosa_b200 has no CPU fallback."
         )
+    try:
+        # If torch is going to be used in this process (bench.py, tests) it must map ITS bundled libnccl.so.2
+        # first; otherwise the system NCCL this library links against would shadow it by soname.
+        import torch  # noqa: F401
+    except Exception:  # pragma: no cover - torch is plumbing, not a requirement of the library
+        pass
     lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
+    for which, struct in enumerate((IcpConfig, Linearization, IcpTrace)):
+        if lib.mb_sizeof(which) != C.sizeof(struct):
+            raise ImportError(f"ABI mismatch: {struct.__name__} is {C.sizeof(struct)} B here, {lib.mb_sizeof(which)} B in the library")
     _lib = lib
     return lib
 

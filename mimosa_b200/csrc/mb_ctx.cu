@@ -16,6 +16,18 @@ void set_error(const char* fmt, ...) {
   g_last_error = buf;
 }
 
+int pinned_reserve(mb_ctx* c, size_t bytes) {
+  if (bytes <= c->pinned_bytes) return MB_OK;
+  MB_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->pinned) MB_CUDA(cudaFreeHost(c->pinned));
+  c->pinned = nullptr;
+  c->pinned_bytes = 0;
+  bytes = (bytes + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
+  MB_CUDA(cudaMallocHost(&c->pinned, bytes));
+  c->pinned_bytes = bytes;
+  return MB_OK;
+}
+
 namespace {
 __global__ void k_fill(uint4* p, size_t n, unsigned v) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -30,6 +42,14 @@ extern "C" {
 
 const char* mb_last_error(void) { return g_last_error.c_str(); }
 int mb_version(void) { return 100; }
+size_t mb_sizeof(int which) {
+  switch (which) {
+    case 0: return sizeof(mb_icp_config);
+    case 1: return sizeof(mb_linearization);
+    case 2: return sizeof(mb_icp_trace);
+    default: return 0;
+  }
+}
 
 int mb_init(int device, mb_ctx** out) {
   MB_REQUIRE(out, "null out");
@@ -66,6 +86,7 @@ int mb_shutdown(mb_ctx* c) {
   cudaStreamSynchronize(c->stream);
   if (c->comm) ncclCommDestroy(c->comm);
   cudaFree(c->flush_buf);
+  if (c->pinned) cudaFreeHost(c->pinned);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
   cudaStreamDestroy(c->stream);

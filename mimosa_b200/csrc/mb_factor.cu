@@ -602,12 +602,20 @@ int mb_factor_create(mb_ctx* ctx, mb_map* map, const void* pts, size_t n, size_t
   }
   // scan: host AoS with arbitrary stride -> device float4 (only xyz is read by the factor,
   // geometric_factor.hpp:277,323,346)
-  std::vector<float4> h(f->ld, make_float4(0.f, 0.f, 0.f, 0.f));
+  {
+    int prc = pinned_reserve(ctx, f->ld * sizeof(float4));
+    if (prc != MB_OK) {
+      mb_factor_release(f);
+      return prc;
+    }
+  }
+  float4* h = (float4*)ctx->pinned;
   for (size_t i = 0; i < f->n; ++i) {
     const float* p = (const float*)((const char*)pts + (shard_begin + i) * stride_bytes);
     h[i] = make_float4(p[0], p[1], p[2], 0.f);
   }
-  MB_CUDA(cudaMemcpyAsync(f->src, h.data(), f->ld * sizeof(float4), cudaMemcpyHostToDevice, st));
+  for (size_t i = f->n; i < f->ld; ++i) h[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  MB_CUDA(cudaMemcpyAsync(f->src, h, f->ld * sizeof(float4), cudaMemcpyHostToDevice, st));
   MB_CUDA(cudaMemsetAsync(f->tickets, 0, 4 * sizeof(unsigned), st));
   MB_CUDA(cudaMemsetAsync(f->packed, 0, (kPack + 8) * sizeof(double), st));
   MB_CUDA(cudaMemsetAsync(f->ds, 0, sizeof(DevState), st));

@@ -59,7 +59,14 @@ struct mb_ctx {
   int rank = 0, world = 1;
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
+  void* pinned = nullptr;  // page-locked staging for host <-> device copies of scans
+  size_t pinned_bytes = 0;
 };
+
+namespace mb {
+// Grow-only page-locked staging buffer of the context (synchronises the stream when it has to grow).
+int pinned_reserve(mb_ctx* c, size_t bytes);
+}
 
 namespace mb {
 

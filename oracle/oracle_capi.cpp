@@ -169,5 +169,8 @@ int orc_solve6(const double* H, double lambda, const double* rhs, double* x) {
 }
 int orc_fast_floor(double x) { return fast_floor1(x); }
 int orc_max_threads() { return omp_get_max_threads(); }
+size_t orc_sizeof(int which) {
+  return which == 0 ? sizeof(RegistrationConfigRef) : which == 1 ? sizeof(LinearizationRef) : which == 2 ? sizeof(IcpTraceRef) : 0;
+}
 
 }  // extern "C"

@@ -97,10 +97,13 @@ def lib() -> C.CDLL:
             "orc_solve6": (C.c_int, [_P, C.c_double, _P, _P]),
             "orc_fast_floor": (C.c_int, [C.c_double]),
             "orc_max_threads": (C.c_int, []),
+            "orc_sizeof": (_SZ, [C.c_int]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
+        for which, struct in enumerate((IcpConfig, Linearization, IcpTrace)):
+            assert L.orc_sizeof(which) == C.sizeof(struct), (struct.__name__, L.orc_sizeof(which), C.sizeof(struct))
         _lib = L
     return _lib
 

@@ -1,0 +1,69 @@
+"""CPU: the C-ABI library loads and exports exactly the symbols include/mimosa_b200.h declares; without a GPU
+the product fails loudly instead of falling back."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "mimosa_b200.h")).read()
+    return sorted(set(re.findall(r"MB_API\s+[\w\s\*]+?\b(mb_\w+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    from mimosa_b200 import capi
+
+    assert declared_symbols() == sorted(capi.SIGNATURES)
+
+
+def test_library_exports_every_declared_symbol():
+    from mimosa_b200 import capi
+
+    lib = capi.load()
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+    assert lib.mb_version() >= 100
+
+
+def test_struct_layouts_match_oracle_binding(oracle):
+    from mimosa_b200 import capi
+
+    for a, b in ((capi.IcpConfig, oracle.IcpConfig), (capi.Linearization, oracle.Linearization), (capi.IcpTrace, oracle.IcpTrace)):
+        assert C.sizeof(a) == C.sizeof(b)
+        assert [(n, t) for n, t in a._fields_] == [(n, t) for n, t in b._fields_]
+    lib = capi.load()
+    L = oracle.lib()
+    for which, s in enumerate((capi.IcpConfig, capi.Linearization, capi.IcpTrace)):
+        assert lib.mb_sizeof(which) == C.sizeof(s) == L.orc_sizeof(which)
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mimosa_b200 import capi
+
+    lib = capi.load()
+    h = C.c_void_p()
+    assert lib.mb_init(0, C.byref(h)) == capi.MB_ERR_NO_DEVICE
+    assert b"no CPU path" in lib.mb_last_error()
+    import mimosa_b200
+
+    with pytest.raises(capi.MimosaError):
+        mimosa_b200.Context(0)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "mimosa_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                txt = open(os.path.join(dirpath, fn), errors="replace").read()
+                assert "oracle_py" not in txt and "liboracle" not in txt, fn
+                assert not re.search(r"#\s*include[^\n]*(oracle|_ref\.hpp)", txt), fn
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, re.M), fn

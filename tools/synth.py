@@ -38,9 +38,15 @@ def sample_ground(n: int, half_extent: float, rng, noise: float = 0.01) -> np.nd
     return p.astype(np.float32)
 
 
-def sample_boxes(n: int, rng, noise: float = 0.01, grid: int = BOX_GRID) -> np.ndarray:
+def boxes_within(half_extent: float) -> np.ndarray:
+    """Centres of the world's boxes that lie entirely inside |x|,|y| <= half_extent."""
+    c = box_centers()
+    return c[(np.abs(c[:, 0]) + BOX_HALF <= half_extent) & (np.abs(c[:, 1]) + BOX_HALF <= half_extent)]
+
+
+def sample_boxes(n: int, rng, noise: float = 0.01, centers=None) -> np.ndarray:
     """Uniform per area over the 4 walls and the top of every box."""
-    centers = box_centers(grid)
+    centers = box_centers() if centers is None else centers
     side = 2 * BOX_HALF
     areas = np.array([side * BOX_HEIGHT] * 4 + [side * side])
     face = rng.choice(5, size=n, p=areas / areas.sum())
@@ -70,13 +76,13 @@ def sample_boxes(n: int, rng, noise: float = 0.01, grid: int = BOX_GRID) -> np.n
 
 def sample_world(n: int, half_extent: float, rng, noise: float = 0.01) -> np.ndarray:
     """Ground + boxes inside |x|,|y| <= half_extent, area-proportional, shuffled."""
-    grid = int(min(BOX_GRID, max(0, np.floor(2 * half_extent / BOX_PITCH))))
+    centers = boxes_within(half_extent)
     ground_area = (2 * half_extent) ** 2
-    box_area = grid * grid * (4 * 2 * BOX_HALF * BOX_HEIGHT + (2 * BOX_HALF) ** 2)
-    n_box = int(round(n * box_area / (ground_area + box_area))) if grid > 0 else 0
+    box_area = centers.shape[0] * (4 * 2 * BOX_HALF * BOX_HEIGHT + (2 * BOX_HALF) ** 2)
+    n_box = int(round(n * box_area / (ground_area + box_area))) if centers.shape[0] else 0
     parts = [sample_ground(n - n_box, half_extent, rng, noise)]
     if n_box:
-        parts.append(sample_boxes(n_box, rng, noise, grid))
+        parts.append(sample_boxes(n_box, rng, noise, centers))
     p = np.concatenate(parts, axis=0)
     return p[rng.permutation(p.shape[0])]
 
