@@ -58,7 +58,8 @@ __global__ void k_run_starts(const uint32_t* __restrict__ head, const uint32_t* 
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (head[i]) run_start[run_id[i]] = (uint32_t)i;
-  if (i == n - 1) run_start[run_id[i] + 1] = (uint32_t)n;
+  // exclusive scan: a head sees its own run index, a non-head already counts its run's head
+  if (i == n - 1) run_start[run_id[i] + head[i]] = (uint32_t)n;  // sentinel at index n_runs
 }
 
 // counters[0] = number of runs, counters[1] = number of new voxels

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import synth
-from helpers import assert_linearization_close, assert_state_equal, load_golden, rel_err
+from helpers import assert_linearization_close, assert_state_equal, g_err, load_golden, rel_err
 from mimosa_b200 import HORNBILL_MAP, ICPFactor, IncrementalVoxelMap, hornbill_config
 from mimosa_b200.capi import MB_ERR_INVALID_ARG, MB_ERR_UNSUPPORTED, MimosaError
 
@@ -207,7 +207,7 @@ def test_c1_icp_run_matches_golden(ctx):
             assert list(tr.counts) == g["tr_counts"][it].tolist(), it
             assert tr.n_searched == g["tr_n_searched"][it] and tr.solve_ok == 1
             assert rel_err(np.array(tr.H).reshape(6, 6), g["tr_H"][it]) <= 1e-7
-            assert rel_err(tr.g, g["tr_g"][it]) <= 1e-7
+            assert g_err(tr.g, g["tr_g"][it], g["tr_H"][it], g["tr_f"][it]) <= 1e-7
             assert abs(tr.f - g["tr_f"][it]) <= 1e-7 * g["tr_f"][it]
             assert np.abs(np.array(tr.R).reshape(3, 3) - g["tr_R"][it]).max() <= POSE_TOL
             assert np.abs(np.array(tr.t) - g["tr_t"][it]).max() <= POSE_TOL
@@ -252,7 +252,7 @@ def test_world_icp_matches_oracle(ctx, oracle):
     for it, (a, b) in enumerate(zip(trg, tro)):
         assert list(a.counts) == list(b.counts), (it, list(a.counts), list(b.counts))
         assert a.n_searched == b.n_searched and a.solve_ok == b.solve_ok == 1
-        assert rel_err(a.H, b.H) <= 1e-7 and rel_err(a.g, b.g) <= 1e-6
+        assert rel_err(a.H, b.H) <= 1e-7 and g_err(a.g, b.g, b.H, b.f) <= 1e-7
         assert np.abs(np.array(a.R) - np.array(b.R)).max() <= POSE_TOL
         assert np.abs(np.array(a.t) - np.array(b.t)).max() <= POSE_TOL
     assert_state_equal(fg.download_state(), fo.download_state(), float_tol=1e-9)
