@@ -223,7 +223,7 @@ def main():
     import torch.distributed as dist
 
     import synth
-    from mimosa_b200 import HORNBILL_MAP, Context, ICPFactor, IncrementalVoxelMap, hornbill_config, shard_range
+    from mimosa_b200 import HORNBILL_MAP, Context, ICPFactor, IncrementalVoxelMap, gn_step, hornbill_config, shard_range
     from mimosa_b200.capi import Linearization
 
     if world > 1:
@@ -306,7 +306,7 @@ def main():
             Re, te = R0, t0
             for _ in range(ITERS):
                 L = fe.linearize(Re, te)  # H2D pose, D2H normal equations
-                Re, te = host_gn_step(L, Re, te, LAMBDA)
+                Re, te, _, _ = gn_step(L, Re, te, LAMBDA)  # host-side 6x6 solve + retract (mb_gn_step)
             ctx.sync()
             t_b = time.perf_counter()
             fe.release()

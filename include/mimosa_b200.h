@@ -184,7 +184,13 @@ MB_API int mb_factor_download_state(mb_factor* f, uint8_t* status, double* p_da,
                                     double* loc_rot, double* loc_trans, uint64_t* knn_idx);
 /* R,t updated in place; trace may be NULL or hold `iters` entries. */
 MB_API int mb_icp_run(mb_factor* f, double R[9], double t[3], int iters, double lambda, mb_icp_trace* trace);
-/* Debug/ablation switches: bit0 = disable the data-association cache ("forced" search every call). */
+/* Host-side Gauss-Newton step of the harness (what mb_icp_run does on the device between two linearisations,
+ * for callers that drive mb_factor_linearize themselves):  delta = (H + lambda I)^-1 g,  T <- T * Expmap(delta).
+ * Returns MB_OK and leaves T unchanged (delta = 0, *solve_ok = 0) when a pivot is not positive. */
+MB_API int mb_gn_step(const double H[36], const double g[6], double lambda, double R[9], double t[3], double delta[6],
+                      int* solve_ok);
+/* Debug/ablation switches: bit0 = disable the data-association cache ("forced" search every call);
+ * bit1 = run mb_icp_run as one captured CUDA graph. */
 MB_API int mb_factor_set_flags(mb_factor* f, uint32_t flags);
 
 /* ---- scan preparation ("next" rows of the scope table) ----------------------------------------------

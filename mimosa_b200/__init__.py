@@ -10,6 +10,7 @@ from .host import (  # noqa: F401
     IncrementalVoxelMap,
     RegistrationConfig,
     degeneracy_flags,
+    gn_step,
     hornbill_config,
     shard_range,
 )

@@ -125,6 +125,7 @@ SIGNATURES = {
     "mb_factor_download_state": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "mb_icp_run": (C.c_int, [_P, _P, _P, C.c_int, C.c_double, _P]),
     "mb_factor_set_flags": (C.c_int, [_P, C.c_uint32]),
+    "mb_gn_step": (C.c_int, [_P, _P, C.c_double, _P, _P, _P, C.POINTER(C.c_int)]),
     "mb_downsample": (C.c_int, [_P, _P, _SZ, _SZ, C.c_float, _SZ, C.c_float, _P, C.POINTER(_SZ)]),
 }
 

@@ -1,4 +1,5 @@
 // Context, error reporting, timing and communicator plumbing of libmimosa_b200.so.
+#include <algorithm>
 #include <mutex>
 
 #include "mb_internal.cuh"
@@ -26,6 +27,46 @@ int pinned_reserve(mb_ctx* c, size_t bytes) {
   MB_CUDA(cudaMallocHost(&c->pinned, bytes));
   c->pinned_bytes = bytes;
   return MB_OK;
+}
+
+int dev_alloc(mb_ctx* c, void** p, size_t bytes) {
+  bytes = std::max<size_t>((bytes + 255) & ~(size_t)255, 256);
+  for (size_t i = 0; i < c->pool.size(); ++i)
+    if (c->pool[i].bytes == bytes) {
+      *p = c->pool[i].p;
+      c->pool_bytes -= bytes;
+      c->pool[i] = c->pool.back();
+      c->pool.pop_back();
+      return MB_OK;
+    }
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) {
+    dev_pool_release(c);  // give cached blocks back and retry once
+    e = cudaMalloc(p, bytes);
+  }
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    *p = nullptr;
+    return MB_ERR_CUDA;
+  }
+  return MB_OK;
+}
+
+void dev_free(mb_ctx* c, void* p, size_t bytes) {
+  if (!p) return;
+  bytes = std::max<size_t>((bytes + 255) & ~(size_t)255, 256);
+  if (c->pool.size() < 64 && c->pool_bytes + bytes <= ((size_t)2 << 30)) {
+    c->pool.push_back({p, bytes});
+    c->pool_bytes += bytes;
+  } else {
+    cudaFree(p);
+  }
+}
+
+void dev_pool_release(mb_ctx* c) {
+  for (auto& b : c->pool) cudaFree(b.p);
+  c->pool.clear();
+  c->pool_bytes = 0;
 }
 
 namespace {
@@ -76,6 +117,7 @@ int mb_init(int device, mb_ctx** out) {
   MB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   MB_CUDA(cudaEventCreate(&c->ev0));
   MB_CUDA(cudaEventCreate(&c->ev1));
+  MB_CUDA(cudaMallocHost(&c->pin_small, 4096));
   *out = c;
   return MB_OK;
 }
@@ -87,6 +129,8 @@ int mb_shutdown(mb_ctx* c) {
   if (c->comm) ncclCommDestroy(c->comm);
   cudaFree(c->flush_buf);
   if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->pin_small) cudaFreeHost(c->pin_small);
+  dev_pool_release(c);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
   cudaStreamDestroy(c->stream);
@@ -139,6 +183,27 @@ int mb_flush_l2(mb_ctx* c, size_t bytes) {
   k_fill<<<c->sm_count * 4, 256, 0, c->stream>>>((uint4*)c->flush_buf, bytes / 16, ++tick);
   ++c->launches;
   MB_CUDA(cudaGetLastError());
+  return MB_OK;
+}
+
+int mb_gn_step(const double H[36], const double g[6], double lambda, double R[9], double t[3], double delta[6],
+               int* solve_ok) {
+  MB_REQUIRE(H && g && R && t && delta, "null argument");
+  for (int a = 0; a < 6; ++a) delta[a] = 0.0;
+  const bool ok = solve6_ldlt(H, lambda, g, delta);
+  if (ok) {
+    m33 Rm;
+    for (int a = 0; a < 9; ++a) Rm.m[a] = R[a];
+    d3 T = mk3(t[0], t[1], t[2]);
+    se3_retract(Rm, T, delta);
+    for (int a = 0; a < 9; ++a) R[a] = Rm.m[a];
+    t[0] = T.x;
+    t[1] = T.y;
+    t[2] = T.z;
+  } else {
+    for (int a = 0; a < 6; ++a) delta[a] = 0.0;
+  }
+  if (solve_ok) *solve_ok = ok ? 1 : 0;
   return MB_OK;
 }
 

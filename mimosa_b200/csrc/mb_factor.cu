@@ -1,20 +1,25 @@
 // Point-to-plane scan-to-map ICP factor on the device: the body of mimosa::lidar::ICPFactor::linearize
 // (mimosa/include/mimosa/lidar/geometric_factor.hpp:231-562) and estimatePlane (:176-229).
 //
-//   k_linearize   transform + data-association gate (:276-287), warp-cooperative restricted k-NN
-//                 (:294, via mb_internal.cuh::knn_warp), gates (:296-302), plane fit (:176-229), residual,
-//                 s-check, Huber, Jacobian (:319-355), per-point localizability vectors (:351-352) and the
-//                 J^T J / J^T e / e^2 / status-count reduction (:364-366, 396-403) — ONE kernel, the
-//                 neighbour points never leave the SM.
+//   k_linearize   per tile of 128 scan points, in one kernel:
+//                   A  transform + data-association gate (:276-287), block-compaction of the points that
+//                      must re-associate;
+//                   B  restricted k-NN (:294; one query per thread, mb_internal.cuh::knn_thread), the two
+//                      distance gates (:296-302) and the plane fit (:176-229) for the compacted points;
+//                   C  residual, s-check, Huber, Jacobian, per-point localizability vectors (:319-355) and the
+//                      [J e]^T [J e] / status-count reduction (:364-366, 396-403).
+//                 The neighbour points never leave the SM; per-point state is read and written once.
 //   k_finalize    6x6 assembly, localizability eigen-decompositions, Schur complements, 4-DoF projection
 //                 (:405-428, 464-475) and — for the stand-alone Gauss-Newton harness — the LDL^T solve and
 //                 SE(3) retract that ISAM2 performs in the reference (mimosa/src/graph/manager.cpp:585-588).
+//                 Five independent roles run on five warps.
 //   k_loc_comp    the component-localizability second pass over valid points (:434-457).
 // With more than one rank the 40-double packet between k_linearize and k_finalize (and the 6 doubles after
 // k_loc_comp) are all-reduced with NCCL; every rank then computes the identical step.
 //
 // Per-point state (status, DA anchor, plane mean/normal, localizability vectors) lives in HBM inside the
 // factor handle as structure-of-arrays, mirroring the `mutable` vectors at geometric_factor.hpp:79-106.
+// Every reduction has a fixed order, so results are bitwise repeatable for a given launch shape.
 #include <algorithm>
 #include <vector>
 
@@ -23,10 +28,12 @@
 namespace mb {
 namespace {
 
-constexpr int kLinWarps = 4;
+constexpr int kLinThreads = 128;
+constexpr int kLinWarps = kLinThreads / 32;
 constexpr int kPack = 40;  // 21 H upper-tri, 6 J^T e, 1 f, 9 status counts, 1 n_searched, 2 pad
-constexpr int kPackH = 0, kPackB = 21, kPackF = 27, kPackCnt = 28, kPackSearched = 37;
-static_assert(kPackF == 27 && kPackB == 21, "packing matches the lane ownership in k_linearize");
+constexpr int kPackB = 21, kPackF = 27, kPackCnt = 28, kPackSearched = 37;
+constexpr int kGroup = 32;  // blocks per first-level reduction group
+constexpr int kLocThreads = 256;
 
 struct FactorView {
   const float4* src;
@@ -37,19 +44,21 @@ struct FactorView {
   int k, use_huber;
   uint32_t flags;
   double da_gate, max_corr_sq, sigma, kh, pvd;
-  double* partials;  // [grid][kPack]
-  unsigned* ticket;
-  double* packed;    // [kPack]
-  double* partials2; // [grid2][8]
+  double* partials;    // [grid][kPack]
+  double* gpartials;   // [n_groups][kPack]
+  unsigned* gtickets;  // [n_groups]
+  unsigned* ticket;    // final
+  double* packed;      // [kPack]
+  double* partials2;   // [grid2][8]
   unsigned* ticket2;
-  double* loc_out;   // [8]: trans comp (3), rot comp (3)
+  double* loc_out;     // [8]: trans comp (3), rot comp (3)
 };
 
-struct DevState {          // small device-resident block per factor
-  double pose[12];         // R row-major (9), t (3)
+struct DevState {        // small device-resident block per factor
+  double pose[12];       // R row-major (9), t (3)
   double gravity[3];
   double lambda;
-  mb_linearization lin;    // result of the most recent linearisation (loc_*_comp filled on the host)
+  mb_linearization lin;  // result of the most recent linearisation (loc_*_comp filled on the host)
 };
 
 __device__ __forceinline__ d3 ld3(const double* base, size_t ld, size_t i) {
@@ -63,21 +72,26 @@ __device__ __forceinline__ void st3(double* base, size_t ld, size_t i, d3 v) {
 
 // Plane through the k neighbours (geometric_factor.hpp:176-229).  Returns the new status
 // (MB_UNPROCESSED = all gates passed); mean is always written, normal once the eigen gates pass.
-__device__ __forceinline__ uint8_t fit_plane(const float4* nb, int k, d3 origin, double pvd, d3& mean, d3& normal,
+template <int K>
+__device__ __forceinline__ uint8_t fit_plane(const float4 (&nb)[K], int k, d3 origin, double pvd, d3& mean, d3& normal,
                                              bool& normal_set) {
   d3 s = mk3(0, 0, 0);
-  for (int j = 0; j < k; ++j) s = add3(s, mk3((double)nb[j].x, (double)nb[j].y, (double)nb[j].z));
+#pragma unroll
+  for (int j = 0; j < K; ++j)
+    if (j < k) s = add3(s, mk3((double)nb[j].x, (double)nb[j].y, (double)nb[j].z));
   mean = div3(s, (double)k);
   double c00 = 0, c10 = 0, c11 = 0, c20 = 0, c21 = 0, c22 = 0;
-  for (int j = 0; j < k; ++j) {
-    const d3 c = sub3(mk3((double)nb[j].x, (double)nb[j].y, (double)nb[j].z), mean);
-    c00 += c.x * c.x;
-    c10 += c.y * c.x;
-    c11 += c.y * c.y;
-    c20 += c.z * c.x;
-    c21 += c.z * c.y;
-    c22 += c.z * c.z;
-  }
+#pragma unroll
+  for (int j = 0; j < K; ++j)
+    if (j < k) {
+      const d3 c = sub3(mk3((double)nb[j].x, (double)nb[j].y, (double)nb[j].z), mean);
+      c00 += c.x * c.x;
+      c10 += c.y * c.x;
+      c11 += c.y * c.y;
+      c20 += c.z * c.x;
+      c21 += c.z * c.y;
+      c22 += c.z * c.z;
+    }
   const double dn = (double)(k - 1);
   m33 cov;
   cov.m[0] = c00 / dn;
@@ -100,27 +114,62 @@ __device__ __forceinline__ uint8_t fit_plane(const float4* nb, int k, d3 origin,
   normal = nrm;
   normal_set = true;
   bool invalid = false;
-  for (int j = 0; j < k; ++j) {
-    const d3 c = sub3(mk3((double)nb[j].x, (double)nb[j].y, (double)nb[j].z), mean);
-    if (fabs(dot3(c, nrm)) > pvd) invalid = true;
-  }
+#pragma unroll
+  for (int j = 0; j < K; ++j)
+    if (j < k) {
+      const d3 c = sub3(mk3((double)nb[j].x, (double)nb[j].y, (double)nb[j].z), mean);
+      if (fabs(dot3(c, nrm)) > pvd) invalid = true;
+    }
   return invalid ? MB_CORRES_PLANE_INVALID : MB_UNPROCESSED;
 }
 
-__global__ void __launch_bounds__(kLinWarps * 32)
+// Sum `count` rows of `width`-double records (row stride = width) in ascending row order into out[0..width),
+// using all `threads` threads of the block: thread t owns value t % width and every (threads / width)-th row.
+// Loads are issued eight at a time.  s_tmp holds (threads / width) * width doubles.
+__device__ __forceinline__ void block_sum_rows(const double* rows, int count, int width, double* s_tmp, double* out,
+                                               int threads) {
+  const int parts = threads / width;
+  const int a = threadIdx.x % width, part = threadIdx.x / width;
+  if (part < parts) {
+    double v = 0.0;
+    int b = part;
+    for (; b + 7 * parts < count; b += 8 * parts) {
+      double x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) x[u] = __ldcg(rows + (size_t)(b + u * parts) * width + a);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v += x[u];
+    }
+    for (; b < count; b += parts) v += __ldcg(rows + (size_t)b * width + a);
+    s_tmp[part * width + a] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < width) {
+    double v = 0.0;
+    for (int p = 0; p < parts; ++p) v += s_tmp[p * width + threadIdx.x];
+    out[threadIdx.x] = v;
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kLinThreads, 5)
     k_linearize(MapView mv, FactorView fv, const double* __restrict__ pose) {
   __shared__ int8_t s_off[32 * 3];
-  __shared__ uint32_t s_vox_all[kLinWarps][32];
-  __shared__ float4 s_nb_all[kLinWarps][32][MB_MAX_K];
-  __shared__ double s_row_all[kLinWarps][32][7];  // per point of the tile: whitened [J (6), e]
+  // s_pk (phase B: probed neighbour words, [n_off][thread]) is re-used as s_row (phase C: whitened
+  // [J (6), e] per point, [warp][32][7] doubles = 7168 B <= 27 * 128 * 4 B).
+  __shared__ __align__(16) uint32_t s_pk_all[kMaxNbr * kLinThreads];
+  __shared__ double s_pt[3][kLinThreads];          // transformed point of each tile member
+  __shared__ double s_mean[3][kLinThreads], s_normal[3][kLinThreads];
+  __shared__ double s_dk[kLinThreads];             // squared distance of the k-th neighbour
+  __shared__ uint8_t s_status[kLinThreads];
+  __shared__ uint16_t s_queue[kLinThreads];
+  __shared__ int s_warp_need[kLinWarps];
   __shared__ double s_red[kLinWarps][kPack];
+  __shared__ double s_tmp[(kLinThreads / kPack) * kPack];
   __shared__ bool s_last;
-  if (threadIdx.x < kMaxNbr * 3) s_off[threadIdx.x] = mv.off[threadIdx.x];
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t* s_vox = s_vox_all[warp];
-  float4(*s_nb)[MB_MAX_K] = s_nb_all[warp];
-  double(*s_row)[7] = s_row_all[warp];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < kMaxNbr * 3) s_off[tid] = mv.off[tid];
+  double(*s_row)[7] = reinterpret_cast<double(*)[7]>(s_pk_all) + warp * 32;
   // Lane a < 28 owns entry a of the packed upper triangle of [J e]^T [J e] (7x7): the 21 entries of
   // J^T J first (row-major, c >= r), then J^T e (6), then e^2.
   int pr = 0, pc = 0;
@@ -150,12 +199,13 @@ __global__ void __launch_bounds__(kLinWarps * 32)
 
   double acc = 0.0;
   int cnt = 0;  // lane s < 9: points with status s; lane 9: points searched
+  __syncthreads();
 
-  const size_t n_tiles = (fv.n + 31) / 32;
-  const size_t warps_total = (size_t)gridDim.x * kLinWarps;
-  for (size_t tile = (size_t)blockIdx.x * kLinWarps + warp; tile < n_tiles; tile += warps_total) {
-    const size_t i = tile * 32 + lane;
+  const size_t n_tiles = (fv.n + kLinThreads - 1) / kLinThreads;
+  for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const size_t i = tile * kLinThreads + tid;
     const bool act = i < fv.n;
+    // ---- A: transform, gate, compaction ------------------------------------------------------------
     d3 ps = mk3(0, 0, 0), pt = mk3(0, 0, 0);
     uint8_t st = MB_UNPROCESSED;
     bool need = false;
@@ -167,47 +217,88 @@ __global__ void __launch_bounds__(kLinWarps * 32)
       const d3 da = ld3(fv.p_da, fv.ld, i);
       need = forced || sqrt(sqnorm3(sub3(pt, da))) > fv.da_gate;
     }
+    s_pt[0][tid] = pt.x;
+    s_pt[1][tid] = pt.y;
+    s_pt[2][tid] = pt.z;
     const unsigned mask = __ballot_sync(kFull, need);
-    int my_found = 0;
-    double my_dk = 0.0;
-    for (unsigned m = mask; m; m &= m - 1) {
-      const int src_lane = __ffs(m) - 1;
-      const double qx = __shfl_sync(kFull, pt.x, src_lane), qy = __shfl_sync(kFull, pt.y, src_lane),
-                   qz = __shfl_sync(kFull, pt.z, src_lane);
-      KnnOut o;
-      knn_warp(mv, s_off, s_vox, qx, qy, qz, k, lane, o);
-      if (lane < k) {
-        uint64_t g = ~0ull;
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (o.seq != 0xffffffffu) g = knn_fetch(mv, s_vox, o.seq, p);
-        s_nb[src_lane][lane] = p;
-        if (fv.knn_idx) fv.knn_idx[(tile * 32 + src_lane) * k + lane] = o.found == k ? g : ~0ull;
-      }
-      const double dk = __shfl_sync(kFull, o.d2, k - 1);
-      if (lane == src_lane) {
-        my_found = o.found;
-        my_dk = dk;
-      }
-      __syncwarp();
+    if (lane == 0) s_warp_need[warp] = __popc(mask);
+    __syncthreads();
+    int base = 0, n_need = 0;
+#pragma unroll
+    for (int w = 0; w < kLinWarps; ++w) {
+      if (w < warp) base += s_warp_need[w];
+      n_need += s_warp_need[w];
     }
+    if (need) s_queue[base + __popc(mask & ((1u << lane) - 1))] = (uint16_t)tid;
+    __syncthreads();
 
+    // ---- B: search + plane fit for the compacted points -------------------------------------------
+    for (int q0 = warp * 32; q0 < n_need; q0 += kLinThreads) {
+      const int qi = q0 + lane;
+      const bool on = qi < n_need;
+      const int li = on ? (int)s_queue[qi] : 0;
+      const double qx = s_pt[0][li], qy = s_pt[1][li], qz = s_pt[2][li];
+      double bd[K];
+      uint32_t bs[K];
+      uint32_t* s_pk = s_pk_all + tid;
+      knn_thread<K>(mv, s_off, s_pk, kLinThreads, qx, qy, qz, k, on, bd, bs);
+      if (on) {
+        const size_t gi = tile * kLinThreads + li;
+        int found = 0;
+        float4 nb[K];
+        double dk = 0.0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          nb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (j < k) {
+            uint64_t g = ~0ull;
+            if (bs[j] != 0xffffffffu) {
+              g = knn_resolve(mv, s_pk, kLinThreads, bs[j], nb[j]);
+              ++found;
+            }
+            if (j == k - 1) dk = bd[j];
+            // indices are only meaningful when all k exist (the reference discards partial results)
+            if (fv.knn_idx) fv.knn_idx[gi * k + j] = g;
+          }
+        }
+        uint8_t rs = MB_UNPROCESSED;
+        d3 mean = mk3(0, 0, 0), normal = mk3(0, 0, 0);
+        if (found != k) {
+          rs = MB_INSUFFICIENT_CORRES_POINTS;
+          if (fv.knn_idx)
+            for (int j = 0; j < k; ++j) fv.knn_idx[gi * k + j] = ~0ull;
+        } else if (dk > fv.max_corr_sq) {
+          rs = MB_CORRES_MAX_DIST;
+        } else {
+          bool normal_set;
+          rs = fit_plane<K>(nb, k, T, fv.pvd, mean, normal, normal_set);
+          st3(fv.mean, fv.ld, gi, mean);
+          if (normal_set) st3(fv.normal, fv.ld, gi, normal);
+        }
+        s_status[li] = rs;
+        s_mean[0][li] = mean.x;
+        s_mean[1][li] = mean.y;
+        s_mean[2][li] = mean.z;
+        s_normal[0][li] = normal.x;
+        s_normal[1][li] = normal.y;
+        s_normal[2][li] = normal.z;
+        s_dk[li] = dk;
+      }
+    }
+    __syncthreads();
+
+    // ---- C: residual, Jacobian, accumulation (own point) --------------------------------------------
     double row[7] = {0, 0, 0, 0, 0, 0, 0};
     if (act) {
       bool proceed = false;
       d3 mean = mk3(0, 0, 0), normal = mk3(0, 0, 0);
       if (need) {
         st3(fv.p_da, fv.ld, i, pt);
-        st = MB_UNPROCESSED;
-        if (my_found != k) {
-          st = MB_INSUFFICIENT_CORRES_POINTS;
-        } else if (my_dk > fv.max_corr_sq) {
-          st = MB_CORRES_MAX_DIST;
-        } else {
-          bool normal_set;
-          st = fit_plane(s_nb[lane], k, T, fv.pvd, mean, normal, normal_set);
-          st3(fv.mean, fv.ld, i, mean);
-          if (normal_set) st3(fv.normal, fv.ld, i, normal);
-          proceed = st == MB_UNPROCESSED;
+        st = s_status[tid];
+        if (st == MB_UNPROCESSED) {
+          mean = mk3(s_mean[0][tid], s_mean[1][tid], s_mean[2][tid]);
+          normal = mk3(s_normal[0][tid], s_normal[1][tid], s_normal[2][tid]);
+          proceed = true;
         }
       } else if (st > MB_CORRES_PLANE_INVALID) {
         mean = ld3(fv.mean, fv.ld, i);
@@ -244,7 +335,7 @@ __global__ void __launch_bounds__(kLinWarps * 32)
       }
       fv.status[i] = st;
     }
-    // [J e]^T [J e] over the tile: lane a sums its entry over the 32 rows in point order.
+    // [J e]^T [J e] over the warp's 32 points: lane a sums its entry over the rows in point order.
     const unsigned any_valid = __ballot_sync(kFull, act && st == MB_VALID);
     if (any_valid) {
 #pragma unroll
@@ -252,7 +343,6 @@ __global__ void __launch_bounds__(kLinWarps * 32)
       __syncwarp();
 #pragma unroll 8
       for (int p = 0; p < 32; ++p) acc += s_row[p][pr] * s_row[p][pc];
-      __syncwarp();
     }
 #pragma unroll
     for (int s = 0; s < 9; ++s) {
@@ -260,32 +350,40 @@ __global__ void __launch_bounds__(kLinWarps * 32)
       if (lane == s) cnt += c;
     }
     if (lane == 9) cnt += __popc(mask);
+    __syncthreads();  // s_row (= s_pk), s_queue, s_status ... are rewritten by the next tile
   }
 
-  // warp -> block -> grid reduction (fixed order, deterministic for a given launch shape)
+  // ---- block partial -> group partial -> packet (two ticketed levels, fixed order) ------------------------
   if (lane < 28) s_red[warp][lane] = acc;
   if (lane >= 30) s_red[warp][lane + 8] = 0.0;  // pad entries 38, 39
   if (lane < 10) s_red[warp][kPackCnt + lane] = (double)cnt;
   __syncthreads();
-  if (threadIdx.x < kPack) {
+  if (tid < kPack) {
     double v = 0.0;
 #pragma unroll
-    for (int w = 0; w < kLinWarps; ++w) v += s_red[w][threadIdx.x];
-    fv.partials[(size_t)blockIdx.x * kPack + threadIdx.x] = v;
+    for (int w = 0; w < kLinWarps; ++w) v += s_red[w][tid];
+    fv.partials[(size_t)blockIdx.x * kPack + tid] = v;
   }
+  const int g = blockIdx.x / kGroup;
+  const int n_groups = (gridDim.x + kGroup - 1) / kGroup;
+  const int g_size = min(kGroup, (int)gridDim.x - g * kGroup);
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(fv.ticket, 1u) == gridDim.x - 1;
+  if (tid == 0) s_last = atomicAdd(fv.gtickets + g, 1u) == (unsigned)g_size - 1;
   __syncthreads();
-  if (s_last) {
-    __threadfence();
-    if (threadIdx.x < kPack) {
-      double v = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(fv.partials + (size_t)b * kPack + threadIdx.x);
-      fv.packed[threadIdx.x] = v;
-    }
-    if (threadIdx.x == 0) *fv.ticket = 0u;
-  }
+  if (!s_last) return;
+  __threadfence();
+  block_sum_rows(fv.partials + (size_t)g * kGroup * kPack, g_size, kPack, s_tmp, fv.gpartials + (size_t)g * kPack,
+                 kLinThreads);
+  if (tid == 0) fv.gtickets[g] = 0u;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(fv.ticket, 1u) == (unsigned)n_groups - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  block_sum_rows(fv.gpartials, n_groups, kPack, s_tmp, fv.packed, kLinThreads);
+  if (tid == 0) *fv.ticket = 0u;
 }
 
 __device__ __forceinline__ void localizability(const m33& JtJ, double loc[3], m33& V) {
@@ -294,112 +392,142 @@ __device__ __forceinline__ void localizability(const m33& JtJ, double loc[3], m3
   for (int a = 0; a < 3; ++a) loc[a] = sqrt(lam[a]);
 }
 
-// Single thread: everything after the per-point loop of ICPFactor::linearize, plus the harness GN step.
-__global__ void k_finalize(const double* __restrict__ packed, DevState* ds, int reg_4_dof, int linearize_count,
-                           int do_step, int iter, mb_icp_trace* trace) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double H[36], b[6];
+// Everything after the per-point loop of ICPFactor::linearize, plus the harness GN step.  Lane 0 of warp w
+// plays role w: 0/1 localizability of the rotational / translational block, 2/3 Schur-complement degeneracy
+// info, 4 projection + packing + solve + retract.
+__global__ void __launch_bounds__(160) k_finalize(const double* __restrict__ packed, DevState* ds, int reg_4_dof,
+                                                  int linearize_count, int do_step, int iter, mb_icp_trace* trace) {
+  if ((threadIdx.x & 31) != 0) return;
+  const int role = threadIdx.x >> 5;
+  double H[36];
   {
     int u = 0;
+#pragma unroll
     for (int a = 0; a < 6; ++a)
+#pragma unroll
       for (int c = a; c < 6; ++c) {
-        H[6 * a + c] = packed[kPackH + u];
-        H[6 * c + a] = packed[kPackH + u];
+        H[6 * a + c] = packed[u];
+        H[6 * c + a] = packed[u];
         ++u;
       }
   }
-  for (int a = 0; a < 6; ++a) b[a] = packed[kPackB + a];
-  const double f = packed[kPackF];
   mb_linearization& L = ds->lin;
   m33 Hrr, Hrt, Htr, Htt;
+#pragma unroll
   for (int r = 0; r < 3; ++r)
+#pragma unroll
     for (int c = 0; c < 3; ++c) {
       Hrr.m[3 * r + c] = H[6 * r + c];
       Hrt.m[3 * r + c] = H[6 * r + 3 + c];
       Htr.m[3 * r + c] = H[6 * (r + 3) + c];
       Htt.m[3 * r + c] = H[6 * (r + 3) + 3 + c];
     }
-  m33 Vr, Vt, Dr, Dt;
-  localizability(Hrr, L.loc_rot_final, Vr);
-  localizability(Htt, L.loc_trans_final, Vt);
-  const m33 Srr = inv33(sub33(Hrr, mul33(mul33(Hrt, inv33(Htt)), Htr)));
-  const m33 Stt = inv33(sub33(Htt, mul33(mul33(Htr, inv33(Hrr)), Hrt)));
-  localizability(Srr, L.degen_rot, Dr);
-  localizability(Stt, L.degen_trans, Dt);
-  for (int a = 0; a < 3; ++a) L.degen_rot[a] = L.degen_rot[a] * 57.29578;
-
-  m33 R;
-  for (int a = 0; a < 9; ++a) R.m[a] = ds->pose[a];
-  d3 T = mk3(ds->pose[9], ds->pose[10], ds->pose[11]);
-  if (reg_4_dof) {
-    const d3 gz = mk3(-ds->gravity[0], -ds->gravity[1], -ds->gravity[2]);
-    const d3 lz = mul33Tv(R, gz);
-    const double l[3] = {lz.x, lz.y, lz.z};
-    m33 P;
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) P.m[3 * r + c] = l[r] * l[c];
-    const m33 nrr = mul33(mul33(P, Hrr), P);
-    const m33 nrt = mul33(P, Hrt);
-    const m33 ntr = mul33(Htr, P);
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) {
-        H[6 * r + c] = nrr.m[3 * r + c];
-        H[6 * r + 3 + c] = nrt.m[3 * r + c];
-        H[6 * (r + 3) + c] = ntr.m[3 * r + c];
-      }
-    const d3 pb = mul33v(P, mk3(b[0], b[1], b[2]));
-    b[0] = pb.x;
-    b[1] = pb.y;
-    b[2] = pb.z;
-  }
-  for (int a = 0; a < 36; ++a) L.H[a] = H[a];
-  for (int a = 0; a < 6; ++a) L.g[a] = -b[a];
-  L.f = f;
-  for (int a = 0; a < 9; ++a) L.counts[a] = (int64_t)packed[kPackCnt + a];
-  for (int a = 0; a < 9; ++a) {
-    L.eigvec_rot[a] = Vr.m[a];
-    L.eigvec_trans[a] = Vt.m[a];
-    L.degen_eigvec_rot[a] = Dr.m[a];
-    L.degen_eigvec_trans[a] = Dt.m[a];
-  }
-  L.linearize_count = linearize_count;
-  L.n_searched = (int32_t)packed[kPackSearched];
-
-  if (do_step) {
-    double delta[6] = {0, 0, 0, 0, 0, 0};
-    const bool ok = solve6_ldlt(L.H, ds->lambda, L.g, delta);
-    if (ok) {
-      se3_retract(R, T, delta);
-      for (int a = 0; a < 9; ++a) ds->pose[a] = R.m[a];
-      ds->pose[9] = T.x;
-      ds->pose[10] = T.y;
-      ds->pose[11] = T.z;
+  if (role == 0) {
+    m33 V;
+    double loc[3];
+    localizability(Hrr, loc, V);
+    for (int a = 0; a < 3; ++a) L.loc_rot_final[a] = loc[a];
+    for (int a = 0; a < 9; ++a) L.eigvec_rot[a] = V.m[a];
+  } else if (role == 1) {
+    m33 V;
+    double loc[3];
+    localizability(Htt, loc, V);
+    for (int a = 0; a < 3; ++a) L.loc_trans_final[a] = loc[a];
+    for (int a = 0; a < 9; ++a) L.eigvec_trans[a] = V.m[a];
+  } else if (role == 2) {
+    const m33 Srr = inv33(sub33(Hrr, mul33(mul33(Hrt, inv33(Htt)), Htr)));
+    m33 V;
+    double loc[3];
+    localizability(Srr, loc, V);
+    for (int a = 0; a < 3; ++a) L.degen_rot[a] = loc[a] * 57.29578;
+    for (int a = 0; a < 9; ++a) L.degen_eigvec_rot[a] = V.m[a];
+  } else if (role == 3) {
+    const m33 Stt = inv33(sub33(Htt, mul33(mul33(Htr, inv33(Hrr)), Hrt)));
+    m33 V;
+    double loc[3];
+    localizability(Stt, loc, V);
+    for (int a = 0; a < 3; ++a) L.degen_trans[a] = loc[a];
+    for (int a = 0; a < 9; ++a) L.degen_eigvec_trans[a] = V.m[a];
+  } else {
+    double b[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) b[a] = packed[kPackB + a];
+    const double f = packed[kPackF];
+    m33 R;
+#pragma unroll
+    for (int a = 0; a < 9; ++a) R.m[a] = ds->pose[a];
+    d3 T = mk3(ds->pose[9], ds->pose[10], ds->pose[11]);
+    if (reg_4_dof) {
+      const d3 gz = mk3(-ds->gravity[0], -ds->gravity[1], -ds->gravity[2]);
+      const d3 lz = mul33Tv(R, gz);
+      const double l[3] = {lz.x, lz.y, lz.z};
+      m33 P;
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) P.m[3 * r + c] = l[r] * l[c];
+      const m33 nrr = mul33(mul33(P, Hrr), P);
+      const m33 nrt = mul33(P, Hrt);
+      const m33 ntr = mul33(Htr, P);
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+          H[6 * r + c] = nrr.m[3 * r + c];
+          H[6 * r + 3 + c] = nrt.m[3 * r + c];
+          H[6 * (r + 3) + c] = ntr.m[3 * r + c];
+        }
+      const d3 pb = mul33v(P, mk3(b[0], b[1], b[2]));
+      b[0] = pb.x;
+      b[1] = pb.y;
+      b[2] = pb.z;
     }
-    if (trace) {
-      mb_icp_trace& tr = trace[iter];
-      for (int a = 0; a < 36; ++a) tr.H[a] = L.H[a];
-      for (int a = 0; a < 6; ++a) {
-        tr.g[a] = L.g[a];
-        tr.delta[a] = delta[a];
+    double g[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) g[a] = -b[a];
+#pragma unroll
+    for (int a = 0; a < 36; ++a) L.H[a] = H[a];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) L.g[a] = g[a];
+    L.f = f;
+    for (int a = 0; a < 9; ++a) L.counts[a] = (int64_t)packed[kPackCnt + a];
+    L.linearize_count = linearize_count;
+    L.n_searched = (int32_t)packed[kPackSearched];
+    if (do_step) {
+      double delta[6] = {0, 0, 0, 0, 0, 0};
+      const bool ok = solve6_ldlt(H, ds->lambda, g, delta);
+      if (ok) {
+        se3_retract(R, T, delta);
+#pragma unroll
+        for (int a = 0; a < 9; ++a) ds->pose[a] = R.m[a];
+        ds->pose[9] = T.x;
+        ds->pose[10] = T.y;
+        ds->pose[11] = T.z;
       }
-      tr.f = L.f;
-      for (int a = 0; a < 9; ++a) {
-        tr.R[a] = R.m[a];
-        tr.counts[a] = L.counts[a];
+      if (trace) {
+        mb_icp_trace& tr = trace[iter];
+#pragma unroll
+        for (int a = 0; a < 36; ++a) tr.H[a] = H[a];
+        for (int a = 0; a < 6; ++a) {
+          tr.g[a] = g[a];
+          tr.delta[a] = delta[a];
+        }
+        tr.f = f;
+        for (int a = 0; a < 9; ++a) {
+          tr.R[a] = R.m[a];
+          tr.counts[a] = (int64_t)packed[kPackCnt + a];
+        }
+        tr.t[0] = T.x;
+        tr.t[1] = T.y;
+        tr.t[2] = T.z;
+        tr.n_searched = (int32_t)packed[kPackSearched];
+        tr.solve_ok = ok ? 1 : 0;
       }
-      tr.t[0] = T.x;
-      tr.t[1] = T.y;
-      tr.t[2] = T.z;
-      tr.n_searched = L.n_searched;
-      tr.solve_ok = ok ? 1 : 0;
     }
   }
 }
 
 // Component localizabilities (geometric_factor.hpp:434-457): sum over Valid points of |loc_i^T V| with
 // entries below 0.5 zeroed.
-__global__ void __launch_bounds__(256) k_loc_comp(FactorView fv, const DevState* __restrict__ ds) {
-  __shared__ double s_red[8][6];
+__global__ void __launch_bounds__(kLocThreads) k_loc_comp(FactorView fv, const DevState* __restrict__ ds) {
+  __shared__ double s_red[kLocThreads / 32][8];
+  __shared__ double s_tmp[(kLocThreads / 8) * 8];
   __shared__ bool s_last;
   m33 Vr, Vt;
 #pragma unroll
@@ -425,25 +553,21 @@ __global__ void __launch_bounds__(256) k_loc_comp(FactorView fv, const DevState*
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
     if (lane == 0) s_red[warp][a] = v;
   }
+  if (lane == 0) s_red[warp][6] = s_red[warp][7] = 0.0;
   __syncthreads();
-  if (threadIdx.x < 6) {
+  if (threadIdx.x < 8) {
     double v = 0.0;
-    for (int w = 0; w < 8; ++w) v += s_red[w][threadIdx.x];
+    for (int w = 0; w < kLocThreads / 32; ++w) v += s_red[w][threadIdx.x];
     fv.partials2[(size_t)blockIdx.x * 8 + threadIdx.x] = v;
   }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = atomicAdd(fv.ticket2, 1u) == gridDim.x - 1;
   __syncthreads();
-  if (s_last) {
-    __threadfence();
-    if (threadIdx.x < 6) {
-      double v = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(fv.partials2 + (size_t)b * 8 + threadIdx.x);
-      fv.loc_out[threadIdx.x] = v;
-    }
-    if (threadIdx.x == 0) *fv.ticket2 = 0u;
-  }
+  if (!s_last) return;
+  __threadfence();
+  block_sum_rows(fv.partials2, (int)gridDim.x, 8, s_tmp, fv.loc_out, kLocThreads);
+  if (threadIdx.x == 0) *fv.ticket2 = 0u;
 }
 
 }  // namespace
@@ -456,24 +580,27 @@ struct mb_factor {
   mb_map* map = nullptr;
   mb_icp_config cfg{};
   size_t n = 0, ld = 0, n_total = 0, begin = 0;
+  // one pooled device block, carved into the arrays below
+  void* block = nullptr;
+  size_t block_bytes = 0;
   float4* src = nullptr;
   uint8_t* status = nullptr;
   double* vecs = nullptr;  // 5 SoA blocks of 3*ld doubles: p_da, mean, normal, loc_rot, loc_trans
   uint64_t* knn_idx = nullptr;
   double* partials = nullptr;
+  double* gpartials = nullptr;
   double* partials2 = nullptr;
-  double* packed = nullptr;   // kPack + 8 (loc_out)
-  unsigned* tickets = nullptr;
+  double* packed = nullptr;  // kPack + 8 (loc_out)
+  unsigned* tickets = nullptr;  // [0] final, [1] loc, [2..] groups
   DevState* ds = nullptr;
   mb_icp_trace* d_trace = nullptr;
   int trace_cap = 0;
-  int grid = 0, grid2 = 0;
+  int grid = 0, grid2 = 0, n_groups = 0;
   int linearize_count = 0;
   uint32_t flags = 0;
   // cached CUDA graph of an mb_icp_run sequence
   cudaGraphExec_t graph = nullptr;
   int graph_iters = 0, graph_count0 = -1;
-  bool graph_trace = false;
 
   FactorView view() const {
     FactorView v;
@@ -498,6 +625,8 @@ struct mb_factor {
     v.kh = (double)cfg.huber_threshold;
     v.pvd = (double)cfg.plane_validity_distance;
     v.partials = partials;
+    v.gpartials = gpartials;
+    v.gtickets = tickets + 2;
     v.ticket = tickets;
     v.packed = packed;
     v.partials2 = partials2;
@@ -512,8 +641,8 @@ namespace {
 int reset_state(mb_factor* f) {
   cudaStream_t st = f->ctx->stream;
   if (f->n) {
-    MB_CUDA(cudaMemsetAsync(f->status, 0, f->n, st));
-    MB_CUDA(cudaMemsetAsync(f->vecs, 0, 15 * f->ld * sizeof(double), st));
+    // status, the five vector blocks and the index block are contiguous: one memset for the zeros
+    MB_CUDA(cudaMemsetAsync(f->vecs, 0, 15 * f->ld * sizeof(double) + f->ld, st));
     MB_CUDA(cudaMemsetAsync(f->knn_idx, 0xff, f->n * f->cfg.num_corres_points * sizeof(uint64_t), st));
   }
   f->linearize_count = 0;
@@ -525,10 +654,13 @@ int enqueue_linearize(mb_factor* f, int do_step, int iter, mb_icp_trace* d_trace
   mb_ctx* c = f->ctx;
   cudaStream_t st = c->stream;
   const FactorView fv = f->view();
-  k_linearize<<<f->grid, kLinWarps * 32, 0, st>>>(f->map->view(), fv, f->ds->pose);
+  if (fv.k == 5)
+    k_linearize<5><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds->pose);
+  else
+    k_linearize<MB_MAX_K><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds->pose);
   if (c->world > 1) MB_NCCL(ncclAllReduce(f->packed, f->packed, kPack, ncclDouble, ncclSum, c->comm, st));
-  k_finalize<<<1, 32, 0, st>>>(f->packed, f->ds, f->cfg.reg_4_dof, linearize_count, do_step, iter, d_trace);
-  k_loc_comp<<<f->grid2, 256, 0, st>>>(fv, f->ds);
+  k_finalize<<<1, 160, 0, st>>>(f->packed, f->ds, f->cfg.reg_4_dof, linearize_count, do_step, iter, d_trace);
+  k_loc_comp<<<f->grid2, kLocThreads, 0, st>>>(fv, f->ds);
   if (c->world > 1) MB_NCCL(ncclAllReduce(f->packed + kPack, f->packed + kPack, 6, ncclDouble, ncclSum, c->comm, st));
   c->launches += 3;
   MB_CUDA(cudaGetLastError());
@@ -541,6 +673,8 @@ void drop_graph(mb_factor* f) {
   f->graph_iters = 0;
   f->graph_count0 = -1;
 }
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
@@ -573,41 +707,60 @@ int mb_factor_create(mb_ctx* ctx, mb_map* map, const void* pts, size_t n, size_t
   f->n_total = n;
   f->begin = shard_begin;
   f->n = shard_end - shard_begin;
-  f->ld = std::max<size_t>((f->n + 31) & ~(size_t)31, 32);
+  f->ld = std::max<size_t>(align_up(f->n, 32), 32);
   const size_t k = cfg->num_corres_points;
-  const size_t n_tiles = (f->n + 31) / 32;
-  f->grid = (int)std::max<size_t>(1, std::min<size_t>((n_tiles + kLinWarps - 1) / kLinWarps, (size_t)ctx->sm_count * 8));
-  f->grid2 = (int)std::max<size_t>(1, std::min<size_t>((f->n + 255) / 256, (size_t)ctx->sm_count * 2));
-  int rc = MB_OK;
-  auto alloc = [&](void** p, size_t bytes) {
-    if (rc != MB_OK) return;
-    cudaError_t e = cudaMalloc(p, std::max<size_t>(bytes, 256));
-    if (e != cudaSuccess) {
-      set_error("mb_factor_create: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
-      rc = MB_ERR_CUDA;
-    }
+  const size_t n_tiles = (f->n + kLinThreads - 1) / kLinThreads;
+  int per_sm = 4;
+  if (k == 5)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<5>, kLinThreads, 0);
+  else
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<MB_MAX_K>, kLinThreads, 0);
+  per_sm = std::max(per_sm, 1);
+  f->grid = (int)std::max<size_t>(1, std::min<size_t>(n_tiles, (size_t)ctx->sm_count * per_sm));
+  f->n_groups = (f->grid + kGroup - 1) / kGroup;
+  f->grid2 = (int)std::max<size_t>(1, std::min<size_t>((f->n + kLocThreads - 1) / kLocThreads, (size_t)ctx->sm_count));
+
+  // carve one block: [src | vecs (15 ld doubles) | status (ld bytes) | knn_idx | partials | gpartials |
+  //                   partials2 | packed | tickets | DevState]
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
   };
-  alloc((void**)&f->src, f->ld * sizeof(float4));
-  alloc((void**)&f->status, f->ld);
-  alloc((void**)&f->vecs, 15 * f->ld * sizeof(double));
-  alloc((void**)&f->knn_idx, f->ld * k * sizeof(uint64_t));
-  alloc((void**)&f->partials, (size_t)f->grid * kPack * sizeof(double));
-  alloc((void**)&f->partials2, (size_t)f->grid2 * 8 * sizeof(double));
-  alloc((void**)&f->packed, (kPack + 8) * sizeof(double));
-  alloc((void**)&f->tickets, 4 * sizeof(unsigned));
-  alloc((void**)&f->ds, sizeof(DevState));
+  const size_t o_src = take(f->ld * sizeof(float4));
+  const size_t o_vecs = take(15 * f->ld * sizeof(double) + f->ld);  // status follows the vectors directly
+  const size_t o_idx = take(f->ld * k * sizeof(uint64_t));
+  const size_t o_par = take((size_t)f->grid * kPack * sizeof(double));
+  const size_t o_gpar = take((size_t)f->n_groups * kPack * sizeof(double));
+  const size_t o_par2 = take((size_t)f->grid2 * 8 * sizeof(double));
+  const size_t o_packed = take((kPack + 8) * sizeof(double));
+  const size_t o_tick = take((2 + (size_t)f->n_groups) * sizeof(unsigned));
+  const size_t o_ds = take(sizeof(DevState));
+  f->block_bytes = off;
+  int rc = dev_alloc(ctx, &f->block, f->block_bytes);
   if (rc != MB_OK) {
     mb_factor_release(f);
     return rc;
   }
-  // scan: host AoS with arbitrary stride -> device float4 (only xyz is read by the factor,
-  // geometric_factor.hpp:277,323,346)
-  {
-    int prc = pinned_reserve(ctx, f->ld * sizeof(float4));
-    if (prc != MB_OK) {
-      mb_factor_release(f);
-      return prc;
-    }
+  char* base = (char*)f->block;
+  f->src = (float4*)(base + o_src);
+  f->vecs = (double*)(base + o_vecs);
+  f->status = (uint8_t*)(base + o_vecs + 15 * f->ld * sizeof(double));
+  f->knn_idx = (uint64_t*)(base + o_idx);
+  f->partials = (double*)(base + o_par);
+  f->gpartials = (double*)(base + o_gpar);
+  f->partials2 = (double*)(base + o_par2);
+  f->packed = (double*)(base + o_packed);
+  f->tickets = (unsigned*)(base + o_tick);
+  f->ds = (DevState*)(base + o_ds);
+
+  // scan: host AoS with arbitrary stride -> page-locked float4 staging -> device (only xyz is read by the
+  // factor, geometric_factor.hpp:277,323,346)
+  rc = pinned_reserve(ctx, f->ld * sizeof(float4));
+  if (rc != MB_OK) {
+    mb_factor_release(f);
+    return rc;
   }
   float4* h = (float4*)ctx->pinned;
   for (size_t i = 0; i < f->n; ++i) {
@@ -616,11 +769,10 @@ int mb_factor_create(mb_ctx* ctx, mb_map* map, const void* pts, size_t n, size_t
   }
   for (size_t i = f->n; i < f->ld; ++i) h[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   MB_CUDA(cudaMemcpyAsync(f->src, h, f->ld * sizeof(float4), cudaMemcpyHostToDevice, st));
-  MB_CUDA(cudaMemsetAsync(f->tickets, 0, 4 * sizeof(unsigned), st));
-  MB_CUDA(cudaMemsetAsync(f->packed, 0, (kPack + 8) * sizeof(double), st));
-  MB_CUDA(cudaMemsetAsync(f->ds, 0, sizeof(DevState), st));
+  // everything from `packed` to the end of the block (packet, tickets, DevState) starts at zero
+  MB_CUDA(cudaMemsetAsync(base + o_packed, 0, f->block_bytes - o_packed, st));
   MB_TRY(reset_state(f));
-  MB_CUDA(cudaStreamSynchronize(st));
+  MB_CUDA(cudaStreamSynchronize(st));  // the pinned staging buffer is free again
   *out = f;
   return MB_OK;
 }
@@ -630,16 +782,8 @@ int mb_factor_release(mb_factor* f) {
   cudaSetDevice(f->ctx->device);
   cudaStreamSynchronize(f->ctx->stream);
   drop_graph(f);
-  cudaFree(f->src);
-  cudaFree(f->status);
-  cudaFree(f->vecs);
-  cudaFree(f->knn_idx);
-  cudaFree(f->partials);
-  cudaFree(f->partials2);
-  cudaFree(f->packed);
-  cudaFree(f->tickets);
-  cudaFree(f->ds);
-  cudaFree(f->d_trace);
+  dev_free(f->ctx, f->block, f->block_bytes);
+  if (f->d_trace) dev_free(f->ctx, f->d_trace, (size_t)f->trace_cap * sizeof(mb_icp_trace));
   mb_map_release(f->map);
   delete f;
   return MB_OK;
@@ -663,17 +807,22 @@ int mb_factor_linearize(mb_factor* f, const double R[9], const double t[3], cons
   MB_REQUIRE(f && R && t && gravity_unit && out, "null argument");
   MB_CUDA(cudaSetDevice(f->ctx->device));
   cudaStream_t st = f->ctx->stream;
-  double h[15];
-  std::memcpy(h, R, 9 * sizeof(double));
-  std::memcpy(h + 9, t, 3 * sizeof(double));
-  std::memcpy(h + 12, gravity_unit, 3 * sizeof(double));
-  MB_CUDA(cudaMemcpyAsync(f->ds->pose, h, sizeof(h), cudaMemcpyHostToDevice, st));
+  // page-locked staging: [pose 12 | gravity 3] in, [mb_linearization | loc 6] out
+  double* hin = (double*)f->ctx->pin_small;
+  char* hout = (char*)f->ctx->pin_small + 256;
+  static_assert(256 + sizeof(mb_linearization) + 6 * sizeof(double) <= 4096, "pin_small too small");
+  std::memcpy(hin, R, 9 * sizeof(double));
+  std::memcpy(hin + 9, t, 3 * sizeof(double));
+  std::memcpy(hin + 12, gravity_unit, 3 * sizeof(double));
+  MB_CUDA(cudaMemcpyAsync(f->ds->pose, hin, 15 * sizeof(double), cudaMemcpyHostToDevice, st));
   ++f->linearize_count;
   MB_TRY(enqueue_linearize(f, 0, 0, nullptr, f->linearize_count));
-  double loc[6];
-  MB_CUDA(cudaMemcpyAsync(out, &f->ds->lin, sizeof(mb_linearization), cudaMemcpyDeviceToHost, st));
-  MB_CUDA(cudaMemcpyAsync(loc, f->packed + kPack, sizeof(loc), cudaMemcpyDeviceToHost, st));
+  MB_CUDA(cudaMemcpyAsync(hout, &f->ds->lin, sizeof(mb_linearization), cudaMemcpyDeviceToHost, st));
+  MB_CUDA(cudaMemcpyAsync(hout + sizeof(mb_linearization), f->packed + kPack, 6 * sizeof(double),
+                          cudaMemcpyDeviceToHost, st));
   MB_CUDA(cudaStreamSynchronize(st));
+  std::memcpy(out, hout, sizeof(mb_linearization));
+  const double* loc = (const double*)(hout + sizeof(mb_linearization));
   for (int a = 0; a < 3; ++a) {
     out->loc_trans_comp[a] = loc[a];
     out->loc_rot_comp[a] = loc[3 + a];
@@ -715,20 +864,21 @@ int mb_icp_run(mb_factor* f, double R[9], double t[3], int iters, double lambda,
   if (iters > f->trace_cap) {
     MB_CUDA(cudaStreamSynchronize(st));
     drop_graph(f);
-    cudaFree(f->d_trace);
+    if (f->d_trace) dev_free(f->ctx, f->d_trace, (size_t)f->trace_cap * sizeof(mb_icp_trace));
     f->d_trace = nullptr;
-    MB_CUDA(cudaMalloc(&f->d_trace, (size_t)iters * sizeof(mb_icp_trace)));
+    f->trace_cap = 0;
+    MB_TRY(dev_alloc(f->ctx, (void**)&f->d_trace, (size_t)iters * sizeof(mb_icp_trace)));
     f->trace_cap = iters;
   }
-  double h[16];
-  std::memcpy(h, R, 9 * sizeof(double));
-  std::memcpy(h + 9, t, 3 * sizeof(double));
-  h[12] = 0.0;
-  h[13] = 0.0;
-  h[14] = -1.0;
-  h[15] = lambda;
-  MB_CUDA(cudaMemcpyAsync(f->ds->pose, h, sizeof(h), cudaMemcpyHostToDevice, st));
-  const bool use_graph = (f->flags & 2u) != 0;
+  double* hin = (double*)f->ctx->pin_small;
+  std::memcpy(hin, R, 9 * sizeof(double));
+  std::memcpy(hin + 9, t, 3 * sizeof(double));
+  hin[12] = 0.0;
+  hin[13] = 0.0;
+  hin[14] = -1.0;
+  hin[15] = lambda;
+  MB_CUDA(cudaMemcpyAsync(f->ds->pose, hin, 16 * sizeof(double), cudaMemcpyHostToDevice, st));
+  const bool use_graph = (f->flags & 2u) != 0 && iters > 0;
   if (use_graph) {
     // The captured sequence bakes the iteration index and linearize_count into k_finalize's arguments.
     if (!f->graph || f->graph_iters != iters || f->graph_count0 != f->linearize_count) {
@@ -760,13 +910,13 @@ int mb_icp_run(mb_factor* f, double R[9], double t[3], int iters, double lambda,
       MB_TRY(enqueue_linearize(f, 1, it, f->d_trace, f->linearize_count));
     }
   }
-  double ho[12];
-  MB_CUDA(cudaMemcpyAsync(ho, f->ds->pose, sizeof(ho), cudaMemcpyDeviceToHost, st));
+  double* hout = (double*)((char*)f->ctx->pin_small + 256);
+  MB_CUDA(cudaMemcpyAsync(hout, f->ds->pose, 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (trace && iters)
     MB_CUDA(cudaMemcpyAsync(trace, f->d_trace, (size_t)iters * sizeof(mb_icp_trace), cudaMemcpyDeviceToHost, st));
   MB_CUDA(cudaStreamSynchronize(st));
-  std::memcpy(R, ho, 9 * sizeof(double));
-  std::memcpy(t, ho + 9, 3 * sizeof(double));
+  std::memcpy(R, hout, 9 * sizeof(double));
+  std::memcpy(t, hout + 9, 3 * sizeof(double));
   return MB_OK;
 }
 

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/mimosa_b200.h"
 #include "mb_math.cuh"
@@ -61,11 +62,25 @@ struct mb_ctx {
   size_t flush_bytes = 0;
   void* pinned = nullptr;  // page-locked staging for host <-> device copies of scans
   size_t pinned_bytes = 0;
+  void* pin_small = nullptr;  // 4 KiB page-locked block for poses in / normal equations out
+  // Size-keyed cache of released device blocks: a factor is created and destroyed for every scan with the
+  // same sizes, and cudaMalloc/cudaFree would otherwise dominate the per-scan host cost.
+  struct Block {
+    void* p;
+    size_t bytes;
+  };
+  std::vector<Block> pool;
+  size_t pool_bytes = 0;
 };
 
 namespace mb {
 // Grow-only page-locked staging buffer of the context (synchronises the stream when it has to grow).
 int pinned_reserve(mb_ctx* c, size_t bytes);
+// Pooled device allocations (exact-size reuse).  dev_free never synchronises: the caller guarantees that no
+// work touching the block is still pending on the context's stream.
+int dev_alloc(mb_ctx* c, void** p, size_t bytes);
+void dev_free(mb_ctx* c, void* p, size_t bytes);
+void dev_pool_release(mb_ctx* c);
 }
 
 namespace mb {
@@ -107,114 +122,138 @@ __device__ __forceinline__ uint32_t table_find(const int4* __restrict__ table, u
   }
 }
 
-constexpr int kKnnRounds = 8;                  // candidate slots per lane and chunk
-constexpr int kKnnChunk = kKnnRounds * 32;     // 256 candidate slots per chunk
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kSeqShift = 5;  // sequence number = (offset index << 5) | point index  (cap <= 31)
 
-struct KnnOut {     // lane j (< k) holds the j-th nearest neighbour
-  double d2;        // +inf when fewer than j+1 candidates exist
-  uint32_t seq;     // ordinal * cap + j  (ordinal = rank of the voxel among the found ones); ~0 if none
-  int found;        // number of neighbours found (same value in every lane)
-};
+// Index of the (0,0,0) offset in the reference's visiting order for each neighbourhood mode.
+__host__ __device__ __forceinline__ int centre_offset_index(int n_off) { return n_off == 19 ? 9 : n_off == 27 ? 13 : 0; }
 
-// Warp-cooperative restricted k-NN for ONE query (all 32 lanes must call, converged).
-//   1. lane l < n_off probes neighbour voxel l of the query's voxel in the hash table;
-//   2. found voxels are compacted (visiting order kept) into s_vox[] = packed slot/count words;
-//   3. candidate slot c = ordinal * cap + j is evaluated by lane c % 32 in round c / 32: one coalesced
-//      float4 load per lane and round, fp64 distance, kept in registers;
-//   4. the k smallest under the total order (d2, visiting sequence) are extracted with k rounds of three
-//      32-bit warp min-reductions (high word, low word, sequence) — equal distances therefore resolve to
-//      the earlier visitor exactly like the reference's strict-'<' insertion sort
-//      (gtsam_points KnnResult::push; restated in oracle/ivox_ref.hpp).
-// s_vox: per-warp shared scratch of 32 words; still valid (for knn_fetch) until the next call.
-__device__ __forceinline__ void knn_warp(const MapView& mv, const int8_t* __restrict__ s_off, uint32_t* s_vox,
-                                         double qx, double qy, double qz, int k, int lane, KnnOut& out) {
-  const int cx = fast_floor(qx * mv.inv_leaf), cy = fast_floor(qy * mv.inv_leaf), cz = fast_floor(qz * mv.inv_leaf);
-  uint32_t packed = kEmpty;
-  if (lane < mv.n_off)
-    packed = table_find(mv.table, mv.table_mask, cx + s_off[3 * lane], cy + s_off[3 * lane + 1], cz + s_off[3 * lane + 2]);
-  const bool hit = packed != kEmpty && (packed & ((1u << kCountBits) - 1)) != 0;
-  const unsigned hits = __ballot_sync(kFull, hit);
-  const int n_found_vox = __popc(hits);
-  __syncwarp();
-  if (hit) s_vox[__popc(hits & ((1u << lane) - 1))] = packed;
-  __syncwarp();
-
-  const int cap = mv.cap;
-  const int n_slots = n_found_vox * cap;
+// Restricted k-NN, ONE QUERY PER THREAD (every lane of the warp must call; `active` = false idles a lane).
+//
+// The reference (gtsam_points KnnResult::push over the neighbour voxels, restated in oracle/ivox_ref.hpp) scans
+// the stored points of the 1/7/19/27 voxels around the query's voxel in a fixed visiting order and keeps the k
+// smallest squared distances with a strict-'<' insertion sort, so equal distances resolve to the earlier
+// visitor.  Here every thread runs that scan for its own query with three changes that keep the result
+// bit-identical:
+//   * candidates carry their visiting sequence number ((offset index << 5) | point index) and the list is
+//     ordered by (d2, sequence), which makes the outcome independent of the order voxels are processed in;
+//   * the query's own voxel is processed first, after which a neighbour voxel is skipped when the squared
+//     distance from the query to that voxel's box (shrunk by 1e-6 voxel to stay conservative under rounding)
+//     already exceeds the current k-th best — none of its points could enter the list;
+//   * the hash probes of the neighbourhood are issued in batches of four independent loads.
+// K is the compile-time list length (5 = the reference's num_corres_points, 8 = generic: the k nearest are the
+// first k of the 8 nearest).  s_pk is this thread's column of a shared [n_off][pk_stride] array that receives
+// the packed (voxel id << 5 | count) word of every probed neighbour; it stays valid for knn_resolve().
+template <int K>
+__device__ __forceinline__ void knn_thread(const MapView& mv, const int8_t* __restrict__ s_off, uint32_t* s_pk,
+                                           int pk_stride, double qx, double qy, double qz, int k, bool active,
+                                           double (&bd)[K], uint32_t (&bs)[K]) {
   const double kInf = __longlong_as_double(0x7ff0000000000000ll);
-
-  // best-so-far: lane j (< k) holds the j-th best; re-offered as the "carry" candidate when a further
-  // chunk of candidates is merged in.
-  double best_d2 = kInf;
-  uint32_t best_seq = 0xffffffffu;
-
-  for (int base = 0; base < n_slots; base += kKnnChunk) {
-    double cd[kKnnRounds];
 #pragma unroll
-    for (int r = 0; r < kKnnRounds; ++r) {
-      cd[r] = kInf;
-      const int c = base + r * 32 + lane;
-      if (base + r * 32 < n_slots) {  // warp-uniform
-        if (c < n_slots) {
-          const int ord = c / cap;
-          const int j = c - ord * cap;
-          const uint32_t pk = s_vox[ord];
-          if (j < (int)(pk & ((1u << kCountBits) - 1))) {
-            const float4 p = __ldg(mv.pts + (size_t)(pk >> kCountBits) * cap + j);
-            cd[r] = sqdist4((double)p.x, (double)p.y, (double)p.z, qx, qy, qz);
-          }
-        }
-      }
+  for (int i = 0; i < K; ++i) {
+    bd[i] = kInf;
+    bs[i] = 0xffffffffu;
+  }
+  const int n_off = mv.n_off;
+  const double ux = qx * mv.inv_leaf, uy = qy * mv.inv_leaf, uz = qz * mv.inv_leaf;
+  const int cx = fast_floor(ux), cy = fast_floor(uy), cz = fast_floor(uz);
+
+  // ---- probe the neighbourhood ----------------------------------------------------------------------
+  for (int o0 = 0; o0 < n_off; o0 += 4) {
+    uint32_t h[4];
+    int4 e[4];
+    int x[4], y[4], z[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int o = min(o0 + u, n_off - 1);
+      x[u] = cx + s_off[3 * o];
+      y[u] = cy + s_off[3 * o + 1];
+      z[u] = cz + s_off[3 * o + 2];
+      h[u] = hash_coord(x[u], y[u], z[u]) & mv.table_mask;
+      e[u] = make_int4(0, 0, 0, (int)kEmpty);
+      if (active) e[u] = __ldg(mv.table + h[u]);
     }
-    double carry_d2 = best_d2;
-    uint32_t carry_seq = best_seq;
-    best_d2 = kInf;
-    best_seq = 0xffffffffu;
-    for (int sel = 0; sel < k; ++sel) {
-      // lane-local minimum: strict '<' scanning in round order keeps the earliest sequence on ties; the
-      // carry comes from an earlier chunk (smaller sequence), so it is the initial value and wins ties.
-      double md = carry_d2;
-      uint32_t ms = carry_seq;
 #pragma unroll
-      for (int r = 0; r < kKnnRounds; ++r) {
-        if (cd[r] < md) {
-          md = cd[r];
-          ms = (uint32_t)(base + r * 32 + lane);
+    for (int u = 0; u < 4; ++u) {
+      if (o0 + u < n_off) {
+        while ((uint32_t)e[u].w != kEmpty && !(e[u].x == x[u] && e[u].y == y[u] && e[u].z == z[u])) {
+          h[u] = (h[u] + 1) & mv.table_mask;
+          e[u] = __ldg(mv.table + h[u]);
         }
-      }
-      const uint32_t hi = (uint32_t)__double2hiint(md), lo = (uint32_t)__double2loint(md);
-      const uint32_t mhi = __reduce_min_sync(kFull, hi);
-      if (mhi >= 0x7ff00000u) break;  // nothing left (warp-uniform)
-      const uint32_t mlo = __reduce_min_sync(kFull, hi == mhi ? lo : 0xffffffffu);
-      const bool tie = hi == mhi && lo == mlo;
-      const uint32_t mseq = __reduce_min_sync(kFull, tie ? ms : 0xffffffffu);
-      if (lane == sel) {
-        best_d2 = __hiloint2double((int)mhi, (int)mlo);
-        best_seq = mseq;
-      }
-      if (tie && ms == mseq) {  // the winning lane retires that candidate
-        if (ms == carry_seq) {
-          carry_d2 = kInf;
-          carry_seq = 0xffffffffu;
-        } else {
-#pragma unroll
-          for (int r = 0; r < kKnnRounds; ++r)
-            if ((uint32_t)(base + r * 32 + lane) == ms) cd[r] = kInf;
-        }
+        s_pk[(o0 + u) * pk_stride] = (uint32_t)e[u].w;
       }
     }
   }
-  out.d2 = best_d2;
-  out.seq = best_seq;
-  out.found = __popc(__ballot_sync(kFull, best_seq != 0xffffffffu));
+
+  // ---- scan the candidates --------------------------------------------------------------------------
+  // fractional position of the query inside its voxel, in voxel units, for the box lower bounds
+  const double fx = ux - (double)cx, fy = uy - (double)cy, fz = uz - (double)cz;
+  const double kMargin = 1e-6;
+  const double leaf = 1.0 / mv.inv_leaf;
+  const int centre = centre_offset_index(n_off);
+  const int cap = mv.cap;
+  int ei = -1;       // position in the processing order: 0 = centre voxel, then the others in visiting order
+  int o = 0;         // offset index of the current entry
+  int j = 0, cnt = 0;
+  const float4* bucket = mv.pts;
+  bool running = active;
+  while (__any_sync(kFull, running)) {
+    if (running && j >= cnt) {
+      // advance to the next occupied, unpruned voxel
+      while (true) {
+        ++ei;
+        if (ei >= n_off) {
+          running = false;
+          break;
+        }
+        o = ei == 0 ? centre : (ei <= centre ? ei - 1 : ei);
+        const uint32_t pk = s_pk[o * pk_stride];
+        if (pk == kEmpty || (pk & ((1u << kCountBits) - 1)) == 0) continue;
+        if (ei > 0) {
+          // current k-th best (static indexing only)
+          double worst = bd[K - 1];
+#pragma unroll
+          for (int i = 0; i < K; ++i)
+            if (i == k - 1) worst = bd[i];
+          const int ox = s_off[3 * o], oy = s_off[3 * o + 1], oz = s_off[3 * o + 2];
+          const double gx = fmax(0.0, (ox < 0 ? fx : ox > 0 ? 1.0 - fx : 0.0) - kMargin);
+          const double gy = fmax(0.0, (oy < 0 ? fy : oy > 0 ? 1.0 - fy : 0.0) - kMargin);
+          const double gz = fmax(0.0, (oz < 0 ? fz : oz > 0 ? 1.0 - fz : 0.0) - kMargin);
+          const double lb = ((gx * gx + gy * gy) + gz * gz) * (leaf * leaf) * (1.0 - 1e-9);
+          if (lb > worst) continue;
+        }
+        cnt = (int)(pk & ((1u << kCountBits) - 1));
+        bucket = mv.pts + (size_t)(pk >> kCountBits) * cap;
+        j = 0;
+        break;
+      }
+    }
+    if (running) {
+      const float4 p = __ldg(bucket + j);
+      const double d = sqdist4((double)p.x, (double)p.y, (double)p.z, qx, qy, qz);
+      const uint32_t s = ((uint32_t)o << kSeqShift) | (uint32_t)j;
+      ++j;
+      if (d < bd[K - 1] || (d == bd[K - 1] && s < bs[K - 1])) {
+        bool lt[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) lt[i] = d < bd[i] || (d == bd[i] && s < bs[i]);
+#pragma unroll
+        for (int i = K - 1; i > 0; --i) {
+          bd[i] = lt[i - 1] ? bd[i - 1] : (lt[i] ? d : bd[i]);
+          bs[i] = lt[i - 1] ? bs[i - 1] : (lt[i] ? s : bs[i]);
+        }
+        bd[0] = lt[0] ? d : bd[0];
+        bs[0] = lt[0] ? s : bs[0];
+      }
+    }
+  }
 }
 
 // Translate a winner's sequence number into the reference's global index and the stored point.
-__device__ __forceinline__ uint64_t knn_fetch(const MapView& mv, const uint32_t* s_vox, uint32_t seq, float4& p) {
-  const int ord = seq / mv.cap;
-  const int j = seq - ord * mv.cap;
-  const uint32_t slot = s_vox[ord] >> kCountBits;
+__device__ __forceinline__ uint64_t knn_resolve(const MapView& mv, const uint32_t* s_pk, int pk_stride, uint32_t seq,
+                                                float4& p) {
+  const uint32_t o = seq >> kSeqShift, j = seq & ((1u << kSeqShift) - 1);
+  const uint32_t slot = s_pk[o * pk_stride] >> kCountBits;
   p = __ldg(mv.pts + (size_t)slot * mv.cap + j);
   return ((uint64_t)slot << 32) | (uint64_t)j;
 }

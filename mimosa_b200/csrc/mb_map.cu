@@ -237,36 +237,47 @@ __global__ void k_ds_scatter(const uint32_t* __restrict__ kept, const uint32_t* 
   out[offset[v] + j] = kept[(size_t)v * cap + j];
 }
 
-constexpr int kKnnWarps = 8;
+constexpr int kKnnThreads = 128;
 
-// Standalone restricted k-NN: one warp per query, warp-strided over the query list.
-__global__ void __launch_bounds__(kKnnWarps * 32)
+// Standalone restricted k-NN: one query per thread (see knn_thread in mb_internal.cuh).
+template <int K>
+__global__ void __launch_bounds__(kKnnThreads)
     k_knn(MapView mv, const double* __restrict__ q, size_t nq, int k, uint64_t* __restrict__ idx,
           double* __restrict__ d2, uint8_t* __restrict__ ok) {
   __shared__ int8_t s_off[32 * 3];
-  __shared__ uint32_t s_vox_all[kKnnWarps][32];
+  __shared__ uint32_t s_pk_all[kMaxNbr * kKnnThreads];
   if (threadIdx.x < kMaxNbr * 3) s_off[threadIdx.x] = mv.off[threadIdx.x];
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t* s_vox = s_vox_all[warp];
-  const size_t stride = (size_t)gridDim.x * kKnnWarps;
-  for (size_t i = (size_t)blockIdx.x * kKnnWarps + warp; i < nq; i += stride) {
-    const double qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
-    KnnOut o;
-    knn_warp(mv, s_off, s_vox, qx, qy, qz, k, lane, o);
-    if (lane < k) {
+  uint32_t* s_pk = s_pk_all + threadIdx.x;
+  const size_t i = (size_t)blockIdx.x * kKnnThreads + threadIdx.x;
+  const bool active = i < nq;
+  double qx = 0, qy = 0, qz = 0;
+  if (active) {
+    qx = q[3 * i];
+    qy = q[3 * i + 1];
+    qz = q[3 * i + 2];
+  }
+  double bd[K];
+  uint32_t bs[K];
+  knn_thread<K>(mv, s_off, s_pk, kKnnThreads, qx, qy, qz, k, active, bd, bs);
+  if (!active) return;
+  int found = 0;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    if (j < k) {
       uint64_t g = ~0ull;
       double d = DBL_MAX;
-      if (o.seq != 0xffffffffu) {
+      if (bs[j] != 0xffffffffu) {
         float4 p;
-        g = knn_fetch(mv, s_vox, o.seq, p);
-        d = o.d2;
+        g = knn_resolve(mv, s_pk, kKnnThreads, bs[j], p);
+        d = bd[j];
+        ++found;
       }
-      idx[i * k + lane] = g;
-      d2[i * k + lane] = d;
+      idx[i * k + j] = g;
+      d2[i * k + j] = d;
     }
-    if (lane == 0) ok[i] = o.found == k;
   }
+  ok[i] = found == k;
 }
 
 __global__ void k_gather_points(const float4* __restrict__ pts, int cap, const uint64_t* __restrict__ idx, size_t n,
@@ -376,9 +387,11 @@ int map_reserve(mb_map* m, size_t want_vox) {
 
 int launch_knn(mb_map* m, const double* d_q, size_t nq, int k, uint64_t* d_idx, double* d_d2, uint8_t* d_ok) {
   if (nq == 0) return MB_OK;
-  const size_t want = (nq + kKnnWarps - 1) / kKnnWarps;
-  const unsigned grid = (unsigned)std::min<size_t>(want, (size_t)m->ctx->sm_count * 8);
-  k_knn<<<grid, kKnnWarps * 32, 0, m->ctx->stream>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
+  const unsigned grid = blocks_for(nq, kKnnThreads);
+  if (k == 5)
+    k_knn<5><<<grid, kKnnThreads, 0, m->ctx->stream>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
+  else
+    k_knn<MB_MAX_K><<<grid, kKnnThreads, 0, m->ctx->stream>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
   ++m->ctx->launches;
   MB_CUDA(cudaGetLastError());
   return MB_OK;

@@ -134,8 +134,8 @@ class Context:
     def downsample(self, xyz: np.ndarray, leaf: float, cap: int, min_dist: float) -> np.ndarray:
         """Geometric::downsample (geometric.cpp:55-126): indices of the kept points, reference order."""
         pts = np.ascontiguousarray(xyz, dtype=np.float32)
-        n, stride = pts.shape[0], pts.strides[0]
-        out = np.empty(n, dtype=np.uint32)
+        n, stride = pts.shape[0], (pts.strides[0] if pts.shape[0] else 12)
+        out = np.empty(max(n, 1), dtype=np.uint32)
         n_out = C.c_size_t()
         check(self.lib.mb_downsample(self.h, _ptr(pts), n, stride, leaf, cap, min_dist, _ptr(out), C.byref(n_out)))
         return out[: n_out.value].copy()
@@ -308,6 +308,18 @@ class ICPFactor:
         trace = (IcpTrace * iters)() if (want_trace and iters) else None
         check(self.lib.mb_icp_run(self.h, _ptr(R), _ptr(t), iters, lam, trace))
         return R.reshape(3, 3), t, (list(trace) if trace is not None else [])
+
+
+def gn_step(L: Linearization, R, t, lam: float = 0.0):
+    """Host-side Gauss-Newton step (mb_gn_step): returns (R, t, delta, ok)."""
+    lib = capi.load()
+    R = np.array(R, dtype=np.float64).reshape(9).copy()
+    t = np.array(t, dtype=np.float64).reshape(3).copy()
+    delta = np.zeros(6)
+    ok = C.c_int()
+    check(lib.mb_gn_step(C.byref(L, Linearization.H.offset), C.byref(L, Linearization.g.offset), lam, _ptr(R), _ptr(t),
+                         _ptr(delta), C.byref(ok)))
+    return R.reshape(3, 3), t, delta, bool(ok.value)
 
 
 def degeneracy_flags(L: Linearization, config: RegistrationConfig):
