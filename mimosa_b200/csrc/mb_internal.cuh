@@ -186,65 +186,93 @@ __device__ __forceinline__ void knn_thread(const MapView& mv, const int8_t* __re
   }
 
   // ---- scan the candidates --------------------------------------------------------------------------
-  // fractional position of the query inside its voxel, in voxel units, for the box lower bounds
-  const double fx = ux - (double)cx, fy = uy - (double)cy, fz = uz - (double)cz;
-  const double kMargin = 1e-6;
-  const double leaf = 1.0 / mv.inv_leaf;
+  // All control flow below is warp-converged (uniform trip counts, per-lane predicates): a lane never runs a
+  // private inner loop while the other 31 wait.
   const int centre = centre_offset_index(n_off);
   const int cap = mv.cap;
-  int ei = -1;       // position in the processing order: 0 = centre voxel, then the others in visiting order
-  int o = 0;         // offset index of the current entry
-  int j = 0, cnt = 0;
-  const float4* bucket = mv.pts;
-  bool running = active;
-  while (__any_sync(kFull, running)) {
-    if (running && j >= cnt) {
-      // advance to the next occupied, unpruned voxel
-      while (true) {
-        ++ei;
-        if (ei >= n_off) {
-          running = false;
-          break;
-        }
-        o = ei == 0 ? centre : (ei <= centre ? ei - 1 : ei);
-        const uint32_t pk = s_pk[o * pk_stride];
-        if (pk == kEmpty || (pk & ((1u << kCountBits) - 1)) == 0) continue;
-        if (ei > 0) {
-          // current k-th best (static indexing only)
-          double worst = bd[K - 1];
+  const uint32_t kCntMask = (1u << kCountBits) - 1;
+
+  // k-th best so far (the pruning radius); for K == 5 the kernel is only launched with k == 5.
+  auto worst_of = [&]() {
+    double w = bd[K - 1];
+    if (K != 5) {
 #pragma unroll
-          for (int i = 0; i < K; ++i)
-            if (i == k - 1) worst = bd[i];
-          const int ox = s_off[3 * o], oy = s_off[3 * o + 1], oz = s_off[3 * o + 2];
-          const double gx = fmax(0.0, (ox < 0 ? fx : ox > 0 ? 1.0 - fx : 0.0) - kMargin);
-          const double gy = fmax(0.0, (oy < 0 ? fy : oy > 0 ? 1.0 - fy : 0.0) - kMargin);
-          const double gz = fmax(0.0, (oz < 0 ? fz : oz > 0 ? 1.0 - fz : 0.0) - kMargin);
-          const double lb = ((gx * gx + gy * gy) + gz * gz) * (leaf * leaf) * (1.0 - 1e-9);
-          if (lb > worst) continue;
-        }
-        cnt = (int)(pk & ((1u << kCountBits) - 1));
-        bucket = mv.pts + (size_t)(pk >> kCountBits) * cap;
-        j = 0;
-        break;
-      }
+      for (int i = 0; i < K; ++i)
+        if (i == k - 1) w = bd[i];
     }
-    if (running) {
-      const float4 p = __ldg(bucket + j);
-      const double d = sqdist4((double)p.x, (double)p.y, (double)p.z, qx, qy, qz);
-      const uint32_t s = ((uint32_t)o << kSeqShift) | (uint32_t)j;
-      ++j;
-      if (d < bd[K - 1] || (d == bd[K - 1] && s < bs[K - 1])) {
-        bool lt[K];
+    return w;
+  };
+  auto offer = [&](const float4* bucket, int o, int j) {
+    const float4 p = __ldg(bucket + j);
+    const double d = sqdist4((double)p.x, (double)p.y, (double)p.z, qx, qy, qz);
+    const uint32_t s = ((uint32_t)o << kSeqShift) | (uint32_t)j;
+    if ((d < bd[K - 1]) | ((d == bd[K - 1]) & (s < bs[K - 1]))) {
+      bool lt[K];
 #pragma unroll
-        for (int i = 0; i < K; ++i) lt[i] = d < bd[i] || (d == bd[i] && s < bs[i]);
+      for (int i = 0; i < K; ++i) lt[i] = (d < bd[i]) | ((d == bd[i]) & (s < bs[i]));
 #pragma unroll
-        for (int i = K - 1; i > 0; --i) {
-          bd[i] = lt[i - 1] ? bd[i - 1] : (lt[i] ? d : bd[i]);
-          bs[i] = lt[i - 1] ? bs[i - 1] : (lt[i] ? s : bs[i]);
-        }
-        bd[0] = lt[0] ? d : bd[0];
-        bs[0] = lt[0] ? s : bs[0];
+      for (int i = K - 1; i > 0; --i) {
+        bd[i] = lt[i - 1] ? bd[i - 1] : (lt[i] ? d : bd[i]);
+        bs[i] = lt[i - 1] ? bs[i - 1] : (lt[i] ? s : bs[i]);
       }
+      bd[0] = lt[0] ? d : bd[0];
+      bs[0] = lt[0] ? s : bs[0];
+    }
+  };
+
+  // (1) the query's own voxel
+  {
+    const uint32_t pk = active ? s_pk[centre * pk_stride] : kEmpty;
+    const int cnt = pk == kEmpty ? 0 : (int)(pk & kCntMask);
+    const float4* bucket = mv.pts + (size_t)(pk == kEmpty ? 0u : (pk >> kCountBits)) * cap;
+    const int max_cnt = __reduce_max_sync(kFull, cnt);
+    for (int j = 0; j < max_cnt; ++j)
+      if (j < cnt) offer(bucket, centre, j);
+  }
+
+  // (2) which neighbours can still contribute: bit o set when the voxel is occupied and the squared distance
+  //     from the query to its box does not exceed the current k-th best
+  const double fx = ux - (double)cx, fy = uy - (double)cy, fz = uz - (double)cz;  // position inside the voxel
+  const double kMargin = 1e-6;
+  const double leaf = 1.0 / mv.inv_leaf;
+  const double lb_scale = (leaf * leaf) * (1.0 - 1e-9);
+  const double glo_x = fmax(0.0, fx - kMargin), ghi_x = fmax(0.0, (1.0 - fx) - kMargin);
+  const double glo_y = fmax(0.0, fy - kMargin), ghi_y = fmax(0.0, (1.0 - fy) - kMargin);
+  const double glo_z = fmax(0.0, fz - kMargin), ghi_z = fmax(0.0, (1.0 - fz) - kMargin);
+  auto box_lb = [&](int o) {
+    const int ox = s_off[3 * o], oy = s_off[3 * o + 1], oz = s_off[3 * o + 2];
+    const double gx = ox < 0 ? glo_x : (ox > 0 ? ghi_x : 0.0);
+    const double gy = oy < 0 ? glo_y : (oy > 0 ? ghi_y : 0.0);
+    const double gz = oz < 0 ? glo_z : (oz > 0 ? ghi_z : 0.0);
+    return ((gx * gx + gy * gy) + gz * gz) * lb_scale;
+  };
+  uint32_t todo = 0;
+  {
+    const double worst = worst_of();
+    for (int o = 0; o < n_off; ++o) {
+      const uint32_t pk = s_pk[o * pk_stride];
+      const bool keep = active & (o != centre) & (pk != kEmpty) & ((pk & kCntMask) != 0) & !(box_lb(o) > worst);
+      todo |= keep ? (1u << o) : 0u;
+    }
+  }
+
+  // (3) the surviving neighbours, one candidate per lane and iteration; a lane moves to its next voxel
+  //     (lowest set bit = visiting order) with a handful of predicated instructions, re-checking the bound
+  //     against the radius as it stands then
+  int o = 0, j = 0, cnt = 0;
+  const float4* bucket = mv.pts;
+  while (__any_sync(kFull, (todo != 0) | (j < cnt))) {
+    if (j >= cnt && todo != 0) {
+      o = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t pk = s_pk[o * pk_stride];
+      cnt = box_lb(o) > worst_of() ? 0 : (int)(pk & kCntMask);
+      bucket = mv.pts + (size_t)(pk >> kCountBits) * cap;
+      j = 0;
+    }
+    if (j < cnt) {
+      offer(bucket, o, j);
+      ++j;
     }
   }
 }
