@@ -314,6 +314,21 @@ def main():
                 e2e_secs.append(t_b - t_a)
     launches = ctx.launch_count() - launches0
 
+    # diagnostic (stderr only): marginal device time of a converged, fully cached iteration
+    def timed_run(iters):
+        f.reset()
+        ctx.sync()
+        ctx.timer_begin()
+        f.icp_run(R0, t0, iters, LAMBDA, want_trace=False)
+        return ctx.timer_end()
+
+    for it_n in (20, 60):
+        timed_run(it_n)
+    t20 = min(timed_run(20) for _ in range(3))
+    t60 = min(timed_run(60) for _ in range(3))
+    log(f"[rank {rank}] warm 20-iter run {t20 * 1e3:.1f} us, 60-iter run {t60 * 1e3:.1f} us -> "
+        f"{(t60 - t20) * 1e3 / 40:.2f} us per cached iteration")
+
     total_ms = float(np.sum(step_ms))
     e2e_total = float(np.sum(e2e_secs))
     if world > 1:

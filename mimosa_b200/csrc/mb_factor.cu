@@ -718,7 +718,7 @@ int mb_factor_create(mb_ctx* ctx, mb_map* map, const void* pts, size_t n, size_t
   per_sm = std::max(per_sm, 1);
   f->grid = (int)std::max<size_t>(1, std::min<size_t>(n_tiles, (size_t)ctx->sm_count * per_sm));
   f->n_groups = (f->grid + kGroup - 1) / kGroup;
-  f->grid2 = (int)std::max<size_t>(1, std::min<size_t>((f->n + kLocThreads - 1) / kLocThreads, (size_t)ctx->sm_count));
+  f->grid2 = (int)std::max<size_t>(1, std::min<size_t>((f->n + kLocThreads - 1) / kLocThreads, (size_t)ctx->sm_count * 4));
 
   // carve one block: [src | vecs (15 ld doubles) | status (ld bytes) | knn_idx | partials | gpartials |
   //                   partials2 | packed | tickets | DevState]

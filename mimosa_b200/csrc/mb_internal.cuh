@@ -123,6 +123,8 @@ __device__ __forceinline__ uint32_t table_find(const int4* __restrict__ table, u
 }
 
 constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 constexpr int kSeqShift = 5;  // sequence number = (offset index << 5) | point index  (cap <= 31)
 
 // Index of the (0,0,0) offset in the reference's visiting order for each neighbourhood mode.
@@ -159,35 +161,49 @@ __device__ __forceinline__ void knn_thread(const MapView& mv, const int8_t* __re
   const int cx = fast_floor(ux), cy = fast_floor(uy), cz = fast_floor(uz);
 
   // ---- probe the neighbourhood ----------------------------------------------------------------------
+  // Pass 1 computes every neighbour's home slot and prefetches its cache line into L2 (no registers held);
+  // pass 2 reads the entries four at a time and resolves collisions by linear probing.
+  for (int o = 0; o < n_off; ++o) {
+    const uint32_t h = hash_coord(cx + s_off[3 * o], cy + s_off[3 * o + 1], cz + s_off[3 * o + 2]) & mv.table_mask;
+    s_pk[o * pk_stride] = h;
+    if (active) prefetch_l2(mv.table + h);
+  }
   for (int o0 = 0; o0 < n_off; o0 += 4) {
     uint32_t h[4];
     int4 e[4];
-    int x[4], y[4], z[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int o = min(o0 + u, n_off - 1);
-      x[u] = cx + s_off[3 * o];
-      y[u] = cy + s_off[3 * o + 1];
-      z[u] = cz + s_off[3 * o + 2];
-      h[u] = hash_coord(x[u], y[u], z[u]) & mv.table_mask;
+      h[u] = s_pk[min(o0 + u, n_off - 1) * pk_stride];
       e[u] = make_int4(0, 0, 0, (int)kEmpty);
       if (active) e[u] = __ldg(mv.table + h[u]);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (o0 + u < n_off) {
-        while ((uint32_t)e[u].w != kEmpty && !(e[u].x == x[u] && e[u].y == y[u] && e[u].z == z[u])) {
+        const int o = o0 + u;
+        const int x = cx + s_off[3 * o], y = cy + s_off[3 * o + 1], z = cz + s_off[3 * o + 2];
+        while ((uint32_t)e[u].w != kEmpty && !(e[u].x == x && e[u].y == y && e[u].z == z)) {
           h[u] = (h[u] + 1) & mv.table_mask;
           e[u] = __ldg(mv.table + h[u]);
         }
-        s_pk[(o0 + u) * pk_stride] = (uint32_t)e[u].w;
+        s_pk[o * pk_stride] = (uint32_t)e[u].w;
+        // the query's own voxel is always scanned: start pulling its bucket in while the other probes resolve
+        // (the neighbours are prefetched later, once the pruning test has decided which of them survive)
+        if (o == centre_offset_index(n_off) && (uint32_t)e[u].w != kEmpty) {
+          const uint32_t c = (uint32_t)e[u].w & ((1u << kCountBits) - 1);
+          const float4* b = mv.pts + (size_t)((uint32_t)e[u].w >> kCountBits) * mv.cap;
+          if (c > 0) prefetch_l2(b);
+          if (c > 8) prefetch_l2(b + 8);
+          if (c > 16) prefetch_l2(b + 16);
+        }
       }
     }
   }
 
   // ---- scan the candidates --------------------------------------------------------------------------
   // All control flow below is warp-converged (uniform trip counts, per-lane predicates): a lane never runs a
-  // private inner loop while the other 31 wait.
+  // private inner loop while the other 31 wait.  Candidates are taken four at a time: four independent loads
+  // in flight per lane, then four ordered insertion tests.
   const int centre = centre_offset_index(n_off);
   const int cap = mv.cap;
   const uint32_t kCntMask = (1u << kCountBits) - 1;
@@ -202,10 +218,7 @@ __device__ __forceinline__ void knn_thread(const MapView& mv, const int8_t* __re
     }
     return w;
   };
-  auto offer = [&](const float4* bucket, int o, int j) {
-    const float4 p = __ldg(bucket + j);
-    const double d = sqdist4((double)p.x, (double)p.y, (double)p.z, qx, qy, qz);
-    const uint32_t s = ((uint32_t)o << kSeqShift) | (uint32_t)j;
+  auto offer = [&](double d, uint32_t s) {
     if ((d < bd[K - 1]) | ((d == bd[K - 1]) & (s < bs[K - 1]))) {
       bool lt[K];
 #pragma unroll
@@ -219,6 +232,18 @@ __device__ __forceinline__ void knn_thread(const MapView& mv, const int8_t* __re
       bs[0] = lt[0] ? s : bs[0];
     }
   };
+  // candidates j .. j+3 of `bucket` (those below cnt), in order
+  auto offer4 = [&](const float4* bucket, int o, int j, int cnt) {
+    float4 p[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) p[u] = __ldg(bucket + min(j + u, cnt - 1));
+    double d[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) d[u] = sqdist4((double)p[u].x, (double)p[u].y, (double)p[u].z, qx, qy, qz);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (j + u < cnt) offer(d[u], ((uint32_t)o << kSeqShift) | (uint32_t)(j + u));
+  };
 
   // (1) the query's own voxel
   {
@@ -226,8 +251,8 @@ __device__ __forceinline__ void knn_thread(const MapView& mv, const int8_t* __re
     const int cnt = pk == kEmpty ? 0 : (int)(pk & kCntMask);
     const float4* bucket = mv.pts + (size_t)(pk == kEmpty ? 0u : (pk >> kCountBits)) * cap;
     const int max_cnt = __reduce_max_sync(kFull, cnt);
-    for (int j = 0; j < max_cnt; ++j)
-      if (j < cnt) offer(bucket, centre, j);
+    for (int j = 0; j < max_cnt; j += 4)
+      if (j < cnt) offer4(bucket, centre, j, cnt);
   }
 
   // (2) which neighbours can still contribute: bit o set when the voxel is occupied and the squared distance
@@ -253,10 +278,16 @@ __device__ __forceinline__ void knn_thread(const MapView& mv, const int8_t* __re
       const uint32_t pk = s_pk[o * pk_stride];
       const bool keep = active & (o != centre) & (pk != kEmpty) & ((pk & kCntMask) != 0) & !(box_lb(o) > worst);
       todo |= keep ? (1u << o) : 0u;
+      if (keep) {
+        const float4* b = mv.pts + (size_t)(pk >> kCountBits) * cap;
+        prefetch_l2(b);
+        if ((pk & kCntMask) > 8) prefetch_l2(b + 8);
+        if ((pk & kCntMask) > 16) prefetch_l2(b + 16);
+      }
     }
   }
 
-  // (3) the surviving neighbours, one candidate per lane and iteration; a lane moves to its next voxel
+  // (3) the surviving neighbours, four candidates per lane and iteration; a lane moves to its next voxel
   //     (lowest set bit = visiting order) with a handful of predicated instructions, re-checking the bound
   //     against the radius as it stands then
   int o = 0, j = 0, cnt = 0;
@@ -271,8 +302,8 @@ __device__ __forceinline__ void knn_thread(const MapView& mv, const int8_t* __re
       j = 0;
     }
     if (j < cnt) {
-      offer(bucket, o, j);
-      ++j;
+      offer4(bucket, o, j, cnt);
+      j += 4;
     }
   }
 }

@@ -14,8 +14,10 @@
 
 #if defined(__CUDACC__)
 #define MB_HD __host__ __device__ __forceinline__
+#define MB_UNROLL _Pragma("unroll")
 #else
 #define MB_HD inline
+#define MB_UNROLL
 #endif
 
 namespace mb {
@@ -57,13 +59,16 @@ MB_HD d3 mul33Tv(const m33& A, d3 v) {
 }
 MB_HD m33 mul33(const m33& A, const m33& B) {
   m33 C;
+  MB_UNROLL
   for (int r = 0; r < 3; ++r)
+    MB_UNROLL
     for (int c = 0; c < 3; ++c)
       C.m[3 * r + c] = A.m[3 * r] * B.m[c] + (A.m[3 * r + 1] * B.m[3 + c] + A.m[3 * r + 2] * B.m[6 + c]);
   return C;
 }
 MB_HD m33 sub33(const m33& A, const m33& B) {
   m33 C;
+  MB_UNROLL
   for (int i = 0; i < 9; ++i) C.m[i] = A.m[i] - B.m[i];
   return C;
 }
@@ -300,8 +305,10 @@ MB_HD m33 so3_exp(d3 w) {
   W.m[3] = w.z; W.m[4] = 0; W.m[5] = -w.x;
   W.m[6] = -w.y; W.m[7] = w.x; W.m[8] = 0;
   m33 R;
+  MB_UNROLL
   for (int i = 0; i < 9; ++i) R.m[i] = (i % 4 == 0) ? 1.0 : 0.0;
   if (th2 <= DBL_EPSILON) {
+    MB_UNROLL
     for (int i = 0; i < 9; ++i) R.m[i] += W.m[i];
     return R;
   }
@@ -310,8 +317,10 @@ MB_HD m33 so3_exp(d3 w) {
   const double s2 = sin(th / 2.0);
   const double omc = 2.0 * s2 * s2;
   m33 K;
+  MB_UNROLL
   for (int i = 0; i < 9; ++i) K.m[i] = W.m[i] / th;
   const m33 KK = mul33(K, K);
+  MB_UNROLL
   for (int i = 0; i < 9; ++i) R.m[i] += sn * K.m[i] + omc * KK.m[i];
   return R;
 }
@@ -333,32 +342,44 @@ MB_HD void se3_retract(m33& R, d3& t, const double xi[6]) {
 
 // (H + lambda I) x = rhs, unpivoted LDL^T; false when a pivot is not strictly positive.
 MB_HD bool solve6_ldlt(const double H[36], double lambda, const double rhs[6], double x[6]) {
+  // Every loop has constant bounds and is fully unrolled on the device, so L, D, y live in registers.
   double L[36], D[6], y[6];
+  bool ok = true;
+  MB_UNROLL
   for (int i = 0; i < 36; ++i) L[i] = 0.0;
+  MB_UNROLL
   for (int j = 0; j < 6; ++j) {
     double d = H[6 * j + j] + lambda;
+    MB_UNROLL
     for (int k = 0; k < j; ++k) d -= L[6 * j + k] * L[6 * j + k] * D[k];
-    if (!(d > 0.0)) return false;
+    ok = ok && (d > 0.0);
     D[j] = d;
     L[6 * j + j] = 1.0;
+    MB_UNROLL
     for (int i = j + 1; i < 6; ++i) {
       double s = H[6 * i + j];
+      MB_UNROLL
       for (int k = 0; k < j; ++k) s -= L[6 * i + k] * L[6 * j + k] * D[k];
       L[6 * i + j] = s / d;
     }
   }
+  MB_UNROLL
   for (int i = 0; i < 6; ++i) {
     double s = rhs[i];
+    MB_UNROLL
     for (int k = 0; k < i; ++k) s -= L[6 * i + k] * y[k];
     y[i] = s;
   }
+  MB_UNROLL
   for (int i = 0; i < 6; ++i) y[i] = y[i] / D[i];
+  MB_UNROLL
   for (int i = 5; i >= 0; --i) {
     double s = y[i];
+    MB_UNROLL
     for (int k = i + 1; k < 6; ++k) s -= L[6 * k + i] * x[k];
     x[i] = s;
   }
-  return true;
+  return ok;
 }
 
 // int(x) - (x < int(x)), mimosa/include/mimosa/lidar/utils.hpp:218-222.

@@ -415,3 +415,36 @@ def test_full_size_properties(ctx, oracle):
     assert_state_equal(fg.download_state(), fo.download_state())
     fg.release()
     mg.release()
+
+
+def test_sharded_factors_sum_to_full(ctx, oracle):
+    """Scan-block sharding (the multi-GPU decomposition) on one GPU: per-shard normal equations add up to the
+    unsharded ones, per-point state of each shard equals the matching slice."""
+    from mimosa_b200 import shard_range
+
+    mg, mo, scan, R0, t0, _, _ = _world_case(ctx, oracle, 200000, 9001, 170, half=40.0)
+    cfg = hornbill_config()
+    full = ICPFactor(ctx, mg, scan, cfg)
+    Lf = full.linearize(R0, t0)
+    sf = full.download_state()
+    H = np.zeros(36)
+    g = np.zeros(6)
+    f = 0.0
+    counts = np.zeros(9, dtype=np.int64)
+    for world in (3,):
+        for r in range(world):
+            b, e = shard_range(scan.shape[0], r, world)
+            part = ICPFactor(ctx, mg, scan, cfg, shard=(b, e))
+            Lp = part.linearize(R0, t0)
+            sp = part.download_state()
+            for k in ("status", "knn_idx", "mean", "normal", "p_da"):
+                assert np.array_equal(sp[k], sf[k][b:e]), k
+            H += np.array(Lp.H)
+            g += np.array(Lp.g)
+            f += Lp.f
+            counts += np.array(Lp.counts)
+            part.release()
+    assert rel_err(H, Lf.H) <= 1e-12 and rel_err(g, Lf.g) <= 1e-9 and abs(f - Lf.f) <= 1e-12 * Lf.f
+    assert counts.tolist() == list(Lf.counts)
+    full.release()
+    mg.release()
