@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(kLinThreads, 5)
   // s_pk (phase B: probed neighbour words, [n_off][thread]) is re-used as s_row (phase C: whitened
   // [J (6), e] per point, [warp][32][7] doubles = 7168 B <= 27 * 128 * 4 B).
   __shared__ __align__(16) uint32_t s_pk_all[kMaxNbr * kLinThreads];
+  __shared__ uint32_t s_blk_all[24 * kLinThreads];  // per-thread {mask_lo, mask_hi, base} of the <= 8 blocks around a query
   __shared__ double s_pt[3][kLinThreads];          // transformed point of each tile member
   __shared__ double s_mean[3][kLinThreads], s_normal[3][kLinThreads];
   __shared__ double s_dk[kLinThreads];             // squared distance of the k-th neighbour
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(kLinThreads, 5)
       double bd[K];
       uint32_t bs[K];
       uint32_t* s_pk = s_pk_all + tid;
-      knn_thread<K>(mv, s_off, s_pk, kLinThreads, qx, qy, qz, k, on, bd, bs);
+      knn_thread<K>(mv, s_off, s_pk, s_blk_all + tid, kLinThreads, qx, qy, qz, k, on, bd, bs);
       if (on) {
         const size_t gi = tile * kLinThreads + li;
         int found = 0;
@@ -701,6 +702,13 @@ int mb_factor_create(mb_ctx* ctx, mb_map* map, const void* pts, size_t n, size_t
   cudaStream_t st = ctx->stream;
   mb_factor* f = new mb_factor;
   f->ctx = ctx;
+  {
+    const int mrc = ensure_mirror(map);  // the map is immutable from here on (refs > 1): build its search mirror once
+    if (mrc != MB_OK) {
+      delete f;
+      return mrc;
+    }
+  }
   f->map = map;
   map->refs.fetch_add(1);
   f->cfg = *cfg;

@@ -89,16 +89,23 @@ constexpr int kMaxNbr = 27;
 constexpr uint32_t kEmpty = 0xffffffffu;
 constexpr int kCountBits = 5;  // cap <= 31 points per voxel (reference: 20)
 
-// What the search kernels need of a map; passed by value.
+// What the search kernels need of a map; passed by value.  Searches run on the map's read-optimised mirror
+// (mb_map.cuh, "search mirror"): voxels grouped into 4x4x4 blocks, blocks hashed, every block entry carrying a
+// 64-bit occupancy mask and the index of its first bucket in a Morton-ordered bucket array.
 struct MapView {
-  const int4* table;    // open addressing; {cx, cy, cz, (slot << 5) | count}; w == kEmpty -> free
-  uint32_t table_mask;  // capacity - 1 (power of two)
-  const float4* pts;    // [slot * cap + j], xyz are the stored (f32-exact) coordinates
+  const int4* btab;     // block table, 2 x int4 per entry: {bx, by, bz, base} {mask_lo, mask_hi, -, -}; base == kEmpty -> free
+  uint32_t bmask;       // entries - 1 (power of two)
+  const float4* pts;    // [slot * cap + j], Morton/block order; xyz are the stored (f32-exact) coordinates
+  const uint32_t* meta; // [slot] = (voxel id << 5) | count
   int cap;
   int n_off;
   double inv_leaf;
   int8_t off[kMaxNbr * 3];  // neighbour offsets in the reference's visiting order
 };
+constexpr int kBlockShift = 2;  // 4 x 4 x 4 voxels per block
+__host__ __device__ __forceinline__ uint32_t cell_of(int x, int y, int z) {
+  return (uint32_t)(x & 3) | ((uint32_t)(y & 3) << 2) | ((uint32_t)(z & 3) << 4);
+}
 
 __host__ __device__ __forceinline__ uint32_t hash_coord(int x, int y, int z) {
   uint32_t h = (uint32_t)x * 73856093u ^ (uint32_t)y * 19349669u ^ (uint32_t)z * 83492791u;
@@ -148,7 +155,8 @@ __host__ __device__ __forceinline__ int centre_offset_index(int n_off) { return 
 // the packed (voxel id << 5 | count) word of every probed neighbour; it stays valid for knn_resolve().
 template <int K>
 __device__ __forceinline__ void knn_thread(const MapView& mv, const int8_t* __restrict__ s_off, uint32_t* s_pk,
-                                           int pk_stride, double qx, double qy, double qz, int k, bool active,
+                                           uint32_t* s_blk, int pk_stride, double qx, double qy, double qz, int k,
+                                           bool active,
                                            double (&bd)[K], uint32_t (&bs)[K]) {
   const double kInf = __longlong_as_double(0x7ff0000000000000ll);
 #pragma unroll
@@ -160,45 +168,68 @@ __device__ __forceinline__ void knn_thread(const MapView& mv, const int8_t* __re
   const double ux = qx * mv.inv_leaf, uy = qy * mv.inv_leaf, uz = qz * mv.inv_leaf;
   const int cx = fast_floor(ux), cy = fast_floor(uy), cz = fast_floor(uz);
 
-  // ---- probe the neighbourhood ----------------------------------------------------------------------
-  // Pass 1 computes every neighbour's home slot and prefetches its cache line into L2 (no registers held);
-  // pass 2 reads the entries four at a time and resolves collisions by linear probing.
-  for (int o = 0; o < n_off; ++o) {
-    const uint32_t h = hash_coord(cx + s_off[3 * o], cy + s_off[3 * o + 1], cz + s_off[3 * o + 2]) & mv.table_mask;
-    s_pk[o * pk_stride] = h;
-    if (active) prefetch_l2(mv.table + h);
+  // ---- locate the neighbourhood's blocks -------------------------------------------------------------
+  // The 3x3x3 neighbourhood touches at most 2 blocks per axis.  s_blk[combo] (combo = ix | iy << 1 | iz << 2)
+  // receives {mask_lo, mask_hi, base} of block (ix ? hi : lo) per axis; duplicates (hi == lo) are copied, not
+  // probed.  Pass 1 hashes and prefetches, pass 2 reads the entries four at a time.
+  const int lx = (cx - 1) >> kBlockShift, hx = (cx + 1) >> kBlockShift;
+  const int ly = (cy - 1) >> kBlockShift, hy = (cy + 1) >> kBlockShift;
+  const int lz = (cz - 1) >> kBlockShift, hz = (cz + 1) >> kBlockShift;
+  const unsigned dup_bits = (hx == lx ? 1u : 0u) | (hy == ly ? 2u : 0u) | (hz == lz ? 4u : 0u);
+#pragma unroll
+  for (int combo = 0; combo < 8; ++combo) {
+    const uint32_t h = hash_coord((combo & 1) ? hx : lx, (combo & 2) ? hy : ly, (combo & 4) ? hz : lz) & mv.bmask;
+    s_blk[(combo * 3) * pk_stride] = h;
+    if (active && (combo & dup_bits) == 0) prefetch_l2(mv.btab + 2 * (size_t)h);
   }
-  for (int o0 = 0; o0 < n_off; o0 += 4) {
+#pragma unroll
+  for (int c0 = 0; c0 < 8; c0 += 4) {
     uint32_t h[4];
     int4 e[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      h[u] = s_pk[min(o0 + u, n_off - 1) * pk_stride];
+      const int combo = c0 + u;
+      h[u] = s_blk[(combo * 3) * pk_stride];
       e[u] = make_int4(0, 0, 0, (int)kEmpty);
-      if (active) e[u] = __ldg(mv.table + h[u]);
+      if (active && (combo & dup_bits) == 0) e[u] = __ldg(mv.btab + 2 * (size_t)h[u]);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      if (o0 + u < n_off) {
-        const int o = o0 + u;
-        const int x = cx + s_off[3 * o], y = cy + s_off[3 * o + 1], z = cz + s_off[3 * o + 2];
-        while ((uint32_t)e[u].w != kEmpty && !(e[u].x == x && e[u].y == y && e[u].z == z)) {
-          h[u] = (h[u] + 1) & mv.table_mask;
-          e[u] = __ldg(mv.table + h[u]);
+      const int combo = c0 + u;
+      uint32_t m_lo = 0, m_hi = 0, base = 0;
+      if ((combo & dup_bits) != 0) {
+        const int src = combo & ~(int)dup_bits;  // already resolved (src < combo)
+        m_lo = s_blk[(src * 3) * pk_stride];
+        m_hi = s_blk[(src * 3 + 1) * pk_stride];
+        base = s_blk[(src * 3 + 2) * pk_stride];
+      } else {
+        const int bx = (combo & 1) ? hx : lx, by = (combo & 2) ? hy : ly, bz = (combo & 4) ? hz : lz;
+        while ((uint32_t)e[u].w != kEmpty && !(e[u].x == bx && e[u].y == by && e[u].z == bz)) {
+          h[u] = (h[u] + 1) & mv.bmask;
+          e[u] = __ldg(mv.btab + 2 * (size_t)h[u]);
         }
-        s_pk[o * pk_stride] = (uint32_t)e[u].w;
-        // the query's own voxel is always scanned: start pulling its bucket in while the other probes resolve
-        // (the neighbours are prefetched later, once the pruning test has decided which of them survive)
-        if (o == centre_offset_index(n_off) && (uint32_t)e[u].w != kEmpty) {
-          const uint32_t c = (uint32_t)e[u].w & ((1u << kCountBits) - 1);
-          const float4* b = mv.pts + (size_t)((uint32_t)e[u].w >> kCountBits) * mv.cap;
-          if (c > 0) prefetch_l2(b);
-          if (c > 8) prefetch_l2(b + 8);
-          if (c > 16) prefetch_l2(b + 16);
+        if ((uint32_t)e[u].w != kEmpty) {
+          const int4 m = __ldg(mv.btab + 2 * (size_t)h[u] + 1);
+          m_lo = (uint32_t)m.x;
+          m_hi = (uint32_t)m.y;
+          base = (uint32_t)e[u].w;
         }
       }
+      s_blk[(combo * 3) * pk_stride] = m_lo;
+      s_blk[(combo * 3 + 1) * pk_stride] = m_hi;
+      s_blk[(combo * 3 + 2) * pk_stride] = base;
     }
   }
+  // bucket index of neighbour o, or kEmpty when that voxel does not exist
+  auto slot_of = [&](int o) -> uint32_t {
+    const int x = cx + s_off[3 * o], y = cy + s_off[3 * o + 1], z = cz + s_off[3 * o + 2];
+    const int combo = ((x >> kBlockShift) != lx ? 1 : 0) | ((y >> kBlockShift) != ly ? 2 : 0) | ((z >> kBlockShift) != lz ? 4 : 0);
+    const uint32_t m_lo = s_blk[(combo * 3) * pk_stride], m_hi = s_blk[(combo * 3 + 1) * pk_stride];
+    const unsigned long long m = ((unsigned long long)m_hi << 32) | m_lo;
+    const uint32_t cell = cell_of(x, y, z);
+    if (((m >> cell) & 1ull) == 0) return kEmpty;
+    return s_blk[(combo * 3 + 2) * pk_stride] + (uint32_t)__popcll(m & ((1ull << cell) - 1ull));
+  };
 
   // ---- scan the candidates --------------------------------------------------------------------------
   // All control flow below is warp-converged (uniform trip counts, per-lane predicates): a lane never runs a
@@ -247,9 +278,11 @@ __device__ __forceinline__ void knn_thread(const MapView& mv, const int8_t* __re
 
   // (1) the query's own voxel
   {
-    const uint32_t pk = active ? s_pk[centre * pk_stride] : kEmpty;
-    const int cnt = pk == kEmpty ? 0 : (int)(pk & kCntMask);
-    const float4* bucket = mv.pts + (size_t)(pk == kEmpty ? 0u : (pk >> kCountBits)) * cap;
+    const uint32_t slot = active ? slot_of(centre) : kEmpty;
+    const uint32_t meta = slot == kEmpty ? 0u : __ldg(mv.meta + slot);
+    const int cnt = (int)(meta & kCntMask);
+    s_pk[centre * pk_stride] = slot == kEmpty ? kEmpty : ((slot << kCountBits) | (uint32_t)cnt);
+    const float4* bucket = mv.pts + (size_t)(slot == kEmpty ? 0u : slot) * cap;
     const int max_cnt = __reduce_max_sync(kFull, cnt);
     for (int j = 0; j < max_cnt; j += 4)
       if (j < cnt) offer4(bucket, centre, j, cnt);
@@ -275,14 +308,17 @@ __device__ __forceinline__ void knn_thread(const MapView& mv, const int8_t* __re
   {
     const double worst = worst_of();
     for (int o = 0; o < n_off; ++o) {
-      const uint32_t pk = s_pk[o * pk_stride];
-      const bool keep = active & (o != centre) & (pk != kEmpty) & ((pk & kCntMask) != 0) & !(box_lb(o) > worst);
-      todo |= keep ? (1u << o) : 0u;
+      uint32_t slot = kEmpty;
+      if (active & (o != centre)) slot = slot_of(o);
+      const bool keep = (slot != kEmpty) && !(box_lb(o) > worst);
       if (keep) {
-        const float4* b = mv.pts + (size_t)(pk >> kCountBits) * cap;
+        const uint32_t cnt = __ldg(mv.meta + slot) & kCntMask;
+        s_pk[o * pk_stride] = (slot << kCountBits) | cnt;
+        const float4* b = mv.pts + (size_t)slot * cap;
         prefetch_l2(b);
-        if ((pk & kCntMask) > 8) prefetch_l2(b + 8);
-        if ((pk & kCntMask) > 16) prefetch_l2(b + 16);
+        if (cnt > 8) prefetch_l2(b + 8);
+        if (cnt > 16) prefetch_l2(b + 16);
+        todo |= cnt ? (1u << o) : 0u;
       }
     }
   }
@@ -314,7 +350,8 @@ __device__ __forceinline__ uint64_t knn_resolve(const MapView& mv, const uint32_
   const uint32_t o = seq >> kSeqShift, j = seq & ((1u << kSeqShift) - 1);
   const uint32_t slot = s_pk[o * pk_stride] >> kCountBits;
   p = __ldg(mv.pts + (size_t)slot * mv.cap + j);
-  return ((uint64_t)slot << 32) | (uint64_t)j;
+  const uint32_t id = __ldg(mv.meta + slot) >> kCountBits;
+  return ((uint64_t)id << 32) | (uint64_t)j;
 }
 #endif  // __CUDACC__
 

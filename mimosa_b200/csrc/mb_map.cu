@@ -191,6 +191,82 @@ __global__ void k_compact(const uint32_t* __restrict__ keep, const uint32_t* __r
   }
 }
 
+// ---- search mirror ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t spread3(uint32_t v) {  // 21 bits -> every third bit
+  uint64_t x = v & 0x1fffffull;
+  x = (x | x << 32) & 0x1f00000000ffffull;
+  x = (x | x << 16) & 0x1f0000ff0000ffull;
+  x = (x | x << 8) & 0x100f00f00f00f00full;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+constexpr int kBlockBias = 1 << 18;  // block coordinates are within +-2^18 (voxel coordinates within +-2^20)
+
+// key = (Morton code of the block << 6) | cell
+__global__ void k_mirror_keys(const int4* __restrict__ info, uint32_t n_vox, uint64_t* __restrict__ keys,
+                              uint32_t* __restrict__ ids) {
+  const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n_vox) return;
+  const int4 c = info[id];
+  const uint32_t bx = (uint32_t)((c.x >> kBlockShift) + kBlockBias), by = (uint32_t)((c.y >> kBlockShift) + kBlockBias),
+                 bz = (uint32_t)((c.z >> kBlockShift) + kBlockBias);
+  const uint64_t morton = spread3(bx) | (spread3(by) << 1) | (spread3(bz) << 2);
+  keys[id] = (morton << 6) | cell_of(c.x, c.y, c.z);
+  ids[id] = id;
+}
+
+// One warp per mirror position: move the bucket, write meta; block heads are flagged for the scan.
+__global__ void k_mirror_gather(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ ids, uint32_t n_vox,
+                                int cap, const float4* __restrict__ pts, const int32_t* __restrict__ count,
+                                float4* __restrict__ r_pts, uint32_t* __restrict__ r_meta, uint32_t* __restrict__ head) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_vox; s += warps) {
+    const uint32_t id = ids[s];
+    const int c = count[id];
+    if (lane < cap) r_pts[(size_t)s * cap + lane] = lane < c ? pts[(size_t)id * cap + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane == 0) {
+      r_meta[s] = (id << kCountBits) | (uint32_t)c;
+      head[s] = (s == 0 || (keys[s] >> 6) != (keys[s - 1] >> 6)) ? 1u : 0u;
+    }
+  }
+}
+
+// Every mirror position ORs its cell bit into its block's mask; block heads record base and coordinates.
+__global__ void k_mirror_blocks(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ ids,
+                                const int4* __restrict__ info, const uint32_t* __restrict__ head,
+                                const uint32_t* __restrict__ block_of, uint32_t n_vox, int4* __restrict__ blk_hdr,
+                                unsigned long long* __restrict__ blk_mask) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_vox) return;
+  const uint32_t b = block_of[s];  // exclusive scan of head: a head sees its own block index, others index + 1
+  const uint32_t blk = head[s] ? b : b - 1;
+  atomicOr(blk_mask + blk, 1ull << (keys[s] & 63ull));
+  if (head[s]) {
+    const int4 c = info[ids[s]];
+    blk_hdr[blk] = make_int4(c.x >> kBlockShift, c.y >> kBlockShift, c.z >> kBlockShift, (int)s);
+  }
+}
+
+__global__ void k_mirror_table(const int4* __restrict__ blk_hdr, const unsigned long long* __restrict__ blk_mask,
+                               uint32_t n_blocks, int4* __restrict__ btab, uint32_t bmask) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_blocks) return;
+  const int4 hd = blk_hdr[b];
+  uint32_t h = hash_coord(hd.x, hd.y, hd.z) & bmask;
+  while (true) {
+    const unsigned old = atomicCAS((unsigned*)&btab[2 * (size_t)h].w, kEmpty, (unsigned)hd.w);
+    if (old == kEmpty) break;
+    h = (h + 1) & bmask;
+  }
+  btab[2 * (size_t)h].x = hd.x;
+  btab[2 * (size_t)h].y = hd.y;
+  btab[2 * (size_t)h].z = hd.z;
+  const unsigned long long m = blk_mask[b];
+  btab[2 * (size_t)h + 1] = make_int4((int)(uint32_t)(m & 0xffffffffull), (int)(uint32_t)(m >> 32), 0, 0);
+}
+
 // ---- Geometric::downsample (mimosa/src/lidar/geometric.cpp:55-126) ----------------------------------
 __global__ void k_ds_mark(const uint32_t* __restrict__ vals, const uint32_t* __restrict__ run_start, uint32_t n_runs,
                           uint32_t* __restrict__ first_flag) {
@@ -246,9 +322,11 @@ __global__ void __launch_bounds__(kKnnThreads, 5)
           double* __restrict__ d2, uint8_t* __restrict__ ok) {
   __shared__ int8_t s_off[32 * 3];
   __shared__ uint32_t s_pk_all[kMaxNbr * kKnnThreads];
+  __shared__ uint32_t s_blk_all[24 * kKnnThreads];
   if (threadIdx.x < kMaxNbr * 3) s_off[threadIdx.x] = mv.off[threadIdx.x];
   __syncthreads();
   uint32_t* s_pk = s_pk_all + threadIdx.x;
+  uint32_t* s_blk = s_blk_all + threadIdx.x;
   const size_t i = (size_t)blockIdx.x * kKnnThreads + threadIdx.x;
   const bool active = i < nq;
   double qx = 0, qy = 0, qz = 0;
@@ -259,7 +337,7 @@ __global__ void __launch_bounds__(kKnnThreads, 5)
   }
   double bd[K];
   uint32_t bs[K];
-  knn_thread<K>(mv, s_off, s_pk, kKnnThreads, qx, qy, qz, k, active, bd, bs);
+  knn_thread<K>(mv, s_off, s_pk, s_blk, kKnnThreads, qx, qy, qz, k, active, bd, bs);
   if (!active) return;
   int found = 0;
 #pragma unroll
@@ -385,8 +463,86 @@ int map_reserve(mb_map* m, size_t want_vox) {
   return MB_OK;
 }
 
+int ensure_mirror(mb_map* m) {
+  if (m->r_fresh) return MB_OK;
+  mb_ctx* c = m->ctx;
+  cudaStream_t st = c->stream;
+  const size_t nv = m->n_vox;
+  if (m->r_cap_vox < std::max<size_t>(nv, 1)) {
+    MB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(m->r_pts);
+    cudaFree(m->r_meta);
+    m->r_pts = nullptr;
+    m->r_meta = nullptr;
+    m->r_cap_vox = 0;
+    const size_t cap_vox = std::max<size_t>(nv + nv / 8, 4096);
+    MB_CUDA(cudaMalloc(&m->r_pts, cap_vox * m->cap * sizeof(float4)));
+    MB_CUDA(cudaMalloc(&m->r_meta, cap_vox * sizeof(uint32_t)));
+    m->r_cap_vox = cap_vox;
+  }
+  size_t want_b = 1024;
+  while (want_b < 2 * std::max<size_t>(nv, 1)) want_b <<= 1;  // >= 2 x blocks for any block count <= n_vox ...
+  // ... but blocks are usually ~10x fewer than voxels: size from the real count below once it is known
+  size_t sort_temp = 0, scan_temp = 0;
+  if (nv) {
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_temp, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)nv, 0, 63, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_temp, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)nv, st);
+  }
+  const size_t temp_bytes = std::max(sort_temp, scan_temp);
+  MB_TRY(ensure_scratch(m, nv * (16 + 8 + 8 + 16 + 8) + temp_bytes + 256 * 12 + 1024));
+  uint32_t n_blocks = 0;
+  int4* blk_hdr = nullptr;
+  unsigned long long* blk_mask = nullptr;
+  if (nv) {
+    Bump b{(char*)m->scratch, 0, m->scratch_bytes};
+    uint64_t* keys = b.take<uint64_t>(nv);
+    uint64_t* keys_s = b.take<uint64_t>(nv);
+    uint32_t* ids = b.take<uint32_t>(nv);
+    uint32_t* ids_s = b.take<uint32_t>(nv);
+    uint32_t* head = b.take<uint32_t>(nv);
+    uint32_t* block_of = b.take<uint32_t>(nv);
+    blk_hdr = b.take<int4>(nv);
+    blk_mask = b.take<unsigned long long>(nv);
+    uint32_t* counters = b.take<uint32_t>(4);
+    void* temp = b.take<unsigned char>(temp_bytes);
+    k_mirror_keys<<<blocks_for(nv, 256), 256, 0, st>>>(m->info, (uint32_t)nv, keys, ids);
+    size_t tb = temp_bytes;
+    MB_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, keys, keys_s, ids, ids_s, (int)nv, 0, 63, st));
+    const unsigned grid = (unsigned)std::min<size_t>((nv + 7) / 8, (size_t)c->sm_count * 32);
+    k_mirror_gather<<<grid, 256, 0, st>>>(keys_s, ids_s, (uint32_t)nv, m->cap, m->pts, m->count, m->r_pts, m->r_meta, head);
+    tb = temp_bytes;
+    MB_CUDA(cub::DeviceScan::ExclusiveSum(temp, tb, head, block_of, (int)nv, st));
+    k_count2<<<1, 1, 0, st>>>(head, block_of, nullptr, nullptr, nv, counters);
+    MB_CUDA(cudaMemsetAsync(blk_mask, 0, nv * sizeof(unsigned long long), st));
+    k_mirror_blocks<<<blocks_for(nv, 256), 256, 0, st>>>(keys_s, ids_s, m->info, head, block_of, (uint32_t)nv, blk_hdr, blk_mask);
+    c->launches += 4 + 6;
+    MB_CUDA(cudaMemcpyAsync(&n_blocks, counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+  }
+  want_b = 1024;
+  while (want_b < 2 * (size_t)n_blocks) want_b <<= 1;
+  if (want_b > m->r_bcap) {
+    MB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(m->r_btab);
+    m->r_btab = nullptr;
+    MB_CUDA(cudaMalloc(&m->r_btab, 2 * want_b * sizeof(int4)));
+    m->r_bcap = want_b;
+  }
+  MB_CUDA(cudaMemsetAsync(m->r_btab, 0xff, 2 * m->r_bcap * sizeof(int4), st));
+  if (n_blocks) {
+    k_mirror_table<<<blocks_for(n_blocks, 256), 256, 0, st>>>(blk_hdr, blk_mask, n_blocks, m->r_btab, (uint32_t)(m->r_bcap - 1));
+    ++c->launches;
+  }
+  MB_CUDA(cudaGetLastError());
+  m->r_nblocks = n_blocks;
+  m->r_fresh = true;
+  return MB_OK;
+}
+
 int launch_knn(mb_map* m, const double* d_q, size_t nq, int k, uint64_t* d_idx, double* d_d2, uint8_t* d_ok) {
   if (nq == 0) return MB_OK;
+  MB_TRY(ensure_mirror(m));
   const unsigned grid = blocks_for(nq, kKnnThreads);
   if (k == 5)
     k_knn<5><<<grid, kKnnThreads, 0, m->ctx->stream>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
@@ -469,6 +625,9 @@ int mb_map_release(mb_map* m) {
   cudaFree(m->epos);
   cudaFree(m->table);
   cudaFree(m->scratch);
+  cudaFree(m->r_pts);
+  cudaFree(m->r_meta);
+  cudaFree(m->r_btab);
   cudaFree(m->q_dev);
   cudaFree(m->q_idx);
   cudaFree(m->q_d2);
@@ -543,6 +702,7 @@ int mb_map_insert(mb_map* m, const float* xyz, size_t n, size_t stride_bytes) {
   MB_REQUIRE(n < 0xffffffffull, "too many points in one insert");
   MB_REQUIRE(m->refs.load() == 1, "map is referenced by a factor: insert into a snapshot (geometric.cpp:494)");
   MB_CUDA(cudaSetDevice(m->ctx->device));
+  m->r_fresh = false;
   cudaStream_t st = m->ctx->stream;
   mb_ctx* ctx = m->ctx;
   if (n > 0) {
@@ -710,6 +870,7 @@ int mb_map_upload(mb_map* m, const int32_t* coords, const int32_t* counts, const
   MB_REQUIRE(m && (n_vox == 0 || (coords && counts && pts)), "null argument");
   MB_REQUIRE(m->refs.load() == 1, "map is referenced by a factor");
   MB_CUDA(cudaSetDevice(m->ctx->device));
+  m->r_fresh = false;
   cudaStream_t st = m->ctx->stream;
   m->n_vox = 0;
   MB_TRY(map_reserve(m, std::max<size_t>(n_vox, 4096)));

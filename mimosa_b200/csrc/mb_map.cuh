@@ -10,6 +10,15 @@
 //   count  int32 [cap_vox]
 //   epos   uint32[cap_vox]         position of the voxel's entry in `table`
 //   table  int4  [table_cap]       open-addressing hash {cx, cy, cz, (id << 5) | count}, load <= 0.5
+// Those arrays are what insert / LRU / snapshot / download work on (the authoritative state).
+//
+// SEARCH MIRROR (rebuilt lazily after the map changed, before the next search; mb::ensure_mirror):
+//   r_pts   float4[n_vox * cap]    the same buckets re-ordered by (Morton code of the voxel's 4x4x4 block, cell
+//                                  index inside the block): spatial neighbours are memory neighbours
+//   r_meta  uint32[n_vox]          (voxel id << 5) | count of the bucket at that position
+//   r_btab  int4[2 * r_bcap]       hashed block table {bx, by, bz, base} {mask_lo, mask_hi, 0, 0}: a 64-bit
+//                                  occupancy mask + first bucket index per block, so the 19 neighbour lookups of a
+//                                  query become <= 8 (typically 1-4) L2-resident block probes plus popcounts
 #pragma once
 #include "mb_internal.cuh"
 
@@ -29,6 +38,12 @@ struct mb_map {
   uint32_t* epos = nullptr;
   int4* table = nullptr;
   unsigned long long* d_npts = nullptr;  // device counter of stored points
+  // search mirror
+  float4* r_pts = nullptr;
+  uint32_t* r_meta = nullptr;
+  int4* r_btab = nullptr;
+  size_t r_cap_vox = 0, r_bcap = 0, r_nblocks = 0;
+  bool r_fresh = false;
   // staged k-NN (roofline timing)
   double* q_dev = nullptr;
   size_t q_n = 0, q_cap = 0;
@@ -40,11 +55,12 @@ struct mb_map {
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
 
-  mb::MapView view() const {
+  mb::MapView view() const {  // valid only while r_fresh (mb::ensure_mirror)
     mb::MapView v;
-    v.table = table;
-    v.table_mask = (uint32_t)(table_cap - 1);
-    v.pts = pts;
+    v.btab = r_btab;
+    v.bmask = (uint32_t)(r_bcap - 1);
+    v.pts = r_pts;
+    v.meta = r_meta;
     v.cap = cap;
     v.n_off = n_off;
     v.inv_leaf = inv_leaf;
@@ -55,6 +71,8 @@ struct mb_map {
 
 namespace mb {
 int map_reserve(mb_map* m, size_t want_vox);
+// (Re)build the search mirror if the map changed since it was last built.  Enqueued on the context stream.
+int ensure_mirror(mb_map* m);
 // Launch the standalone search kernel over device-resident queries (nq x 3 doubles).
 int launch_knn(mb_map* m, const double* d_q, size_t nq, int k, uint64_t* d_idx, double* d_d2, uint8_t* d_ok);
 }  // namespace mb
