@@ -121,15 +121,18 @@ class ClockSampler:
 
 # ---- algorithmic bytes of one k-NN launch ----------------------------------------------------
 def knn_algorithmic_bytes(q: np.ndarray, coords: np.ndarray, counts: np.ndarray, k: int, nbr_mode: int = 19, leaf: float = 1.0):
-    """Compulsory bytes: every query (24 B) read once, every DISTINCT probed hash entry (16 B) once, every
-    DISTINCT occupied neighbour bucket's stored points (count x 16 B) once, results written once
-    (k x (8 + 8) + 1 B per query)."""
+    """Compulsory bytes of the search on the block-grid layout: every query (24 B) read once, every DISTINCT
+    4x4x4 block entry the neighbourhoods touch (32 B) once, the meta word (4 B) and the stored points
+    (count x 16 B) of every DISTINCT occupied neighbour bucket once, results written once (k x (8 + 8) + 1 B per
+    query).  Buckets the pruning test later skips are still counted: the figure does not depend on the pruning."""
     offs = np.array([(i, j, kk) for i in (-1, 0, 1) for j in (-1, 0, 1) for kk in (-1, 0, 1)
                      if nbr_mode == 27 or not (i and j and kk)], dtype=np.int64)
     c = np.floor(q / leaf).astype(np.int64)
     bias = 1 << 20
     pack = lambda a: ((a[..., 0] + bias) << 42) | ((a[..., 1] + bias) << 21) | (a[..., 2] + bias)
-    probed = np.unique(pack(c[:, None, :] + offs[None, :, :]).ravel())
+    nb = c[:, None, :] + offs[None, :, :]
+    probed = np.unique(pack(nb).ravel())
+    blocks = np.unique(pack(nb >> 2).ravel())
     mkeys = pack(coords.astype(np.int64))
     order = np.argsort(mkeys)
     pos = np.searchsorted(mkeys[order], probed)
@@ -137,8 +140,8 @@ def knn_algorithmic_bytes(q: np.ndarray, coords: np.ndarray, counts: np.ndarray,
     hit = mkeys[order][pos] == probed
     bucket_bytes = int(counts[order][pos[hit]].astype(np.int64).sum()) * 16
     nq = q.shape[0]
-    total = nq * 24 + probed.size * 16 + bucket_bytes + nq * (k * 16 + 1)
-    return total, {"queries": nq, "distinct_probed_coords": int(probed.size), "distinct_buckets": int(hit.sum()),
+    total = nq * 24 + blocks.size * 32 + int(hit.sum()) * 4 + bucket_bytes + nq * (k * 16 + 1)
+    return total, {"queries": nq, "distinct_blocks": int(blocks.size), "distinct_buckets": int(hit.sum()),
                    "bucket_bytes": bucket_bytes}
 
 

@@ -142,17 +142,21 @@ __host__ __device__ __forceinline__ int centre_offset_index(int n_off) { return 
 // The reference (gtsam_points KnnResult::push over the neighbour voxels, restated in oracle/ivox_ref.hpp) scans
 // the stored points of the 1/7/19/27 voxels around the query's voxel in a fixed visiting order and keeps the k
 // smallest squared distances with a strict-'<' insertion sort, so equal distances resolve to the earlier
-// visitor.  Here every thread runs that scan for its own query with three changes that keep the result
-// bit-identical:
+// visitor.  Here every thread runs that scan for its own query with these changes, none of which alters the
+// result:
 //   * candidates carry their visiting sequence number ((offset index << 5) | point index) and the list is
 //     ordered by (d2, sequence), which makes the outcome independent of the order voxels are processed in;
+//   * neighbour voxels are located through the block grid of the map's search mirror: <= 8 block probes
+//     (L2-resident table) give occupancy masks, bucket indices follow by popcount — no per-voxel hash probe;
 //   * the query's own voxel is processed first, after which a neighbour voxel is skipped when the squared
 //     distance from the query to that voxel's box (shrunk by 1e-6 voxel to stay conservative under rounding)
-//     already exceeds the current k-th best — none of its points could enter the list;
-//   * the hash probes of the neighbourhood are issued in batches of four independent loads.
+//     already exceeds the current k-th best — none of its points could enter the list; surviving buckets are
+//     prefetched together, candidates are taken four at a time;
+//   * all control flow is warp-converged (uniform trip counts, per-lane predicates).
 // K is the compile-time list length (5 = the reference's num_corres_points, 8 = generic: the k nearest are the
-// first k of the 8 nearest).  s_pk is this thread's column of a shared [n_off][pk_stride] array that receives
-// the packed (voxel id << 5 | count) word of every probed neighbour; it stays valid for knn_resolve().
+// first k of the 8 nearest).  s_pk / s_blk are this thread's columns of shared [n_off][pk_stride] /
+// [24][pk_stride] arrays; s_pk receives (bucket index << 5 | count) of every scanned neighbour and stays valid
+// for knn_resolve().
 template <int K>
 __device__ __forceinline__ void knn_thread(const MapView& mv, const int8_t* __restrict__ s_off, uint32_t* s_pk,
                                            uint32_t* s_blk, int pk_stride, double qx, double qy, double qz, int k,

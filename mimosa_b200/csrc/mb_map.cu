@@ -317,7 +317,7 @@ constexpr int kKnnThreads = 128;
 
 // Standalone restricted k-NN: one query per thread (see knn_thread in mb_internal.cuh).
 template <int K>
-__global__ void __launch_bounds__(kKnnThreads, 5)
+__global__ void __launch_bounds__(kKnnThreads, 8)
     k_knn(MapView mv, const double* __restrict__ q, size_t nq, int k, uint64_t* __restrict__ idx,
           double* __restrict__ d2, uint8_t* __restrict__ ok) {
   __shared__ int8_t s_off[32 * 3];
