@@ -101,6 +101,7 @@ typedef struct mb_icp_trace {
 typedef struct mb_ctx mb_ctx;
 typedef struct mb_map mb_map;
 typedef struct mb_factor mb_factor;
+typedef struct mb_scan mb_scan;
 
 /* ---- context ---------------------------------------------------------------------------------------
  * One context per process and GPU (one process per GPU; `device` is the CUDA ordinal, normally
@@ -193,11 +194,33 @@ MB_API int mb_gn_step(const double H[36], const double g[6], double lambda, doub
  * bit1 = run mb_icp_run as one captured CUDA graph. */
 MB_API int mb_factor_set_flags(mb_factor* f, uint32_t flags);
 
-/* ---- scan preparation ("next" rows of the scope table) ----------------------------------------------
- * mb_downsample <- Geometric::downsample, mimosa/src/lidar/geometric.cpp:55-126 (greedy per-voxel thinning,
- *                  output = kept input indices in voxel-creation order then in-voxel order). */
+/* ---- scan preparation and map update: the steps either side of the factor in the LiDAR callback ---------
+ * A device-resident scan (records of `stride_bytes`, xyz = first three floats; 32 for lidar::Point) lets them
+ * run back to back without host round-trips.  All arithmetic is FLOAT, like the reference.
+ * mb_downsample       <- Geometric::downsample, mimosa/src/lidar/geometric.cpp:55-126 (greedy per-voxel thinning;
+ *                        output = kept input indices in voxel-creation order then in-voxel order); host in/out
+ * mb_scan_upload      <- the PCL cloud handed to lidar::Manager::prepareInput / deskewPoints
+ * mb_scan_deskew      <- lidar::Manager::deskewPoints, per-point part, mimosa/src/lidar/manager.cpp:494-509:
+ *                        p <- R_Le_Lt p + t_Le_Lt with the pose of the point's unique timestamp; `poses` holds
+ *                        n_poses x 12 floats (R row-major, then t), `pose_index[i]` selects the pose of point i.
+ *                        The IMU propagation that produces the poses (:459-492) stays on the host.
+ * mb_scan_transform   <- Geometric::preprocess, p <- R_B_L p + t_B_L, geometric.cpp:153-160
+ * mb_scan_downsample  <- Geometric::downsample on the device scan; returns a new scan (kept records, in order)
+ * mb_factor_create_from_scan <- ICPFactor(key, map, sm_Be_cloud_ds_, config), geometric.cpp:194
+ * mb_map_insert_scan  <- Geometric::updateMap, geometric.cpp:483-495: W = R_W_Be p + t_W_Be in float for the
+ *                        scan, then IncrementalVoxelMapPCL::insert; the caller snapshots first (geometric.cpp:494) */
 MB_API int mb_downsample(mb_ctx* ctx, const float* xyz, size_t n, size_t stride_bytes, float leaf, size_t cap,
                          float min_dist, uint32_t* out_idx, size_t* n_out);
+MB_API int mb_scan_upload(mb_ctx* ctx, const void* pts, size_t n, size_t stride_bytes, mb_scan** out);
+MB_API int mb_scan_release(mb_scan* scan);
+MB_API int mb_scan_size(mb_scan* scan, size_t* n, size_t* stride_bytes);
+MB_API int mb_scan_download(mb_scan* scan, void* pts);
+MB_API int mb_scan_deskew(mb_scan* scan, const uint32_t* pose_index, const float* poses, size_t n_poses);
+MB_API int mb_scan_transform(mb_scan* scan, const float R[9], const float t[3]);
+MB_API int mb_scan_downsample(mb_scan* scan, float leaf, size_t cap, float min_dist, mb_scan** out);
+MB_API int mb_factor_create_from_scan(mb_ctx* ctx, mb_map* map, mb_scan* scan, const mb_icp_config* cfg,
+                                      size_t shard_begin, size_t shard_end, mb_factor** out);
+MB_API int mb_map_insert_scan(mb_map* map, mb_scan* scan, const float R[9], const float t[3]);
 
 #ifdef __cplusplus
 }

@@ -9,6 +9,7 @@ from .host import (  # noqa: F401
     ICPFactor,
     IncrementalVoxelMap,
     RegistrationConfig,
+    Scan,
     degeneracy_flags,
     gn_step,
     hornbill_config,

@@ -127,6 +127,15 @@ SIGNATURES = {
     "mb_factor_set_flags": (C.c_int, [_P, C.c_uint32]),
     "mb_gn_step": (C.c_int, [_P, _P, C.c_double, _P, _P, _P, C.POINTER(C.c_int)]),
     "mb_downsample": (C.c_int, [_P, _P, _SZ, _SZ, C.c_float, _SZ, C.c_float, _P, C.POINTER(_SZ)]),
+    "mb_scan_upload": (C.c_int, [_P, _P, _SZ, _SZ, C.POINTER(_P)]),
+    "mb_scan_release": (C.c_int, [_P]),
+    "mb_scan_size": (C.c_int, [_P, C.POINTER(_SZ), C.POINTER(_SZ)]),
+    "mb_scan_download": (C.c_int, [_P, _P]),
+    "mb_scan_deskew": (C.c_int, [_P, _P, _P, _SZ]),
+    "mb_scan_transform": (C.c_int, [_P, _P, _P]),
+    "mb_scan_downsample": (C.c_int, [_P, C.c_float, _SZ, C.c_float, C.POINTER(_P)]),
+    "mb_factor_create_from_scan": (C.c_int, [_P, _P, _P, C.POINTER(IcpConfig), _SZ, _SZ, C.POINTER(_P)]),
+    "mb_map_insert_scan": (C.c_int, [_P, _P, _P, _P]),
 }
 
 

@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "mb_map.cuh"
+#include "mb_scan.cuh"
 
 namespace mb {
 namespace {
@@ -571,6 +572,19 @@ __global__ void __launch_bounds__(kLocThreads) k_loc_comp(FactorView fv, const D
   if (threadIdx.x == 0) *fv.ticket2 = 0u;
 }
 
+// device scan records -> float4 source points of the factor (xyz only), zero padded to ld
+__global__ void k_pack_src(const unsigned char* __restrict__ data, size_t stride, size_t begin, size_t n, size_t ld,
+                           float4* __restrict__ src) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ld) return;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n) {
+    const float* f = (const float*)(data + (begin + i) * stride);
+    v = make_float4(f[0], f[1], f[2], 0.f);
+  }
+  src[i] = v;
+}
+
 }  // namespace
 }  // namespace mb
 
@@ -679,12 +693,11 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
-extern "C" {
-
-int mb_factor_create(mb_ctx* ctx, mb_map* map, const void* pts, size_t n, size_t stride_bytes,
-                     const mb_icp_config* cfg, size_t shard_begin, size_t shard_end, mb_factor** out) {
+static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const mb_scan* dscan, size_t n,
+                              size_t stride_bytes, const mb_icp_config* cfg, size_t shard_begin, size_t shard_end,
+                              mb_factor** out) {
   MB_REQUIRE(ctx && map && cfg && out, "null argument");
-  MB_REQUIRE(n == 0 || pts, "null scan");
+  MB_REQUIRE(n == 0 || pts || dscan, "null scan");
   MB_REQUIRE(map->ctx == ctx, "map belongs to another context");
   MB_REQUIRE(stride_bytes >= 12 && stride_bytes % 4 == 0, "stride must be >= 12 and a multiple of 4");
   MB_REQUIRE(shard_begin <= shard_end && shard_end <= n, "bad shard range");
@@ -763,26 +776,46 @@ int mb_factor_create(mb_ctx* ctx, mb_map* map, const void* pts, size_t n, size_t
   f->tickets = (unsigned*)(base + o_tick);
   f->ds = (DevState*)(base + o_ds);
 
-  // scan: host AoS with arbitrary stride -> page-locked float4 staging -> device (only xyz is read by the
-  // factor, geometric_factor.hpp:277,323,346)
-  rc = pinned_reserve(ctx, f->ld * sizeof(float4));
-  if (rc != MB_OK) {
-    mb_factor_release(f);
-    return rc;
+  if (dscan) {
+    // device-resident scan: pack xyz straight into the factor's float4 array
+    k_pack_src<<<(unsigned)((f->ld + 255) / 256), 256, 0, st>>>(dscan->data, dscan->stride, shard_begin, f->n, f->ld, f->src);
+    ++ctx->launches;
+  } else {
+    // host AoS with arbitrary stride -> page-locked float4 staging -> device (only xyz is read by the factor,
+    // geometric_factor.hpp:277,323,346)
+    rc = pinned_reserve(ctx, f->ld * sizeof(float4));
+    if (rc != MB_OK) {
+      mb_factor_release(f);
+      return rc;
+    }
+    float4* h = (float4*)ctx->pinned;
+    for (size_t i = 0; i < f->n; ++i) {
+      const float* p = (const float*)((const char*)pts + (shard_begin + i) * stride_bytes);
+      h[i] = make_float4(p[0], p[1], p[2], 0.f);
+    }
+    for (size_t i = f->n; i < f->ld; ++i) h[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    MB_CUDA(cudaMemcpyAsync(f->src, h, f->ld * sizeof(float4), cudaMemcpyHostToDevice, st));
   }
-  float4* h = (float4*)ctx->pinned;
-  for (size_t i = 0; i < f->n; ++i) {
-    const float* p = (const float*)((const char*)pts + (shard_begin + i) * stride_bytes);
-    h[i] = make_float4(p[0], p[1], p[2], 0.f);
-  }
-  for (size_t i = f->n; i < f->ld; ++i) h[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  MB_CUDA(cudaMemcpyAsync(f->src, h, f->ld * sizeof(float4), cudaMemcpyHostToDevice, st));
   // everything from `packed` to the end of the block (packet, tickets, DevState) starts at zero
   MB_CUDA(cudaMemsetAsync(base + o_packed, 0, f->block_bytes - o_packed, st));
   MB_TRY(reset_state(f));
   MB_CUDA(cudaStreamSynchronize(st));  // the pinned staging buffer is free again
   *out = f;
   return MB_OK;
+}
+
+extern "C" {
+
+int mb_factor_create(mb_ctx* ctx, mb_map* map, const void* pts, size_t n, size_t stride_bytes,
+                     const mb_icp_config* cfg, size_t shard_begin, size_t shard_end, mb_factor** out) {
+  return factor_create_impl(ctx, map, pts, nullptr, n, stride_bytes, cfg, shard_begin, shard_end, out);
+}
+
+int mb_factor_create_from_scan(mb_ctx* ctx, mb_map* map, mb_scan* scan, const mb_icp_config* cfg, size_t shard_begin,
+                               size_t shard_end, mb_factor** out) {
+  MB_REQUIRE(scan, "null scan");
+  MB_REQUIRE(scan->ctx == ctx, "scan belongs to another context");
+  return factor_create_impl(ctx, map, nullptr, scan, scan->n, scan->stride, cfg, shard_begin, shard_end, out);
 }
 
 int mb_factor_release(mb_factor* f) {

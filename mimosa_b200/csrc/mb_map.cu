@@ -696,6 +696,12 @@ int mb_map_size(mb_map* m, size_t* n_voxels, size_t* n_points, uint64_t* lru_cou
 }
 
 int mb_map_insert(mb_map* m, const float* xyz, size_t n, size_t stride_bytes) {
+  return mb::map_insert_impl(m, xyz, cudaMemcpyHostToDevice, n, stride_bytes);
+}
+
+}  // extern "C"
+
+int mb::map_insert_impl(mb_map* m, const void* xyz, cudaMemcpyKind kind, size_t n, size_t stride_bytes) {
   MB_REQUIRE(m, "null map");
   MB_REQUIRE(n == 0 || xyz, "null points");
   MB_REQUIRE(stride_bytes >= 12 && stride_bytes % 4 == 0, "stride must be >= 12 and a multiple of 4");
@@ -730,7 +736,7 @@ int mb_map_insert(mb_map* m, const float* xyz, size_t n, size_t stride_bytes) {
     int* err = b.take<int>(1);
     void* temp = b.take<unsigned char>(temp_bytes);
 
-    MB_CUDA(cudaMemcpyAsync(raw, xyz, n * stride_bytes, cudaMemcpyHostToDevice, st));
+    MB_CUDA(cudaMemcpyAsync(raw, xyz, n * stride_bytes, kind, st));
     MB_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
     MB_CUDA(cudaMemsetAsync(new_flag, 0, n * sizeof(uint32_t), st));
     k_make_keys<<<blocks_for(n, 256), 256, 0, st>>>(raw, n, stride_bytes, m->inv_leaf, keys, vals, err);
@@ -820,6 +826,8 @@ int mb_map_insert(mb_map* m, const float* xyz, size_t n, size_t stride_bytes) {
   MB_CUDA(cudaStreamSynchronize(st));
   return MB_OK;
 }
+
+extern "C" {
 
 int mb_map_download(mb_map* m, int32_t* coords, int32_t* counts, uint32_t* lru, float* pts) {
   MB_REQUIRE(m, "null map");
@@ -984,7 +992,15 @@ int mb_map_points(mb_map* m, const uint64_t* idx, size_t n, double* xyz) {
 // Scratch for mb_downsample lives in the context-free path: allocate per call (scan-sized, a few MB).
 int mb_downsample(mb_ctx* ctx, const float* xyz, size_t n, size_t stride_bytes, float leaf, size_t cap,
                   float min_dist, uint32_t* out_idx, size_t* n_out) {
-  MB_REQUIRE(ctx && n_out && (n == 0 || (xyz && out_idx)), "null argument");
+  MB_REQUIRE(n == 0 || out_idx, "null argument");
+  return mb::downsample_impl(ctx, xyz, cudaMemcpyHostToDevice, n, stride_bytes, leaf, cap, min_dist, out_idx, nullptr, n_out);
+}
+
+}  // extern "C"
+
+int mb::downsample_impl(mb_ctx* ctx, const void* xyz, cudaMemcpyKind kind, size_t n, size_t stride_bytes, float leaf,
+                        size_t cap, float min_dist, uint32_t* out_idx, uint32_t* d_out_idx, size_t* n_out) {
+  MB_REQUIRE(ctx && n_out && (n == 0 || xyz), "null argument");
   MB_REQUIRE(stride_bytes >= 12 && stride_bytes % 4 == 0, "stride must be >= 12 and a multiple of 4");
   MB_REQUIRE(leaf > 0.f && min_dist >= 0.f, "leaf must be > 0 and min_dist >= 0");
   MB_REQUIRE(n < 0x7fffffffull, "too many points");
@@ -1033,7 +1049,7 @@ int mb_downsample(mb_ctx* ctx, const float* xyz, size_t n, size_t stride_bytes, 
   int* err = b.take<int>(1);
   void* temp = b.take<unsigned char>(temp_bytes);
 
-  MB_CUDA(cudaMemcpyAsync(raw, xyz, n * stride_bytes, cudaMemcpyHostToDevice, st));
+  MB_CUDA(cudaMemcpyAsync(raw, xyz, n * stride_bytes, kind, st));
   MB_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
   MB_CUDA(cudaMemsetAsync(first_flag, 0, n * sizeof(uint32_t), st));
   k_make_keys<<<blocks_for(n, 256), 256, 0, st>>>(raw, n, stride_bytes, inv_leaf, keys, vals, err);
@@ -1067,11 +1083,10 @@ int mb_downsample(mb_ctx* ctx, const float* xyz, size_t n, size_t stride_bytes, 
   uint32_t total = 0;
   MB_CUDA(cudaMemcpyAsync(&total, counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   MB_CUDA(cudaStreamSynchronize(st));
-  MB_CUDA(cudaMemcpyAsync(out_idx, out_d, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (out_idx) MB_CUDA(cudaMemcpyAsync(out_idx, out_d, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (d_out_idx) MB_CUDA(cudaMemcpyAsync(d_out_idx, out_d, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
   MB_CUDA(cudaStreamSynchronize(st));
   *n_out = total;
   MB_CUDA(cudaGetLastError());
   return MB_OK;
 }
-
-}  // extern "C"

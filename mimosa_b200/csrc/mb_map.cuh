@@ -73,6 +73,11 @@ namespace mb {
 int map_reserve(mb_map* m, size_t want_vox);
 // (Re)build the search mirror if the map changed since it was last built.  Enqueued on the context stream.
 int ensure_mirror(mb_map* m);
+// Insert n records whose first three floats are xyz from host or device memory (`kind`).
+int map_insert_impl(mb_map* m, const void* xyz, cudaMemcpyKind kind, size_t n, size_t stride_bytes);
+// Geometric::downsample on host or device input; kept indices go to out_idx (host) and/or d_out_idx (device).
+int downsample_impl(mb_ctx* ctx, const void* xyz, cudaMemcpyKind kind, size_t n, size_t stride_bytes, float leaf,
+                    size_t cap, float min_dist, uint32_t* out_idx, uint32_t* d_out_idx, size_t* n_out);
 // Launch the standalone search kernel over device-resident queries (nq x 3 doubles).
 int launch_knn(mb_map* m, const double* d_q, size_t nq, int k, uint64_t* d_idx, double* d_d2, uint8_t* d_ok);
 }  // namespace mb

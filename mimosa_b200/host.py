@@ -141,6 +141,53 @@ class Context:
         return out[: n_out.value].copy()
 
 
+class Scan:
+    """Device-resident scan: (n, 8) float32 lidar::Point rows (or any (n, >=3) float32 rows)."""
+
+    def __init__(self, ctx: Context, pts: np.ndarray = None, _handle=None, _cols=None):
+        self.ctx, self.lib = ctx, ctx.lib
+        if _handle is None:
+            pts = np.ascontiguousarray(pts, dtype=np.float32)
+            _cols = pts.shape[1]
+            h = C.c_void_p()
+            check(self.lib.mb_scan_upload(ctx.h, _ptr(pts), pts.shape[0], pts.strides[0] if pts.shape[0] else 4 * _cols, C.byref(h)))
+            _handle = h
+        self.h, self.cols = _handle, _cols
+
+    def release(self):
+        if self.h:
+            self.lib.mb_scan_release(self.h)
+            self.h = None
+
+    @property
+    def n(self) -> int:
+        n, st = C.c_size_t(), C.c_size_t()
+        check(self.lib.mb_scan_size(self.h, C.byref(n), C.byref(st)))
+        return int(n.value)
+
+    def download(self) -> np.ndarray:
+        out = np.empty((self.n, self.cols), dtype=np.float32)
+        check(self.lib.mb_scan_download(self.h, _ptr(out)))
+        return out
+
+    def deskew(self, pose_index: np.ndarray, poses: np.ndarray):
+        """lidar::Manager::deskewPoints (manager.cpp:494-509): poses (n_poses, 12) float32 = [R row-major | t]."""
+        pose_index = np.ascontiguousarray(pose_index, dtype=np.uint32)
+        poses = np.ascontiguousarray(poses, dtype=np.float32).reshape(-1, 12)
+        check(self.lib.mb_scan_deskew(self.h, _ptr(pose_index), _ptr(poses), poses.shape[0]))
+
+    def transform(self, R, t):
+        """Geometric::preprocess T_B_L (geometric.cpp:153-160), float arithmetic."""
+        R = np.ascontiguousarray(R, dtype=np.float32).reshape(9)
+        t = np.ascontiguousarray(t, dtype=np.float32).reshape(3)
+        check(self.lib.mb_scan_transform(self.h, _ptr(R), _ptr(t)))
+
+    def downsample(self, leaf: float, cap: int, min_dist: float) -> "Scan":
+        h = C.c_void_p()
+        check(self.lib.mb_scan_downsample(self.h, leaf, cap, min_dist, C.byref(h)))
+        return Scan(self.ctx, _handle=h, _cols=self.cols)
+
+
 class IncrementalVoxelMap:
     """IncrementalVoxelMapPCL: insert / knn_search / getCloud / copy (snapshot)."""
 
@@ -163,6 +210,12 @@ class IncrementalVoxelMap:
         """xyz: (n, >=3) float32 rows; only the first three columns are read (stride honoured)."""
         pts = np.ascontiguousarray(xyz, dtype=np.float32)
         check(self.lib.mb_map_insert(self.h, _ptr(pts), pts.shape[0], pts.strides[0] if pts.shape[0] else 12))
+
+    def insert_scan(self, scan: "Scan", R, t):
+        """Geometric::updateMap (geometric.cpp:483-495): float world transform of the device scan, then insert."""
+        R = np.ascontiguousarray(R, dtype=np.float32).reshape(9)
+        t = np.ascontiguousarray(t, dtype=np.float32).reshape(3)
+        check(self.lib.mb_map_insert_scan(self.h, scan.h, _ptr(R), _ptr(t)))
 
     def snapshot(self) -> "IncrementalVoxelMap":
         """The deep copy mimosa makes before every insert (geometric.cpp:494)."""
@@ -238,15 +291,20 @@ class ICPFactor:
     def __init__(self, ctx: Context, target: IncrementalVoxelMap, scan: np.ndarray, config: RegistrationConfig,
                  shard=None):
         self.ctx, self.lib, self.target, self.config = ctx, ctx.lib, target, config
-        pts = np.ascontiguousarray(scan, dtype=np.float32)
-        n = pts.shape[0]
-        begin, end = (0, n) if shard is None else shard
-        self.n_total, self.begin, self.end = n, begin, end
         self.k = int(config.num_corres_points)
         h = C.c_void_p()
         cfg = config.to_c()
-        check(self.lib.mb_factor_create(ctx.h, target.h, _ptr(pts), n, pts.strides[0] if n else 12, C.byref(cfg),
-                                        begin, end, C.byref(h)))
+        if isinstance(scan, Scan):  # device-resident scan
+            n = scan.n
+            begin, end = (0, n) if shard is None else shard
+            check(self.lib.mb_factor_create_from_scan(ctx.h, target.h, scan.h, C.byref(cfg), begin, end, C.byref(h)))
+        else:
+            pts = np.ascontiguousarray(scan, dtype=np.float32)
+            n = pts.shape[0]
+            begin, end = (0, n) if shard is None else shard
+            check(self.lib.mb_factor_create(ctx.h, target.h, _ptr(pts), n, pts.strides[0] if n else 12, C.byref(cfg),
+                                            begin, end, C.byref(h)))
+        self.n_total, self.begin, self.end = n, begin, end
         self.h = h
         self.last = None
 

@@ -142,6 +142,20 @@ size_t orc_downsample(const float* xyz, size_t n, size_t stride_bytes, float lea
   return v.size();
 }
 
+// lidar::Manager::deskewPoints per-point part (mimosa/src/lidar/manager.cpp:494-509) and the float transforms of
+// Geometric::preprocess (geometric.cpp:153-160) / updateMap (geometric.cpp:483-490): p <- R p + t in binary32,
+// 3-term sums as a0 + (a1 + a2).  poses: n_poses x 12 floats (R row-major, t); pose_index may be null (pose 0).
+void orc_transform_f32(void* pts, size_t n, size_t stride_bytes, const uint32_t* pose_index, const float* poses) {
+  for (size_t i = 0; i < n; ++i) {
+    float* f = (float*)((char*)pts + i * stride_bytes);
+    const float* P = poses + (pose_index ? (size_t)pose_index[i] * 12 : 0);
+    const float x = f[0], y = f[1], z = f[2];
+    f[0] = (P[0] * x + (P[1] * y + P[2] * z)) + P[9];
+    f[1] = (P[3] * x + (P[4] * y + P[5] * z)) + P[10];
+    f[2] = (P[6] * x + (P[7] * y + P[8] * z)) + P[11];
+  }
+}
+
 // ---- small dense helpers exposed for the known-answer tests ------------------------------------------
 int orc_eigh3(const double* A, double* lam, double* V) {
   M3 a, v;

@@ -91,6 +91,7 @@ def lib() -> C.CDLL:
             "orc_factor_download_state": (None, [_P, _P, _P, _P, _P, _P, _P, _P]),
             "orc_icp_run": (C.c_double, [_P, _P, _P, C.c_int, C.c_double, _P, C.c_int]),
             "orc_downsample": (_SZ, [_P, _SZ, _SZ, C.c_float, _SZ, C.c_float, _P]),
+            "orc_transform_f32": (None, [_P, _SZ, _SZ, _P, _P]),
             "orc_eigh3": (C.c_int, [_P, _P, _P]),
             "orc_se3_expmap": (None, [_P, _P, _P]),
             "orc_se3_retract": (None, [_P, _P, _P]),
@@ -218,6 +219,15 @@ def downsample(xyz, leaf, cap, min_dist):
     out = np.empty(pts.shape[0], np.uint32)
     n = lib().orc_downsample(_ptr(pts), pts.shape[0], pts.strides[0] if pts.shape[0] else 12, leaf, cap, min_dist, _ptr(out))
     return out[:n].copy()
+
+
+def transform_f32(pts, poses, pose_index=None):
+    """In-place float transform of the xyz columns of `pts` ((n, >=3) float32 rows): deskew / T_B_L / T_W_Be."""
+    assert pts.dtype == np.float32 and pts.flags.c_contiguous
+    poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 12)
+    pi = None if pose_index is None else np.ascontiguousarray(pose_index, np.uint32)
+    lib().orc_transform_f32(_ptr(pts), pts.shape[0], pts.strides[0] if pts.shape[0] else 12, _ptr(pi), _ptr(poses))
+    return pts
 
 
 def eigh3(A):

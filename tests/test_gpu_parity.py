@@ -448,3 +448,77 @@ def test_sharded_factors_sum_to_full(ctx, oracle):
     assert counts.tolist() == list(Lf.counts)
     full.release()
     mg.release()
+
+
+@pytest.mark.parametrize("pattern,n_scans,n_pts", [("os0", 12, 8000), ("airy", 3, 65280)])
+def test_streaming_pipeline_matches_oracle(ctx, oracle, pattern, n_scans, n_pts):
+    """Configs C3 / C5 in miniature, device-resident end to end: upload -> deskew (per-timestamp float poses,
+    lidar/manager.cpp:494-509) -> T_B_L (geometric.cpp:153-160) -> voxel downsample (geometric.cpp:55-126) ->
+    ICP factor + GN iterations -> snapshot + float world transform + insert (geometric.cpp:483-495), scan after
+    scan with LRU eviction live, against the oracle fed the identical inputs."""
+    from mimosa_b200 import Scan
+
+    rng = np.random.default_rng(180)
+    mg, mo = both_maps(ctx, oracle, lru_horizon=6)
+    for _ in range(2):
+        pts = synth.sample_world(120000, 60.0, rng)
+        mg.insert(pts)
+        mo.insert(pts)
+    cfg = hornbill_config()
+    R_B_L = synth.rot_from_rpy(0.01, -0.02, 0.03).astype(np.float32)
+    t_B_L = np.array([0.1, -0.05, 0.2], np.float32)
+    T_BL = np.concatenate([R_B_L.reshape(9), t_B_L])[None, :]
+    R_BL64, t_BL64 = R_B_L.astype(np.float64), t_B_L.astype(np.float64)
+    for s in range(n_scans):
+        R_true = synth.rot_from_rpy(0.0, 0.0, 0.05 * s)
+        t_true = np.array([0.6 * s, 0.2 * s, 0.3])
+        # sensor pose = body pose * T_B_L
+        R_s, t_s = R_true @ R_BL64, R_true @ t_BL64 + t_true
+        rec = synth.make_scan(R_s, t_s, n_pts, rng, pattern=pattern, max_range=50.0)
+        n = rec.shape[0]
+        n_poses = 40
+        pose_index = ((np.arange(n, dtype=np.int64) * n_poses) // n).astype(np.uint32)
+        poses = np.zeros((n_poses, 12), np.float32)
+        for p in range(n_poses):
+            a = 1e-3 * (n_poses - 1 - p)
+            poses[p, :9] = synth.rot_from_rpy(0.2 * a, -0.1 * a, a).reshape(9)
+            poses[p, 9:] = [0.5 * a, -0.3 * a, 0.1 * a]
+        # --- GPU
+        sc = Scan(ctx, rec)
+        sc.deskew(pose_index, poses)
+        sc.transform(R_B_L, t_B_L)
+        ds = sc.downsample(cfg.source_voxel_grid_filter_leaf_size, 20, cfg.source_voxel_grid_min_dist_in_voxel)
+        # --- oracle
+        rec_o = rec.copy()
+        oracle.transform_f32(rec_o, poses, pose_index)
+        oracle.transform_f32(rec_o, T_BL)
+        keep = oracle.downsample(rec_o, cfg.source_voxel_grid_filter_leaf_size, 20, cfg.source_voxel_grid_min_dist_in_voxel)
+        ds_o = np.ascontiguousarray(rec_o[keep])
+        assert np.array_equal(sc.download().view(np.uint32), rec_o.view(np.uint32))
+        assert np.array_equal(ds.download().view(np.uint32), ds_o.view(np.uint32))
+        # --- factor + GN
+        R0, t0 = synth.perturbed_start(R_true, t_true, (0.004, -0.003, 0.005, 0.03, -0.02, 0.02))
+        fg, fo = ICPFactor(ctx, mg, ds, cfg), oracle.IcpFactorRef(mo, ds_o, cfg)
+        Rg, tg, trg = fg.icp_run(R0, t0, 6, 1e-6)
+        Ro, to, tro, _ = fo.icp_run(R0, t0, 6, 1e-6, n_threads=4)
+        for a, b in zip(trg, tro):
+            assert list(a.counts) == list(b.counts) and a.n_searched == b.n_searched
+            assert rel_err(a.H, b.H) <= 1e-7
+        assert np.abs(Rg - Ro).max() <= POSE_TOL and np.abs(tg - to).max() <= POSE_TOL
+        assert_state_equal(fg.download_state(), fo.download_state(), float_tol=1e-9)
+        fg.release()
+        # --- keyframe: snapshot, world transform (float), insert (both sides use the oracle's pose estimate)
+        T_W = np.concatenate([Ro.astype(np.float32).reshape(9), to.astype(np.float32)])[None, :]
+        new_g, new_o = mg.snapshot(), mo.snapshot()
+        new_g.insert_scan(sc, T_W[0, :9], T_W[0, 9:])
+        W = rec_o.copy()
+        oracle.transform_f32(W, T_W)
+        new_o.insert(W)
+        mg.release()
+        mg, mo = new_g, new_o
+        assert_maps_equal(mg, mo)
+        sc.release()
+        ds.release()
+    if n_scans >= 10:
+        assert mo.size()[2] >= 10  # the LRU clock crossed a clear cycle
+    mg.release()
