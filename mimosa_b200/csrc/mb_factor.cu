@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(kLinThreads, 5)
   __shared__ double s_tmp[(kLinThreads / kPack) * kPack];
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_launch_dependents();
   if (tid < kMaxNbr * 3) s_off[tid] = mv.off[tid];
   double(*s_row)[7] = reinterpret_cast<double(*)[7]>(s_pk_all) + warp * 32;
   // Lane a < 28 owns entry a of the packed upper triangle of [J e]^T [J e] (7x7): the 21 entries of
@@ -192,6 +193,9 @@ __global__ void __launch_bounds__(kLinThreads, 5)
     if (lane == 27) pr = pc = 6;
   }
 
+  // everything above is independent of earlier kernels; from here on we read the pose the previous iteration's
+  // k_finalize wrote and overwrite per-point state the previous k_loc_comp may still be reading
+  pdl_wait();
   m33 R;
 #pragma unroll
   for (int a = 0; a < 9; ++a) R.m[a] = pose[a];
@@ -388,9 +392,13 @@ __global__ void __launch_bounds__(kLinThreads, 5)
   if (tid == 0) *fv.ticket = 0u;
 }
 
+// computeLocalizability (mimosa/include/mimosa/utils.hpp:308-313).  The closed-form solver (checked a posteriori,
+// iterative fallback) replaces the reference's iterative one here: its input, the reduced 6x6, already differs
+// from the CPU's in the last bits, so bit parity is not at stake, and it is 5x shorter as a single-thread chain.
 __device__ __forceinline__ void localizability(const m33& JtJ, double loc[3], m33& V) {
   double lam[3];
-  eigh33(JtJ, lam, V);
+  eigh33_direct(JtJ, lam, V);
+#pragma unroll
   for (int a = 0; a < 3; ++a) loc[a] = sqrt(lam[a]);
 }
 
@@ -398,9 +406,13 @@ __device__ __forceinline__ void localizability(const m33& JtJ, double loc[3], m3
 // plays role w: 0/1 localizability of the rotational / translational block, 2/3 Schur-complement degeneracy
 // info, 4 projection + packing + solve + retract.
 __global__ void __launch_bounds__(160) k_finalize(const double* __restrict__ packed, DevState* ds, int reg_4_dof,
-                                                  int linearize_count, int do_step, int iter, mb_icp_trace* trace) {
+                                                  int linearize_count, int do_step, int iter, mb_icp_trace* trace,
+                                                  unsigned role_mask) {
+  pdl_launch_dependents();
   if ((threadIdx.x & 31) != 0) return;
   const int role = threadIdx.x >> 5;
+  if (((role_mask >> role) & 1u) == 0) return;  // role_mask != 31 only in the timing diagnostic
+  pdl_wait();
   double H[36];
   {
     int u = 0;
@@ -531,6 +543,8 @@ __global__ void __launch_bounds__(kLocThreads) k_loc_comp(FactorView fv, const D
   __shared__ double s_red[kLocThreads / 32][8];
   __shared__ double s_tmp[(kLocThreads / 8) * 8];
   __shared__ bool s_last;
+  pdl_launch_dependents();
+  pdl_wait();
   m33 Vr, Vt;
 #pragma unroll
   for (int a = 0; a < 9; ++a) {
@@ -670,12 +684,13 @@ int enqueue_linearize(mb_factor* f, int do_step, int iter, mb_icp_trace* d_trace
   cudaStream_t st = c->stream;
   const FactorView fv = f->view();
   if (fv.k == 5)
-    k_linearize<5><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds->pose);
+    MB_CUDA(launch_pdl(k_linearize<5>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (const double*)f->ds->pose));
   else
-    k_linearize<MB_MAX_K><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds->pose);
+    MB_CUDA(launch_pdl(k_linearize<MB_MAX_K>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (const double*)f->ds->pose));
   if (c->world > 1) MB_NCCL(ncclAllReduce(f->packed, f->packed, kPack, ncclDouble, ncclSum, c->comm, st));
-  k_finalize<<<1, 160, 0, st>>>(f->packed, f->ds, f->cfg.reg_4_dof, linearize_count, do_step, iter, d_trace);
-  k_loc_comp<<<f->grid2, kLocThreads, 0, st>>>(fv, f->ds);
+  MB_CUDA(launch_pdl(k_finalize, dim3(1), dim3(160), st, (const double*)f->packed, f->ds, (int)f->cfg.reg_4_dof,
+                     linearize_count, do_step, iter, d_trace, 31u));
+  MB_CUDA(launch_pdl(k_loc_comp, dim3(f->grid2), dim3(kLocThreads), st, fv, (const DevState*)f->ds));
   if (c->world > 1) MB_NCCL(ncclAllReduce(f->packed + kPack, f->packed + kPack, 6, ncclDouble, ncclSum, c->comm, st));
   c->launches += 3;
   MB_CUDA(cudaGetLastError());
@@ -816,6 +831,38 @@ int mb_factor_create_from_scan(mb_ctx* ctx, mb_map* map, mb_scan* scan, const mb
   MB_REQUIRE(scan, "null scan");
   MB_REQUIRE(scan->ctx == ctx, "scan belongs to another context");
   return factor_create_impl(ctx, map, nullptr, scan, scan->n, scan->stride, cfg, shard_begin, shard_end, out);
+}
+
+// Timing diagnostic (not part of the documented ABI): average device time of k_finalize restricted to the roles
+// in `role_mask`, `reps` back-to-back launches on the factor's last reduced packet.
+MB_API int mb_debug_time_finalize(mb_factor* f, unsigned role_mask, int reps, float* us_per_launch) {
+  MB_REQUIRE(f && us_per_launch && reps > 0, "bad argument");
+  MB_CUDA(cudaSetDevice(f->ctx->device));
+  cudaStream_t st = f->ctx->stream;
+  const FactorView fv = f->view();
+  // role_mask < 32: k_finalize with those roles; 32: k_linearize at the current pose (fully cached after one
+  // call); 64: k_loc_comp.  Plain launches, back to back.
+  auto one = [&]() {
+    if (role_mask == 32u) {
+      if (fv.k == 5)
+        k_linearize<5><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds->pose);
+      else
+        k_linearize<MB_MAX_K><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds->pose);
+    } else if (role_mask == 64u) {
+      k_loc_comp<<<f->grid2, kLocThreads, 0, st>>>(fv, f->ds);
+    } else {
+      k_finalize<<<1, 160, 0, st>>>(f->packed, f->ds, f->cfg.reg_4_dof, 0, 0, 0, nullptr, role_mask);
+    }
+  };
+  for (int w = 0; w < 3; ++w) one();
+  MB_CUDA(cudaEventRecord(f->ctx->ev0, st));
+  for (int r = 0; r < reps; ++r) one();
+  MB_CUDA(cudaEventRecord(f->ctx->ev1, st));
+  MB_CUDA(cudaEventSynchronize(f->ctx->ev1));
+  float ms = 0.f;
+  MB_CUDA(cudaEventElapsedTime(&ms, f->ctx->ev0, f->ctx->ev1));
+  *us_per_launch = ms * 1e3f / reps;
+  return MB_OK;
 }
 
 int mb_factor_release(mb_factor* f) {

@@ -297,6 +297,132 @@ MB_HD bool eigh33(const m33& A, double lam[3], m33& V) {
   return ok;
 }
 
+// ---- closed-form symmetric 3x3 eigen-decomposition ----------------------------------------------------
+// Used only where bit-parity with the reference's iterative solver is NOT required (the 6x6-level
+// localizability / degeneracy outputs, whose input already differs from the CPU's by summation order): the
+// iterative QR above is ~1600 dependent fp64 instructions for one thread, this is ~300.  Trigonometric roots of
+// the characteristic polynomial of the shifted, scaled matrix; eigenvectors from cross products of rows of
+// (A - lambda I) (the published "direct" 3x3 method, cf. Eigen's computeDirect); eigenvalues are then
+// re-evaluated as Rayleigh quotients, which squares their error.  lam ascending, column j of V for lam[j].
+MB_HD d3 kernel_vec(const m33& M, d3& rep_row) {
+  // M is singular (rank <= 2): returns a unit vector of its null space; rep_row = the row with the largest
+  // diagonal magnitude, normalised (used to build the next eigenvector).
+  const double a0 = fabs(M.m[0]), a1 = fabs(M.m[4]), a2 = fabs(M.m[8]);
+  const int i0 = a0 >= a1 ? (a0 >= a2 ? 0 : 2) : (a1 >= a2 ? 1 : 2);
+  const d3 r0 = mk3(M.m[0], M.m[1], M.m[2]), r1 = mk3(M.m[3], M.m[4], M.m[5]), r2 = mk3(M.m[6], M.m[7], M.m[8]);
+  const d3 rep = i0 == 0 ? r0 : (i0 == 1 ? r1 : r2);
+  const d3 oa = i0 == 0 ? r1 : r0, ob = i0 == 2 ? r1 : r2;
+  const d3 c0 = cross3(rep, oa), c1 = cross3(rep, ob);
+  const double n0 = sqnorm3(c0), n1 = sqnorm3(c1);
+  const d3 c = n0 > n1 ? c0 : c1;
+  const double n = n0 > n1 ? n0 : n1;
+  rep_row = div3(rep, sqrt(sqnorm3(rep)));
+  return div3(c, sqrt(n));
+}
+MB_HD bool eigh33_direct_raw(const m33& A, double lam[3], m33& V);
+// Closed-form solve with an a-posteriori check: the off-diagonal residue b_ij = v_i^T A v_j bounds the error of
+// each Rayleigh quotient by sum_j b_ij^2 / |lam_i - lam_j|; when that exceeds 1e-10 relative (near-repeated
+// eigenvalues far below the spectral radius — where the trigonometric roots lose digits) the iterative solver
+// is used instead, so the result is always as good as eigh33's to ~1e-10.
+MB_HD void eigh33_direct(const m33& A, double lam[3], m33& V) {
+  if (!eigh33_direct_raw(A, lam, V)) eigh33(A, lam, V);
+}
+MB_HD bool eigh33_direct_raw(const m33& A, double lam[3], m33& V) {
+  const double shift = (A.m[0] + A.m[4] + A.m[8]) / 3.0;
+  double m00 = A.m[0] - shift, m11 = A.m[4] - shift, m22 = A.m[8] - shift;
+  double m10 = A.m[3], m20 = A.m[6], m21 = A.m[7];
+  double scale = fabs(m00);
+  scale = fmax(scale, fabs(m11));
+  scale = fmax(scale, fabs(m22));
+  scale = fmax(scale, fabs(m10));
+  scale = fmax(scale, fabs(m20));
+  scale = fmax(scale, fabs(m21));
+  if (!(scale > 0.0)) {  // multiple of the identity (or NaN input, which then propagates through lam)
+    lam[0] = lam[1] = lam[2] = shift + scale * 0.0;
+    for (int i = 0; i < 9; ++i) V.m[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    return scale == 0.0;  // NaN input -> let the iterative solver produce the reference's answer
+  }
+  const double inv = 1.0 / scale;
+  m00 *= inv; m11 *= inv; m22 *= inv; m10 *= inv; m20 *= inv; m21 *= inv;
+  // roots of x^3 - c2 x^2 + c1 x - c0 with c2 = trace = 0 after the shift
+  const double c0 = m00 * m11 * m22 + 2.0 * m10 * m20 * m21 - m00 * m21 * m21 - m11 * m20 * m20 - m22 * m10 * m10;
+  const double c1 = m00 * m11 - m10 * m10 + m00 * m22 - m20 * m20 + m11 * m22 - m21 * m21;
+  const double c2 = m00 + m11 + m22;
+  const double c2_3 = c2 / 3.0;
+  double a_3 = (c2 * c2_3 - c1) / 3.0;
+  if (a_3 < 0.0) a_3 = 0.0;
+  const double half_b = 0.5 * (c0 + c2_3 * (2.0 * c2_3 * c2_3 - c1));
+  double q = a_3 * a_3 * a_3 - half_b * half_b;
+  if (q < 0.0) q = 0.0;
+  const double rho = sqrt(a_3);
+  const double theta = atan2(sqrt(q), half_b) / 3.0;
+  const double ct = cos(theta), st = sin(theta);
+  const double s3 = 1.7320508075688772;
+  double r0 = c2_3 - rho * (ct + s3 * st), r1 = c2_3 - rho * (ct - s3 * st), r2 = c2_3 + 2.0 * rho * ct;
+  d3 v0, v1, v2;
+  if (r2 - r0 <= DBL_EPSILON) {
+    v0 = mk3(1, 0, 0);
+    v1 = mk3(0, 1, 0);
+    v2 = mk3(0, 0, 1);
+  } else {
+    m33 M;
+    M.m[1] = M.m[3] = m10;
+    M.m[2] = M.m[6] = m20;
+    M.m[5] = M.m[7] = m21;
+    // start with the eigenvalue that is best separated from the other two
+    const double d_hi = r2 - r1, d_lo = r1 - r0;
+    const bool top = d_hi > d_lo;  // true: k = 2 (largest) first, then l = 0; false: k = 0 first, then l = 2
+    const double rk = top ? r2 : r0, rl = top ? r0 : r2;
+    const double d_small = top ? d_lo : d_hi;  // separation of the remaining pair
+    M.m[0] = m00 - rk;
+    M.m[4] = m11 - rk;
+    M.m[8] = m22 - rk;
+    d3 rep;
+    const d3 vk = kernel_vec(M, rep);
+    d3 vl;
+    if (d_small <= 2.0 * DBL_EPSILON * (top ? d_hi : d_lo)) {
+      // the other two eigenvalues coincide: any orthonormal completion will do
+      const d3 tmp = sub3(rep, scale3(vk, dot3(vk, rep)));
+      vl = div3(tmp, sqrt(sqnorm3(tmp)));
+    } else {
+      M.m[0] = m00 - rl;
+      M.m[4] = m11 - rl;
+      M.m[8] = m22 - rl;
+      d3 rep2;
+      vl = kernel_vec(M, rep2);
+      // re-orthogonalise against vk
+      const d3 tmp = sub3(vl, scale3(vk, dot3(vk, vl)));
+      vl = div3(tmp, sqrt(sqnorm3(tmp)));
+    }
+    const d3 vm = cross3(top ? vk : vl, top ? vl : vk);  // middle = v2 x v0 (sign is free)
+    v0 = top ? vl : vk;
+    v2 = top ? vk : vl;
+    v1 = vm;
+  }
+  // Rayleigh quotients on the ORIGINAL matrix
+  const m33 As = A;
+  auto rq = [&](d3 v) { return dot3(v, mul33v(As, v)); };
+  // A may only have its lower triangle meaningful for callers of eigh33; here callers pass full symmetric blocks
+  lam[0] = rq(v0);
+  lam[1] = rq(v1);
+  lam[2] = rq(v2);
+  V.m[0] = v0.x; V.m[3] = v0.y; V.m[6] = v0.z;
+  V.m[1] = v1.x; V.m[4] = v1.y; V.m[7] = v1.z;
+  V.m[2] = v2.x; V.m[5] = v2.y; V.m[8] = v2.z;
+  (void)r1;
+  const d3 Av1 = mul33v(As, v1), Av2 = mul33v(As, v2);
+  const double b01 = dot3(v0, Av1), b02 = dot3(v0, Av2), b12 = dot3(v1, Av2);
+  const double g01 = fabs(lam[1] - lam[0]), g02 = fabs(lam[2] - lam[0]), g12 = fabs(lam[2] - lam[1]);
+  const double rad = fmax(fabs(lam[0]), fabs(lam[2]));
+  const double floor_abs = 1e-15 * rad;
+  const double e0 = b01 * b01 / g01 + b02 * b02 / g02;
+  const double e1 = b01 * b01 / g01 + b12 * b12 / g12;
+  const double e2 = b02 * b02 / g02 + b12 * b12 / g12;
+  // (0/0 = NaN and x/0 = inf both fail the comparisons below, as they should)
+  return e0 <= 1e-10 * fabs(lam[0]) + floor_abs && e1 <= 1e-10 * fabs(lam[1]) + floor_abs &&
+         e2 <= 1e-10 * fabs(lam[2]) + floor_abs;
+}
+
 // ---- SE(3) exponential (gtsam::Pose3::Expmap with the full exponential map, xi = [omega; v]) -------
 MB_HD m33 so3_exp(d3 w) {
   const double th2 = dot3(w, w);

@@ -11,6 +11,14 @@ int shim_eigh33(const double* A, double* lam, double* V) {
   for (int i = 0; i < 9; ++i) V[i] = v.m[i];
   return ok ? 1 : 0;
 }
+int shim_eigh33_direct(const double* A, double* lam, double* V) {
+  mb::m33 a, v;
+  for (int i = 0; i < 9; ++i) a.m[i] = A[i];
+  const bool fast = mb::eigh33_direct_raw(a, lam, v);
+  if (!fast) mb::eigh33(a, lam, v);
+  for (int i = 0; i < 9; ++i) V[i] = v.m[i];
+  return fast ? 1 : 0;
+}
 void shim_se3_retract(double* R, double* t, const double* xi) {
   mb::m33 r;
   for (int i = 0; i < 9; ++i) r.m[i] = R[i];

@@ -69,3 +69,35 @@ def test_retract_solve_floor_bit_exact(shim, oracle):
         assert bool(ok) == ok_o and x.tobytes() == x_o.tobytes()
         v = float(rng.normal() * 100)
         assert shim.shim_fast_floor(v) == oracle.lib().orc_fast_floor(v) == int(np.floor(v))
+
+
+def test_eigh33_direct_accuracy(shim):
+    """The closed-form solver used for the 6x6-level localizability outputs: eigenvalues to 1e-12 of the
+    spectral radius, eigenvectors orthonormal and A V = V diag(lam) to 1e-9, on random, planar-scene-like
+    (two small, one large eigenvalue) and repeated-eigenvalue inputs."""
+    rng = np.random.default_rng(7)
+    cases = []
+    for _ in range(2000):
+        Q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        ev = 10 ** rng.uniform(-3, 6, 3)
+        cases.append(Q @ np.diag(ev) @ Q.T)
+    for _ in range(500):  # planar scene: (a, a(1+eps), huge)
+        Q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        a = 10 ** rng.uniform(0, 3)
+        cases.append(Q @ np.diag([a, a * (1 + 10 ** rng.uniform(-4, -1)), a * 1e3]) @ Q.T)
+    cases += [np.diag([3.0, 1.0, 2.0]), np.eye(3) * 5, np.diag([1.0, 1.0, 7.0]), np.diag([2.0, 9.0, 9.0])]
+    n_fast = 0
+    for A in cases:
+        A = np.ascontiguousarray((A + A.T) / 2)
+        lam, V = np.empty(3), np.empty(9)
+        n_fast += shim.shim_eigh33_direct(_p(A), _p(lam), _p(V))
+        V = V.reshape(3, 3)
+        w = np.linalg.eigvalsh(A)
+        rad = np.abs(w).max()
+        assert np.all(np.diff(lam) >= -1e-12 * rad)
+        assert np.allclose(lam, w, rtol=1e-9, atol=1e-14 * rad), (lam, w)
+        assert np.allclose(V.T @ V, np.eye(3), atol=1e-9)
+        gap_ok = np.min(np.diff(w)) > 1e-6 * rad
+        if gap_ok:
+            assert np.allclose(A @ V, V * lam, atol=1e-8 * rad)
+    assert n_fast > 0.8 * len(cases)  # the closed form answers the bulk; the rest falls back to the QR solver
