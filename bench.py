@@ -201,6 +201,87 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_stream(args, ctx, mg, cfg, synth):
+    """Config C5 (BASELINE.json configs[4]): a 10 Hz scan sequence along a 2 m/s path; per scan the calls
+    lidar::Manager::callback makes on this path — deskew (manager.cpp:494-509), preprocess = T_B_L + voxel
+    downsample (geometric.cpp:128-183), getFactors = ICPFactor + first linearize (geometric.cpp:194-196), then the
+    smoother's 1 + additional_update_iterations(5) linearize calls (graph/manager.cpp:585-588), each followed by a
+    host-side GN step standing in for ISAM2, then updateMap with the reference's keyframe gate (translation > 1 m
+    or any |ypr| > 10 deg, geometric.cpp:439-472): snapshot + float world transform + insert.  Everything enters
+    and leaves through host buffers; timing is host wall clock per scan."""
+    from mimosa_b200 import ICPFactor, Scan, gn_step
+
+    rng = synth.rng_for(5)
+    n_scans = args.stream
+    R_B_L, t_B_L = np.eye(3, dtype=np.float32), np.zeros(3, np.float32)
+    n_poses = 128
+    poses = np.zeros((n_poses, 12), np.float32)
+    for p in range(n_poses):  # constant twist over the 100 ms sweep: 2 m/s, 0.2 rad/s
+        a = (n_poses - 1 - p) / (n_poses - 1) * 0.1
+        poses[p, :9] = synth.rot_from_rpy(0, 0, -0.2 * a).reshape(9)
+        poses[p, 9:] = [-2.0 * a, 0.0, 0.0]
+    scans = []
+    for s in range(n_scans):  # pre-generate the raw scans (host ray casting is not part of the path)
+        R_true = synth.rot_from_rpy(0.0, 0.0, 0.02 * s)
+        t_true = np.array([0.2 * s, 0.05 * s, 0.2])
+        rec = synth.make_scan(R_true, t_true, N_SCAN, rng)
+        scans.append((rec, R_true, t_true))
+    pose_index = ((np.arange(N_SCAN, dtype=np.int64) * n_poses) // N_SCAN).astype(np.uint32)
+    for rec, _, _ in scans:  # skew the ray-cast points so that deskewing restores them: p_raw = R_k^T (p - t_k)
+        Rk = poses[pose_index, :9].reshape(-1, 3, 3).astype(np.float64)
+        tk = poses[pose_index, 9:].astype(np.float64)
+        rec[:, :3] = np.einsum("nji,nj->ni", Rk, rec[:, :3].astype(np.float64) - tk).astype(np.float32)
+    stages = {k: 0.0 for k in ("t_deskew", "t_preprocess", "t_get_factors", "t_updates", "t_update_map")}
+    per_scan, n_key, errs, n_ds = [], 0, [], []
+    last_key_t, last_key_R = None, None
+    cur = mg
+    for s, (rec, R_true, t_true) in enumerate(scans):
+        ctx.sync()
+        t0 = time.perf_counter()
+        sc = Scan(ctx, rec)
+        sc.deskew(pose_index, poses)
+        t1 = time.perf_counter()
+        sc.transform(R_B_L, t_B_L)
+        ds = sc.downsample(cfg.source_voxel_grid_filter_leaf_size, 20, cfg.source_voxel_grid_min_dist_in_voxel)
+        t2 = time.perf_counter()
+        f = ICPFactor(ctx, cur, ds, cfg)
+        R, t = synth.perturbed_start(R_true, t_true, (0.002, -0.002, 0.003, 0.03, -0.02, 0.01))
+        L = f.linearize(R, t)  # geometric.cpp:196 (localizability / degeneracy flags come from this call)
+        t3 = time.perf_counter()
+        for _ in range(6):  # smoother_->update(graph) + 5 additional updates
+            R, t, _, _ = gn_step(L, R, t, 1e-6)
+            L = f.linearize(R, t)
+        t4 = time.perf_counter()
+        is_key = last_key_t is None or np.linalg.norm(t - last_key_t) > 1.0 or \
+            np.abs(np.arctan2((last_key_R.T @ R)[1, 0], (last_key_R.T @ R)[0, 0])) > np.deg2rad(10.0)
+        if is_key:
+            new = cur.snapshot()
+            new.insert_scan(sc, R.astype(np.float32), t.astype(np.float32))
+            if cur is not mg:
+                f.release()
+                cur.release()
+            cur, last_key_t, last_key_R = new, t.copy(), R.copy()
+            n_key += 1
+        f.release()
+        sc.release()
+        n_ds.append(ds.n)
+        ds.release()
+        ctx.sync()
+        t5 = time.perf_counter()
+        for k, v in zip(stages, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
+            stages[k] += v
+        per_scan.append(t5 - t0)
+        errs.append(float(np.abs(t - t_true).max()))
+    warm = per_scan[2:] if len(per_scan) > 4 else per_scan
+    line = {"metric": "stream_scans_per_sec", "value": len(warm) / float(np.sum(warm)), "unit": "scans/s",
+            "config": {"workload": "C5: 131072-pt scans at 10 Hz vs rolling 10M-pt map; per scan deskew + T_B_L + downsample + "
+                       "7 linearize calls + keyframe-gated snapshot/insert; host buffers in and out",
+                       "n_scans": n_scans, "keyframes": n_key, "downsampled_points_mean": float(np.mean(n_ds))},
+            "ms_per_scan": 1e3 * float(np.mean(warm)), "stage_ms_per_scan": {k: 1e3 * v / n_scans for k, v in stages.items()},
+            "max_pose_err_m": max(errs), "map_points_end": cur.size()[1]}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -211,6 +292,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--profile-knn", action="store_true", help="only build inputs and run a few k-NN launches (for ncu)")
     ap.add_argument("--profile-icp", action="store_true", help="only build inputs and run two ICP steps (for ncu)")
+    ap.add_argument("--stream", type=int, default=0, metavar="N_SCANS",
+                    help="config C5: stream N_SCANS scans (upload, deskew, T_B_L, downsample, 1+6 linearize calls, "
+                         "keyframe-gated snapshot + insert) and report end-to-end scans/s; prints its own JSON line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if not (args.profile_knn or args.profile_icp) else args.warmup
 
@@ -253,6 +337,10 @@ def main():
     log(f"[rank {rank}] map: {n_vox} voxels, {n_pts} points; scan {scan.shape}; setup {time.time() - t_setup:.1f}s")
     cfg = hornbill_config()
     shard = shard_range(scan.shape[0], rank, world)
+
+    if args.stream:
+        run_stream(args, ctx, mg, cfg, synth)
+        return
 
     if args.profile_knn or args.profile_icp:
         if args.profile_knn:

@@ -55,7 +55,7 @@ int dev_alloc(mb_ctx* c, void** p, size_t bytes) {
 void dev_free(mb_ctx* c, void* p, size_t bytes) {
   if (!p) return;
   bytes = std::max<size_t>((bytes + 255) & ~(size_t)255, 256);
-  if (c->pool.size() < 64 && c->pool_bytes + bytes <= ((size_t)2 << 30)) {
+  if (c->pool.size() < 96 && c->pool_bytes + bytes <= ((size_t)8 << 30)) {
     c->pool.push_back({p, bytes});
     c->pool_bytes += bytes;
   } else {

@@ -691,7 +691,11 @@ int enqueue_linearize(mb_factor* f, int do_step, int iter, mb_icp_trace* d_trace
   MB_CUDA(launch_pdl(k_finalize, dim3(1), dim3(160), st, (const double*)f->packed, f->ds, (int)f->cfg.reg_4_dof,
                      linearize_count, do_step, iter, d_trace, 31u));
   MB_CUDA(launch_pdl(k_loc_comp, dim3(f->grid2), dim3(kLocThreads), st, fv, (const DevState*)f->ds));
-  if (c->world > 1) MB_NCCL(ncclAllReduce(f->packed + kPack, f->packed + kPack, 6, ncclDouble, ncclSum, c->comm, st));
+  // The cross-rank sum of the six component localizabilities is only needed when they are handed out
+  // (mb_factor_linearize): the harness loop never returns them, so it does not pay a second all-reduce per
+  // iteration for a value nobody reads.  Every rank still computes its own share each iteration.
+  if (c->world > 1 && !do_step)
+    MB_NCCL(ncclAllReduce(f->packed + kPack, f->packed + kPack, 6, ncclDouble, ncclSum, c->comm, st));
   c->launches += 3;
   MB_CUDA(cudaGetLastError());
   return MB_OK;

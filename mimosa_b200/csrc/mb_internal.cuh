@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/mimosa_b200.h"
@@ -71,6 +72,7 @@ struct mb_ctx {
   };
   std::vector<Block> pool;
   size_t pool_bytes = 0;
+  std::unordered_map<void*, size_t> tracked;  // sizes of blocks handed out by dev_alloc_t
 };
 
 namespace mb {
@@ -81,6 +83,26 @@ int pinned_reserve(mb_ctx* c, size_t bytes);
 int dev_alloc(mb_ctx* c, void** p, size_t bytes);
 void dev_free(mb_ctx* c, void* p, size_t bytes);
 void dev_pool_release(mb_ctx* c);
+// Same, with the size remembered per pointer (for owners that do not keep it).
+template <typename T>
+inline int dev_alloc_t(mb_ctx* c, T** p, size_t bytes) {
+  void* v = nullptr;
+  const int rc = dev_alloc(c, &v, bytes);
+  *p = (T*)v;
+  if (rc == MB_OK) c->tracked[v] = bytes;
+  return rc;
+}
+inline void dev_free_t(mb_ctx* c, void* p) {
+  if (!p) return;
+  auto it = c->tracked.find(p);
+  if (it == c->tracked.end()) {
+    cudaFree(p);
+    return;
+  }
+  const size_t bytes = it->second;
+  c->tracked.erase(it);
+  dev_free(c, p, bytes);
+}
 }
 
 namespace mb {

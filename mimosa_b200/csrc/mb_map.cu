@@ -394,10 +394,10 @@ struct Bump {
 int ensure_scratch(mb_map* m, size_t bytes) {
   if (bytes <= m->scratch_bytes) return MB_OK;
   MB_CUDA(cudaStreamSynchronize(m->ctx->stream));
-  if (m->scratch) MB_CUDA(cudaFree(m->scratch));
+  if (m->scratch) dev_free_t(m->ctx, m->scratch);
   m->scratch = nullptr;
   m->scratch_bytes = 0;
-  MB_CUDA(cudaMalloc(&m->scratch, bytes));
+  MB_TRY(dev_alloc_t(m->ctx, &m->scratch, bytes));
   m->scratch_bytes = bytes;
   return MB_OK;
 }
@@ -406,9 +406,9 @@ int rebuild_table(mb_map* m, size_t want_table) {
   cudaStream_t st = m->ctx->stream;
   if (want_table != m->table_cap) {
     MB_CUDA(cudaStreamSynchronize(st));
-    if (m->table) MB_CUDA(cudaFree(m->table));
+    if (m->table) dev_free_t(m->ctx, m->table);
     m->table = nullptr;
-    MB_CUDA(cudaMalloc(&m->table, want_table * sizeof(int4)));
+    MB_TRY(dev_alloc_t(m->ctx, &m->table, want_table * sizeof(int4)));
     m->table_cap = want_table;
   }
   MB_CUDA(cudaMemsetAsync(m->table, 0xff, m->table_cap * sizeof(int4), st));
@@ -430,16 +430,19 @@ int map_reserve(mb_map* m, size_t want_vox) {
     return MB_ERR_CAPACITY;
   }
   if (want_vox > m->cap_vox) {
+    // Grow geometrically while the map is small; round to 64 Ki voxels so that successive snapshots of a
+    // slowly growing map ask the block pool for identical sizes.
     size_t new_cap = std::max<size_t>(want_vox, m->cap_vox + m->cap_vox / 2);
     new_cap = std::max<size_t>(new_cap, 4096);
+    if (new_cap > 65536) new_cap = (new_cap + 65535) & ~(size_t)65535;
     float4* pts2 = nullptr;
     int4* info2 = nullptr;
     int32_t* count2 = nullptr;
     uint32_t* epos2 = nullptr;
-    MB_CUDA(cudaMalloc(&pts2, new_cap * m->cap * sizeof(float4)));
-    MB_CUDA(cudaMalloc(&info2, new_cap * sizeof(int4)));
-    MB_CUDA(cudaMalloc(&count2, new_cap * sizeof(int32_t)));
-    MB_CUDA(cudaMalloc(&epos2, new_cap * sizeof(uint32_t)));
+    MB_TRY(dev_alloc_t(m->ctx, &pts2, new_cap * m->cap * sizeof(float4)));
+    MB_TRY(dev_alloc_t(m->ctx, &info2, new_cap * sizeof(int4)));
+    MB_TRY(dev_alloc_t(m->ctx, &count2, new_cap * sizeof(int32_t)));
+    MB_TRY(dev_alloc_t(m->ctx, &epos2, new_cap * sizeof(uint32_t)));
     if (m->n_vox) {
       MB_CUDA(cudaMemcpyAsync(pts2, m->pts, m->n_vox * m->cap * sizeof(float4), cudaMemcpyDeviceToDevice, st));
       MB_CUDA(cudaMemcpyAsync(info2, m->info, m->n_vox * sizeof(int4), cudaMemcpyDeviceToDevice, st));
@@ -447,10 +450,10 @@ int map_reserve(mb_map* m, size_t want_vox) {
       MB_CUDA(cudaMemcpyAsync(epos2, m->epos, m->n_vox * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     }
     MB_CUDA(cudaStreamSynchronize(st));
-    if (m->pts) cudaFree(m->pts);
-    if (m->info) cudaFree(m->info);
-    if (m->count) cudaFree(m->count);
-    if (m->epos) cudaFree(m->epos);
+    if (m->pts) dev_free_t(m->ctx, m->pts);
+    if (m->info) dev_free_t(m->ctx, m->info);
+    if (m->count) dev_free_t(m->ctx, m->count);
+    if (m->epos) dev_free_t(m->ctx, m->epos);
     m->pts = pts2;
     m->info = info2;
     m->count = count2;
@@ -470,14 +473,15 @@ int ensure_mirror(mb_map* m) {
   const size_t nv = m->n_vox;
   if (m->r_cap_vox < std::max<size_t>(nv, 1)) {
     MB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(m->r_pts);
-    cudaFree(m->r_meta);
+    dev_free_t(m->ctx, m->r_pts);
+    dev_free_t(m->ctx, m->r_meta);
     m->r_pts = nullptr;
     m->r_meta = nullptr;
     m->r_cap_vox = 0;
-    const size_t cap_vox = std::max<size_t>(nv + nv / 8, 4096);
-    MB_CUDA(cudaMalloc(&m->r_pts, cap_vox * m->cap * sizeof(float4)));
-    MB_CUDA(cudaMalloc(&m->r_meta, cap_vox * sizeof(uint32_t)));
+    size_t cap_vox = std::max<size_t>(nv + nv / 8, 4096);
+    if (cap_vox > 65536) cap_vox = (cap_vox + 65535) & ~(size_t)65535;
+    MB_TRY(dev_alloc_t(m->ctx, &m->r_pts, cap_vox * m->cap * sizeof(float4)));
+    MB_TRY(dev_alloc_t(m->ctx, &m->r_meta, cap_vox * sizeof(uint32_t)));
     m->r_cap_vox = cap_vox;
   }
   size_t want_b = 1024;
@@ -524,9 +528,9 @@ int ensure_mirror(mb_map* m) {
   while (want_b < 2 * (size_t)n_blocks) want_b <<= 1;
   if (want_b > m->r_bcap) {
     MB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(m->r_btab);
+    dev_free_t(m->ctx, m->r_btab);
     m->r_btab = nullptr;
-    MB_CUDA(cudaMalloc(&m->r_btab, 2 * want_b * sizeof(int4)));
+    MB_TRY(dev_alloc_t(m->ctx, &m->r_btab, 2 * want_b * sizeof(int4)));
     m->r_bcap = want_b;
   }
   MB_CUDA(cudaMemsetAsync(m->r_btab, 0xff, 2 * m->r_bcap * sizeof(int4), st));
@@ -619,19 +623,19 @@ int mb_map_release(mb_map* m) {
   if (m->refs.fetch_sub(1) > 1) return MB_OK;
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
-  cudaFree(m->pts);
-  cudaFree(m->info);
-  cudaFree(m->count);
-  cudaFree(m->epos);
-  cudaFree(m->table);
-  cudaFree(m->scratch);
-  cudaFree(m->r_pts);
-  cudaFree(m->r_meta);
-  cudaFree(m->r_btab);
-  cudaFree(m->q_dev);
-  cudaFree(m->q_idx);
-  cudaFree(m->q_d2);
-  cudaFree(m->q_ok);
+  dev_free_t(m->ctx, m->pts);
+  dev_free_t(m->ctx, m->info);
+  dev_free_t(m->ctx, m->count);
+  dev_free_t(m->ctx, m->epos);
+  dev_free_t(m->ctx, m->table);
+  dev_free_t(m->ctx, m->scratch);
+  dev_free_t(m->ctx, m->r_pts);
+  dev_free_t(m->ctx, m->r_meta);
+  dev_free_t(m->ctx, m->r_btab);
+  dev_free_t(m->ctx, m->q_dev);
+  dev_free_t(m->ctx, m->q_idx);
+  dev_free_t(m->ctx, m->q_d2);
+  dev_free_t(m->ctx, m->q_ok);
   delete m;
   return MB_OK;
 }
@@ -650,7 +654,8 @@ int mb_map_snapshot(mb_map* m, mb_map** out) {
   std::memcpy(s->off, m->off, sizeof(m->off));
   s->lru_horizon = m->lru_horizon;
   s->lru_counter = m->lru_counter;
-  int st = map_reserve(s, std::max<size_t>(m->n_vox, 4096));
+  // headroom so that the insert which usually follows a snapshot (geometric.cpp:494-495) does not regrow it
+  int st = map_reserve(s, std::max<size_t>(m->n_vox + std::max<size_t>(m->n_vox / 32, 65536), 4096));
   if (st != MB_OK) {
     mb_map_release(s);
     return st;
@@ -805,17 +810,17 @@ int mb::map_insert_impl(mb_map* m, const void* xyz, cudaMemcpyKind kind, size_t 
       float4* pts2 = nullptr;
       int4* info2 = nullptr;
       int32_t* count2 = nullptr;
-      MB_CUDA(cudaMalloc(&pts2, m->cap_vox * m->cap * sizeof(float4)));
-      MB_CUDA(cudaMalloc(&info2, m->cap_vox * sizeof(int4)));
-      MB_CUDA(cudaMalloc(&count2, m->cap_vox * sizeof(int32_t)));
+      MB_TRY(dev_alloc_t(m->ctx, &pts2, m->cap_vox * m->cap * sizeof(float4)));
+      MB_TRY(dev_alloc_t(m->ctx, &info2, m->cap_vox * sizeof(int4)));
+      MB_TRY(dev_alloc_t(m->ctx, &count2, m->cap_vox * sizeof(int32_t)));
       const unsigned grid = (unsigned)std::min<size_t>((m->n_vox + 7) / 8, (size_t)ctx->sm_count * 16);
       k_compact<<<grid, 256, 0, st>>>(keep, new_id, (uint32_t)m->n_vox, m->cap, m->pts, m->info, m->count, pts2, info2,
                                       count2);
       ++ctx->launches;
       MB_CUDA(cudaStreamSynchronize(st));
-      cudaFree(m->pts);
-      cudaFree(m->info);
-      cudaFree(m->count);
+      dev_free_t(m->ctx, m->pts);
+      dev_free_t(m->ctx, m->info);
+      dev_free_t(m->ctx, m->count);
       m->pts = pts2;
       m->info = info2;
       m->count = count2;
@@ -907,19 +912,19 @@ int mb_map_upload(mb_map* m, const int32_t* coords, const int32_t* counts, const
 static int stage_buffers(mb_map* m, size_t nq, int k) {
   if (nq > m->q_cap || k != m->q_k) {
     MB_CUDA(cudaStreamSynchronize(m->ctx->stream));
-    cudaFree(m->q_dev);
-    cudaFree(m->q_idx);
-    cudaFree(m->q_d2);
-    cudaFree(m->q_ok);
+    dev_free_t(m->ctx, m->q_dev);
+    dev_free_t(m->ctx, m->q_idx);
+    dev_free_t(m->ctx, m->q_d2);
+    dev_free_t(m->ctx, m->q_ok);
     m->q_dev = nullptr;
     m->q_idx = nullptr;
     m->q_d2 = nullptr;
     m->q_ok = nullptr;
     m->q_cap = 0;
-    MB_CUDA(cudaMalloc(&m->q_dev, nq * 3 * sizeof(double)));
-    MB_CUDA(cudaMalloc(&m->q_idx, nq * k * sizeof(uint64_t)));
-    MB_CUDA(cudaMalloc(&m->q_d2, nq * k * sizeof(double)));
-    MB_CUDA(cudaMalloc(&m->q_ok, nq));
+    MB_TRY(dev_alloc_t(m->ctx, &m->q_dev, nq * 3 * sizeof(double)));
+    MB_TRY(dev_alloc_t(m->ctx, &m->q_idx, nq * k * sizeof(uint64_t)));
+    MB_TRY(dev_alloc_t(m->ctx, &m->q_d2, nq * k * sizeof(double)));
+    MB_TRY(dev_alloc_t(m->ctx, &m->q_ok, nq));
     m->q_cap = nq;
     m->q_k = k;
   }
@@ -1021,15 +1026,16 @@ int mb::downsample_impl(mb_ctx* ctx, const void* xyz, cudaMemcpyKind kind, size_
   const size_t temp_bytes = std::max(sort_temp, scan_temp);
   const size_t bytes = n * stride_bytes + n * (16 + 8 + 4 * 8) + n * cap * 4 + temp_bytes + 256 * 20;
   void* scratch = nullptr;
-  MB_CUDA(cudaMalloc(&scratch, bytes));
+  MB_TRY(dev_alloc_t(ctx, &scratch, bytes));
   struct Free {
+    mb_ctx* c;
     void* p;
     cudaStream_t s;
     ~Free() {
       cudaStreamSynchronize(s);
-      cudaFree(p);
+      dev_free_t(c, p);
     }
-  } guard{scratch, st};
+  } guard{ctx, scratch, st};
   Bump b{(char*)scratch, 0, bytes};
   unsigned char* raw = b.take<unsigned char>(n * stride_bytes);
   uint64_t* keys = b.take<uint64_t>(n);
