@@ -98,6 +98,31 @@ typedef struct mb_icp_trace {
   int32_t solve_ok;
 } mb_icp_trace;
 
+/* Where the fields of one point sit inside a sensor_msgs/PointCloud2 record (one descriptor covers the nine
+ * vendor structs of mimosa/include/mimosa/lidar/point.hpp:41-178).  Offsets in bytes, -1 = field absent. */
+typedef struct mb_cloud_layout {
+  uint32_t point_step;
+  int32_t off_x, off_y, off_z; /* float32 */
+  int32_t off_intensity;
+  int32_t intensity_type; /* 0: float32 intensity; 1: uint16 reflectivity (PointOusterOdyssey) */
+  int32_t off_time;
+  int32_t time_type; /* 0: uint32 ns since header (Ouster t, LivoxFromCustom2 t); 1: float32 s since header (Velodyne time);
+                        2: float64 absolute s (Hesai / Rslidar timestamp); 3: float64 absolute ns (Livox timestamp) */
+  int32_t off_ring;  /* -1: no ring filter (Livox, OusterOdyssey, VelodyneAnybotics) */
+  int32_t ring_type; /* 0: uint16; 1: uint8 */
+  int32_t off_tag;   /* Livox tag byte, -1 otherwise */
+} mb_cloud_layout;
+
+/* lidar::ManagerConfig's input filters (mimosa/include/mimosa/lidar/manager.hpp:30-34) + the two skip divisors of
+ * GeometricConfig (geometric_config.hpp:48-49); float fields stay float like the reference's. */
+typedef struct mb_input_filter {
+  float intensity_min, intensity_max, range_min, range_max;
+  float ns_max; /* compared as (float)t_ns > ns_max, manager.cpp:306 */
+  int32_t point_skip_divisor, ring_skip_divisor, create_full_res_pointcloud;
+  float z_offset;   /* manager.cpp:18 */
+  double header_ts; /* msg.header.stamp in seconds */
+} mb_input_filter;
+
 typedef struct mb_ctx mb_ctx;
 typedef struct mb_map mb_map;
 typedef struct mb_factor mb_factor;
@@ -212,9 +237,23 @@ MB_API int mb_factor_set_flags(mb_factor* f, uint32_t flags);
 MB_API int mb_downsample(mb_ctx* ctx, const float* xyz, size_t n, size_t stride_bytes, float leaf, size_t cap,
                          float min_dist, uint32_t* out_idx, size_t* n_out);
 MB_API int mb_scan_upload(mb_ctx* ctx, const void* pts, size_t n, size_t stride_bytes, mb_scan** out);
+/* lidar::Manager::prepareInput, mimosa/src/lidar/manager.cpp:149-383: decode the PointCloud2 payload, apply the
+ * NaN / Livox-tag / intensity / range / ns_max filters and the point / ring skip divisors, and group the kept
+ * points by timestamp.  points_full <- lidar::Point records (x, y, z + z_offset, intensity, t_ns, original index,
+ * range); geometric_idx[0..*n_geometric) indexes points_full (geometric_point_idxs_); unique_ns[0..*n_unique) are
+ * the distinct timestamps ascending and pose_index[j] the timestamp group of points_full[j] — what
+ * mb_scan_deskew takes once the host has propagated one pose per timestamp.  Host arrays need room for n_points
+ * entries.  transpose_pointcloud / organize_pointcloud_by_ring are not covered. */
+MB_API int mb_scan_from_cloud(mb_ctx* ctx, const void* data, size_t n_points, const mb_cloud_layout* layout,
+                              const mb_input_filter* filter, mb_scan** points_full, uint32_t* geometric_idx,
+                              size_t* n_geometric, uint32_t* pose_index, uint32_t* unique_ns, size_t* n_unique,
+                              uint32_t* last_point_ns);
 MB_API int mb_scan_release(mb_scan* scan);
 MB_API int mb_scan_size(mb_scan* scan, size_t* n, size_t* stride_bytes);
 MB_API int mb_scan_download(mb_scan* scan, void* pts);
+/* Records idx[0..n) of `scan`, in that order, as a new scan: Geometric::preprocess works on
+ * points_deskewed[geometric_point_idxs] (mimosa/src/lidar/geometric.cpp:151-158). */
+MB_API int mb_scan_gather(mb_scan* scan, const uint32_t* idx, size_t n, mb_scan** out);
 MB_API int mb_scan_deskew(mb_scan* scan, const uint32_t* pose_index, const float* poses, size_t n_poses);
 MB_API int mb_scan_transform(mb_scan* scan, const float R[9], const float t[3]);
 MB_API int mb_scan_downsample(mb_scan* scan, float leaf, size_t cap, float min_dist, mb_scan** out);

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libmimosa_b200.so")
-SOURCES = ["mb_ctx.cu", "mb_map.cu", "mb_factor.cu", "mb_scan.cu"]
+SOURCES = ["mb_ctx.cu", "mb_map.cu", "mb_factor.cu", "mb_scan.cu", "mb_decode.cu"]
 # -fmad=false: no multiply-add contraction — the op-by-op IEEE behaviour the parity contract relies on.
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",

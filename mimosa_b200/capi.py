@@ -55,6 +55,18 @@ class IcpConfig(C.Structure):
     ]
 
 
+class CloudLayout(C.Structure):
+    _fields_ = [("point_step", C.c_uint32), ("off_x", C.c_int32), ("off_y", C.c_int32), ("off_z", C.c_int32),
+                ("off_intensity", C.c_int32), ("intensity_type", C.c_int32), ("off_time", C.c_int32), ("time_type", C.c_int32),
+                ("off_ring", C.c_int32), ("ring_type", C.c_int32), ("off_tag", C.c_int32)]
+
+
+class InputFilter(C.Structure):
+    _fields_ = [("intensity_min", C.c_float), ("intensity_max", C.c_float), ("range_min", C.c_float), ("range_max", C.c_float),
+                ("ns_max", C.c_float), ("point_skip_divisor", C.c_int32), ("ring_skip_divisor", C.c_int32),
+                ("create_full_res_pointcloud", C.c_int32), ("z_offset", C.c_float), ("header_ts", C.c_double)]
+
+
 class Linearization(C.Structure):
     _fields_ = [
         ("H", C.c_double * 36),
@@ -128,6 +140,9 @@ SIGNATURES = {
     "mb_gn_step": (C.c_int, [_P, _P, C.c_double, _P, _P, _P, C.POINTER(C.c_int)]),
     "mb_downsample": (C.c_int, [_P, _P, _SZ, _SZ, C.c_float, _SZ, C.c_float, _P, C.POINTER(_SZ)]),
     "mb_scan_upload": (C.c_int, [_P, _P, _SZ, _SZ, C.POINTER(_P)]),
+    "mb_scan_from_cloud": (C.c_int, [_P, _P, _SZ, C.POINTER(CloudLayout), C.POINTER(InputFilter), C.POINTER(_P), _P,
+                                    C.POINTER(_SZ), _P, _P, C.POINTER(_SZ), C.POINTER(C.c_uint32)]),
+    "mb_scan_gather": (C.c_int, [_P, _P, _SZ, C.POINTER(_P)]),
     "mb_scan_release": (C.c_int, [_P]),
     "mb_scan_size": (C.c_int, [_P, C.POINTER(_SZ), C.POINTER(_SZ)]),
     "mb_scan_download": (C.c_int, [_P, _P]),

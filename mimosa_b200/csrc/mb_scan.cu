@@ -193,6 +193,41 @@ int mb_scan_downsample(mb_scan* s, float leaf, size_t cap, float min_dist, mb_sc
   return MB_OK;
 }
 
+int mb_scan_gather(mb_scan* s, const uint32_t* idx, size_t n, mb_scan** out) {
+  MB_REQUIRE(s && out && (n == 0 || idx), "null argument");
+  for (size_t i = 0; i < n; ++i) MB_REQUIRE(idx[i] < s->n, "index out of range");
+  mb_ctx* c = s->ctx;
+  MB_CUDA(cudaSetDevice(c->device));
+  mb_scan* o = nullptr;
+  MB_TRY(scan_alloc(c, n, s->stride, &o));
+  if (n) {
+    uint32_t* d_idx = nullptr;
+    int rc = dev_alloc(c, (void**)&d_idx, n * sizeof(uint32_t));
+    if (rc == MB_OK) rc = pinned_reserve(c, n * sizeof(uint32_t));
+    if (rc == MB_OK) {
+      std::memcpy(c->pinned, idx, n * sizeof(uint32_t));
+      cudaError_t e = cudaMemcpyAsync(d_idx, c->pinned, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+      if (e == cudaSuccess) {
+        k_gather_records<<<blocks_for(n * (s->stride / 4), 256), 256, 0, c->stream>>>(s->data, s->stride, d_idx, n, o->data);
+        ++c->launches;
+        e = cudaGetLastError();
+      }
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+      if (e != cudaSuccess) {
+        set_error("scan gather failed: %s", cudaGetErrorString(e));
+        rc = MB_ERR_CUDA;
+      }
+    }
+    dev_free(c, d_idx, n * sizeof(uint32_t));
+    if (rc != MB_OK) {
+      mb_scan_release(o);
+      return rc;
+    }
+  }
+  *out = o;
+  return MB_OK;
+}
+
 int mb_map_insert_scan(mb_map* map, mb_scan* s, const float R[9], const float t[3]) {
   MB_REQUIRE(map && s && R && t, "null argument");
   MB_REQUIRE(map->ctx == s->ctx, "map and scan belong to different contexts");

@@ -18,7 +18,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import capi
-from .capi import IcpConfig, IcpTrace, Linearization, check
+from .capi import CloudLayout, IcpConfig, IcpTrace, InputFilter, Linearization, check
 
 
 def _ptr(a):
@@ -153,6 +153,28 @@ class Scan:
             check(self.lib.mb_scan_upload(ctx.h, _ptr(pts), pts.shape[0], pts.strides[0] if pts.shape[0] else 4 * _cols, C.byref(h)))
             _handle = h
         self.h, self.cols = _handle, _cols
+
+    @staticmethod
+    def from_cloud(ctx: Context, data: np.ndarray, layout: CloudLayout, filt: InputFilter):
+        """lidar::Manager::prepareInput (manager.cpp:149-383).  `data`: (n, point_step) uint8 PointCloud2 payload.
+        Returns (points_full Scan, geometric_idx, pose_index, unique_ns, last_point_ns)."""
+        data = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1, layout.point_step)
+        n = data.shape[0]
+        geo = np.empty(max(n, 1), np.uint32)
+        pi = np.empty(max(n, 1), np.uint32)
+        uns = np.empty(max(n, 1), np.uint32)
+        h, n_geo, n_un, last = C.c_void_p(), C.c_size_t(), C.c_size_t(), C.c_uint32()
+        check(ctx.lib.mb_scan_from_cloud(ctx.h, _ptr(data), n, C.byref(layout), C.byref(filt), C.byref(h), _ptr(geo),
+                                         C.byref(n_geo), _ptr(pi), _ptr(uns), C.byref(n_un), C.byref(last)))
+        sc = Scan(ctx, _handle=h, _cols=8)
+        return sc, geo[: n_geo.value].copy(), pi[: sc.n].copy(), uns[: n_un.value].copy(), int(last.value)
+
+    def gather(self, idx: np.ndarray) -> "Scan":
+        """points[idx] as a new scan (Geometric::preprocess's idxs, geometric.cpp:151-158)."""
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        h = C.c_void_p()
+        check(self.lib.mb_scan_gather(self.h, _ptr(idx), idx.size, C.byref(h)))
+        return Scan(self.ctx, _handle=h, _cols=self.cols)
 
     def release(self):
         if self.h:

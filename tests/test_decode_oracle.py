@@ -1,0 +1,61 @@
+"""CPU known-answer tests pinning the numpy restatement of lidar::Manager::prepareInput (oracle/decode_ref.py)."""
+import numpy as np
+
+import decode_ref
+from cloud_layouts import LAYOUTS, OUSTER, default_filter, make_cloud
+
+
+def _ouster(rows):
+    c = np.zeros(len(rows), OUSTER)
+    for i, r in enumerate(rows):
+        c[i] = r
+    return c.view(np.uint8).reshape(len(rows), 32)
+
+
+def test_filters_hand_checked():
+    lay = LAYOUTS["ouster"][1]
+    #        x     y    z    inten  t_ns   refl ring
+    rows = [(3.0, 0.0, 0.0, 10.0, 500, 0, 0),       # kept, geometric (i=0)
+            (3.0, 4.0, 0.0, 10.0, 100, 0, 1),       # kept (full res), not geometric (i=1, skip 2)
+            (np.nan, 0.0, 0.0, 10.0, 0, 0, 0),      # NaN
+            (1.0, 0.0, 0.0, 10.0, 0, 0, 0),         # range < 2
+            (3.0, 0.0, 0.0, 300.0, 0, 0, 0),        # intensity > max
+            (3.0, 0.0, 0.0, 10.0, 20_000_000, 0, 0),  # t_ns > ns_max
+            (0.0, 0.0, 5.0, 10.0, 100, 0, 3),       # kept, i=6 geometric by skip but ring 3 % 2 != 0
+            (0.0, 70.0, 0.0, 10.0, 100, 0, 0),      # range > 60
+            (0.0, 6.0, 8.0, 20.0, 500, 0, 2)]       # kept, geometric (i=8, ring 2)
+    f = default_filter(create_full_res_pointcloud=1, point_skip_divisor=2, ring_skip_divisor=2)
+    pts, geo, pose_index, unique_ns, last = decode_ref.prepare_input(_ouster(rows), lay, f)
+    assert pts[:, 6].view(np.uint32).tolist() == [0, 1, 6, 8]
+    assert pts[:, 5].view(np.uint32).tolist() == [500, 100, 100, 500]
+    assert np.allclose(pts[:, 7], [3.0, 5.0, 5.0, 10.0]) and np.allclose(pts[:, 2], [0.036, 0.036, 5.036, 8.036])
+    assert geo.tolist() == [0, 3]
+    assert unique_ns.tolist() == [100, 500] and pose_index.tolist() == [1, 0, 0, 1] and last == 500
+    # without full resolution only every point_skip-th input point is even looked at
+    f2 = default_filter(create_full_res_pointcloud=0, point_skip_divisor=2, ring_skip_divisor=1)
+    pts2, geo2, *_ = decode_ref.prepare_input(_ouster(rows), lay, f2)
+    assert pts2[:, 6].view(np.uint32).tolist() == [0, 6, 8] and geo2.tolist() == [0, 1, 2]
+
+
+def test_time_encodings_agree():
+    rng = np.random.default_rng(3)
+    ref = None
+    for name in ("ouster", "velodyne", "hesai"):
+        data, lay = make_cloud(name, 4096, np.random.default_rng(3))
+        pts, geo, pi, uns, last = decode_ref.prepare_input(data, lay, default_filter())
+        t = pts[:, 5].view(np.uint32)
+        if ref is None:
+            ref = t
+        else:  # float32 seconds / float64 absolute seconds decode to the same nanoseconds within rounding
+            assert t.shape == ref.shape and np.abs(t.astype(np.int64) - ref.astype(np.int64)).max() <= 1000
+        assert np.array_equal(uns[pi], t) and np.all(np.diff(uns.astype(np.int64)) > 0)
+
+
+def test_livox_tag_and_reflectivity_layouts():
+    data, lay = make_cloud("livox", 2000, np.random.default_rng(4))
+    pts, geo, *_ = decode_ref.prepare_input(data, lay, default_filter(create_full_res_pointcloud=1))
+    tags = data[pts[:, 6].view(np.uint32), 20]
+    assert np.all(((tags & 0x30) == 0x10) | ((tags & 0x30) == 0x00)) and 0 < pts.shape[0] < 2000
+    data, lay = make_cloud("ouster_odyssey", 2000, np.random.default_rng(5))
+    pts, geo, *_ = decode_ref.prepare_input(data, lay, default_filter(create_full_res_pointcloud=1))
+    assert np.all(pts[:, 4] <= 250.0) and pts.shape[0] > 0

@@ -522,3 +522,34 @@ def test_streaming_pipeline_matches_oracle(ctx, oracle, pattern, n_scans, n_pts)
     if n_scans >= 10:
         assert mo.size()[2] >= 10  # the LRU clock crossed a clear cycle
     mg.release()
+
+
+@pytest.mark.parametrize("name", ["ouster", "ouster_odyssey", "velodyne", "hesai", "livox"])
+def test_pointcloud2_decode_matches_oracle(ctx, name):
+    """lidar::Manager::prepareInput (manager.cpp:149-383) on the device vs the numpy restatement, for five vendor
+    layouts, full-resolution and skipped; then the decoded scan flows into deskew + gather like in the callback."""
+    import decode_ref
+    from cloud_layouts import default_filter, make_cloud
+    from mimosa_b200 import Scan
+
+    rng = np.random.default_rng(200)
+    data, lay = make_cloud(name, 60000, rng)
+    for full, skip, ring_skip in ((1, 4, 2), (0, 4, 1), (1, 1, 1)):
+        f = default_filter(create_full_res_pointcloud=full, point_skip_divisor=skip, ring_skip_divisor=ring_skip)
+        want = decode_ref.prepare_input(data, lay, f)
+        sc, geo, pose_index, unique_ns, last = Scan.from_cloud(ctx, data, lay, f)
+        got = sc.download()
+        assert got.shape == want[0].shape and got.shape[0] > 100
+        assert np.array_equal(got.view(np.uint32), want[0].view(np.uint32))
+        assert np.array_equal(geo, want[1]) and np.array_equal(pose_index, want[2])
+        assert np.array_equal(unique_ns, want[3]) and last == want[4]
+        # one pose per timestamp -> deskew -> the geometric subset, as lidar::Manager::callback chains them
+        poses = np.tile(np.concatenate([np.eye(3).reshape(9), [0.0, 0.0, 0.0]]).astype(np.float32), (unique_ns.size, 1))
+        poses[:, 9] = np.linspace(0.0, 0.2, unique_ns.size, dtype=np.float32)
+        sc.deskew(pose_index, poses)
+        sub = sc.gather(geo)
+        expect = want[0].copy()
+        expect[:, 0] = expect[:, 0] + poses[pose_index, 9]
+        assert np.array_equal(sub.download().view(np.uint32), expect[geo].view(np.uint32))
+        sub.release()
+        sc.release()
