@@ -185,8 +185,8 @@ __host__ __device__ __forceinline__ int centre_offset_index(int n_off) { return 
 //   * all control flow is warp-converged (uniform trip counts, per-lane predicates).
 // K is the compile-time list length (5 = the reference's num_corres_points, 8 = generic: the k nearest are the
 // first k of the 8 nearest).  s_pk / s_blk are this thread's columns of shared [n_off][pk_stride] /
-// [24][pk_stride] arrays; s_pk receives (bucket index << 5 | count) of every scanned neighbour and stays valid
-// for knn_resolve().
+// [24][pk_stride] arrays; s_pk receives the bucket index of every scanned neighbour and stays valid for
+// knn_resolve().
 template <int K>
 __device__ __forceinline__ void knn_thread(const MapView& mv, const int8_t* __restrict__ s_off, uint32_t* s_pk,
                                            uint32_t* s_blk, int pk_stride, double qx, double qy, double qz, int k,
@@ -204,54 +204,43 @@ __device__ __forceinline__ void knn_thread(const MapView& mv, const int8_t* __re
 
   // ---- locate the neighbourhood's blocks -------------------------------------------------------------
   // The 3x3x3 neighbourhood touches at most 2 blocks per axis.  s_blk[combo] (combo = ix | iy << 1 | iz << 2)
-  // receives {mask_lo, mask_hi, base} of block (ix ? hi : lo) per axis; duplicates (hi == lo) are copied, not
-  // probed.  Pass 1 hashes and prefetches, pass 2 reads the entries four at a time.
+  // receives {mask_lo, mask_hi, base} of block (ix ? hi : lo) per axis.  Duplicate combos (hi == lo) are neither
+  // probed nor read: slot_of() can only form a combo bit when the two blocks differ.  Both halves of an entry
+  // are fetched together, four entries in flight.
   const int lx = (cx - 1) >> kBlockShift, hx = (cx + 1) >> kBlockShift;
   const int ly = (cy - 1) >> kBlockShift, hy = (cy + 1) >> kBlockShift;
   const int lz = (cz - 1) >> kBlockShift, hz = (cz + 1) >> kBlockShift;
   const unsigned dup_bits = (hx == lx ? 1u : 0u) | (hy == ly ? 2u : 0u) | (hz == lz ? 4u : 0u);
 #pragma unroll
-  for (int combo = 0; combo < 8; ++combo) {
-    const uint32_t h = hash_coord((combo & 1) ? hx : lx, (combo & 2) ? hy : ly, (combo & 4) ? hz : lz) & mv.bmask;
-    s_blk[(combo * 3) * pk_stride] = h;
-    if (active && (combo & dup_bits) == 0) prefetch_l2(mv.btab + 2 * (size_t)h);
-  }
-#pragma unroll
   for (int c0 = 0; c0 < 8; c0 += 4) {
     uint32_t h[4];
-    int4 e[4];
+    int4 e[4], m[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int combo = c0 + u;
-      h[u] = s_blk[(combo * 3) * pk_stride];
+      h[u] = hash_coord((combo & 1) ? hx : lx, (combo & 2) ? hy : ly, (combo & 4) ? hz : lz) & mv.bmask;
       e[u] = make_int4(0, 0, 0, (int)kEmpty);
-      if (active && (combo & dup_bits) == 0) e[u] = __ldg(mv.btab + 2 * (size_t)h[u]);
+      m[u] = make_int4(0, 0, 0, 0);
+      if (active && (combo & dup_bits) == 0) {
+        e[u] = __ldg(mv.btab + 2 * (size_t)h[u]);
+        m[u] = __ldg(mv.btab + 2 * (size_t)h[u] + 1);
+      }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int combo = c0 + u;
-      uint32_t m_lo = 0, m_hi = 0, base = 0;
-      if ((combo & dup_bits) != 0) {
-        const int src = combo & ~(int)dup_bits;  // already resolved (src < combo)
-        m_lo = s_blk[(src * 3) * pk_stride];
-        m_hi = s_blk[(src * 3 + 1) * pk_stride];
-        base = s_blk[(src * 3 + 2) * pk_stride];
-      } else {
+      if ((combo & dup_bits) == 0) {
         const int bx = (combo & 1) ? hx : lx, by = (combo & 2) ? hy : ly, bz = (combo & 4) ? hz : lz;
         while ((uint32_t)e[u].w != kEmpty && !(e[u].x == bx && e[u].y == by && e[u].z == bz)) {
           h[u] = (h[u] + 1) & mv.bmask;
           e[u] = __ldg(mv.btab + 2 * (size_t)h[u]);
+          m[u] = __ldg(mv.btab + 2 * (size_t)h[u] + 1);
         }
-        if ((uint32_t)e[u].w != kEmpty) {
-          const int4 m = __ldg(mv.btab + 2 * (size_t)h[u] + 1);
-          m_lo = (uint32_t)m.x;
-          m_hi = (uint32_t)m.y;
-          base = (uint32_t)e[u].w;
-        }
+        const bool hit = (uint32_t)e[u].w != kEmpty;
+        s_blk[(combo * 3) * pk_stride] = hit ? (uint32_t)m[u].x : 0u;
+        s_blk[(combo * 3 + 1) * pk_stride] = hit ? (uint32_t)m[u].y : 0u;
+        s_blk[(combo * 3 + 2) * pk_stride] = hit ? (uint32_t)e[u].w : 0u;
       }
-      s_blk[(combo * 3) * pk_stride] = m_lo;
-      s_blk[(combo * 3 + 1) * pk_stride] = m_hi;
-      s_blk[(combo * 3 + 2) * pk_stride] = base;
     }
   }
   // bucket index of neighbour o, or kEmpty when that voxel does not exist
@@ -259,16 +248,16 @@ __device__ __forceinline__ void knn_thread(const MapView& mv, const int8_t* __re
     const int x = cx + s_off[3 * o], y = cy + s_off[3 * o + 1], z = cz + s_off[3 * o + 2];
     const int combo = ((x >> kBlockShift) != lx ? 1 : 0) | ((y >> kBlockShift) != ly ? 2 : 0) | ((z >> kBlockShift) != lz ? 4 : 0);
     const uint32_t m_lo = s_blk[(combo * 3) * pk_stride], m_hi = s_blk[(combo * 3 + 1) * pk_stride];
-    const unsigned long long m = ((unsigned long long)m_hi << 32) | m_lo;
+    const unsigned long long mk = ((unsigned long long)m_hi << 32) | m_lo;
     const uint32_t cell = cell_of(x, y, z);
-    if (((m >> cell) & 1ull) == 0) return kEmpty;
-    return s_blk[(combo * 3 + 2) * pk_stride] + (uint32_t)__popcll(m & ((1ull << cell) - 1ull));
+    if (((mk >> cell) & 1ull) == 0) return kEmpty;
+    return s_blk[(combo * 3 + 2) * pk_stride] + (uint32_t)__popcll(mk & ((1ull << cell) - 1ull));
   };
 
   // ---- scan the candidates --------------------------------------------------------------------------
-  // All control flow below is warp-converged (uniform trip counts, per-lane predicates): a lane never runs a
-  // private inner loop while the other 31 wait.  Candidates are taken four at a time: four independent loads
-  // in flight per lane, then four ordered insertion tests.
+  // All control flow below is warp-converged (uniform trip counts, per-lane predicates).  Candidates are taken
+  // four at a time: four independent loads in flight per lane, then four ordered insertion tests.  A bucket's
+  // fill count travels in the .w of its first point, so no separate metadata load precedes the first chunk.
   const int centre = centre_offset_index(n_off);
   const int cap = mv.cap;
   const uint32_t kCntMask = (1u << kCountBits) - 1;
@@ -297,33 +286,40 @@ __device__ __forceinline__ void knn_thread(const MapView& mv, const int8_t* __re
       bs[0] = lt[0] ? s : bs[0];
     }
   };
-  // candidates j .. j+3 of `bucket` (those below cnt), in order
-  auto offer4 = [&](const float4* bucket, int o, int j, int cnt) {
+  // candidates j .. j+3 of `bucket` (those below its count), in order; returns the bucket's count, which is read
+  // from the first point when j == 0 (`cnt` is only a lower bound >= 1 then)
+  auto offer4 = [&](const float4* bucket, int o, int j, int cnt) -> int {
     float4 p[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) p[u] = __ldg(bucket + min(j + u, cnt - 1));
+    for (int u = 0; u < 4; ++u) p[u] = __ldg(bucket + min(j + u, cap - 1));
+    if (j == 0) {
+      cnt = (int)((uint32_t)__float_as_int(p[0].w) & kCntMask);
+      if (cnt > 8) prefetch_l2(bucket + 8);
+      if (cnt > 16) prefetch_l2(bucket + 16);
+    }
     double d[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) d[u] = sqdist4((double)p[u].x, (double)p[u].y, (double)p[u].z, qx, qy, qz);
 #pragma unroll
     for (int u = 0; u < 4; ++u)
       if (j + u < cnt) offer(d[u], ((uint32_t)o << kSeqShift) | (uint32_t)(j + u));
+    return cnt;
   };
 
   // (1) the query's own voxel
   {
     const uint32_t slot = active ? slot_of(centre) : kEmpty;
-    const uint32_t meta = slot == kEmpty ? 0u : __ldg(mv.meta + slot);
-    const int cnt = (int)(meta & kCntMask);
-    s_pk[centre * pk_stride] = slot == kEmpty ? kEmpty : ((slot << kCountBits) | (uint32_t)cnt);
+    s_pk[centre * pk_stride] = slot;
     const float4* bucket = mv.pts + (size_t)(slot == kEmpty ? 0u : slot) * cap;
+    int cnt = 0;
+    if (slot != kEmpty) cnt = offer4(bucket, centre, 0, 1);
     const int max_cnt = __reduce_max_sync(kFull, cnt);
-    for (int j = 0; j < max_cnt; j += 4)
+    for (int j = 4; j < max_cnt; j += 4)
       if (j < cnt) offer4(bucket, centre, j, cnt);
   }
 
-  // (2) which neighbours can still contribute: bit o set when the voxel is occupied and the squared distance
-  //     from the query to its box does not exceed the current k-th best
+  // (2) which neighbours can still contribute: bit o set when the voxel exists and the squared distance from
+  //     the query to its box does not exceed the current k-th best; their first cache lines are prefetched
   const double fx = ux - (double)cx, fy = uy - (double)cy, fz = uz - (double)cz;  // position inside the voxel
   const double kMargin = 1e-6;
   const double leaf = 1.0 / mv.inv_leaf;
@@ -344,15 +340,10 @@ __device__ __forceinline__ void knn_thread(const MapView& mv, const int8_t* __re
     for (int o = 0; o < n_off; ++o) {
       uint32_t slot = kEmpty;
       if (active & (o != centre)) slot = slot_of(o);
-      const bool keep = (slot != kEmpty) && !(box_lb(o) > worst);
-      if (keep) {
-        const uint32_t cnt = __ldg(mv.meta + slot) & kCntMask;
-        s_pk[o * pk_stride] = (slot << kCountBits) | cnt;
-        const float4* b = mv.pts + (size_t)slot * cap;
-        prefetch_l2(b);
-        if (cnt > 8) prefetch_l2(b + 8);
-        if (cnt > 16) prefetch_l2(b + 16);
-        todo |= cnt ? (1u << o) : 0u;
+      if (slot != kEmpty && !(box_lb(o) > worst)) {
+        s_pk[o * pk_stride] = slot;
+        prefetch_l2(mv.pts + (size_t)slot * cap);
+        todo |= 1u << o;
       }
     }
   }
@@ -366,13 +357,12 @@ __device__ __forceinline__ void knn_thread(const MapView& mv, const int8_t* __re
     if (j >= cnt && todo != 0) {
       o = __ffs(todo) - 1;
       todo &= todo - 1;
-      const uint32_t pk = s_pk[o * pk_stride];
-      cnt = box_lb(o) > worst_of() ? 0 : (int)(pk & kCntMask);
-      bucket = mv.pts + (size_t)(pk >> kCountBits) * cap;
+      cnt = box_lb(o) > worst_of() ? 0 : 1;  // real count arrives with the first chunk
+      bucket = mv.pts + (size_t)s_pk[o * pk_stride] * cap;
       j = 0;
     }
     if (j < cnt) {
-      offer4(bucket, o, j, cnt);
+      cnt = offer4(bucket, o, j, cnt);
       j += 4;
     }
   }
@@ -382,7 +372,7 @@ __device__ __forceinline__ void knn_thread(const MapView& mv, const int8_t* __re
 __device__ __forceinline__ uint64_t knn_resolve(const MapView& mv, const uint32_t* s_pk, int pk_stride, uint32_t seq,
                                                 float4& p) {
   const uint32_t o = seq >> kSeqShift, j = seq & ((1u << kSeqShift) - 1);
-  const uint32_t slot = s_pk[o * pk_stride] >> kCountBits;
+  const uint32_t slot = s_pk[o * pk_stride];
   p = __ldg(mv.pts + (size_t)slot * mv.cap + j);
   const uint32_t id = __ldg(mv.meta + slot) >> kCountBits;
   return ((uint64_t)id << 32) | (uint64_t)j;

@@ -225,7 +225,11 @@ __global__ void k_mirror_gather(const uint64_t* __restrict__ keys, const uint32_
   for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_vox; s += warps) {
     const uint32_t id = ids[s];
     const int c = count[id];
-    if (lane < cap) r_pts[(size_t)s * cap + lane] = lane < c ? pts[(size_t)id * cap + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < cap) {
+      float4 p = lane < c ? pts[(size_t)id * cap + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane == 0) p.w = __int_as_float(c);  // the fill count rides in the first point: no metadata load before it
+      r_pts[(size_t)s * cap + lane] = p;
+    }
     if (lane == 0) {
       r_meta[s] = (id << kCountBits) | (uint32_t)c;
       head[s] = (s == 0 || (keys[s] >> 6) != (keys[s - 1] >> 6)) ? 1u : 0u;
