@@ -152,6 +152,22 @@ __device__ __forceinline__ uint32_t table_find(const int4* __restrict__ table, u
 }
 
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kOffBytes = 96 + 32;  // neighbour offsets (3 x 32 int8) + processing order (32 int8)
+
+// Fill the per-block shared copy of the neighbour table: s_off[3 o .. 3 o + 2] = offset o, s_off[96 + p] = the
+// offset index scanned at position p (ordered by |dx| + |dy| + |dz|, ties by visiting order).  Call with all
+// threads of the block, then __syncthreads().
+__device__ __forceinline__ void fill_offset_table(const MapView& mv, int8_t* s_off) {
+  if (threadIdx.x < kMaxNbr * 3) s_off[threadIdx.x] = mv.off[threadIdx.x];
+  if (threadIdx.x == 0) {
+    int p = 0;
+    for (int cls = 0; cls <= 3; ++cls)
+      for (int o = 0; o < mv.n_off; ++o) {
+        const int a = abs((int)mv.off[3 * o]) + abs((int)mv.off[3 * o + 1]) + abs((int)mv.off[3 * o + 2]);
+        if (a == cls) s_off[96 + p++] = (int8_t)o;
+      }
+  }
+}
 
 // Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl() may start while its predecessor
 // on the stream is still running; pdl_wait() blocks until the predecessor has completed and its writes are
@@ -334,28 +350,31 @@ __device__ __forceinline__ void knn_thread(const MapView& mv, const int8_t* __re
     const double gz = oz < 0 ? glo_z : (oz > 0 ? ghi_z : 0.0);
     return ((gx * gx + gy * gy) + gz * gz) * lb_scale;
   };
+  // bit p of `todo` stands for offset s_off[96 + p]: positions are ordered faces, then edges, then corners, so
+  // the nearer boxes are scanned first and the radius has tightened by the time the farther ones are re-checked
   uint32_t todo = 0;
   {
     const double worst = worst_of();
-    for (int o = 0; o < n_off; ++o) {
+    for (int p = 0; p < n_off; ++p) {
+      const int o = s_off[96 + p];
       uint32_t slot = kEmpty;
       if (active & (o != centre)) slot = slot_of(o);
       if (slot != kEmpty && !(box_lb(o) > worst)) {
         s_pk[o * pk_stride] = slot;
         prefetch_l2(mv.pts + (size_t)slot * cap);
-        todo |= 1u << o;
+        todo |= 1u << p;
       }
     }
   }
 
   // (3) the surviving neighbours, four candidates per lane and iteration; a lane moves to its next voxel
-  //     (lowest set bit = visiting order) with a handful of predicated instructions, re-checking the bound
+  //     (lowest set bit = nearest class of box) with a handful of predicated instructions, re-checking the bound
   //     against the radius as it stands then
   int o = 0, j = 0, cnt = 0;
   const float4* bucket = mv.pts;
   while (__any_sync(kFull, (todo != 0) | (j < cnt))) {
     if (j >= cnt && todo != 0) {
-      o = __ffs(todo) - 1;
+      o = s_off[96 + __ffs(todo) - 1];
       todo &= todo - 1;
       cnt = box_lb(o) > worst_of() ? 0 : 1;  // real count arrives with the first chunk
       bucket = mv.pts + (size_t)s_pk[o * pk_stride] * cap;

@@ -324,10 +324,10 @@ template <int K>
 __global__ void __launch_bounds__(kKnnThreads, 8)
     k_knn(MapView mv, const double* __restrict__ q, size_t nq, int k, uint64_t* __restrict__ idx,
           double* __restrict__ d2, uint8_t* __restrict__ ok) {
-  __shared__ int8_t s_off[32 * 3];
+  __shared__ int8_t s_off[kOffBytes];
   __shared__ uint32_t s_pk_all[kMaxNbr * kKnnThreads];
   __shared__ uint32_t s_blk_all[24 * kKnnThreads];
-  if (threadIdx.x < kMaxNbr * 3) s_off[threadIdx.x] = mv.off[threadIdx.x];
+  fill_offset_table(mv, s_off);
   __syncthreads();
   uint32_t* s_pk = s_pk_all + threadIdx.x;
   uint32_t* s_blk = s_blk_all + threadIdx.x;
