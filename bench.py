@@ -159,6 +159,53 @@ def host_gn_step(L, R, t, lam):
     return R @ dR, R @ dt + t
 
 
+def knn_roofline(ctx, mg, scan, R0, t0, synth):
+    """The restricted k-NN kernel alone, "spread" regime (131 072 queries over the whole map, L2 flushed before
+    every launch) and, for context, the "local" regime (the scan's own first-iteration queries).  Returns the
+    `roofline` object of the JSON line plus the downloaded map arrays."""
+    coords, counts, _, pts, lru_counter = mg.download()
+    cloud = pts[np.arange(pts.shape[1])[None, :] < counts[:, None]]
+    q = synth.spread_queries(cloud, N_SCAN, synth.rng_for(40))
+    bytes_alg, parts = knn_algorithmic_bytes(q, coords, counts, K_NN)
+    mg.knn_stage(q, K_NN)
+    for _ in range(3):
+        ctx.flush_l2()
+        mg.knn_staged_run()
+    knn_ms = []
+    for _ in range(10):
+        ctx.flush_l2()
+        ctx.sync()
+        ctx.timer_begin()
+        mg.knn_staged_run()
+        knn_ms.append(ctx.timer_end())
+    t_knn = float(np.mean(knn_ms)) * 1e-3
+    peak, peak_src = peaks()
+    achieved = bytes_alg / t_knn / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("k_knn_dram_bytes_per_launch")
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "kernel": "k_knn (restricted 19-voxel k-NN, k=5), spread queries over the "
+            "whole map, L2 flushed before every launch", "algorithmic_bytes": int(bytes_alg),
+            "us_per_launch": t_knn * 1e6, "us_min": float(np.min(knn_ms)) * 1e3, "peak_source": peak_src,
+            "queries_per_s": N_SCAN / t_knn, **parts}
+    # local regime for context: the scan's own first-iteration queries (working set << L2)
+    q_loc = scan[:, :3].astype(np.float64) @ R0.T + t0
+    b_loc, _ = knn_algorithmic_bytes(q_loc, coords, counts, K_NN)
+    mg.knn_stage(q_loc, K_NN)
+    loc_ms = []
+    for _ in range(8):
+        ctx.flush_l2()
+        ctx.sync()
+        ctx.timer_begin()
+        mg.knn_staged_run()
+        loc_ms.append(ctx.timer_end())
+    roof["local_regime"] = {"us_per_launch": float(np.mean(loc_ms[3:])) * 1e3, "algorithmic_bytes": int(b_loc),
+                            "achieved_gbs": b_loc / (float(np.mean(loc_ms[3:])) * 1e-3) / 1e9}
+    return roof, (coords, counts, pts, lru_counter)
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle (port of the reference's ICPFactor / iVox path) on the host cores."""
     if rank != 0:
@@ -291,6 +338,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--profile-knn", action="store_true", help="only build inputs and run a few k-NN launches (for ncu)")
+    ap.add_argument("--knn-only", action="store_true", help="development: time only the k-NN kernel (roofline object)")
     ap.add_argument("--profile-icp", action="store_true", help="only build inputs and run two ICP steps (for ncu)")
     ap.add_argument("--stream", type=int, default=0, metavar="N_SCANS",
                     help="config C5: stream N_SCANS scans (upload, deskew, T_B_L, downsample, 1+6 linearize calls, "
@@ -340,6 +388,11 @@ def main():
 
     if args.stream:
         run_stream(args, ctx, mg, cfg, synth)
+        return
+
+    if args.knn_only:
+        roof, _ = knn_roofline(ctx, mg, scan, R0, t0, synth)
+        print(json.dumps({"roofline": roof}), flush=True)
         return
 
     if args.profile_knn or args.profile_icp:
@@ -452,47 +505,7 @@ def main():
     }
 
     if rank == 0 and world == 1:
-        # ---- roofline: the restricted k-NN kernel, spread regime ---------------------------------------
-        coords, counts, _, pts, lru_counter = mg.download()
-        cloud = pts[np.arange(pts.shape[1])[None, :] < counts[:, None]]
-        q = synth.spread_queries(cloud, N_SCAN, synth.rng_for(40))
-        bytes_alg, parts = knn_algorithmic_bytes(q, coords, counts, K_NN)
-        mg.knn_stage(q, K_NN)
-        for _ in range(3):
-            ctx.flush_l2()
-            mg.knn_staged_run()
-        knn_ms = []
-        for _ in range(10):
-            ctx.flush_l2()
-            ctx.sync()
-            ctx.timer_begin()
-            mg.knn_staged_run()
-            knn_ms.append(ctx.timer_end())
-        t_knn = float(np.mean(knn_ms)) * 1e-3
-        peak, peak_src = peaks()
-        achieved = bytes_alg / t_knn / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("k_knn_dram_bytes_per_launch")
-        line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": traffic, "kernel": "k_knn (restricted 19-voxel k-NN, k=5), spread queries over the "
-                            "whole map, L2 flushed before every launch", "algorithmic_bytes": int(bytes_alg),
-                            "us_per_launch": t_knn * 1e6, "us_min": float(np.min(knn_ms)) * 1e3, "peak_source": peak_src,
-                            "queries_per_s": N_SCAN / t_knn, **parts}
-        # local regime for context: the scan's own first-iteration queries (working set << L2)
-        q_loc = scan[:, :3].astype(np.float64) @ R0.T + t0
-        b_loc, _ = knn_algorithmic_bytes(q_loc, coords, counts, K_NN)
-        mg.knn_stage(q_loc, K_NN)
-        loc_ms = []
-        for _ in range(8):
-            ctx.flush_l2()
-            ctx.sync()
-            ctx.timer_begin()
-            mg.knn_staged_run()
-            loc_ms.append(ctx.timer_end())
-        line["roofline"]["local_regime"] = {"us_per_launch": float(np.mean(loc_ms[3:])) * 1e3, "algorithmic_bytes": int(b_loc),
-                                            "achieved_gbs": b_loc / (float(np.mean(loc_ms[3:])) * 1e-3) / 1e9}
+        line["roofline"], (coords, counts, pts, lru_counter) = knn_roofline(ctx, mg, scan, R0, t0, synth)
 
         # ---- cpu_baseline: the oracle on the host cores, same map + scan ----------------------------------
         if not args.no_cpu_baseline:

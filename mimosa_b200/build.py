@@ -28,7 +28,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", OUT, *srcs, "-lnccl"]
+    cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("MB_NVCC_EXTRA", "").split(), "-o", OUT, *srcs, "-lnccl"]  # MB_NVCC_EXTRA: development
     if verbose:
         cmd += ["-Xptxas", "-v"]
     env = dict(os.environ)

@@ -155,7 +155,7 @@ __device__ __forceinline__ void block_sum_rows(const double* rows, int count, in
 template <int K>
 __global__ void __launch_bounds__(kLinThreads, 5)
     k_linearize(MapView mv, FactorView fv, const double* __restrict__ pose) {
-  __shared__ int8_t s_off[kOffBytes];
+  __shared__ uint16_t s_tab[kTabEntries];
   // s_pk (phase B: probed neighbour words, [n_off][thread]) is re-used as s_row (phase C: whitened
   // [J (6), e] per point, [warp][32][7] doubles = 7168 B <= 27 * 128 * 4 B).
   __shared__ __align__(16) uint32_t s_pk_all[kMaxNbr * kLinThreads];
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kLinThreads, 5)
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   pdl_launch_dependents();
-  fill_offset_table(mv, s_off);
+  fill_scan_table(mv, s_tab);
   double(*s_row)[7] = reinterpret_cast<double(*)[7]>(s_pk_all) + warp * 32;
   // Lane a < 28 owns entry a of the packed upper triangle of [J e]^T [J e] (7x7): the 21 entries of
   // J^T J first (row-major, c >= r), then J^T e (6), then e^2.
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(kLinThreads, 5)
       double bd[K];
       uint32_t bs[K];
       uint32_t* s_pk = s_pk_all + tid;
-      knn_thread<K>(mv, s_off, s_pk, s_blk_all + tid, kLinThreads, qx, qy, qz, k, on, bd, bs);
+      knn_thread<K>(mv, s_tab, s_pk, s_blk_all + tid, kLinThreads, qx, qy, qz, k, on, bd, bs);
       if (on) {
         const size_t gi = tile * kLinThreads + li;
         int found = 0;

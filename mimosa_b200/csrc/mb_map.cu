@@ -227,7 +227,8 @@ __global__ void k_mirror_gather(const uint64_t* __restrict__ keys, const uint32_
     const int c = count[id];
     if (lane < cap) {
       float4 p = lane < c ? pts[(size_t)id * cap + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (lane == 0) p.w = __int_as_float(c);  // the fill count rides in the first point: no metadata load before it
+      // the meta word (id << 5 | count) rides in the first point: no separate metadata load in the search
+      if (lane == 0) p.w = __int_as_float((int)((id << kCountBits) | (uint32_t)c));
       r_pts[(size_t)s * cap + lane] = p;
     }
     if (lane == 0) {
@@ -321,13 +322,13 @@ constexpr int kKnnThreads = 128;
 
 // Standalone restricted k-NN: one query per thread (see knn_thread in mb_internal.cuh).
 template <int K>
-__global__ void __launch_bounds__(kKnnThreads, 8)
+__global__ void __launch_bounds__(kKnnThreads, 7)
     k_knn(MapView mv, const double* __restrict__ q, size_t nq, int k, uint64_t* __restrict__ idx,
           double* __restrict__ d2, uint8_t* __restrict__ ok) {
-  __shared__ int8_t s_off[kOffBytes];
+  __shared__ uint16_t s_tab[kTabEntries];
   __shared__ uint32_t s_pk_all[kMaxNbr * kKnnThreads];
   __shared__ uint32_t s_blk_all[24 * kKnnThreads];
-  fill_offset_table(mv, s_off);
+  fill_scan_table(mv, s_tab);
   __syncthreads();
   uint32_t* s_pk = s_pk_all + threadIdx.x;
   uint32_t* s_blk = s_blk_all + threadIdx.x;
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(kKnnThreads, 8)
   }
   double bd[K];
   uint32_t bs[K];
-  knn_thread<K>(mv, s_off, s_pk, s_blk, kKnnThreads, qx, qy, qz, k, active, bd, bs);
+  knn_thread<K>(mv, s_tab, s_pk, s_blk, kKnnThreads, qx, qy, qz, k, active, bd, bs);
   if (!active) return;
   int found = 0;
 #pragma unroll
@@ -587,32 +588,9 @@ int mb_map_create(mb_ctx* ctx, float leaf, float min_dist, int cap, int nbr_mode
   m->cap = cap;
   m->nbr_mode = nbr_mode;
   m->lru_horizon = lru_horizon;
-  int n = 0;
-  auto push = [&](int i, int j, int k) {
-    m->off[3 * n] = (int8_t)i;
-    m->off[3 * n + 1] = (int8_t)j;
-    m->off[3 * n + 2] = (int8_t)k;
-    ++n;
-  };
-  if (nbr_mode == 1) {
-    push(0, 0, 0);
-  } else if (nbr_mode == 7) {
-    push(0, 0, 0);
-    push(1, 0, 0);
-    push(-1, 0, 0);
-    push(0, 1, 0);
-    push(0, -1, 0);
-    push(0, 0, 1);
-    push(0, 0, -1);
-  } else {
-    for (int i = -1; i <= 1; ++i)
-      for (int j = -1; j <= 1; ++j)
-        for (int k = -1; k <= 1; ++k) {
-          if (nbr_mode == 19 && i != 0 && j != 0 && k != 0) continue;
-          push(i, j, k);
-        }
-  }
+  const int n = neighbor_offsets(nbr_mode, m->off);
   m->n_off = n;
+  if (const char* e = getenv("MB_KNN_PREF")) m->pref_frac = atof(e);  // development knob
   int s = map_reserve(m, 4096);
   if (s != MB_OK) {
     delete m;
@@ -656,6 +634,7 @@ int mb_map_snapshot(mb_map* m, mb_map** out) {
   s->nbr_mode = m->nbr_mode;
   s->n_off = m->n_off;
   std::memcpy(s->off, m->off, sizeof(m->off));
+  s->pref_frac = m->pref_frac;
   s->lru_horizon = m->lru_horizon;
   s->lru_counter = m->lru_counter;
   // headroom so that the insert which usually follows a snapshot (geometric.cpp:494-495) does not regrow it

@@ -28,7 +28,8 @@ struct mb_map {
   // parameters
   double leaf = 1.0, inv_leaf = 1.0, min_sq_dist = 0.0;
   int cap = 20, nbr_mode = 7, n_off = 7;
-  int8_t off[mb::kMaxNbr * 3] = {0};
+  int8_t off[mb::kMaxNbr * 3] = {0};  // neighbour offsets in the reference's visiting order
+  double pref_frac = 0.4;             // early-prefetch radius of the search, in voxels (MapView::pref2)
   uint64_t lru_horizon = 100, lru_counter = 0;
   // storage
   size_t cap_vox = 0, n_vox = 0, table_cap = 0;
@@ -64,7 +65,8 @@ struct mb_map {
     v.cap = cap;
     v.n_off = n_off;
     v.inv_leaf = inv_leaf;
-    std::memcpy(v.off, off, sizeof(off));
+    v.pref2 = pref_frac * pref_frac * leaf * leaf;
+    mb::fill_view_tables(v, off, n_off);
     return v;
   }
 };
