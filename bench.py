@@ -165,7 +165,7 @@ def knn_roofline(ctx, mg, scan, R0, t0, synth):
     `roofline` object of the JSON line plus the downloaded map arrays."""
     coords, counts, _, pts, lru_counter = mg.download()
     cloud = pts[np.arange(pts.shape[1])[None, :] < counts[:, None]]
-    q = synth.spread_queries(cloud, N_SCAN, synth.rng_for(40))
+    q = synth.spread_queries(cloud, int(os.environ.get("MB_BENCH_NQ", N_SCAN)), synth.rng_for(40))  # MB_BENCH_NQ: development
     bytes_alg, parts = knn_algorithmic_bytes(q, coords, counts, K_NN)
     mg.knn_stage(q, K_NN)
     for _ in range(3):

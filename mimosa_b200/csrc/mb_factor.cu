@@ -250,21 +250,16 @@ __global__ void __launch_bounds__(kLinThreads, 5)
       knn_thread<K>(mv, s_tab, s_pk, s_blk_all + tid, kLinThreads, qx, qy, qz, k, on, bd, bs);
       if (on) {
         const size_t gi = tile * kLinThreads + li;
-        int found = 0;
         float4 nb[K];
+        uint64_t g[K];
+        const int found = knn_resolve_all<K, true>(mv, s_pk, kLinThreads, bs, k, g, nb);
         double dk = 0.0;
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-          nb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (j < k) {
-            uint64_t g = ~0ull;
-            if (bs[j] != 0xffffffffu) {
-              g = knn_resolve(mv, s_pk, kLinThreads, bs[j], nb[j]);
-              ++found;
-            }
             if (j == k - 1) dk = bd[j];
             // indices are only meaningful when all k exist (the reference discards partial results)
-            if (fv.knn_idx) fv.knn_idx[gi * k + j] = g;
+            if (fv.knn_idx) fv.knn_idx[gi * k + j] = g[j];
           }
         }
         uint8_t rs = MB_UNPROCESSED;

@@ -344,20 +344,14 @@ __global__ void __launch_bounds__(kKnnThreads, 7)
   uint32_t bs[K];
   knn_thread<K>(mv, s_tab, s_pk, s_blk, kKnnThreads, qx, qy, qz, k, active, bd, bs);
   if (!active) return;
-  int found = 0;
+  uint64_t g[K];
+  float4 pts_unused[K];
+  const int found = knn_resolve_all<K, false>(mv, s_pk, kKnnThreads, bs, k, g, pts_unused);
 #pragma unroll
   for (int j = 0; j < K; ++j) {
     if (j < k) {
-      uint64_t g = ~0ull;
-      double d = DBL_MAX;
-      if (bs[j] != 0xffffffffu) {
-        float4 p;
-        g = knn_resolve(mv, s_pk, kKnnThreads, bs[j], p);
-        d = bd[j];
-        ++found;
-      }
-      idx[i * k + j] = g;
-      d2[i * k + j] = d;
+      idx[i * k + j] = g[j];
+      d2[i * k + j] = g[j] != ~0ull ? bd[j] : DBL_MAX;
     }
   }
   ok[i] = found == k;

@@ -141,7 +141,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // K is the compile-time list length (5 = the reference's num_corres_points, 8 = generic: the k nearest are the
 // first k of the 8 nearest).  s_pk / s_blk are this thread's columns of shared [n_off][pk_stride] /
 // [24][pk_stride] arrays; s_pk receives the bucket index of every existing neighbour (by visiting rank) and
-// stays valid for knn_resolve().
+// stays valid for knn_resolve_all().
 template <int K>
 MB_DEV void knn_thread(const MapView& mv, const uint16_t* __restrict__ s_tab, uint32_t* s_pk,
                                            uint32_t* s_blk, int pk_stride, double qx, double qy, double qz, int k,
@@ -259,6 +259,8 @@ MB_UNROLL
 MB_UNROLL
             for (int v = 0; v < 4; ++v) p0[v] = __ldg(own_bucket + min(v, cap - 1));
             prefetch_l2(own_bucket + 4);
+            if (cap > 8) prefetch_l2(own_bucket + 8);    // most buckets hold more than 8 points: do not wait for the
+            if (cap > 16) prefetch_l2(own_bucket + 16);  // count to request the later cache lines of the own bucket
           }
         }
       }
@@ -349,6 +351,9 @@ MB_UNROLL
       if (mv.rank[c] != 0xffu && !(box_lb(c / 9, (c / 3) % 3, c % 3) > wq_f)) todo |= 1u << cube_pos(c);
     }
     todo &= exist;
+#if defined(MB_KNN_SKIP_NB)  // experiment only (wrong results): cost of everything but the neighbour loop
+    todo = 0;
+#endif
     uint32_t late = todo & ~near;
     while (__any_sync(kFull, late != 0)) {
       if (late != 0) {
@@ -374,13 +379,22 @@ MB_UNROLL
     if (j >= cnt && todo != 0) {
       const uint32_t e = s_tab[__ffs(todo) - 1];
       todo &= todo - 1;
-      const int ix = (e >> 5) & 3, iy = (e >> 7) & 3, iz = (e >> 9) & 3;
       rk = e >> 11;
+#if defined(MB_KNN_RECHECK)
+      // re-check the bound against the radius as it stands now (only refreshed at drains, so rarely tighter than
+      // when `todo` was formed: measured not worth its ~45 predicated instructions per iteration)
+      const int ix = (e >> 5) & 3, iy = (e >> 7) & 3, iz = (e >> 9) & 3;
       const float lx = ix == 0 ? g2x[0] : (ix == 2 ? g2x[2] : 0.f);
       const float ly = iy == 0 ? g2y[0] : (iy == 2 ? g2y[2] : 0.f);
       const float lz = iz == 0 ? g2z[0] : (iz == 2 ? g2z[2] : 0.f);
       cnt = __fadd_rz(__fadd_rz(lx, ly), lz) > wq_f ? 0 : 1;  // real count arrives with the first chunk
+#else
+      cnt = 1;  // real count arrives with the first chunk
+#endif
       bucket = mv.pts + (size_t)s_pk[rk * pk_stride] * cap;
+#if defined(MB_KNN_FAKE_L1)  // experiment only (wrong results): what if every neighbour load hit L1?
+      bucket = own_bucket;
+#endif
       j = 0;
     }
     if (j < cnt) {
@@ -429,13 +443,34 @@ MB_UNROLL
 }
 
 // Translate a winner's sequence number into the reference's global index and the stored point.
-MB_DEV uint64_t knn_resolve(const MapView& mv, const uint32_t* s_pk, int pk_stride, uint32_t seq,
-                                                float4& p) {
-  const uint32_t o = seq >> kSeqShift, j = seq & ((1u << kSeqShift) - 1);
-  const uint32_t slot = s_pk[o * pk_stride];
-  p = __ldg(mv.pts + (size_t)slot * mv.cap + j);
-  // the bucket's meta word (voxel id << 5 | count) rides in the .w of its first point (cached by the scan)
-  const uint32_t id = (uint32_t)__float_as_int(__ldg(mv.pts + (size_t)slot * mv.cap).w) >> kCountBits;
-  return ((uint64_t)id << 32) | (uint64_t)j;
+// Translate the winners' sequence numbers into the reference's global indices ((voxel id << 32) | point id) and,
+// when kWantPts, fetch the stored points.  All loads are issued before the first use: a winner's bucket is usually
+// still in L1 / L2 from the scan, but the loads of different winners must not wait for one another.  The bucket's
+// meta word (voxel id << 5 | count) rides in the .w of its first point.  Returns how many of the first k exist.
+template <int K, bool kWantPts>
+MB_DEV int knn_resolve_all(const MapView& mv, const uint32_t* s_pk, int pk_stride, const uint32_t (&bs)[K], int k,
+                           uint64_t (&g)[K], float4 (&p)[K]) {
+  float w[K];
+  MB_UNROLL
+  for (int j = 0; j < K; ++j) {
+    w[j] = 0.f;
+    p[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < k && bs[j] != 0xffffffffu) {
+      const float4* bucket = mv.pts + (size_t)s_pk[(bs[j] >> kSeqShift) * pk_stride] * mv.cap;
+      w[j] = __ldg(&bucket->w);
+      if (kWantPts) p[j] = __ldg(bucket + (bs[j] & ((1u << kSeqShift) - 1)));
+    }
+  }
+  int found = 0;
+  MB_UNROLL
+  for (int j = 0; j < K; ++j) {
+    g[j] = ~0ull;
+    if (j < k && bs[j] != 0xffffffffu) {
+      g[j] = ((uint64_t)((uint32_t)__float_as_int(w[j]) >> kCountBits) << 32) | (uint64_t)(bs[j] & ((1u << kSeqShift) - 1));
+      ++found;
+    }
+  }
+  return found;
 }
+
 }  // namespace mb

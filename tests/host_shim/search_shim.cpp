@@ -133,18 +133,12 @@ void run(const HostMirror& M, const double* q, size_t nq, int k, uint64_t* idx, 
     std::fill(s_pk.begin(), s_pk.end(), 0xdeadbeefu);  // stale contents must never be used
     std::fill(s_blk.begin(), s_blk.end(), 0xdeadbeefu);
     mb::knn_thread<K>(M.view, s_tab, s_pk.data(), s_blk.data(), 1, q[3 * i], q[3 * i + 1], q[3 * i + 2], k, true, bd, bs);
-    int found = 0;
+    uint64_t g[K];
+    float4 pts[K];
+    const int found = mb::knn_resolve_all<K, true>(M.view, s_pk.data(), 1, bs, k, g, pts);
     for (int j = 0; j < k; ++j) {
-      uint64_t g = ~0ull;
-      double d = 1.7976931348623157e308;
-      if (bs[j] != 0xffffffffu) {
-        float4 p;
-        g = mb::knn_resolve(M.view, s_pk.data(), 1, bs[j], p);
-        d = bd[j];
-        ++found;
-      }
-      idx[i * k + j] = g;
-      d2[i * k + j] = d;
+      idx[i * k + j] = g[j];
+      d2[i * k + j] = g[j] != ~0ull ? bd[j] : 1.7976931348623157e308;
     }
     ok[i] = found == k;
   }
