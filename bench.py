@@ -338,6 +338,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--profile-knn", action="store_true", help="only build inputs and run a few k-NN launches (for ncu)")
+    ap.add_argument("--value-only", action="store_true", help="development: only the device-resident ICP loop timing")
     ap.add_argument("--knn-only", action="store_true", help="development: time only the k-NN kernel (roofline object)")
     ap.add_argument("--profile-icp", action="store_true", help="only build inputs and run two ICP steps (for ncu)")
     ap.add_argument("--stream", type=int, default=0, metavar="N_SCANS",
@@ -427,6 +428,10 @@ def main():
 
     for _ in range(args.warmup):
         dev_step()
+    if args.value_only:
+        ms = [dev_step()[0] for _ in range(args.steps)]
+        print(json.dumps({"value_only_ms_per_step": float(np.mean(ms)), "min": float(np.min(ms))}), flush=True)
+        return
     launches0 = ctx.launch_count()
     flush_launches = 0
     with ClockSampler(local_rank) as clocks:
@@ -439,23 +444,35 @@ def main():
         ctx.sync()
         barrier()
         # ---- e2e: reference-facing calls with host buffers -------------------------------------------------
+        # One call of the C++ caller (mimosa_b200/host/e2e_caller.cpp) per step: ICPFactor(host scan) [H2D], then
+        # 20 x { mb_factor_linearize(host pose) -> host H, g, f [D2H] ; mb_gn_step on the host }, timed on the host
+        # around the whole sequence, including the final synchronisation.
+        import ctypes as C
+
+        from mimosa_b200.build import E2E_OUT
+
+        e2e_lib = C.CDLL(E2E_OUT)
+        e2e_lib.mb_e2e_scan.restype = C.c_int
+        scan_h = np.ascontiguousarray(scan, dtype=np.float32)
+        cfg_c = cfg.to_c()
+        R0c = np.ascontiguousarray(R0, np.float64).reshape(9)
+        t0c = np.ascontiguousarray(t0, np.float64).reshape(3)
+        Re, te, secs = np.zeros(9), np.zeros(3), C.c_double()
         e2e_secs = []
-        lin_bytes = 0
         for s in range(args.warmup + args.steps):
             ctx.flush_l2()
             ctx.sync()
             barrier()
-            t_a = time.perf_counter()
-            fe = ICPFactor(ctx, mg, scan, cfg, shard)  # H2D: this rank's block of the scan
-            Re, te = R0, t0
-            for _ in range(ITERS):
-                L = fe.linearize(Re, te)  # H2D pose, D2H normal equations
-                Re, te, _, _ = gn_step(L, Re, te, LAMBDA)  # host-side 6x6 solve + retract (mb_gn_step)
-            ctx.sync()
-            t_b = time.perf_counter()
-            fe.release()
+            rc = e2e_lib.mb_e2e_scan(ctx.h, mg.h, scan_h.ctypes.data_as(C.c_void_p), C.c_size_t(scan_h.shape[0]),
+                                     C.c_size_t(scan_h.strides[0]), C.byref(cfg_c), C.c_size_t(shard[0]), C.c_size_t(shard[1]),
+                                     R0c.ctypes.data_as(C.c_void_p), t0c.ctypes.data_as(C.c_void_p), C.c_int(ITERS),
+                                     C.c_double(LAMBDA), Re.ctypes.data_as(C.c_void_p), te.ctypes.data_as(C.c_void_p),
+                                     C.byref(secs))
+            if rc != 0:
+                raise RuntimeError(f"mb_e2e_scan failed: {rc}")
             if s >= args.warmup:
-                e2e_secs.append(t_b - t_a)
+                e2e_secs.append(secs.value)
+        e2e_pose_err = float(np.abs(te - t_true).max())
     launches = ctx.launch_count() - launches0
 
     # diagnostic (stderr only): marginal device time of a converged, fully cached iteration
@@ -499,7 +516,8 @@ def main():
                    "cuda_graph": not args.no_graph, "final_pose_err_m": pose_err},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_total / args.steps,
-                "what": "mb_factor_create(host scan) + 20 x [mb_factor_linearize(host pose) -> host H,g,f + host 6x6 solve/retract]"},
+                "what": "C++ caller over the C ABI (host/e2e_caller.cpp): mb_factor_create(host scan) + 20 x [mb_factor_linearize("
+                        "host pose) -> host H,g,f + mb_gn_step on the host], host clock", "final_pose_err_m": e2e_pose_err},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
     }

@@ -40,7 +40,23 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building libmimosa_b200.so")
     if verbose:
         sys.stderr.write(r.stderr)
+    build_e2e_caller()
     return OUT
+
+
+E2E_OUT = os.path.join(HERE, "lib", "libmb_e2e_caller.so")
+
+
+def build_e2e_caller() -> str:
+    """host/e2e_caller.cpp -> lib/libmb_e2e_caller.so: plain C++ over the C ABI (bench.py's e2e loop)."""
+    src = os.path.join(HERE, "host", "e2e_caller.cpp")
+    lib_dir = os.path.dirname(OUT)
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", src, "-L", lib_dir, "-lmimosa_b200", "-Wl,-rpath,$ORIGIN", "-o", E2E_OUT]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building libmb_e2e_caller.so")
+    return E2E_OUT
 
 
 if __name__ == "__main__":

@@ -118,6 +118,7 @@ int mb_init(int device, mb_ctx** out) {
   MB_CUDA(cudaEventCreate(&c->ev0));
   MB_CUDA(cudaEventCreate(&c->ev1));
   MB_CUDA(cudaMallocHost(&c->pin_small, 4096));
+  std::memset(c->pin_small, 0, 4096);
   *out = c;
   return MB_OK;
 }

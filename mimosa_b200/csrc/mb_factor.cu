@@ -23,6 +23,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <type_traits>
+
 #include "mb_map.cuh"
 #include "mb_scan.cuh"
 
@@ -53,6 +55,20 @@ struct FactorView {
   double* partials2;   // [grid2][8]
   unsigned* ticket2;
   double* loc_out;     // [8]: trans comp (3), rot comp (3)
+};
+
+// Pose handed to k_linearize BY VALUE (kernel parameter space) on the host-facing single-call path: no H2D copy
+// is enqueued for 15 doubles.
+struct PoseArg {
+  double v[16];  // R (9), t (3), gravity (3), lambda
+};
+
+// Where the last block of k_loc_comp leaves the finished linearisation for the host (mapped page-locked
+// memory; out == nullptr: nothing is written).  The host polls `flag` for `seq` instead of synchronising the stream.
+struct HostOut {
+  unsigned long long* out;  // sizeof(mb_linearization) / 8 words, then the six component localizabilities
+  volatile unsigned* flag;
+  unsigned seq;
 };
 
 struct DevState {        // small device-resident block per factor
@@ -152,9 +168,14 @@ __device__ __forceinline__ void block_sum_rows(const double* rows, int count, in
   }
 }
 
-template <int K>
-__global__ void __launch_bounds__(kLinThreads, 5)
-    k_linearize(MapView mv, FactorView fv, const double* __restrict__ pose) {
+#ifndef MB_LIN_BLOCKS
+#define MB_LIN_BLOCKS 4  // measured: 4 x 128 threads at 128 registers (no spills) beat 5 x 96 and 3 x 156
+#endif
+// PoseT = PoseArg: host-facing single call (pose in the kernel parameters); PoseT = NoPose: device-resident loop.
+struct NoPose {};
+template <int K, typename PoseT>
+__global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
+    k_linearize(MapView mv, FactorView fv, double* pose_dev, PoseT pa) {
   __shared__ uint16_t s_tab[kTabEntries];
   // s_pk (phase B: probed neighbour words, [n_off][thread]) is re-used as s_row (phase C: whitened
   // [J (6), e] per point, [warp][32][7] doubles = 7168 B <= 27 * 128 * 4 B).
@@ -198,8 +219,17 @@ __global__ void __launch_bounds__(kLinThreads, 5)
   pdl_wait();
   m33 R;
 #pragma unroll
-  for (int a = 0; a < 9; ++a) R.m[a] = pose[a];
-  const d3 T = mk3(pose[9], pose[10], pose[11]);
+  d3 T;
+  if constexpr (std::is_same<PoseT, PoseArg>::value) {
+    if (blockIdx.x == 0 && tid < 16) pose_dev[tid] = pa.v[tid];  // k_finalize reads pose / gravity / lambda there
+#pragma unroll
+    for (int a = 0; a < 9; ++a) R.m[a] = pa.v[a];
+    T = mk3(pa.v[9], pa.v[10], pa.v[11]);
+  } else {
+#pragma unroll
+    for (int a = 0; a < 9; ++a) R.m[a] = pose_dev[a];
+    T = mk3(pose_dev[9], pose_dev[10], pose_dev[11]);
+  }
   const int k = fv.k;
   const bool forced = (fv.flags & 1u) != 0;
 
@@ -534,7 +564,8 @@ __global__ void __launch_bounds__(160) k_finalize(const double* __restrict__ pac
 
 // Component localizabilities (geometric_factor.hpp:434-457): sum over Valid points of |loc_i^T V| with
 // entries below 0.5 zeroed.
-__global__ void __launch_bounds__(kLocThreads) k_loc_comp(FactorView fv, const DevState* __restrict__ ds) {
+template <bool kHostOut>
+__global__ void __launch_bounds__(kLocThreads) k_loc_comp(FactorView fv, const DevState* __restrict__ ds, HostOut ho) {
   __shared__ double s_red[kLocThreads / 32][8];
   __shared__ double s_tmp[(kLocThreads / 8) * 8];
   __shared__ bool s_last;
@@ -579,6 +610,16 @@ __global__ void __launch_bounds__(kLocThreads) k_loc_comp(FactorView fv, const D
   __threadfence();
   block_sum_rows(fv.partials2, (int)gridDim.x, 8, s_tmp, fv.loc_out, kLocThreads);
   if (threadIdx.x == 0) *fv.ticket2 = 0u;
+  if (kHostOut) {  // hand the finished linearisation to the polling host
+    __syncthreads();
+    constexpr int kWords = (int)(sizeof(mb_linearization) / 8);
+    const unsigned long long* lin = reinterpret_cast<const unsigned long long*>(&ds->lin);
+    for (int w = threadIdx.x; w < kWords; w += kLocThreads) ho.out[w] = lin[w];
+    if (threadIdx.x < 6) ho.out[kWords + threadIdx.x] = (unsigned long long)__double_as_longlong(fv.loc_out[threadIdx.x]);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) *ho.flag = ho.seq;
+  }
 }
 
 // device scan records -> float4 source points of the factor (xyz only), zero padded to ld
@@ -674,18 +715,32 @@ int reset_state(mb_factor* f) {
 }
 
 // Enqueue one linearisation (+ optional GN step) on the context stream.
-int enqueue_linearize(mb_factor* f, int do_step, int iter, mb_icp_trace* d_trace, int linearize_count) {
+int enqueue_linearize(mb_factor* f, int do_step, int iter, mb_icp_trace* d_trace, int linearize_count,
+                      const PoseArg* pose_arg = nullptr, const HostOut* host_out = nullptr) {
   mb_ctx* c = f->ctx;
   cudaStream_t st = c->stream;
   const FactorView fv = f->view();
-  if (fv.k == 5)
-    MB_CUDA(launch_pdl(k_linearize<5>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (const double*)f->ds->pose));
-  else
-    MB_CUDA(launch_pdl(k_linearize<MB_MAX_K>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (const double*)f->ds->pose));
+  if (pose_arg) {
+    if (fv.k == 5)
+      MB_CUDA(launch_pdl(k_linearize<5, PoseArg>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, *pose_arg));
+    else
+      MB_CUDA(launch_pdl(k_linearize<MB_MAX_K, PoseArg>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, *pose_arg));
+  } else {
+    if (fv.k == 5)
+      MB_CUDA(launch_pdl(k_linearize<5, NoPose>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, NoPose{}));
+    else
+      MB_CUDA(launch_pdl(k_linearize<MB_MAX_K, NoPose>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, NoPose{}));
+  }
   if (c->world > 1) MB_NCCL(ncclAllReduce(f->packed, f->packed, kPack, ncclDouble, ncclSum, c->comm, st));
   MB_CUDA(launch_pdl(k_finalize, dim3(1), dim3(160), st, (const double*)f->packed, f->ds, (int)f->cfg.reg_4_dof,
                      linearize_count, do_step, iter, d_trace, 31u));
-  MB_CUDA(launch_pdl(k_loc_comp, dim3(f->grid2), dim3(kLocThreads), st, fv, (const DevState*)f->ds));
+  if (host_out) {
+    MB_CUDA(launch_pdl(k_loc_comp<true>, dim3(f->grid2), dim3(kLocThreads), st, fv, (const DevState*)f->ds, *host_out));
+  } else {
+    HostOut none;
+    none.out = nullptr, none.flag = nullptr, none.seq = 0;
+    MB_CUDA(launch_pdl(k_loc_comp<false>, dim3(f->grid2), dim3(kLocThreads), st, fv, (const DevState*)f->ds, none));
+  }
   // The cross-rank sum of the six component localizabilities is only needed when they are handed out
   // (mb_factor_linearize): the harness loop never returns them, so it does not pay a second all-reduce per
   // iteration for a value nobody reads.  Every rank still computes its own share each iteration.
@@ -747,9 +802,9 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
   const size_t n_tiles = (f->n + kLinThreads - 1) / kLinThreads;
   int per_sm = 4;
   if (k == 5)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<5>, kLinThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<5, NoPose>, kLinThreads, 0);
   else
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<MB_MAX_K>, kLinThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<MB_MAX_K, NoPose>, kLinThreads, 0);
   per_sm = std::max(per_sm, 1);
   f->grid = (int)std::max<size_t>(1, std::min<size_t>(n_tiles, (size_t)ctx->sm_count * per_sm));
   f->n_groups = (f->grid + kGroup - 1) / kGroup;
@@ -841,14 +896,17 @@ MB_API int mb_debug_time_finalize(mb_factor* f, unsigned role_mask, int reps, fl
   const FactorView fv = f->view();
   // role_mask < 32: k_finalize with those roles; 32: k_linearize at the current pose (fully cached after one
   // call); 64: k_loc_comp.  Plain launches, back to back.
+  const NoPose no_pose{};
+  HostOut no_out;
+  no_out.out = nullptr, no_out.flag = nullptr, no_out.seq = 0;
   auto one = [&]() {
     if (role_mask == 32u) {
       if (fv.k == 5)
-        k_linearize<5><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds->pose);
+        k_linearize<5, NoPose><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds->pose, no_pose);
       else
-        k_linearize<MB_MAX_K><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds->pose);
+        k_linearize<MB_MAX_K, NoPose><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds->pose, no_pose);
     } else if (role_mask == 64u) {
-      k_loc_comp<<<f->grid2, kLocThreads, 0, st>>>(fv, f->ds);
+      k_loc_comp<false><<<f->grid2, kLocThreads, 0, st>>>(fv, f->ds, no_out);
     } else {
       k_finalize<<<1, 160, 0, st>>>(f->packed, f->ds, f->cfg.reg_4_dof, 0, 0, 0, nullptr, role_mask);
     }
@@ -894,20 +952,50 @@ int mb_factor_linearize(mb_factor* f, const double R[9], const double t[3], cons
   MB_REQUIRE(f && R && t && gravity_unit && out, "null argument");
   MB_CUDA(cudaSetDevice(f->ctx->device));
   cudaStream_t st = f->ctx->stream;
-  // page-locked staging: [pose 12 | gravity 3] in, [mb_linearization | loc 6] out
+  // page-locked, device-mapped staging: [pose 12 | gravity 3] in at 0, [mb_linearization | loc 6] out at 256,
+  // completion flag at 2048
   double* hin = (double*)f->ctx->pin_small;
   char* hout = (char*)f->ctx->pin_small + 256;
-  static_assert(256 + sizeof(mb_linearization) + 6 * sizeof(double) <= 4096, "pin_small too small");
-  std::memcpy(hin, R, 9 * sizeof(double));
-  std::memcpy(hin + 9, t, 3 * sizeof(double));
-  std::memcpy(hin + 12, gravity_unit, 3 * sizeof(double));
-  MB_CUDA(cudaMemcpyAsync(f->ds->pose, hin, 15 * sizeof(double), cudaMemcpyHostToDevice, st));
+  static_assert(256 + sizeof(mb_linearization) + 6 * sizeof(double) <= 2048, "pin_small too small");
+  static_assert(sizeof(mb_linearization) % 8 == 0, "mb_linearization is copied as 8-byte words");
   ++f->linearize_count;
-  MB_TRY(enqueue_linearize(f, 0, 0, nullptr, f->linearize_count));
-  MB_CUDA(cudaMemcpyAsync(hout, &f->ds->lin, sizeof(mb_linearization), cudaMemcpyDeviceToHost, st));
-  MB_CUDA(cudaMemcpyAsync(hout + sizeof(mb_linearization), f->packed + kPack, 6 * sizeof(double),
-                          cudaMemcpyDeviceToHost, st));
-  MB_CUDA(cudaStreamSynchronize(st));
+  if (f->ctx->world == 1) {
+    // Single GPU: the pose travels in the kernel parameters, the last block of k_loc_comp writes the result
+    // straight into mapped host memory and raises a flag the host polls — no copy operation and no stream
+    // synchronisation on the per-iteration path (each costs several microseconds of a ~50 us call).
+    PoseArg pa;
+    std::memcpy(pa.v, R, 9 * sizeof(double));
+    std::memcpy(pa.v + 9, t, 3 * sizeof(double));
+    std::memcpy(pa.v + 12, gravity_unit, 3 * sizeof(double));
+    pa.v[15] = 0.0;
+    HostOut ho;
+    ho.out = (unsigned long long*)hout;
+    ho.flag = (volatile unsigned*)((char*)f->ctx->pin_small + 2048);
+    ho.seq = ++f->ctx->host_seq;
+    if (ho.seq == 0) ho.seq = ++f->ctx->host_seq;
+    MB_TRY(enqueue_linearize(f, 0, 0, nullptr, f->linearize_count, &pa, &ho));
+    unsigned spins = 0;
+    while (__atomic_load_n((const unsigned*)ho.flag, __ATOMIC_ACQUIRE) != ho.seq) {
+      if ((++spins & 0x3fffu) == 0) {  // every ~16k polls make sure the stream is still healthy
+        const cudaError_t q = cudaStreamQuery(st);
+        if (q == cudaSuccess) break;
+        if (q != cudaErrorNotReady) MB_CUDA(q);
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+  } else {
+    std::memcpy(hin, R, 9 * sizeof(double));
+    std::memcpy(hin + 9, t, 3 * sizeof(double));
+    std::memcpy(hin + 12, gravity_unit, 3 * sizeof(double));
+    MB_CUDA(cudaMemcpyAsync(f->ds->pose, hin, 15 * sizeof(double), cudaMemcpyHostToDevice, st));
+    MB_TRY(enqueue_linearize(f, 0, 0, nullptr, f->linearize_count));
+    MB_CUDA(cudaMemcpyAsync(hout, &f->ds->lin, sizeof(mb_linearization), cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaMemcpyAsync(hout + sizeof(mb_linearization), f->packed + kPack, 6 * sizeof(double),
+                            cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+  }
   std::memcpy(out, hout, sizeof(mb_linearization));
   const double* loc = (const double*)(hout + sizeof(mb_linearization));
   for (int a = 0; a < 3; ++a) {

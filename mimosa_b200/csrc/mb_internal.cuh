@@ -63,7 +63,8 @@ struct mb_ctx {
   size_t flush_bytes = 0;
   void* pinned = nullptr;  // page-locked staging for host <-> device copies of scans
   size_t pinned_bytes = 0;
-  void* pin_small = nullptr;  // 4 KiB page-locked block for poses in / normal equations out
+  void* pin_small = nullptr;  // 4 KiB page-locked (device-mapped) block for poses in / normal equations out / flag
+  unsigned host_seq = 0;      // sequence number of the last host-polled completion (mb_factor_linearize)
   // Size-keyed cache of released device blocks: a factor is created and destroyed for every scan with the
   // same sizes, and cudaMalloc/cudaFree would otherwise dominate the per-scan host cost.
   struct Block {
