@@ -376,6 +376,11 @@ def main():
             uid = torch.frombuffer(bytearray(ctx.comm_unique_id()), dtype=torch.uint8).clone()
         dist.broadcast(uid, src=0)
         ctx.comm_init(rank, world, bytes(uid.numpy().tobytes()))
+        if not os.environ.get("MB_BENCH_NCCL"):  # default: packets travel through peer memory, not ncclAllReduce
+            mine = torch.frombuffer(bytearray(ctx.comm_ipc_handle()), dtype=torch.uint8).clone()
+            every = [torch.zeros(64, dtype=torch.uint8) for _ in range(world)]
+            dist.all_gather(every, mine)
+            ctx.comm_ipc_open(b"".join(bytes(h.numpy().tobytes()) for h in every))
 
     # ---- inputs (every rank builds the identical replicated map) -----------------------------------------
     t_setup = time.time()
@@ -510,8 +515,10 @@ def main():
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "iters_per_step": ITERS, "map_points": n_pts, "map_voxels": n_vox,
-                   "scan_points": int(scan.shape[0]), "parallelism": f"scan-block shard x{world}, map replicated, "
-                   "40-double NCCL allreduce/iter" if world > 1 else "1 GPU",
+                   "scan_points": int(scan.shape[0]), "parallelism": (f"scan-block shard x{world}, map replicated, 40-double packet per iteration "
+                                   + ("all-reduced with NCCL" if os.environ.get("MB_BENCH_NCCL") else
+                                      "exchanged through peer memory (NVLink stores + flags), summed in rank order"))
+                   if world > 1 else "1 GPU",
                    "l2": "flushed (256 MiB write) before every timed step, outside the event bracket",
                    "cuda_graph": not args.no_graph, "final_pose_err_m": pose_err},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

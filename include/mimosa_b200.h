@@ -155,6 +155,13 @@ MB_API int mb_flush_l2(mb_ctx* ctx, size_t bytes);
  * (torch.distributed / MPI / anything) and every rank calls mb_comm_init. */
 MB_API int mb_comm_unique_id(void* id128);
 MB_API int mb_comm_init(mb_ctx* ctx, int rank, int world, const void* id128);
+/* Optional, single node: exchange the per-iteration packet through peer memory (NVLink / NVSwitch) instead of an
+ * NCCL all-reduce.  After mb_comm_init every rank calls mb_comm_ipc_handle (64-byte CUDA IPC handle of its
+ * mailbox), the caller all-gathers the handles in rank order, and every rank calls mb_comm_ipc_open with all
+ * `world` handles.  From then on the last block of the linearisation kernel stores its packet into every rank's
+ * mailbox and the post-reduction kernel sums the mailbox in rank order — no collective call on that path. */
+MB_API int mb_comm_ipc_handle(mb_ctx* ctx, void* handle64);
+MB_API int mb_comm_ipc_open(mb_ctx* ctx, const void* handles /* world x 64 bytes */);
 
 /* ---- map: mimosa::lidar::IncrementalVoxelMapPCL over gtsam_points::iVox ------------------------------
  * mb_map_create   <- IncrementalVoxelMapPCL(leaf) + set_lru_horizon + set_neighbor_voxel_mode +

@@ -128,6 +128,10 @@ int mb_shutdown(mb_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->comm) ncclCommDestroy(c->comm);
+  for (int r = 0; r < kMaxRanks; ++r)
+    if (c->xchg_peer[r]) cudaIpcCloseMemHandle(c->xchg_peer[r]);
+  if (c->d_peer) cudaFree(c->d_peer);
+  if (c->xchg_block) cudaFree(c->xchg_block);
   cudaFree(c->flush_buf);
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->pin_small) cudaFreeHost(c->pin_small);
@@ -214,6 +218,47 @@ int mb_comm_unique_id(void* id128) {
   ncclUniqueId id;
   MB_NCCL(ncclGetUniqueId(&id));
   std::memcpy(id128, &id, sizeof(id));
+  return MB_OK;
+}
+
+int mb_comm_ipc_handle(mb_ctx* c, void* handle64) {
+  MB_REQUIRE(c && handle64, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
+  MB_CUDA(cudaSetDevice(c->device));
+  if (!c->xchg_block) {
+    MB_CUDA(cudaMalloc(&c->xchg_block, kXchgBlockBytes));  // its own allocation: IPC handles cover whole allocations
+    MB_CUDA(cudaMemset(c->xchg_block, 0, kXchgBlockBytes));
+    MB_CUDA(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  MB_CUDA(cudaIpcGetMemHandle(&h, c->xchg_block));
+  std::memcpy(handle64, &h, sizeof(h));
+  return MB_OK;
+}
+
+int mb_comm_ipc_open(mb_ctx* c, const void* handles) {
+  MB_REQUIRE(c && handles, "null argument");
+  MB_REQUIRE(c->world > 1 && c->world <= kMaxRanks, "mb_comm_init with 2..8 ranks first");
+  MB_REQUIRE(c->xchg_block, "call mb_comm_ipc_handle first");
+  MB_CUDA(cudaSetDevice(c->device));
+  PeerTable t;
+  std::memset(&t, 0, sizeof(t));
+  t.world = c->world;
+  t.rank = c->rank;
+  for (int r = 0; r < c->world; ++r) {
+    void* base = c->xchg_block;
+    if (r != c->rank) {
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, (const char*)handles + 64 * (size_t)r, sizeof(h));
+      if (!c->xchg_peer[r]) MB_CUDA(cudaIpcOpenMemHandle(&c->xchg_peer[r], h, cudaIpcMemLazyEnablePeerAccess));
+      base = c->xchg_peer[r];
+    }
+    t.mbox[r] = (double*)base;
+    t.flag[r] = (unsigned long long*)((char*)base + kXchgMboxBytes);
+  }
+  t.xseq = (unsigned long long*)((char*)c->xchg_block + kXchgMboxBytes + kXchgFlagBytes);
+  if (!c->d_peer) MB_CUDA(cudaMalloc((void**)&c->d_peer, sizeof(PeerTable)));
+  MB_CUDA(cudaMemcpy(c->d_peer, &t, sizeof(t), cudaMemcpyHostToDevice));
   return MB_OK;
 }
 

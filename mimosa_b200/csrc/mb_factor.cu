@@ -173,9 +173,18 @@ __device__ __forceinline__ void block_sum_rows(const double* rows, int count, in
 #endif
 // PoseT = PoseArg: host-facing single call (pose in the kernel parameters); PoseT = NoPose: device-resident loop.
 struct NoPose {};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 template <int K, typename PoseT>
 __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
-    k_linearize(MapView mv, FactorView fv, double* pose_dev, PoseT pa) {
+    k_linearize(MapView mv, FactorView fv, double* pose_dev, PoseT pa, const PeerTable* __restrict__ peer) {
   __shared__ uint16_t s_tab[kTabEntries];
   // s_pk (phase B: probed neighbour words, [n_off][thread]) is re-used as s_row (phase C: whitened
   // [J (6), e] per point, [warp][32][7] doubles = 7168 B <= 27 * 128 * 4 B).
@@ -415,6 +424,21 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
   __threadfence();
   block_sum_rows(fv.gpartials, n_groups, kPack, s_tmp, fv.packed, kLinThreads);
   if (tid == 0) *fv.ticket = 0u;
+  if (peer) {
+    // Several ranks: this rank's packet goes straight into every rank's mailbox (peer stores over NVLink),
+    // then the flags are raised — k_finalize on each rank sums the mailbox in rank order (mb_internal.cuh).
+    __syncthreads();  // the packet written by this block's first kPack threads is visible to all of them
+    const int world = peer->world, rank = peer->rank;
+    const unsigned long long seq = *peer->xseq + 1ull;
+    const size_t slot = (size_t)((seq & 1ull) * kMaxRanks + (unsigned)rank);
+    for (int x = tid; x < world * kPack; x += kLinThreads) {
+      const int dst = x / kPack, e = x - dst * kPack;
+      peer->mbox[dst][slot * kXchgDoubles + e] = fv.packed[e];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < world) st_release_sys(peer->flag[tid] + slot, seq);
+  }
 }
 
 // computeLocalizability (mimosa/include/mimosa/utils.hpp:308-313).  The closed-form solver (checked a posteriori,
@@ -430,14 +454,41 @@ __device__ __forceinline__ void localizability(const m33& JtJ, double loc[3], m3
 // Everything after the per-point loop of ICPFactor::linearize, plus the harness GN step.  Lane 0 of warp w
 // plays role w: 0/1 localizability of the rotational / translational block, 2/3 Schur-complement degeneracy
 // info, 4 projection + packing + solve + retract.
-__global__ void __launch_bounds__(160) k_finalize(const double* __restrict__ packed, DevState* ds, int reg_4_dof,
+__global__ void __launch_bounds__(160) k_finalize(const double* packed_in, DevState* ds, int reg_4_dof,
                                                   int linearize_count, int do_step, int iter, mb_icp_trace* trace,
-                                                  unsigned role_mask) {
+                                                  unsigned role_mask, const PeerTable* __restrict__ peer,
+                                                  double* packed_out) {
+  __shared__ double s_packed[kXchgDoubles];
   pdl_launch_dependents();
+  const double* packed = packed_in;
+  if (peer) {
+    // wait for every rank's packet of this exchange, add them in rank order (identical on every rank)
+    pdl_wait();
+    const int world = peer->world, rank = peer->rank;
+    const unsigned long long seq = *peer->xseq + 1ull;
+    const size_t base = (size_t)((seq & 1ull) * kMaxRanks);
+    if ((int)threadIdx.x < world) {
+      const unsigned long long* fl = peer->flag[rank] + base + threadIdx.x;
+      while (ld_acquire_sys(fl) != seq) {
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x < kPack) {
+      const double* mb = peer->mbox[rank] + base * kXchgDoubles + threadIdx.x;
+      double v = 0.0;
+      for (int r = 0; r < world; ++r) v += __ldcg(mb + (size_t)r * kXchgDoubles);
+      s_packed[threadIdx.x] = v;
+      packed_out[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *peer->xseq = seq;
+    packed = s_packed;
+  }
   if ((threadIdx.x & 31) != 0) return;
   const int role = threadIdx.x >> 5;
   if (((role_mask >> role) & 1u) == 0) return;  // role_mask != 31 only in the timing diagnostic
-  pdl_wait();
+  if (!peer) pdl_wait();
   double H[36];
   {
     int u = 0;
@@ -720,20 +771,21 @@ int enqueue_linearize(mb_factor* f, int do_step, int iter, mb_icp_trace* d_trace
   mb_ctx* c = f->ctx;
   cudaStream_t st = c->stream;
   const FactorView fv = f->view();
+  const PeerTable* peer = c->world > 1 ? c->d_peer : nullptr;  // nullptr: single rank, or NCCL all-reduce
   if (pose_arg) {
     if (fv.k == 5)
-      MB_CUDA(launch_pdl(k_linearize<5, PoseArg>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, *pose_arg));
+      MB_CUDA(launch_pdl(k_linearize<5, PoseArg>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, *pose_arg, peer));
     else
-      MB_CUDA(launch_pdl(k_linearize<MB_MAX_K, PoseArg>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, *pose_arg));
+      MB_CUDA(launch_pdl(k_linearize<MB_MAX_K, PoseArg>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, *pose_arg, peer));
   } else {
     if (fv.k == 5)
-      MB_CUDA(launch_pdl(k_linearize<5, NoPose>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, NoPose{}));
+      MB_CUDA(launch_pdl(k_linearize<5, NoPose>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, NoPose{}, peer));
     else
-      MB_CUDA(launch_pdl(k_linearize<MB_MAX_K, NoPose>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, NoPose{}));
+      MB_CUDA(launch_pdl(k_linearize<MB_MAX_K, NoPose>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, NoPose{}, peer));
   }
-  if (c->world > 1) MB_NCCL(ncclAllReduce(f->packed, f->packed, kPack, ncclDouble, ncclSum, c->comm, st));
+  if (c->world > 1 && !peer) MB_NCCL(ncclAllReduce(f->packed, f->packed, kPack, ncclDouble, ncclSum, c->comm, st));
   MB_CUDA(launch_pdl(k_finalize, dim3(1), dim3(160), st, (const double*)f->packed, f->ds, (int)f->cfg.reg_4_dof,
-                     linearize_count, do_step, iter, d_trace, 31u));
+                     linearize_count, do_step, iter, d_trace, 31u, peer, f->packed));
   if (host_out) {
     MB_CUDA(launch_pdl(k_loc_comp<true>, dim3(f->grid2), dim3(kLocThreads), st, fv, (const DevState*)f->ds, *host_out));
   } else {
@@ -902,13 +954,13 @@ MB_API int mb_debug_time_finalize(mb_factor* f, unsigned role_mask, int reps, fl
   auto one = [&]() {
     if (role_mask == 32u) {
       if (fv.k == 5)
-        k_linearize<5, NoPose><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds->pose, no_pose);
+        k_linearize<5, NoPose><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds->pose, no_pose, nullptr);
       else
-        k_linearize<MB_MAX_K, NoPose><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds->pose, no_pose);
+        k_linearize<MB_MAX_K, NoPose><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds->pose, no_pose, nullptr);
     } else if (role_mask == 64u) {
       k_loc_comp<false><<<f->grid2, kLocThreads, 0, st>>>(fv, f->ds, no_out);
     } else {
-      k_finalize<<<1, 160, 0, st>>>(f->packed, f->ds, f->cfg.reg_4_dof, 0, 0, 0, nullptr, role_mask);
+      k_finalize<<<1, 160, 0, st>>>(f->packed, f->ds, f->cfg.reg_4_dof, 0, 0, 0, nullptr, role_mask, nullptr, f->packed);
     }
   };
   for (int w = 0; w < 3; ++w) one();

@@ -50,6 +50,30 @@ void set_error(const char* fmt, ...);
 
 }  // namespace mb
 
+namespace mb {
+// ---- peer-memory exchange of the per-iteration packet (single node, NVLink / NVSwitch) -----------------
+// Every rank owns one small cudaMalloc'd block, exported to the other ranks with cudaIpcGetMemHandle:
+//   mailbox  double[2 parity][kMaxRanks source][kXchgDoubles]   the packets of all ranks for one exchange
+//   flags    u64   [2 parity][kMaxRanks source]                 exchange number the packet belongs to
+//   xseq     u64                                                number of exchanges this rank has completed
+// The last block of k_linearize STORES its packet straight into every rank's mailbox (peer stores over NVLink)
+// and then raises the flags (release, system scope); k_finalize polls its OWN flags (local memory), adds the
+// packets in rank order — bit-identical on every rank — and proceeds.  No collective call, no extra kernel,
+// and the transfer overlaps the tail of the reduction.  Two parities: a fast rank may already write exchange
+// n + 1 while a slow one still reads exchange n; it cannot reach n + 2 before every rank has consumed n.
+constexpr int kMaxRanks = 8;
+constexpr int kXchgDoubles = 48;
+struct PeerTable {
+  int world, rank;
+  double* mbox[kMaxRanks];
+  unsigned long long* flag[kMaxRanks];
+  unsigned long long* xseq;
+};
+constexpr size_t kXchgMboxBytes = 2 * kMaxRanks * kXchgDoubles * sizeof(double);
+constexpr size_t kXchgFlagBytes = 2 * kMaxRanks * sizeof(unsigned long long);
+constexpr size_t kXchgBlockBytes = 8192;
+}  // namespace mb
+
 // ---- handles ----------------------------------------------------------------------------------------
 struct mb_ctx {
   int device = 0;
@@ -59,6 +83,9 @@ struct mb_ctx {
   uint64_t launches = 0;
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
+  void* xchg_block = nullptr;           // this rank's mailbox / flags / counter (cudaMalloc, IPC-exported)
+  void* xchg_peer[mb::kMaxRanks] = {};  // the other ranks' blocks, opened with cudaIpcOpenMemHandle
+  mb::PeerTable* d_peer = nullptr;      // device copy of the table the kernels read; nullptr = use NCCL
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
   void* pinned = nullptr;  // page-locked staging for host <-> device copies of scans

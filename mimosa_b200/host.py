@@ -131,6 +131,17 @@ class Context:
         check(self.lib.mb_comm_init(self.h, rank, world, buf))
         self.rank, self.world = rank, world
 
+    def comm_ipc_handle(self) -> bytes:
+        """64-byte CUDA IPC handle of this rank's packet mailbox (peer-memory exchange, single node)."""
+        buf = C.create_string_buffer(64)
+        check(self.lib.mb_comm_ipc_handle(self.h, buf))
+        return buf.raw
+
+    def comm_ipc_open(self, handles: bytes):
+        """`handles` = the world x 64 bytes of every rank's mb_comm_ipc_handle, in rank order."""
+        buf = C.create_string_buffer(handles, len(handles))
+        check(self.lib.mb_comm_ipc_open(self.h, buf))
+
     def downsample(self, xyz: np.ndarray, leaf: float, cap: int, min_dist: float) -> np.ndarray:
         """Geometric::downsample (geometric.cpp:55-126): indices of the kept points, reference order."""
         pts = np.ascontiguousarray(xyz, dtype=np.float32)
