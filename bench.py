@@ -172,8 +172,11 @@ def knn_roofline(ctx, mg, scan, R0, t0, synth):
         ctx.flush_l2()
         mg.knn_staged_run()
     knn_ms = []
+    warm_code = int(os.environ.get("MB_BENCH_WARM_CODE", "0"))  # development experiment
     for _ in range(10):
         ctx.flush_l2()
+        if warm_code:
+            mg.knn_staged_run(prefix=warm_code)
         ctx.sync()
         ctx.timer_begin()
         mg.knn_staged_run()

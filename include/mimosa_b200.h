@@ -191,6 +191,7 @@ MB_API int mb_map_upload(mb_map* map, const int32_t* coords, const int32_t* coun
  * mb_map_knn_stage); runs only the search kernel, results stay on the device.  For roofline timing. */
 MB_API int mb_map_knn_stage(mb_map* map, const double* q, size_t nq, int k);
 MB_API int mb_map_knn_staged_run(mb_map* map);
+MB_API int mb_map_knn_staged_run_prefix(mb_map* map, size_t nq); /* only the first nq staged queries (bench: code warm-up) */
 MB_API int mb_map_knn_staged_fetch(mb_map* map, uint64_t* idx, double* d2, uint8_t* ok);
 
 /* ---- factor: mimosa::lidar::ICPFactor (unary) -------------------------------------------------------

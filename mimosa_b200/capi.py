@@ -131,6 +131,7 @@ SIGNATURES = {
     "mb_map_upload": (C.c_int, [_P, _P, _P, _P, _P, _SZ, C.c_uint64]),
     "mb_map_knn_stage": (C.c_int, [_P, _P, _SZ, C.c_int]),
     "mb_map_knn_staged_run": (C.c_int, [_P]),
+    "mb_map_knn_staged_run_prefix": (C.c_int, [_P, C.c_size_t]),
     "mb_map_knn_staged_fetch": (C.c_int, [_P, _P, _P, _P]),
     "mb_factor_create": (C.c_int, [_P, _P, _P, _SZ, _SZ, C.POINTER(IcpConfig), _SZ, _SZ, C.POINTER(_P)]),
     "mb_factor_release": (C.c_int, [_P]),

@@ -928,6 +928,12 @@ int mb_map_knn_staged_run(mb_map* m) {
   return launch_knn(m, m->q_dev, m->q_n, m->q_k, m->q_idx, m->q_d2, m->q_ok);
 }
 
+int mb_map_knn_staged_run_prefix(mb_map* m, size_t nq) {
+  MB_REQUIRE(m && m->q_n > 0, "nothing staged");
+  MB_CUDA(cudaSetDevice(m->ctx->device));
+  return launch_knn(m, m->q_dev, std::min(nq, m->q_n), m->q_k, m->q_idx, m->q_d2, m->q_ok);
+}
+
 int mb_map_knn_staged_fetch(mb_map* m, uint64_t* idx, double* d2, uint8_t* ok) {
   MB_REQUIRE(m && m->q_n > 0, "nothing staged");
   MB_CUDA(cudaSetDevice(m->ctx->device));

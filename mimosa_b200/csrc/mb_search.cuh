@@ -259,8 +259,6 @@ MB_UNROLL
 MB_UNROLL
             for (int v = 0; v < 4; ++v) p0[v] = __ldg(own_bucket + min(v, cap - 1));
             prefetch_l2(own_bucket + 4);
-            if (cap > 8) prefetch_l2(own_bucket + 8);    // most buckets hold more than 8 points: do not wait for the
-            if (cap > 16) prefetch_l2(own_bucket + 16);  // count to request the later cache lines of the own bucket
           }
         }
       }

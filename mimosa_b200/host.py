@@ -276,8 +276,11 @@ class IncrementalVoxelMap:
         self._staged = (q.shape[0], k)
         check(self.lib.mb_map_knn_stage(self.h, _ptr(q), q.shape[0], k))
 
-    def knn_staged_run(self):
-        check(self.lib.mb_map_knn_staged_run(self.h))
+    def knn_staged_run(self, prefix: int = 0):
+        if prefix:
+            check(self.lib.mb_map_knn_staged_run_prefix(self.h, prefix))
+        else:
+            check(self.lib.mb_map_knn_staged_run(self.h))
 
     def knn_staged_fetch(self):
         nq, k = self._staged
