@@ -355,6 +355,13 @@ __global__ void __launch_bounds__(kKnnThreads, 7)
     }
   }
   ok[i] = found == k;
+#if defined(MB_KNN_TIMING)
+  MB_KNN_T(6);
+  if (blockIdx.x == MB_KNN_TIMING && threadIdx.x == 0)
+    printf("knn timing block %d: probes %lld  existence %lld  own %lld  phase4 %lld  loop %lld  resolve+store %lld  (cycles)\n",
+           (int)blockIdx.x, g_knn_t[1] - g_knn_t[0], g_knn_t[2] - g_knn_t[1], g_knn_t[3] - g_knn_t[2], g_knn_t[4] - g_knn_t[3],
+           g_knn_t[5] - g_knn_t[4], g_knn_t[6] - g_knn_t[5]);
+#endif
 }
 
 __global__ void k_gather_points(const float4* __restrict__ pts, int cap, const uint64_t* __restrict__ idx, size_t n,

@@ -142,6 +142,13 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // first k of the 8 nearest).  s_pk / s_blk are this thread's columns of shared [n_off][pk_stride] /
 // [24][pk_stride] arrays; s_pk receives the bucket index of every existing neighbour (by visiting rank) and
 // stays valid for knn_resolve_all().
+#if defined(MB_KNN_TIMING) && defined(__CUDACC__)
+__device__ long long g_knn_t[16];
+#define MB_KNN_T(i) do { if (blockIdx.x == MB_KNN_TIMING && threadIdx.x == 0) g_knn_t[i] = clock64(); } while (0)
+#else
+#define MB_KNN_T(i) do { } while (0)
+#endif
+
 template <int K>
 MB_DEV void knn_thread(const MapView& mv, const uint16_t* __restrict__ s_tab, uint32_t* s_pk,
                                            uint32_t* s_blk, int pk_stride, double qx, double qy, double qz, int k,
@@ -206,6 +213,7 @@ MB_UNROLL
     return take4(p, bucket, rk, j, cnt);
   };
 
+  MB_KNN_T(0);
   // ---- (1) locate the neighbourhood's blocks; start the own bucket's loads ---------------------------------
   // Per axis the cube touches the own block ob and, when the voxel sits on a block face, one other block nb.
   // s_blk[combo] (combo bit a set = the other block on axis a) receives {mask_lo, mask_hi, base}.  Combos that
@@ -265,6 +273,7 @@ MB_UNROLL
     }
   }
 
+  MB_KNN_T(1);
   // ---- (2) which neighbours exist; prefetch the near ones ---------------------------------------------------
   // Lower bounds of the squared distance from the query to a neighbour's box, in FLOAT and rounded towards zero at
   // every step (the gaps are shrunk by 1e-6 voxel first): cheap to combine, never above the true bound.
@@ -325,6 +334,7 @@ MB_UNROLL
     }
   }
 
+  MB_KNN_T(2);
   // ---- (3) the query's own voxel ------------------------------------------------------------------------------
   const uint32_t rk_own = mv.rank[kCentre];
   s_pk[rk_own * pk_stride] = own_slot;
@@ -336,6 +346,7 @@ MB_UNROLL
       if (j < cnt) offer4(own_bucket, rk_own, j, cnt);
   }
 
+  MB_KNN_T(3);
   // ---- (4) which neighbours can still contribute ---------------------------------------------------------------
   // bit p of `todo` = the cell at scan position p exists and the lower bound of its box does not exceed the
   // current k-th best (rounded up to float); those not prefetched yet are prefetched now
@@ -362,6 +373,7 @@ MB_UNROLL
     }
   }
 
+  MB_KNN_T(4);
   // ---- (5) the surviving neighbours, four candidates per lane and iteration ---------------------------------
   // A lane moves to its next voxel (lowest set bit = nearest class of box) with a handful of predicated
   // instructions, re-checking the bound against the radius.  Candidates within the radius are only PUSHED onto
@@ -438,6 +450,7 @@ MB_UNROLL
       wq_f = __double2float_ru(wq);
     }
   }
+  MB_KNN_T(5);
 }
 
 // Translate a winner's sequence number into the reference's global index and the stored point.
