@@ -24,6 +24,9 @@
 #include <vector>
 
 #include <type_traits>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "mb_map.cuh"
 #include "mb_scan.cuh"
@@ -910,11 +913,23 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
       return rc;
     }
     float4* h = (float4*)ctx->pinned;
-    for (size_t i = 0; i < f->n; ++i) {
-      const float* p = (const float*)((const char*)pts + (shard_begin + i) * stride_bytes);
+    const char* rec = (const char*)pts + shard_begin * stride_bytes;
+    size_t i = 0;
+#if defined(__SSE2__)
+    // records of >= 16 bytes: one unaligned 16-byte load per point, w masked to zero (the last record is done
+    // scalar so that nothing is read past the end of the caller's buffer)
+    if (stride_bytes >= 16 && f->n > 1) {
+      const __m128 keep_xyz = _mm_castsi128_ps(_mm_set_epi32(0, -1, -1, -1));
+      for (; i + 1 < f->n; ++i)
+        _mm_stream_ps((float*)(h + i), _mm_and_ps(_mm_loadu_ps((const float*)(rec + i * stride_bytes)), keep_xyz));
+      _mm_sfence();
+    }
+#endif
+    for (; i < f->n; ++i) {
+      const float* p = (const float*)(rec + i * stride_bytes);
       h[i] = make_float4(p[0], p[1], p[2], 0.f);
     }
-    for (size_t i = f->n; i < f->ld; ++i) h[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (size_t z = f->n; z < f->ld; ++z) h[z] = make_float4(0.f, 0.f, 0.f, 0.f);
     MB_CUDA(cudaMemcpyAsync(f->src, h, f->ld * sizeof(float4), cudaMemcpyHostToDevice, st));
   }
   // everything from `packed` to the end of the block (packet, tickets, DevState) starts at zero

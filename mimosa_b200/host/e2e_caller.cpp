@@ -6,6 +6,8 @@
 // depends on this file.
 #include <chrono>
 #include <cstddef>
+#include <cstdio>
+#include <cstdlib>
 
 #include "../../include/mimosa_b200.h"
 
@@ -18,6 +20,7 @@ extern "C" __attribute__((visibility("default"))) int mb_e2e_scan(
   mb_factor* f = nullptr;
   int rc = mb_factor_create(ctx, map, scan, n, stride_bytes, cfg, shard_begin, shard_end, &f);  // H2D: the scan
   if (rc != MB_OK) return rc;
+  const auto a1 = std::chrono::steady_clock::now();
   double R[9], t[3], delta[6];
   for (int i = 0; i < 9; ++i) R[i] = R0[i];
   for (int i = 0; i < 3; ++i) t[i] = t0[i];
@@ -30,6 +33,9 @@ extern "C" __attribute__((visibility("default"))) int mb_e2e_scan(
   if (rc == MB_OK) rc = mb_sync(ctx);
   const auto b = std::chrono::steady_clock::now();
   *seconds = std::chrono::duration<double>(b - a).count();
+  if (std::getenv("MB_E2E_VERBOSE"))
+    std::fprintf(stderr, "[e2e] factor create %.1f us, %d x (linearize + gn_step) %.1f us\n",
+                 1e6 * std::chrono::duration<double>(a1 - a).count(), iters, 1e6 * std::chrono::duration<double>(b - a1).count());
   for (int i = 0; i < 9; ++i) R_out[i] = R[i];
   for (int i = 0; i < 3; ++i) t_out[i] = t[i];
   const int rc2 = mb_factor_release(f);
