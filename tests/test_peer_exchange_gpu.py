@@ -1,0 +1,94 @@
+"""Two ranks on two GPUs: the per-iteration packet exchanged through peer memory (mb_comm_ipc_*: CUDA IPC
+mailboxes, NVLink stores + flags, rank-ordered sum inside k_finalize) and, for comparison, through ncclAllReduce.
+Both must give the SAME pose bit for bit on both ranks, agree with the single-GPU run to 1e-10 and with the oracle
+to 1e-8.  Needs two devices: skipped on a one-GPU box."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ITERS = 6
+
+
+def _inputs():
+    import synth
+
+    rng = np.random.default_rng(11)
+    world_pts = synth.sample_world(200000, 40.0, rng)
+    R_true, t_true = synth.rot_from_rpy(0.0, 0.01, 0.15), np.array([0.8, -0.3, 0.1])
+    scan = synth.make_scan(R_true, t_true, 12000, rng, max_range=36.0)
+    R0, t0 = synth.perturbed_start(R_true, t_true)
+    return world_pts, scan, R0, t0
+
+
+def _worker(rank, world, port, use_peer, out):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tools")):
+        sys.path.insert(0, p)
+    from mimosa_b200 import HORNBILL_MAP, Context, ICPFactor, IncrementalVoxelMap, hornbill_config, shard_range
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    ctx = Context(rank)
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(ctx.comm_unique_id()), dtype=torch.uint8).clone()
+    dist.broadcast(uid, src=0)
+    ctx.comm_init(rank, world, bytes(uid.numpy().tobytes()))
+    if use_peer:
+        mine = torch.frombuffer(bytearray(ctx.comm_ipc_handle()), dtype=torch.uint8).clone()
+        every = [torch.zeros(64, dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(every, mine)
+        ctx.comm_ipc_open(b"".join(bytes(h.numpy().tobytes()) for h in every))
+    world_pts, scan, R0, t0 = _inputs()
+    m = IncrementalVoxelMap(ctx, **HORNBILL_MAP)
+    m.insert(world_pts)
+    f = ICPFactor(ctx, m, scan, hornbill_config(), shard_range(scan.shape[0], rank, world))
+    poses = []
+    for graph in (False, True, True):  # eager launches, then the captured graph twice (device-side exchange counter)
+        f.reset()
+        f.set_flags(cuda_graph=graph)
+        R, t, _ = f.icp_run(R0, t0, ITERS, 0.0, want_trace=False)
+        poses.append(np.concatenate([np.asarray(R).ravel(), np.asarray(t).ravel()]))
+    assert all(np.array_equal(poses[0], p) for p in poses), "eager and graph replays differ"
+    gathered = [torch.zeros(12, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(gathered, torch.tensor(poses[0]))
+    assert all(torch.equal(gathered[0], x) for x in gathered), "ranks disagree"
+    if rank == 0:
+        np.save(out, poses[0])
+    f.release()
+    m.release()
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_peer_memory_exchange_two_gpus(tmp_path, ctx, oracle):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from mimosa_b200 import HORNBILL_MAP, ICPFactor, IncrementalVoxelMap, hornbill_config
+
+    got = {}
+    for use_peer in (True, False):
+        out = str(tmp_path / f"pose_{int(use_peer)}.npy")
+        port = 29600 + (os.getpid() % 1500) + int(use_peer)
+        mp.spawn(_worker, args=(2, port, use_peer, out), nprocs=2, join=True)
+        got[use_peer] = np.load(out)
+    assert np.array_equal(got[True], got[False]), "peer-memory sum (rank order) and NCCL sum differ"
+    world_pts, scan, R0, t0 = _inputs()
+    m = IncrementalVoxelMap(ctx, **HORNBILL_MAP)
+    m.insert(world_pts)
+    f = ICPFactor(ctx, m, scan, hornbill_config())
+    R1, t1, _ = f.icp_run(R0, t0, ITERS, 0.0, want_trace=False)
+    one = np.concatenate([np.asarray(R1).ravel(), np.asarray(t1).ravel()])
+    assert np.abs(got[True] - one).max() < 1e-10
+    mo = oracle.IVoxRef(**HORNBILL_MAP)
+    mo.insert(world_pts)
+    Ro, to, _, _ = oracle.IcpFactorRef(mo, scan, hornbill_config()).icp_run(R0, t0, ITERS, 0.0)
+    assert np.abs(got[True] - np.concatenate([Ro.ravel(), to])).max() < 1e-8
+    f.release()
+    m.release()
