@@ -462,6 +462,7 @@ def main():
         e2e_lib = C.CDLL(E2E_OUT)
         e2e_lib.mb_e2e_scan.restype = C.c_int
         scan_h = np.ascontiguousarray(scan, dtype=np.float32)
+        ctx.host_register(scan_h)  # the step's input lives in pinned host memory (as a driver's scan buffer would)
         cfg_c = cfg.to_c()
         R0c = np.ascontiguousarray(R0, np.float64).reshape(9)
         t0c = np.ascontiguousarray(t0, np.float64).reshape(3)
@@ -481,6 +482,7 @@ def main():
             if s >= args.warmup:
                 e2e_secs.append(secs.value)
         e2e_pose_err = float(np.abs(te - t_true).max())
+        ctx.host_unregister(scan_h)
     launches = ctx.launch_count() - launches0
 
     # diagnostic (stderr only): marginal device time of a converged, fully cached iteration
@@ -508,7 +510,7 @@ def main():
     e2e_value = ITERS * args.steps / e2e_total
     pose_err = float(np.abs(np.asarray(t) - t_true).max())
     n_shard = shard[1] - shard[0]
-    h2d = ((n_shard + 31) // 32 * 32) * 16 + ITERS * 15 * 8
+    h2d = n_shard * int(scan.strides[0]) + ITERS * 15 * 8  # the rank's block of 32-byte records + the poses (kernel parameters)
     import ctypes as C
 
     d2h = ITERS * (C.sizeof(Linearization) + 6 * 8)

@@ -148,6 +148,11 @@ MB_API int mb_timer_end(mb_ctx* ctx, float* ms);
 MB_API int mb_launch_count(mb_ctx* ctx, uint64_t* out);
 /* Write `bytes` of device memory (L2 flush between timed iterations). */
 MB_API int mb_flush_l2(mb_ctx* ctx, size_t bytes);
+/* Page-lock a caller-owned host buffer (cudaHostRegister) so that scans handed to mb_factor_create /
+ * mb_scan_upload from it are fetched by DMA without a CPU staging pass; e.g. the point buffer a LiDAR driver
+ * re-uses for every scan.  Purely an optimisation: pageable buffers work everywhere. */
+MB_API int mb_host_register(void* p, size_t bytes);
+MB_API int mb_host_unregister(void* p);
 
 /* Multi-GPU: scan blocks are sharded across ranks, the map is replicated, and the packed normal equations
  * are all-reduced once per iteration (new in this implementation; the reference is single-process).

@@ -212,6 +212,18 @@ int mb_gn_step(const double H[36], const double g[6], double lambda, double R[9]
   return MB_OK;
 }
 
+int mb_host_register(void* p, size_t bytes) {
+  MB_REQUIRE(p && bytes, "null argument");
+  MB_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+  return MB_OK;
+}
+
+int mb_host_unregister(void* p) {
+  MB_REQUIRE(p, "null argument");
+  MB_CUDA(cudaHostUnregister(p));
+  return MB_OK;
+}
+
 int mb_comm_unique_id(void* id128) {
   MB_REQUIRE(id128, "null id");
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");

@@ -900,10 +900,31 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
   f->tickets = (unsigned*)(base + o_tick);
   f->ds = (DevState*)(base + o_ds);
 
+  bool staged = true;  // the context's pinned staging buffer was used: wait for the copy before returning
+  bool copied_from_caller = false;
   if (dscan) {
+    staged = false;
     // device-resident scan: pack xyz straight into the factor's float4 array
     k_pack_src<<<(unsigned)((f->ld + 255) / 256), 256, 0, st>>>(dscan->data, dscan->stride, shard_begin, f->n, f->ld, f->src);
     ++ctx->launches;
+  } else if (f->n > 0 && host_is_page_locked(pts)) {
+    // The caller's records are page-locked (cudaHostAlloc / mb_host_register): the copy engine takes this
+    // rank's block of them as it is and a kernel extracts xyz — no CPU pass over the scan, and nothing here
+    // has to wait for the copy (the first linearisation follows it in stream order).
+    const size_t raw_bytes = f->n * stride_bytes;
+    unsigned char* raw = nullptr;
+    rc = dev_alloc(ctx, (void**)&raw, raw_bytes);
+    if (rc != MB_OK) {
+      mb_factor_release(f);
+      return rc;
+    }
+    MB_CUDA(cudaMemcpyAsync(raw, (const char*)pts + shard_begin * stride_bytes, raw_bytes, cudaMemcpyHostToDevice, st));
+    MB_CUDA(cudaEventRecord(ctx->ev1, st));  // the caller's buffer is free again once this copy has run (below)
+    k_pack_src<<<(unsigned)((f->ld + 255) / 256), 256, 0, st>>>(raw, stride_bytes, 0, f->n, f->ld, f->src);
+    ++ctx->launches;
+    dev_free(ctx, raw, raw_bytes);  // pooled: only ever handed out again to work on this same stream
+    staged = false;
+    copied_from_caller = true;
   } else {
     // host AoS with arbitrary stride -> page-locked float4 staging -> device (only xyz is read by the factor,
     // geometric_factor.hpp:277,323,346)
@@ -935,7 +956,15 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
   // everything from `packed` to the end of the block (packet, tickets, DevState) starts at zero
   MB_CUDA(cudaMemsetAsync(base + o_packed, 0, f->block_bytes - o_packed, st));
   MB_TRY(reset_state(f));
-  MB_CUDA(cudaStreamSynchronize(st));  // the pinned staging buffer is free again
+  if (staged) MB_CUDA(cudaStreamSynchronize(st));  // the pinned staging buffer is free again
+  // Like the reference's constructor (geometric_factor.hpp:125 copies the cloud), the caller's buffer has been
+  // consumed when this returns; the pack kernel, the memsets and whatever is enqueued next are not waited for.
+  if (copied_from_caller) {
+    cudaError_t q;
+    while ((q = cudaEventQuery(ctx->ev1)) == cudaErrorNotReady) {
+    }
+    MB_CUDA(q);
+  }
   *out = f;
   return MB_OK;
 }

@@ -111,6 +111,15 @@ int pinned_reserve(mb_ctx* c, size_t bytes);
 int dev_alloc(mb_ctx* c, void** p, size_t bytes);
 void dev_free(mb_ctx* c, void* p, size_t bytes);
 void dev_pool_release(mb_ctx* c);
+// true when `p` points into page-locked host memory the device can read by DMA (cudaHostAlloc / cudaHostRegister)
+inline bool host_is_page_locked(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
 // Same, with the size remembered per pointer (for owners that do not keep it).
 template <typename T>
 inline int dev_alloc_t(mb_ctx* c, T** p, size_t bytes) {

@@ -75,7 +75,11 @@ int mb_scan_upload(mb_ctx* ctx, const void* pts, size_t n, size_t stride_bytes, 
   MB_CUDA(cudaSetDevice(ctx->device));
   mb_scan* s = nullptr;
   MB_TRY(scan_alloc(ctx, n, stride_bytes, &s));
-  if (n) {
+  if (n && host_is_page_locked(pts)) {
+    // page-locked caller buffer (mb_host_register): DMA straight from it, no CPU staging pass
+    MB_CUDA(cudaMemcpyAsync(s->data, pts, n * stride_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));  // the caller's buffer has been consumed when this returns
+  } else if (n) {
     int rc = pinned_reserve(ctx, n * stride_bytes);
     if (rc != MB_OK) {
       mb_scan_release(s);

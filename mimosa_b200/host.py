@@ -121,6 +121,14 @@ class Context:
     def flush_l2(self, nbytes: int = 256 << 20):
         check(self.lib.mb_flush_l2(self.h, nbytes))
 
+    def host_register(self, a: np.ndarray):
+        """Page-lock a C-contiguous numpy array in place (mb_host_register); scans taken from it skip the CPU staging pass."""
+        assert a.flags["C_CONTIGUOUS"]
+        check(self.lib.mb_host_register(_ptr(a), a.nbytes))
+
+    def host_unregister(self, a: np.ndarray):
+        check(self.lib.mb_host_unregister(_ptr(a)))
+
     def comm_unique_id(self) -> bytes:
         buf = C.create_string_buffer(128)
         check(self.lib.mb_comm_unique_id(buf))
