@@ -267,8 +267,9 @@ int mb_comm_ipc_open(mb_ctx* c, const void* handles) {
     }
     t.mbox[r] = (double*)base;
     t.flag[r] = (unsigned long long*)((char*)base + kXchgMboxBytes);
+    t.lflag[r] = (unsigned long long*)((char*)base + kXchgMboxBytes + kXchgFlagBytes);
   }
-  t.xseq = (unsigned long long*)((char*)c->xchg_block + kXchgMboxBytes + kXchgFlagBytes);
+  t.xseq = (unsigned long long*)((char*)c->xchg_block + kXchgMboxBytes + 2 * kXchgFlagBytes);
   if (!c->d_peer) MB_CUDA(cudaMalloc((void**)&c->d_peer, sizeof(PeerTable)));
   MB_CUDA(cudaMemcpy(c->d_peer, &t, sizeof(t), cudaMemcpyHostToDevice));
   return MB_OK;

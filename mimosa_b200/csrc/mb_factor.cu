@@ -619,7 +619,8 @@ __global__ void __launch_bounds__(160) k_finalize(const double* packed_in, DevSt
 // Component localizabilities (geometric_factor.hpp:434-457): sum over Valid points of |loc_i^T V| with
 // entries below 0.5 zeroed.
 template <bool kHostOut>
-__global__ void __launch_bounds__(kLocThreads) k_loc_comp(FactorView fv, const DevState* __restrict__ ds, HostOut ho) {
+__global__ void __launch_bounds__(kLocThreads) k_loc_comp(FactorView fv, const DevState* __restrict__ ds, HostOut ho,
+                                                          const PeerTable* __restrict__ peer) {
   __shared__ double s_red[kLocThreads / 32][8];
   __shared__ double s_tmp[(kLocThreads / 8) * 8];
   __shared__ bool s_last;
@@ -664,6 +665,33 @@ __global__ void __launch_bounds__(kLocThreads) k_loc_comp(FactorView fv, const D
   __threadfence();
   block_sum_rows(fv.partials2, (int)gridDim.x, 8, s_tmp, fv.loc_out, kLocThreads);
   if (threadIdx.x == 0) *fv.ticket2 = 0u;
+  if (peer) {
+    // Several ranks, sums wanted by the caller: the six partial sums travel through the same mailboxes as the
+    // packet (doubles 40..45 of this exchange's slot, their own flags) and are added in rank order right here.
+    __syncthreads();
+    const int world = peer->world, rank = peer->rank;
+    const unsigned long long seq = *peer->xseq;  // k_finalize has already counted this exchange
+    const size_t par = (size_t)((seq & 1ull) * kMaxRanks);
+    if ((int)threadIdx.x < world * 6) {
+      const int dst = threadIdx.x / 6, e = threadIdx.x - dst * 6;
+      peer->mbox[dst][(par + (unsigned)rank) * kXchgDoubles + kPack + e] = fv.loc_out[e];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+      st_release_sys(peer->lflag[threadIdx.x] + par + (unsigned)rank, seq);
+      const unsigned long long* fl = peer->lflag[rank] + par + threadIdx.x;
+      while (ld_acquire_sys(fl) != seq) {
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      double v = 0.0;
+      for (int r = 0; r < world; ++r) v += __ldcg(peer->mbox[rank] + (par + (unsigned)r) * kXchgDoubles + kPack + threadIdx.x);
+      fv.loc_out[threadIdx.x] = v;
+    }
+  }
   if (kHostOut) {  // hand the finished linearisation to the polling host
     __syncthreads();
     constexpr int kWords = (int)(sizeof(mb_linearization) / 8);
@@ -790,16 +818,17 @@ int enqueue_linearize(mb_factor* f, int do_step, int iter, mb_icp_trace* d_trace
   MB_CUDA(launch_pdl(k_finalize, dim3(1), dim3(160), st, (const double*)f->packed, f->ds, (int)f->cfg.reg_4_dof,
                      linearize_count, do_step, iter, d_trace, 31u, peer, f->packed));
   if (host_out) {
-    MB_CUDA(launch_pdl(k_loc_comp<true>, dim3(f->grid2), dim3(kLocThreads), st, fv, (const DevState*)f->ds, *host_out));
+    MB_CUDA(launch_pdl(k_loc_comp<true>, dim3(f->grid2), dim3(kLocThreads), st, fv, (const DevState*)f->ds, *host_out, peer));
   } else {
     HostOut none;
     none.out = nullptr, none.flag = nullptr, none.seq = 0;
-    MB_CUDA(launch_pdl(k_loc_comp<false>, dim3(f->grid2), dim3(kLocThreads), st, fv, (const DevState*)f->ds, none));
+    MB_CUDA(launch_pdl(k_loc_comp<false>, dim3(f->grid2), dim3(kLocThreads), st, fv, (const DevState*)f->ds, none,
+                       do_step ? (const PeerTable*)nullptr : peer));
   }
   // The cross-rank sum of the six component localizabilities is only needed when they are handed out
   // (mb_factor_linearize): the harness loop never returns them, so it does not pay a second all-reduce per
   // iteration for a value nobody reads.  Every rank still computes its own share each iteration.
-  if (c->world > 1 && !do_step)
+  if (c->world > 1 && !do_step && !peer)
     MB_NCCL(ncclAllReduce(f->packed + kPack, f->packed + kPack, 6, ncclDouble, ncclSum, c->comm, st));
   c->launches += 3;
   MB_CUDA(cudaGetLastError());
@@ -1002,7 +1031,7 @@ MB_API int mb_debug_time_finalize(mb_factor* f, unsigned role_mask, int reps, fl
       else
         k_linearize<MB_MAX_K, NoPose><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds->pose, no_pose, nullptr);
     } else if (role_mask == 64u) {
-      k_loc_comp<false><<<f->grid2, kLocThreads, 0, st>>>(fv, f->ds, no_out);
+      k_loc_comp<false><<<f->grid2, kLocThreads, 0, st>>>(fv, f->ds, no_out, nullptr);
     } else {
       k_finalize<<<1, 160, 0, st>>>(f->packed, f->ds, f->cfg.reg_4_dof, 0, 0, 0, nullptr, role_mask, nullptr, f->packed);
     }
@@ -1055,8 +1084,8 @@ int mb_factor_linearize(mb_factor* f, const double R[9], const double t[3], cons
   static_assert(256 + sizeof(mb_linearization) + 6 * sizeof(double) <= 2048, "pin_small too small");
   static_assert(sizeof(mb_linearization) % 8 == 0, "mb_linearization is copied as 8-byte words");
   ++f->linearize_count;
-  if (f->ctx->world == 1) {
-    // Single GPU: the pose travels in the kernel parameters, the last block of k_loc_comp writes the result
+  if (f->ctx->world == 1 || f->ctx->d_peer) {
+    // Single GPU, or several with the peer-memory exchange set up: the pose travels in the kernel parameters, the last block of k_loc_comp writes the result
     // straight into mapped host memory and raises a flag the host polls — no copy operation and no stream
     // synchronisation on the per-iteration path (each costs several microseconds of a ~50 us call).
     PoseArg pa;

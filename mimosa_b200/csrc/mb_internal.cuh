@@ -55,6 +55,8 @@ namespace mb {
 // Every rank owns one small cudaMalloc'd block, exported to the other ranks with cudaIpcGetMemHandle:
 //   mailbox  double[2 parity][kMaxRanks source][kXchgDoubles]   the packets of all ranks for one exchange
 //   flags    u64   [2 parity][kMaxRanks source]                 exchange number the packet belongs to
+//   lflags   u64   [2 parity][kMaxRanks source]                 same, for the six component localizabilities that
+//                                                               k_loc_comp's last block puts into doubles 40..45
 //   xseq     u64                                                number of exchanges this rank has completed
 // The last block of k_linearize STORES its packet straight into every rank's mailbox (peer stores over NVLink)
 // and then raises the flags (release, system scope); k_finalize polls its OWN flags (local memory), adds the
@@ -67,6 +69,7 @@ struct PeerTable {
   int world, rank;
   double* mbox[kMaxRanks];
   unsigned long long* flag[kMaxRanks];
+  unsigned long long* lflag[kMaxRanks];
   unsigned long long* xseq;
 };
 constexpr size_t kXchgMboxBytes = 2 * kMaxRanks * kXchgDoubles * sizeof(double);

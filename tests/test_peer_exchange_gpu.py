@@ -57,8 +57,16 @@ def _worker(rank, world, port, use_peer, out):
     gathered = [torch.zeros(12, dtype=torch.float64) for _ in range(world)]
     dist.all_gather(gathered, torch.tensor(poses[0]))
     assert all(torch.equal(gathered[0], x) for x in gathered), "ranks disagree"
+    # the host-facing single call: packet AND component localizabilities exchanged, result polled from mapped memory
+    f.reset()
+    L = f.linearize(R0, t0)
+    lin = np.concatenate([np.array(L.H), np.array(L.g), [L.f], np.array(L.loc_trans_comp), np.array(L.loc_rot_comp),
+                          np.array(L.counts, dtype=np.float64)])
+    gathered = [torch.zeros(lin.size, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(gathered, torch.tensor(lin))
+    assert all(torch.equal(gathered[0], x) for x in gathered), "ranks disagree on the linearisation"
     if rank == 0:
-        np.save(out, poses[0])
+        np.save(out, np.concatenate([poses[0], lin]))
     f.release()
     m.release()
     dist.barrier()
@@ -79,6 +87,8 @@ def test_peer_memory_exchange_two_gpus(tmp_path, ctx, oracle):
         mp.spawn(_worker, args=(2, port, use_peer, out), nprocs=2, join=True)
         got[use_peer] = np.load(out)
     assert np.array_equal(got[True], got[False]), "peer-memory sum (rank order) and NCCL sum differ"
+    lin2 = got[True][12:]
+    got = {k: v[:12] for k, v in got.items()}
     world_pts, scan, R0, t0 = _inputs()
     m = IncrementalVoxelMap(ctx, **HORNBILL_MAP)
     m.insert(world_pts)
@@ -86,6 +96,12 @@ def test_peer_memory_exchange_two_gpus(tmp_path, ctx, oracle):
     R1, t1, _ = f.icp_run(R0, t0, ITERS, 0.0, want_trace=False)
     one = np.concatenate([np.asarray(R1).ravel(), np.asarray(t1).ravel()])
     assert np.abs(got[True] - one).max() < 1e-10
+    f.reset()
+    L = f.linearize(R0, t0)
+    lin1 = np.concatenate([np.array(L.H), np.array(L.g), [L.f], np.array(L.loc_trans_comp), np.array(L.loc_rot_comp),
+                           np.array(L.counts, dtype=np.float64)])
+    assert np.array_equal(lin1[-9:], lin2[-9:])  # status histogram
+    assert np.allclose(lin1, lin2, rtol=1e-9, atol=1e-9 * np.abs(lin1[:36]).max())
     mo = oracle.IVoxRef(**HORNBILL_MAP)
     mo.insert(world_pts)
     Ro, to, _, _ = oracle.IcpFactorRef(mo, scan, hornbill_config()).icp_run(R0, t0, ITERS, 0.0)
