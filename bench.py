@@ -281,6 +281,7 @@ def run_stream(args, ctx, mg, cfg, synth):
         Rk = poses[pose_index, :9].reshape(-1, 3, 3).astype(np.float64)
         tk = poses[pose_index, 9:].astype(np.float64)
         rec[:, :3] = np.einsum("nji,nj->ni", Rk, rec[:, :3].astype(np.float64) - tk).astype(np.float32)
+        ctx.host_register(rec)  # the driver's scan buffer is page-locked: mb_scan_upload fetches it by DMA
     stages = {k: 0.0 for k in ("t_deskew", "t_preprocess", "t_get_factors", "t_updates", "t_update_map")}
     per_scan, n_key, errs, n_ds = [], 0, [], []
     last_key_t, last_key_R = None, None
