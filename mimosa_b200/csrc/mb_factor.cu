@@ -248,11 +248,18 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
   double acc = 0.0;
   int cnt = 0;  // lane s < 9: points with status s; lane 9: points searched
   __syncthreads();
+#if defined(MB_LIN_TIMING)
+  long long lt_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define MB_LIN_T(i) do { if (blockIdx.x == MB_LIN_TIMING && tid == 0 && tile == blockIdx.x) lt_[i] = clock64(); } while (0)
+#else
+#define MB_LIN_T(i) do { } while (0)
+#endif
 
   const size_t n_tiles = (fv.n + kLinThreads - 1) / kLinThreads;
   for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const size_t i = tile * kLinThreads + tid;
     const bool act = i < fv.n;
+    MB_LIN_T(0);
     // ---- A: transform, gate, compaction ------------------------------------------------------------
     d3 ps = mk3(0, 0, 0), pt = mk3(0, 0, 0);
     uint8_t st = MB_UNPROCESSED;
@@ -280,6 +287,7 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
     if (need) s_queue[base + __popc(mask & ((1u << lane) - 1))] = (uint16_t)tid;
     __syncthreads();
 
+    MB_LIN_T(1);
     // ---- B: search + plane fit for the compacted points -------------------------------------------
     for (int q0 = warp * 32; q0 < n_need; q0 += kLinThreads) {
       const int qi = q0 + lane;
@@ -290,6 +298,7 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
       uint32_t bs[K];
       uint32_t* s_pk = s_pk_all + tid;
       knn_thread<K>(mv, s_tab, s_pk, s_blk_all + tid, kLinThreads, qx, qy, qz, k, on, bd, bs);
+      MB_LIN_T(2);
       if (on) {
         const size_t gi = tile * kLinThreads + li;
         float4 nb[K];
@@ -330,6 +339,7 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
     }
     __syncthreads();
 
+    MB_LIN_T(3);
     // ---- C: residual, Jacobian, accumulation (own point) --------------------------------------------
     double row[7] = {0, 0, 0, 0, 0, 0, 0};
     if (act) {
@@ -394,6 +404,12 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
     }
     if (lane == 9) cnt += __popc(mask);
     __syncthreads();  // s_row (= s_pk), s_queue, s_status ... are rewritten by the next tile
+    MB_LIN_T(4);
+#if defined(MB_LIN_TIMING)
+    if (blockIdx.x == MB_LIN_TIMING && tid == 0 && tile == blockIdx.x)
+      printf("lin timing: A %lld  knn %lld  resolve+fit(+wait other warps) %lld  C %lld  (cycles), n_need %d\n", lt_[1] - lt_[0],
+             lt_[2] - lt_[1], lt_[3] - lt_[2], lt_[4] - lt_[3], n_need);
+#endif
   }
 
   // ---- block partial -> group partial -> packet (two ticketed levels, fixed order) ------------------------
