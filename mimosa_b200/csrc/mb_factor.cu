@@ -185,17 +185,16 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-template <int K, typename PoseT>
+// ROWS = rows of the per-thread neighbour-slot table: 19 covers neighbourhood modes 1 / 7 / 19, 27 the full cube.
+template <int K, typename PoseT, int ROWS>
 __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
     k_linearize(MapView mv, FactorView fv, double* pose_dev, PoseT pa, const PeerTable* __restrict__ peer) {
   __shared__ uint16_t s_tab[kTabEntries];
   // s_pk (phase B: probed neighbour words, [n_off][thread]) is re-used as s_row (phase C: whitened
-  // [J (6), e] per point, [warp][32][7] doubles = 7168 B <= 27 * 128 * 4 B).
-  __shared__ __align__(16) uint32_t s_pk_all[kMaxNbr * kLinThreads];
+  // [J (6), e] per point, [warp][32][7] doubles = 7168 B <= 19 * 128 * 4 B).
+  __shared__ __align__(16) uint32_t s_pk_all[ROWS * kLinThreads];
   __shared__ uint32_t s_blk_all[24 * kLinThreads];  // per-thread {mask_lo, mask_hi, base} of the <= 8 blocks around a query
   __shared__ double s_pt[3][kLinThreads];          // transformed point of each tile member
-  __shared__ double s_mean[3][kLinThreads], s_normal[3][kLinThreads];
-  __shared__ double s_dk[kLinThreads];             // squared distance of the k-th neighbour
   __shared__ uint8_t s_status[kLinThreads];
   __shared__ uint16_t s_queue[kLinThreads];
   __shared__ int s_warp_need[kLinWarps];
@@ -327,14 +326,7 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
           st3(fv.mean, fv.ld, gi, mean);
           if (normal_set) st3(fv.normal, fv.ld, gi, normal);
         }
-        s_status[li] = rs;
-        s_mean[0][li] = mean.x;
-        s_mean[1][li] = mean.y;
-        s_mean[2][li] = mean.z;
-        s_normal[0][li] = normal.x;
-        s_normal[1][li] = normal.y;
-        s_normal[2][li] = normal.z;
-        s_dk[li] = dk;
+        s_status[li] = rs;  // a fitted plane itself reaches its owner through fv.mean / fv.normal (same block, barrier below)
       }
     }
     __syncthreads();
@@ -349,8 +341,8 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
         st3(fv.p_da, fv.ld, i, pt);
         st = s_status[tid];
         if (st == MB_UNPROCESSED) {
-          mean = mk3(s_mean[0][tid], s_mean[1][tid], s_mean[2][tid]);
-          normal = mk3(s_normal[0][tid], s_normal[1][tid], s_normal[2][tid]);
+          mean = ld3(fv.mean, fv.ld, i);
+          normal = ld3(fv.normal, fv.ld, i);
           proceed = true;
         }
       } else if (st > MB_CORRES_PLANE_INVALID) {
@@ -820,15 +812,15 @@ int enqueue_linearize(mb_factor* f, int do_step, int iter, mb_icp_trace* d_trace
   const FactorView fv = f->view();
   const PeerTable* peer = c->world > 1 ? c->d_peer : nullptr;  // nullptr: single rank, or NCCL all-reduce
   if (pose_arg) {
-    if (fv.k == 5)
-      MB_CUDA(launch_pdl(k_linearize<5, PoseArg>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, *pose_arg, peer));
+    if (fv.k == 5 && f->map->n_off <= 19)  // the specialised kernel: k = 5 and at most 19 neighbour voxels
+      MB_CUDA(launch_pdl(k_linearize<5, PoseArg, 19>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, *pose_arg, peer));
     else
-      MB_CUDA(launch_pdl(k_linearize<MB_MAX_K, PoseArg>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, *pose_arg, peer));
+      MB_CUDA(launch_pdl(k_linearize<MB_MAX_K, PoseArg, 27>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, *pose_arg, peer));
   } else {
-    if (fv.k == 5)
-      MB_CUDA(launch_pdl(k_linearize<5, NoPose>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, NoPose{}, peer));
+    if (fv.k == 5 && f->map->n_off <= 19)
+      MB_CUDA(launch_pdl(k_linearize<5, NoPose, 19>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, NoPose{}, peer));
     else
-      MB_CUDA(launch_pdl(k_linearize<MB_MAX_K, NoPose>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, NoPose{}, peer));
+      MB_CUDA(launch_pdl(k_linearize<MB_MAX_K, NoPose, 27>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, NoPose{}, peer));
   }
   if (c->world > 1 && !peer) MB_NCCL(ncclAllReduce(f->packed, f->packed, kPack, ncclDouble, ncclSum, c->comm, st));
   MB_CUDA(launch_pdl(k_finalize, dim3(1), dim3(160), st, (const double*)f->packed, f->ds, (int)f->cfg.reg_4_dof,
@@ -901,10 +893,10 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
   const size_t k = cfg->num_corres_points;
   const size_t n_tiles = (f->n + kLinThreads - 1) / kLinThreads;
   int per_sm = 4;
-  if (k == 5)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<5, NoPose>, kLinThreads, 0);
+  if (k == 5 && map->n_off <= 19)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<5, NoPose, 19>, kLinThreads, 0);
   else
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<MB_MAX_K, NoPose>, kLinThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<MB_MAX_K, NoPose, 27>, kLinThreads, 0);
   per_sm = std::max(per_sm, 1);
   f->grid = (int)std::max<size_t>(1, std::min<size_t>(n_tiles, (size_t)ctx->sm_count * per_sm));
   f->n_groups = (f->grid + kGroup - 1) / kGroup;
@@ -1042,10 +1034,10 @@ MB_API int mb_debug_time_finalize(mb_factor* f, unsigned role_mask, int reps, fl
   no_out.out = nullptr, no_out.flag = nullptr, no_out.seq = 0;
   auto one = [&]() {
     if (role_mask == 32u) {
-      if (fv.k == 5)
-        k_linearize<5, NoPose><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds->pose, no_pose, nullptr);
+      if (fv.k == 5 && f->map->n_off <= 19)
+        k_linearize<5, NoPose, 19><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds->pose, no_pose, nullptr);
       else
-        k_linearize<MB_MAX_K, NoPose><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds->pose, no_pose, nullptr);
+        k_linearize<MB_MAX_K, NoPose, 27><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds->pose, no_pose, nullptr);
     } else if (role_mask == 64u) {
       k_loc_comp<false><<<f->grid2, kLocThreads, 0, st>>>(fv, f->ds, no_out, nullptr);
     } else {
