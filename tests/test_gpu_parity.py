@@ -7,7 +7,7 @@ import pytest
 
 import synth
 from helpers import assert_linearization_close, assert_state_equal, g_err, load_golden, rel_err
-from mimosa_b200 import HORNBILL_MAP, ICPFactor, IncrementalVoxelMap, hornbill_config
+from mimosa_b200 import HORNBILL_MAP, ICPFactor, IncrementalVoxelMap, Scan, hornbill_config
 from mimosa_b200.capi import MB_ERR_INVALID_ARG, MB_ERR_UNSUPPORTED, MimosaError
 
 pytestmark = pytest.mark.gpu
@@ -330,6 +330,40 @@ def test_ragged_and_tiny_scans(ctx, oracle):
     L = fg.linearize(np.eye(3), np.zeros(3))
     assert L.counts[1] == 64 and not np.any(np.array(L.H)) and L.f == 0.0
     fg.release()
+    mg.release()
+
+
+def test_page_locked_scan_buffers_take_the_dma_path(ctx, oracle):
+    """A scan handed over from page-locked memory (mb_host_register) is fetched by DMA and unpacked on the device;
+    results must be identical to the pageable path (CPU staging), for the factor and for mb_scan_upload, and a
+    sharded factor must pick its own block of the registered buffer."""
+    mg, mo, scan, R0, t0, _, _ = _world_case(ctx, oracle, 100000, 3000, 151, half=30.0)
+    cfg = hornbill_config()
+    pageable = np.ascontiguousarray(scan, dtype=np.float32)
+    locked = pageable.copy()
+    ctx.host_register(locked)
+    try:
+        for shard in (None, (100, 2077)):
+            fa, fb = ICPFactor(ctx, mg, pageable, cfg, shard), ICPFactor(ctx, mg, locked, cfg, shard)
+            locked_backup = locked.copy()
+            La, Lb = fa.linearize(R0, t0), fb.linearize(R0, t0)
+            assert np.array_equal(np.array(La.H), np.array(Lb.H)) and list(La.counts) == list(Lb.counts)
+            sa, sb = fa.download_state(), fb.download_state()
+            for k in sa:
+                assert np.array_equal(sa[k], sb[k]), k
+            assert np.array_equal(locked, locked_backup)
+            fa.release()
+            fb.release()
+        fo = oracle.IcpFactorRef(mo, scan, cfg)
+        fg = ICPFactor(ctx, mg, locked, cfg)
+        assert_linearization_close(fg.linearize(R0, t0), fo.linearize(R0, t0), H_TOL)
+        fg.release()
+        sa, sb = Scan(ctx, pageable), Scan(ctx, locked)
+        assert np.array_equal(sa.download(), sb.download())
+        sa.release()
+        sb.release()
+    finally:
+        ctx.host_unregister(locked)
     mg.release()
 
 
