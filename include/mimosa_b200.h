@@ -96,6 +96,7 @@ typedef struct mb_icp_trace {
   int64_t counts[9];
   int32_t n_searched;
   int32_t solve_ok;
+  double loc_trans_comp[3], loc_rot_comp[3]; /* component localizabilities of this iteration's linearisation */
 } mb_icp_trace;
 
 /* Where the fields of one point sit inside a sensor_msgs/PointCloud2 record (one descriptor covers the nine

@@ -99,6 +99,8 @@ class IcpTrace(C.Structure):
         ("counts", C.c_int64 * 9),
         ("n_searched", C.c_int32),
         ("solve_ok", C.c_int32),
+        ("loc_trans_comp", C.c_double * 3),
+        ("loc_rot_comp", C.c_double * 3),
     ]
 
 

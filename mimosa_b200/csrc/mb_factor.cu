@@ -36,8 +36,10 @@ namespace {
 
 constexpr int kLinThreads = 128;
 constexpr int kLinWarps = kLinThreads / 32;
-constexpr int kPack = 40;  // 21 H upper-tri, 6 J^T e, 1 f, 9 status counts, 1 n_searched, 2 pad
-constexpr int kPackB = 21, kPackF = 27, kPackCnt = 28, kPackSearched = 37;
+// 21 H upper-tri, 6 J^T e, 1 f, 9 status counts, 1 n_searched, 2 pad, then (device-resident loop only) the six
+// component localizabilities of the PREVIOUS linearisation, folded into this pass (see k_linearize), 2 pad
+constexpr int kPack = 48;
+constexpr int kPackB = 21, kPackF = 27, kPackCnt = 28, kPackSearched = 37, kPackLoc = 40;
 constexpr int kGroup = 32;  // blocks per first-level reduction group
 constexpr int kLocThreads = 256;
 
@@ -49,6 +51,7 @@ struct FactorView {
   size_t n, ld;
   int k, use_huber;
   uint32_t flags;
+  int fold_loc;  // 1: also sum the component localizabilities of the previous linearisation (device-resident loop)
   double da_gate, max_corr_sq, sigma, kh, pvd;
   double* partials;    // [grid][kPack]
   double* gpartials;   // [n_groups][kPack]
@@ -188,7 +191,8 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 // ROWS = rows of the per-thread neighbour-slot table: 19 covers neighbourhood modes 1 / 7 / 19, 27 the full cube.
 template <int K, typename PoseT, int ROWS>
 __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
-    k_linearize(MapView mv, FactorView fv, double* pose_dev, PoseT pa, const PeerTable* __restrict__ peer) {
+    k_linearize(MapView mv, FactorView fv, DevState* ds, PoseT pa, const PeerTable* __restrict__ peer) {
+  double* pose_dev = ds->pose;
   __shared__ uint16_t s_tab[kTabEntries];
   // s_pk (phase B: probed neighbour words, [n_off][thread]) is re-used as s_row (phase C: whitened
   // [J (6), e] per point, [warp][32][7] doubles = 7168 B <= 19 * 128 * 4 B).
@@ -244,8 +248,14 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
   const int k = fv.k;
   const bool forced = (fv.flags & 1u) != 0;
 
-  double acc = 0.0;
+  double acc = 0.0, lacc = 0.0;  // lacc: lane a < 6 sums component a of the previous linearisation's localizability pass
   int cnt = 0;  // lane s < 9: points with status s; lane 9: points searched
+  // Folded localizability pass (device-resident loop): before a point's status and localizability vectors are
+  // overwritten, its contribution |loc^T V| (entries below 0.5 dropped, geometric_factor.hpp:434-457) to the
+  // component localizabilities of the PREVIOUS linearisation is taken with that linearisation's eigenvectors, which
+  // the previous k_finalize left in ds->lin.  It saves a pass over the points and a kernel launch per iteration.
+  __shared__ double s_V[18];
+  if (fv.fold_loc && tid < 18) s_V[tid] = tid < 9 ? ds->lin.eigvec_trans[tid] : ds->lin.eigvec_rot[tid - 9];
   __syncthreads();
 #if defined(MB_LIN_TIMING)
   long long lt_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -334,6 +344,29 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
     MB_LIN_T(3);
     // ---- C: residual, Jacobian, accumulation (own point) --------------------------------------------
     double row[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (fv.fold_loc) {
+      double v[6] = {0, 0, 0, 0, 0, 0};
+      if (act && st == MB_VALID) {  // st is still the status the previous linearisation left
+        const d3 lt = ld3(fv.loc_trans, fv.ld, i), lr = ld3(fv.loc_rot, fv.ld, i);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {  // column a of V: (V^T loc)_a, in mul33Tv's order of operations
+          const double tc = fabs(s_V[a] * lt.x + (s_V[3 + a] * lt.y + s_V[6 + a] * lt.z));
+          const double rc = fabs(s_V[9 + a] * lr.x + (s_V[12 + a] * lr.y + s_V[15 + a] * lr.z));
+          v[a] = tc >= 0.5 ? tc : 0.0;
+          v[3 + a] = rc >= 0.5 ? rc : 0.0;
+        }
+      }
+      if (__ballot_sync(kFull, act && st == MB_VALID)) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) s_row[lane][a] = v[a];
+        __syncwarp();
+        if (lane < 6) {
+#pragma unroll 8
+          for (int p = 0; p < 32; ++p) lacc += s_row[p][lane];
+        }
+        __syncwarp();
+      }
+    }
     if (act) {
       bool proceed = false;
       d3 mean = mk3(0, 0, 0), normal = mk3(0, 0, 0);
@@ -406,8 +439,9 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
 
   // ---- block partial -> group partial -> packet (two ticketed levels, fixed order) ------------------------
   if (lane < 28) s_red[warp][lane] = acc;
-  if (lane >= 30) s_red[warp][lane + 8] = 0.0;  // pad entries 38, 39
+  if (lane >= 30) s_red[warp][lane + 8] = s_red[warp][lane + 16] = 0.0;  // pad entries 38, 39, 46, 47
   if (lane < 10) s_red[warp][kPackCnt + lane] = (double)cnt;
+  if (lane < 6) s_red[warp][kPackLoc + lane] = lacc;
   __syncthreads();
   if (tid < kPack) {
     double v = 0.0;
@@ -619,6 +653,13 @@ __global__ void __launch_bounds__(160) k_finalize(const double* packed_in, DevSt
         tr.t[2] = T.z;
         tr.n_searched = (int32_t)packed[kPackSearched];
         tr.solve_ok = ok ? 1 : 0;
+        // the packet also carries the component localizabilities of the PREVIOUS linearisation (folded pass)
+        if (iter > 0) {
+          for (int a = 0; a < 3; ++a) {
+            trace[iter - 1].loc_trans_comp[a] = packed[kPackLoc + a];
+            trace[iter - 1].loc_rot_comp[a] = packed[kPackLoc + 3 + a];
+          }
+        }
       }
     }
   }
@@ -772,6 +813,7 @@ struct mb_factor {
     v.k = (int)cfg.num_corres_points;
     v.use_huber = cfg.use_huber;
     v.flags = flags;
+    v.fold_loc = 0;
     const float da_gate_f = cfg.target_ivox_map_min_dist_in_voxel / 4;          // geometric_factor.hpp:283
     v.da_gate = (double)da_gate_f;
     const float max_corr_f = cfg.max_corres_distance * cfg.max_corres_distance;  // :299
@@ -809,37 +851,49 @@ int enqueue_linearize(mb_factor* f, int do_step, int iter, mb_icp_trace* d_trace
                       const PoseArg* pose_arg = nullptr, const HostOut* host_out = nullptr) {
   mb_ctx* c = f->ctx;
   cudaStream_t st = c->stream;
-  const FactorView fv = f->view();
+  FactorView fv = f->view();
+  // Device-resident loop: the localizability pass of this linearisation is folded into the NEXT k_linearize (and
+  // mb_icp_run launches k_loc_comp once, after the last iteration); the host-facing single call runs it right away.
+  fv.fold_loc = do_step ? 1 : 0;
   const PeerTable* peer = c->world > 1 ? c->d_peer : nullptr;  // nullptr: single rank, or NCCL all-reduce
   if (pose_arg) {
     if (fv.k == 5 && f->map->n_off <= 19)  // the specialised kernel: k = 5 and at most 19 neighbour voxels
-      MB_CUDA(launch_pdl(k_linearize<5, PoseArg, 19>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, *pose_arg, peer));
+      MB_CUDA(launch_pdl(k_linearize<5, PoseArg, 19>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, f->ds, *pose_arg, peer));
     else
-      MB_CUDA(launch_pdl(k_linearize<MB_MAX_K, PoseArg, 27>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, *pose_arg, peer));
+      MB_CUDA(launch_pdl(k_linearize<MB_MAX_K, PoseArg, 27>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, f->ds, *pose_arg, peer));
   } else {
     if (fv.k == 5 && f->map->n_off <= 19)
-      MB_CUDA(launch_pdl(k_linearize<5, NoPose, 19>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, NoPose{}, peer));
+      MB_CUDA(launch_pdl(k_linearize<5, NoPose, 19>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, f->ds, NoPose{}, peer));
     else
-      MB_CUDA(launch_pdl(k_linearize<MB_MAX_K, NoPose, 27>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, (double*)f->ds->pose, NoPose{}, peer));
+      MB_CUDA(launch_pdl(k_linearize<MB_MAX_K, NoPose, 27>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, f->ds, NoPose{}, peer));
   }
   if (c->world > 1 && !peer) MB_NCCL(ncclAllReduce(f->packed, f->packed, kPack, ncclDouble, ncclSum, c->comm, st));
   MB_CUDA(launch_pdl(k_finalize, dim3(1), dim3(160), st, (const double*)f->packed, f->ds, (int)f->cfg.reg_4_dof,
                      linearize_count, do_step, iter, d_trace, 31u, peer, f->packed));
   if (host_out) {
     MB_CUDA(launch_pdl(k_loc_comp<true>, dim3(f->grid2), dim3(kLocThreads), st, fv, (const DevState*)f->ds, *host_out, peer));
-  } else {
+  } else if (!do_step) {
     HostOut none;
     none.out = nullptr, none.flag = nullptr, none.seq = 0;
-    MB_CUDA(launch_pdl(k_loc_comp<false>, dim3(f->grid2), dim3(kLocThreads), st, fv, (const DevState*)f->ds, none,
-                       do_step ? (const PeerTable*)nullptr : peer));
+    MB_CUDA(launch_pdl(k_loc_comp<false>, dim3(f->grid2), dim3(kLocThreads), st, fv, (const DevState*)f->ds, none, peer));
   }
   // The cross-rank sum of the six component localizabilities is only needed when they are handed out
-  // (mb_factor_linearize): the harness loop never returns them, so it does not pay a second all-reduce per
-  // iteration for a value nobody reads.  Every rank still computes its own share each iteration.
+  // (mb_factor_linearize): through the peer mailboxes inside k_loc_comp, or with NCCL as the fallback.
   if (c->world > 1 && !do_step && !peer)
     MB_NCCL(ncclAllReduce(f->packed + kPack, f->packed + kPack, 6, ncclDouble, ncclSum, c->comm, st));
+  if (do_step) --c->launches;  // no k_loc_comp in this sequence
   c->launches += 3;
   MB_CUDA(cudaGetLastError());
+  return MB_OK;
+}
+
+// The localizability pass of the loop's LAST linearisation (the earlier ones were folded into their successors).
+int enqueue_last_loc_comp(mb_factor* f) {
+  HostOut none;
+  none.out = nullptr, none.flag = nullptr, none.seq = 0;
+  MB_CUDA(launch_pdl(k_loc_comp<false>, dim3(f->grid2), dim3(kLocThreads), f->ctx->stream, f->view(), (const DevState*)f->ds,
+                     none, (const PeerTable*)nullptr));
+  ++f->ctx->launches;
   return MB_OK;
 }
 
@@ -1035,9 +1089,9 @@ MB_API int mb_debug_time_finalize(mb_factor* f, unsigned role_mask, int reps, fl
   auto one = [&]() {
     if (role_mask == 32u) {
       if (fv.k == 5 && f->map->n_off <= 19)
-        k_linearize<5, NoPose, 19><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds->pose, no_pose, nullptr);
+        k_linearize<5, NoPose, 19><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds, no_pose, nullptr);
       else
-        k_linearize<MB_MAX_K, NoPose, 27><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds->pose, no_pose, nullptr);
+        k_linearize<MB_MAX_K, NoPose, 27><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds, no_pose, nullptr);
     } else if (role_mask == 64u) {
       k_loc_comp<false><<<f->grid2, kLocThreads, 0, st>>>(fv, f->ds, no_out, nullptr);
     } else {
@@ -1196,6 +1250,7 @@ int mb_icp_run(mb_factor* f, double R[9], double t[3], int iters, double lambda,
       int rc = MB_OK;
       for (int it = 0; it < iters && rc == MB_OK; ++it)
         rc = enqueue_linearize(f, 1, it, f->d_trace, f->linearize_count + it + 1);
+      if (rc == MB_OK) rc = enqueue_last_loc_comp(f);
       cudaError_t e = cudaStreamEndCapture(st, &g);
       if (rc != MB_OK) {
         if (g) cudaGraphDestroy(g);
@@ -1208,7 +1263,7 @@ int mb_icp_run(mb_factor* f, double R[9], double t[3], int iters, double lambda,
       f->graph_iters = iters;
       f->graph_count0 = f->linearize_count;
     } else {
-      f->ctx->launches += 3ull * iters;
+      f->ctx->launches += 2ull * iters + 1ull;
     }
     MB_CUDA(cudaGraphLaunch(f->graph, st));
     f->linearize_count += iters;
@@ -1217,12 +1272,22 @@ int mb_icp_run(mb_factor* f, double R[9], double t[3], int iters, double lambda,
       ++f->linearize_count;
       MB_TRY(enqueue_linearize(f, 1, it, f->d_trace, f->linearize_count));
     }
+    if (iters) MB_TRY(enqueue_last_loc_comp(f));
   }
   double* hout = (double*)((char*)f->ctx->pin_small + 256);
   MB_CUDA(cudaMemcpyAsync(hout, f->ds->pose, 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (trace && iters)
+  double* hloc = hout + 16;  // the last iteration's component localizabilities, from the trailing k_loc_comp
+  if (trace && iters) {
     MB_CUDA(cudaMemcpyAsync(trace, f->d_trace, (size_t)iters * sizeof(mb_icp_trace), cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaMemcpyAsync(hloc, f->packed + kPack, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
   MB_CUDA(cudaStreamSynchronize(st));
+  if (trace && iters) {
+    for (int a = 0; a < 3; ++a) {
+      trace[iters - 1].loc_trans_comp[a] = hloc[a];
+      trace[iters - 1].loc_rot_comp[a] = hloc[3 + a];
+    }
+  }
   std::memcpy(R, hout, 9 * sizeof(double));
   std::memcpy(t, hout + 9, 3 * sizeof(double));
   return MB_OK;

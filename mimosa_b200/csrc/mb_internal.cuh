@@ -56,7 +56,7 @@ namespace mb {
 //   mailbox  double[2 parity][kMaxRanks source][kXchgDoubles]   the packets of all ranks for one exchange
 //   flags    u64   [2 parity][kMaxRanks source]                 exchange number the packet belongs to
 //   lflags   u64   [2 parity][kMaxRanks source]                 same, for the six component localizabilities that
-//                                                               k_loc_comp's last block puts into doubles 40..45
+//                                                               k_loc_comp's last block puts into doubles 48..53
 //   xseq     u64                                                number of exchanges this rank has completed
 // The last block of k_linearize STORES its packet straight into every rank's mailbox (peer stores over NVLink)
 // and then raises the flags (release, system scope); k_finalize polls its OWN flags (local memory), adds the
@@ -64,7 +64,7 @@ namespace mb {
 // and the transfer overlaps the tail of the reduction.  Two parities: a fast rank may already write exchange
 // n + 1 while a slow one still reads exchange n; it cannot reach n + 2 before every rank has consumed n.
 constexpr int kMaxRanks = 8;
-constexpr int kXchgDoubles = 48;
+constexpr int kXchgDoubles = 56;  // >= the 48-double packet + the six component localizabilities of k_loc_comp
 struct PeerTable {
   int world, rank;
   double* mbox[kMaxRanks];

@@ -29,7 +29,9 @@ struct mb_map {
   double leaf = 1.0, inv_leaf = 1.0, min_sq_dist = 0.0;
   int cap = 20, nbr_mode = 7, n_off = 7;
   int8_t off[mb::kMaxNbr * 3] = {0};  // neighbour offsets in the reference's visiting order
-  double pref_frac = 0.4;             // early-prefetch radius of the search, in voxels (MapView::pref2)
+  // early-prefetch radius of the search, in voxels (MapView::pref2).  Measured neutral on time from 0 to 0.6 and
+  // costing DRAM traffic beyond the compulsory bytes (profiles/r1_experiments.md), hence off by default.
+  double pref_frac = 0.0;
   uint64_t lru_horizon = 100, lru_counter = 0;
   // storage
   size_t cap_vox = 0, n_vox = 0, table_cap = 0;

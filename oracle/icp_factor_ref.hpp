@@ -360,6 +360,7 @@ struct IcpTraceRef {  // one Gauss-Newton harness iteration
   int64_t counts[9];
   int32_t n_searched;
   int32_t solve_ok;
+  double loc_trans_comp[3], loc_rot_comp[3];  // of this iteration's linearisation (geometric_factor.hpp:434-457)
 };
 
 // delta = (H + lambda I)^-1 g with g = -J^T e, T <- T * Exp(delta).
@@ -389,6 +390,10 @@ inline void icp_run_ref(IcpFactorRef& f, Pose& T, int iters, double lambda, IcpT
       tr.t[2] = T.t.z;
       tr.n_searched = L.n_searched;
       tr.solve_ok = ok ? 1 : 0;
+      for (int a = 0; a < 3; ++a) {
+        tr.loc_trans_comp[a] = L.loc_trans_comp[a];
+        tr.loc_rot_comp[a] = L.loc_rot_comp[a];
+      }
     }
   }
 }

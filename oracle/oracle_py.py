@@ -60,6 +60,7 @@ class IcpTrace(C.Structure):
         ("H", C.c_double * 36), ("g", C.c_double * 6), ("f", C.c_double), ("delta", C.c_double * 6),
         ("R", C.c_double * 9), ("t", C.c_double * 3), ("counts", C.c_int64 * 9),
         ("n_searched", C.c_int32), ("solve_ok", C.c_int32),
+        ("loc_trans_comp", C.c_double * 3), ("loc_rot_comp", C.c_double * 3),
     ]
 
 

@@ -252,6 +252,10 @@ def test_world_icp_matches_oracle(ctx, oracle):
     for it, (a, b) in enumerate(zip(trg, tro)):
         assert list(a.counts) == list(b.counts), (it, list(a.counts), list(b.counts))
         assert a.n_searched == b.n_searched and a.solve_ok == b.solve_ok == 1
+        # component localizabilities: iterations before the last come out of the pass folded into the next
+        # k_linearize, the last one out of k_loc_comp
+        assert np.allclose(np.array(a.loc_trans_comp), np.array(b.loc_trans_comp), rtol=1e-4)  # same tolerance as helpers
+        assert np.allclose(np.array(a.loc_rot_comp), np.array(b.loc_rot_comp), rtol=1e-4)
         assert rel_err(a.H, b.H) <= 1e-7 and g_err(a.g, b.g, b.H, b.f) <= 1e-7
         assert np.abs(np.array(a.R) - np.array(b.R)).max() <= POSE_TOL
         assert np.abs(np.array(a.t) - np.array(b.t)).max() <= POSE_TOL
