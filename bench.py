@@ -522,7 +522,7 @@ def main():
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "iters_per_step": ITERS, "map_points": n_pts, "map_voxels": n_vox,
-                   "scan_points": int(scan.shape[0]), "parallelism": (f"scan-block shard x{world}, map replicated, 40-double packet per iteration "
+                   "scan_points": int(scan.shape[0]), "parallelism": (f"scan-block shard x{world}, map replicated, 48-double packet per iteration "
                                    + ("all-reduced with NCCL" if os.environ.get("MB_BENCH_NCCL") else
                                       "exchanged through peer memory (NVLink stores + flags), summed in rank order"))
                    if world > 1 else "1 GPU",

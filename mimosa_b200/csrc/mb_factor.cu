@@ -13,9 +13,12 @@
 //                 (:405-428, 464-475) and — for the stand-alone Gauss-Newton harness — the LDL^T solve and
 //                 SE(3) retract that ISAM2 performs in the reference (mimosa/src/graph/manager.cpp:585-588).
 //                 Five independent roles run on five warps.
-//   k_loc_comp    the component-localizability second pass over valid points (:434-457).
-// With more than one rank the 40-double packet between k_linearize and k_finalize (and the 6 doubles after
-// k_loc_comp) are all-reduced with NCCL; every rank then computes the identical step.
+//   k_loc_comp    the component-localizability second pass over valid points (:434-457); in the device-resident
+//                 loop that pass is folded into the next k_linearize and this kernel only runs after the last
+//                 iteration.  Its last block hands the finished linearisation to the polling host.
+// With more than one rank the 48-double packet between k_linearize and k_finalize (and the 6 doubles after
+// k_loc_comp) travel through peer-memory mailboxes (mb_internal.cuh) or, as the fallback, ncclAllReduce; every
+// rank then computes the identical step.
 //
 // Per-point state (status, DA anchor, plane mean/normal, localizability vectors) lives in HBM inside the
 // factor handle as structure-of-arrays, mirroring the `mutable` vectors at geometric_factor.hpp:79-106.
