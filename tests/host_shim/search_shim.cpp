@@ -1,14 +1,21 @@
-// Test-only HOST build of the search code the kernels run (mimosa_b200/csrc/mb_search.cuh), one emulated lane per
-// query: the warp intrinsics collapse to their single-lane meaning, loads are plain reads, prefetches vanish.
+// Test-only HOST build of the search code the kernels run (mimosa_b200/csrc/mb_search.cuh).  Two emulations:
+//   * one lane per query: the warp intrinsics collapse to their single-lane meaning;
+//   * a 32-lane warp: 32 host threads run the same code in lock step, every warp intrinsic (__any_sync,
+//     __ballot_sync, __shfl_sync, __reduce_max_sync, __syncwarp) is an exchange through a std::barrier — legal
+//     because the search code is warp-converged by construction (every lane reaches the same intrinsics in the
+//     same order), which is exactly the property this emulation checks along with max-over-lanes loop logic.
+// Loads are plain reads, prefetches vanish.
 // The search mirror (block-ordered buckets + hashed block table with occupancy masks) is rebuilt here on the
 // host from a voxel dump with the same rules as k_mirror_* in mb_map.cu.  Lets the CPU test-suite check the
 // search logic (block probes, cell masks, pruning bounds, deferred insertion, tie order) against the oracle
 // without a GPU.  Not a product path.
 #include <algorithm>
+#include <barrier>
 #include <cfenv>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 struct float4 {
@@ -21,8 +28,64 @@ static inline float4 make_float4(float x, float y, float z, float w) { return fl
 static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 template <typename T>
 static inline T __ldg(const T* p) { return *p; }
-static inline bool __any_sync(unsigned, bool p) { return p; }
-static inline int __reduce_max_sync(unsigned, int v) { return v; }
+// ---- warp emulation -------------------------------------------------------------------------------------
+struct WarpCtx {
+  std::barrier<> bar{32};
+  unsigned long long slot[32];
+};
+static thread_local WarpCtx* t_warp = nullptr;  // nullptr: single-lane emulation
+static thread_local int t_lane = 0;
+template <typename F>
+static inline auto warp_exchange(unsigned long long mine, F combine) {
+  WarpCtx& w = *t_warp;
+  w.slot[t_lane] = mine;
+  w.bar.arrive_and_wait();
+  const auto r = combine(w.slot);
+  w.bar.arrive_and_wait();
+  return r;
+}
+static inline unsigned __ballot_sync(unsigned, bool p) {
+  if (!t_warp) return p ? 1u : 0u;
+  return warp_exchange(p ? 1ull : 0ull, [](const unsigned long long* s) {
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l) m |= (unsigned)s[l] << l;
+    return m;
+  });
+}
+static inline bool __any_sync(unsigned m, bool p) { return __ballot_sync(m, p) != 0u; }
+static inline int __reduce_max_sync(unsigned, int v) {
+  if (!t_warp) return v;
+  return warp_exchange((unsigned long long)(long long)v, [](const unsigned long long* s) {
+    int m = (int)(long long)s[0];
+    for (int l = 1; l < 32; ++l) m = std::max(m, (int)(long long)s[l]);
+    return m;
+  });
+}
+static inline unsigned long long shfl_bits(unsigned long long v, int src) {
+  if (!t_warp) return v;
+  return warp_exchange(v, [src](const unsigned long long* s) { return s[src & 31]; });
+}
+static inline unsigned __shfl_sync(unsigned, unsigned v, int src) { return (unsigned)shfl_bits(v, src); }
+static inline int __shfl_sync(unsigned, int v, int src) { return (int)(unsigned)shfl_bits((unsigned)v, src); }
+static inline double __shfl_sync(unsigned, double v, int src) {
+  unsigned long long u;
+  std::memcpy(&u, &v, 8);
+  u = shfl_bits(u, src);
+  std::memcpy(&v, &u, 8);
+  return v;
+}
+static inline void __syncwarp(unsigned = 0xffffffffu) {
+  if (t_warp) {
+    t_warp->bar.arrive_and_wait();
+  }
+}
+static inline int emu_lane_id() { return t_lane; }
+static inline unsigned __fns(unsigned mask, unsigned base, int offset) {  // offset-th set bit at or above `base` (offset >= 1)
+  for (unsigned b = base; b < 32; ++b)
+    if ((mask >> b) & 1u)
+      if (--offset == 0) return b;
+  return 0xffffffffu;
+}
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
@@ -143,6 +206,41 @@ void run(const HostMirror& M, const double* q, size_t nq, int k, uint64_t* idx, 
     ok[i] = found == k;
   }
 }
+// 32 queries per emulated warp, one host thread per lane, shared-memory columns laid out as on the device
+template <int K>
+void run_warps(const HostMirror& M, const double* q, size_t nq, int k, uint64_t* idx, double* d2, uint8_t* ok) {
+  uint16_t s_tab[mb::kTabEntries] = {0};
+  for (int p = 0; p < mb::kScan; ++p) s_tab[p] = M.view.scan[p];
+  for (size_t w0 = 0; w0 < nq; w0 += 32) {
+    WarpCtx ctx;
+    std::vector<uint32_t> s_pk(mb::kMaxNbr * 32, 0xdeadbeefu), s_blk(24 * 32, 0xdeadbeefu);
+    std::vector<std::thread> lanes;
+    for (int lane = 0; lane < 32; ++lane)
+      lanes.emplace_back([&, lane] {
+        t_warp = &ctx;
+        t_lane = lane;
+        const size_t i = w0 + lane;
+        const bool active = i < nq;
+        const size_t qi = active ? i : 0;
+        double bd[K];
+        uint32_t bs[K];
+        mb::knn_thread<K>(M.view, s_tab, s_pk.data() + lane, s_blk.data() + lane, 32, q[3 * qi], q[3 * qi + 1], q[3 * qi + 2], k,
+                          active, bd, bs);
+        if (active) {
+          uint64_t g[K];
+          float4 pts[K];
+          const int found = mb::knn_resolve_all<K, true>(M.view, s_pk.data() + lane, 32, bs, k, g, pts);
+          for (int j = 0; j < k; ++j) {
+            idx[i * k + j] = g[j];
+            d2[i * k + j] = g[j] != ~0ull ? bd[j] : 1.7976931348623157e308;
+          }
+          ok[i] = found == k;
+        }
+        t_warp = nullptr;
+      });
+    for (auto& t : lanes) t.join();
+  }
+}
 }  // namespace
 
 extern "C" int shim_knn(const int32_t* coords, const int32_t* counts, const float* xyz, uint32_t n_vox, int cap, int nbr_mode,
@@ -154,5 +252,19 @@ extern "C" int shim_knn(const int32_t* coords, const int32_t* counts, const floa
     run<5>(M, q, nq, k, idx, d2, ok);
   else
     run<8>(M, q, nq, k, idx, d2, ok);
+  return 0;
+}
+
+// same, 32-lane warp emulation
+extern "C" int shim_knn_warp(const int32_t* coords, const int32_t* counts, const float* xyz, uint32_t n_vox, int cap,
+                             int nbr_mode, double leaf, double pref_frac, const double* q, size_t nq, int k, uint64_t* idx,
+                             double* d2, uint8_t* ok) {
+  if (k < 1 || k > 8) return 1;
+  HostMirror M;
+  build_mirror(M, coords, counts, xyz, n_vox, cap, nbr_mode, leaf, pref_frac);
+  if (k == 5)
+    run_warps<5>(M, q, nq, k, idx, d2, ok);
+  else
+    run_warps<8>(M, q, nq, k, idx, d2, ok);
   return 0;
 }

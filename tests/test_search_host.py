@@ -19,8 +19,8 @@ def shim():
     out = os.path.join(HERE, "host_shim", "libsearch_shim.so")
     hdrs = [os.path.join(HERE, "..", "mimosa_b200", "csrc", h) for h in ("mb_search.cuh", "mb_math.cuh")]
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(p) for p in [src] + hdrs):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-frounding-math", "-fPIC", "-shared", src, "-o", out],
-                       check=True)
+        subprocess.run(["g++", "-O2", "-std=c++20", "-ffp-contract=off", "-frounding-math", "-fPIC", "-shared", "-pthread", src,
+                        "-o", out], check=True)
     return C.CDLL(out)
 
 
@@ -28,22 +28,22 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def shim_knn(shim, m, q, k, nbr_mode, leaf, pref_frac=0.4):
+def shim_knn(shim, m, q, k, nbr_mode, leaf, pref_frac=0.4, warp=False):
     coords, counts, _, pts, _ = m.download()
     q = np.ascontiguousarray(q, np.float64).reshape(-1, 3)
     nq = q.shape[0]
     idx, d2, ok = np.empty((nq, k), np.uint64), np.empty((nq, k), np.float64), np.empty(nq, np.uint8)
-    rc = shim.shim_knn(_p(coords), _p(counts), _p(pts), C.c_uint32(coords.shape[0]), C.c_int(m.cap), C.c_int(nbr_mode),
+    rc = (shim.shim_knn_warp if warp else shim.shim_knn)(_p(coords), _p(counts), _p(pts), C.c_uint32(coords.shape[0]), C.c_int(m.cap), C.c_int(nbr_mode),
                        C.c_double(leaf), C.c_double(pref_frac), _p(q), C.c_size_t(nq), C.c_int(k), _p(idx), _p(d2), _p(ok))
     assert rc == 0
     return idx, d2, ok.astype(bool)
 
 
-def check(shim, oracle, pts, q, k, mode, leaf, min_dist, pref_frac=0.4, cap=20):
+def check(shim, oracle, pts, q, k, mode, leaf, min_dist, pref_frac=0.4, cap=20, warp=False):
     m = oracle.IVoxRef(leaf, min_dist, cap, mode, 1000)
     m.insert(pts)
     io, do, oo = m.knn_search(q, k)
-    ih, dh, oh = shim_knn(shim, m, q, k, mode, leaf, pref_frac)
+    ih, dh, oh = shim_knn(shim, m, q, k, mode, leaf, pref_frac, warp)
     assert np.array_equal(oo, oh)
     assert np.array_equal(io[oo], ih[oo]), f"indices differ (mode {mode}, k {k})"
     assert np.array_equal(do[oo], dh[oo]), "squared distances differ"
@@ -94,3 +94,20 @@ def test_search_sparse_voxels_and_small_cap(shim, oracle):
     dense = rng.uniform(-2, 2, (20000, 3)).astype(np.float32)
     check(shim, oracle, dense, rng.uniform(-2, 2, (2000, 3)), 5, 19, 1.0, 0.0, cap=7)  # cap not a multiple of 4
     check(shim, oracle, dense, rng.uniform(-2, 2, (2000, 3)), 5, 19, 1.0, 0.0, cap=31)
+
+
+@pytest.mark.parametrize("mode,k", [(19, 5), (27, 8), (7, 3)])
+def test_search_32_lane_warp_emulation(shim, oracle, mode, k):
+    """The same code run as a 32-lane warp (32 host threads in lock step, warp intrinsics exchanged through a
+    barrier): every lane must reach the same intrinsics in the same order (or the emulation dead-locks and the
+    test times out) and the max-over-lanes loops, deferred insertion and drains must still give every lane its own
+    exact result.  Lanes of a warp are deliberately heterogeneous: dense and sparse regions, far queries, a ragged
+    last warp."""
+    import synth
+
+    rng = synth.rng_for(900 + mode + k)
+    pts = np.concatenate([synth.sample_world(40000, 25.0, rng), rng.uniform(-25, 25, (3000, 3)).astype(np.float32)])
+    q = np.concatenate([pts[rng.integers(0, pts.shape[0], 500), :3].astype(np.float64) + rng.normal(0, 0.2, (500, 3)),
+                        rng.uniform(-30, 30, (141, 3))])
+    q = q[rng.permutation(q.shape[0])]  # 641 queries: 20 full warps + one lane
+    assert check(shim, oracle, pts, q, k, mode, 1.0, 0.2, warp=True) > 300
