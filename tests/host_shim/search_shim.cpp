@@ -79,7 +79,9 @@ static inline void __syncwarp(unsigned = 0xffffffffu) {
     t_warp->bar.arrive_and_wait();
   }
 }
-static inline int emu_lane_id() { return t_lane; }
+namespace mb {
+static inline int lane_id() { return t_lane; }
+}  // namespace mb
 static inline unsigned __fns(unsigned mask, unsigned base, int offset) {  // offset-th set bit at or above `base` (offset >= 1)
   for (unsigned b = base; b < 32; ++b)
     if ((mask >> b) & 1u)
