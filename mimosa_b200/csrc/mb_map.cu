@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "mb_map.cuh"
+#include "mb_search_coop.cuh"
 
 namespace mb {
 
@@ -415,6 +416,65 @@ __global__ void __launch_bounds__(kKnnThreads, 7)
 #endif
 }
 
+// EXPERIMENTAL restricted k-NN with G lanes per query (mb_search_coop.cuh); MB_KNN_VARIANT=coop4 / coop8 selects it.
+// 128 threads = 128 / G queries per block; winner j of a query is resolved and written by group lane j % G.
+template <int K, int G>
+__global__ void __launch_bounds__(kKnnThreads, 5)
+    k_knn_coop(MapView mv, const double* __restrict__ q, size_t nq, int k, uint64_t* __restrict__ idx,
+               double* __restrict__ d2, uint8_t* __restrict__ ok) {
+  constexpr int kQ = kKnnThreads / G;  // queries per block
+  __shared__ uint32_t s_ctab[kTabEntries];
+  __shared__ uint32_t s_pk_all[kCube * kQ];
+  __shared__ uint32_t s_blk_all[kCoopBlk * kQ];
+  __shared__ uint32_t s_q_all[kCoopQueue * kQ];
+  __shared__ uint32_t s_st_all[3 * kCoopStack * kKnnThreads];
+  if (threadIdx.x < kScan) s_ctab[threadIdx.x] = coop_tab_entry(mv.scan[threadIdx.x]);
+  __syncthreads();
+  const int grp = threadIdx.x / G, gl = threadIdx.x % G;
+  uint32_t* s_pk = s_pk_all + grp * kCube;
+  const size_t i = (size_t)blockIdx.x * kQ + grp;
+  const bool active = i < nq;
+  double qx = 0, qy = 0, qz = 0;
+  if (active) {
+    qx = q[3 * i];
+    qy = q[3 * i + 1];
+    qz = q[3 * i + 2];
+  }
+  double bd[K];
+  uint32_t bs[K];
+  knn_group<K, G>(mv, s_ctab, s_pk, s_blk_all + grp * kCoopBlk, s_q_all + grp * kCoopQueue, s_st_all + threadIdx.x, kKnnThreads, qx,
+                  qy, qz, k, active, bd, bs);
+  if (!active) return;
+  uint64_t* const idx_q = idx + i * (size_t)k;
+  double* const d2_q = d2 + i * (size_t)k;
+#pragma unroll
+  for (int r = 0; r < (K + G - 1) / G; ++r) {
+    const int j = gl + G * r;
+    if (j < k) {
+      double dj = 0.0;
+      uint32_t sj = 0xffffffffu;
+#pragma unroll
+      for (int a = 0; a < K; ++a)
+        if (a == j) dj = bd[a], sj = bs[a];
+      uint64_t g = ~0ull;
+      if (sj != 0xffffffffu) {
+        const float4* bucket = mv.pts + (size_t)s_pk[sj >> kSeqShift] * mv.cap;
+        const uint32_t w = (uint32_t)__float_as_int(__ldg(&bucket->w));  // (voxel id << 5) | count
+        g = ((uint64_t)(w >> kCountBits) << 32) | (uint64_t)(sj & ((1u << kSeqShift) - 1));
+      }
+      idx_q[j] = g;
+      d2_q[j] = g != ~0ull ? dj : DBL_MAX;
+    }
+  }
+  if (gl == 0) {  // the list is ordered: all k exist iff the k-th does
+    uint32_t sk = 0xffffffffu;
+#pragma unroll
+    for (int a = 0; a < K; ++a)
+      if (a == k - 1) sk = bs[a];
+    ok[i] = sk != 0xffffffffu;
+  }
+}
+
 __global__ void k_gather_points(const float4* __restrict__ pts, int cap, const uint64_t* __restrict__ idx, size_t n,
                                 double* __restrict__ out) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -604,11 +664,39 @@ int ensure_mirror(mb_map* m) {
 int launch_knn(mb_map* m, const double* d_q, size_t nq, int k, uint64_t* d_idx, double* d_d2, uint8_t* d_ok) {
   if (nq == 0) return MB_OK;
   MB_TRY(ensure_mirror(m));
-  const unsigned grid = blocks_for(nq, kKnnThreads);
-  if (k == 5)
-    k_knn<5><<<grid, kKnnThreads, 0, m->ctx->stream>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
-  else
-    k_knn<MB_MAX_K><<<grid, kKnnThreads, 0, m->ctx->stream>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
+  // development switch: MB_KNN_VARIANT=coop4 / coop8 runs the experimental lanes-per-query search instead
+  // (read at every launch so that one process can compare the variants; an unknown value is an error, not a fallback)
+  int coop = 0;
+  if (const char* e = getenv("MB_KNN_VARIANT")) {
+    if (!strcmp(e, "coop4"))
+      coop = 4;
+    else if (!strcmp(e, "coop8"))
+      coop = 8;
+    else if (strcmp(e, "thread") && e[0]) {
+      set_error("MB_KNN_VARIANT=%s: expected thread, coop4 or coop8", e);
+      return MB_ERR_INVALID_ARG;
+    }
+  }
+  cudaStream_t st = m->ctx->stream;
+  if (coop == 4) {
+    const unsigned grid = blocks_for(nq, kKnnThreads / 4);
+    if (k == 5)
+      k_knn_coop<5, 4><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
+    else
+      k_knn_coop<MB_MAX_K, 4><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
+  } else if (coop == 8) {
+    const unsigned grid = blocks_for(nq, kKnnThreads / 8);
+    if (k == 5)
+      k_knn_coop<5, 8><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
+    else
+      k_knn_coop<MB_MAX_K, 8><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
+  } else {
+    const unsigned grid = blocks_for(nq, kKnnThreads);
+    if (k == 5)
+      k_knn<5><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
+    else
+      k_knn<MB_MAX_K><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
+  }
   ++m->ctx->launches;
   MB_CUDA(cudaGetLastError());
   return MB_OK;

@@ -124,6 +124,7 @@ static inline void prefetch_l2(const void*) {}
 using std::min;
 
 #include "../../mimosa_b200/csrc/mb_search.cuh"
+#include "../../mimosa_b200/csrc/mb_search_coop.cuh"
 
 namespace {
 struct HostMirror {
@@ -243,7 +244,67 @@ void run_warps(const HostMirror& M, const double* q, size_t nq, int k, uint64_t*
     for (auto& t : lanes) t.join();
   }
 }
+// G lanes per query (mb_search_coop.cuh): 32 / G queries per emulated warp, shared arrays laid out as in k_knn_coop
+template <int K, int G>
+void run_coop(const HostMirror& M, const double* q, size_t nq, int k, uint64_t* idx, double* d2, uint8_t* ok) {
+  constexpr int QW = 32 / G;
+  uint32_t s_ctab[mb::kTabEntries] = {0};
+  for (int p = 0; p < mb::kScan; ++p) s_ctab[p] = mb::coop_tab_entry(M.view.scan[p]);
+  for (size_t w0 = 0; w0 < nq; w0 += QW) {
+    WarpCtx ctx;
+    std::vector<uint32_t> s_pk(mb::kCube * QW, 0xdeadbeefu), s_q(mb::kCoopQueue * QW, 0xdeadbeefu),
+        s_blk(mb::kCoopBlk * QW, 0xdeadbeefu), s_st(3 * mb::kCoopStack * 32, 0xdeadbeefu);
+    std::vector<std::thread> lanes;
+    for (int lane = 0; lane < 32; ++lane)
+      lanes.emplace_back([&, lane] {
+        t_warp = &ctx;
+        t_lane = lane;
+        const int grp = lane / G, gl = lane % G;
+        const size_t i = w0 + grp;
+        const bool active = i < nq;
+        const size_t qi = active ? i : 0;
+        double bd[K];
+        uint32_t bs[K];
+        uint32_t* pk = s_pk.data() + grp * mb::kCube;
+        mb::knn_group<K, G>(M.view, s_ctab, pk, s_blk.data() + grp * mb::kCoopBlk, s_q.data() + grp * mb::kCoopQueue, s_st.data() + lane, 32, q[3 * qi], q[3 * qi + 1],
+                            q[3 * qi + 2], k, active, bd, bs);
+        if (active) {
+          // winner j is written by group lane j % G, as in the kernel
+          uint64_t g[K];
+          float4 pts[K];
+          const int found = mb::knn_resolve_all<K, true>(M.view, pk, 1, bs, k, g, pts);
+          for (int j = gl; j < k; j += G) {
+            idx[i * k + j] = g[j];
+            d2[i * k + j] = g[j] != ~0ull ? bd[j] : 1.7976931348623157e308;
+          }
+          if (gl == 0) ok[i] = found == k;
+        }
+        t_warp = nullptr;
+      });
+    for (auto& t : lanes) t.join();
+  }
+}
 }  // namespace
+
+extern "C" int shim_knn_coop(const int32_t* coords, const int32_t* counts, const float* xyz, uint32_t n_vox, int cap, int nbr_mode,
+                             double leaf, double pref_frac, const double* q, size_t nq, int k, int lanes_per_query, uint64_t* idx,
+                             double* d2, uint8_t* ok) {
+  if (k < 1 || k > 8 || (lanes_per_query != 4 && lanes_per_query != 8)) return 1;
+  HostMirror M;
+  build_mirror(M, coords, counts, xyz, n_vox, cap, nbr_mode, leaf, pref_frac);
+  if (lanes_per_query == 4) {
+    if (k == 5)
+      run_coop<5, 4>(M, q, nq, k, idx, d2, ok);
+    else
+      run_coop<8, 4>(M, q, nq, k, idx, d2, ok);
+  } else {
+    if (k == 5)
+      run_coop<5, 8>(M, q, nq, k, idx, d2, ok);
+    else
+      run_coop<8, 8>(M, q, nq, k, idx, d2, ok);
+  }
+  return 0;
+}
 
 extern "C" int shim_knn(const int32_t* coords, const int32_t* counts, const float* xyz, uint32_t n_vox, int cap, int nbr_mode,
                         double leaf, double pref_frac, const double* q, size_t nq, int k, uint64_t* idx, double* d2, uint8_t* ok) {

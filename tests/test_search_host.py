@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def shim():
     src = os.path.join(HERE, "host_shim", "search_shim.cpp")
     out = os.path.join(HERE, "host_shim", "libsearch_shim.so")
-    hdrs = [os.path.join(HERE, "..", "mimosa_b200", "csrc", h) for h in ("mb_search.cuh", "mb_math.cuh")]
+    hdrs = [os.path.join(HERE, "..", "mimosa_b200", "csrc", h) for h in ("mb_search.cuh", "mb_search_coop.cuh", "mb_math.cuh")]
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(p) for p in [src] + hdrs):
         subprocess.run(["g++", "-O2", "-std=c++20", "-ffp-contract=off", "-frounding-math", "-fPIC", "-shared", "-pthread", src,
                         "-o", out], check=True)
@@ -28,22 +28,28 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def shim_knn(shim, m, q, k, nbr_mode, leaf, pref_frac=0.4, warp=False):
+def shim_knn(shim, m, q, k, nbr_mode, leaf, pref_frac=0.4, warp=False, coop=0):
     coords, counts, _, pts, _ = m.download()
     q = np.ascontiguousarray(q, np.float64).reshape(-1, 3)
     nq = q.shape[0]
     idx, d2, ok = np.empty((nq, k), np.uint64), np.empty((nq, k), np.float64), np.empty(nq, np.uint8)
+    if coop:  # G lanes per query (mb_search_coop.cuh), always as an emulated 32-lane warp
+        rc = shim.shim_knn_coop(_p(coords), _p(counts), _p(pts), C.c_uint32(coords.shape[0]), C.c_int(m.cap), C.c_int(nbr_mode),
+                                C.c_double(leaf), C.c_double(pref_frac), _p(q), C.c_size_t(nq), C.c_int(k), C.c_int(coop), _p(idx),
+                                _p(d2), _p(ok))
+        assert rc == 0
+        return idx, d2, ok.astype(bool)
     rc = (shim.shim_knn_warp if warp else shim.shim_knn)(_p(coords), _p(counts), _p(pts), C.c_uint32(coords.shape[0]), C.c_int(m.cap), C.c_int(nbr_mode),
                        C.c_double(leaf), C.c_double(pref_frac), _p(q), C.c_size_t(nq), C.c_int(k), _p(idx), _p(d2), _p(ok))
     assert rc == 0
     return idx, d2, ok.astype(bool)
 
 
-def check(shim, oracle, pts, q, k, mode, leaf, min_dist, pref_frac=0.4, cap=20, warp=False):
+def check(shim, oracle, pts, q, k, mode, leaf, min_dist, pref_frac=0.4, cap=20, warp=False, coop=0):
     m = oracle.IVoxRef(leaf, min_dist, cap, mode, 1000)
     m.insert(pts)
     io, do, oo = m.knn_search(q, k)
-    ih, dh, oh = shim_knn(shim, m, q, k, mode, leaf, pref_frac, warp)
+    ih, dh, oh = shim_knn(shim, m, q, k, mode, leaf, pref_frac, warp, coop)
     assert np.array_equal(oo, oh)
     assert np.array_equal(io[oo], ih[oo]), f"indices differ (mode {mode}, k {k})"
     assert np.array_equal(do[oo], dh[oo]), "squared distances differ"
@@ -111,3 +117,43 @@ def test_search_32_lane_warp_emulation(shim, oracle, mode, k):
                         rng.uniform(-30, 30, (141, 3))])
     q = q[rng.permutation(q.shape[0])]  # 641 queries: 20 full warps + one lane
     assert check(shim, oracle, pts, q, k, mode, 1.0, 0.2, warp=True) > 300
+
+
+# ---- the cooperative variant (G lanes per query, mb_search_coop.cuh), run as emulated 32-lane warps -----------------
+@pytest.mark.parametrize("lanes", [4, 8])
+@pytest.mark.parametrize("mode,k", [(19, 5), (27, 8), (7, 3), (1, 5), (27, 1)])
+def test_coop_search_matches_oracle_world(shim, oracle, lanes, mode, k):
+    import synth
+
+    rng = synth.rng_for(1200 + mode + k)
+    pts = np.concatenate([synth.sample_world(40000, 25.0, rng), rng.uniform(-25, 25, (3000, 3)).astype(np.float32)])
+    q = np.concatenate([pts[rng.integers(0, pts.shape[0], 400), :3].astype(np.float64) + rng.normal(0, 0.2, (400, 3)),
+                        rng.uniform(-30, 30, (101, 3))])
+    q = q[rng.permutation(q.shape[0])]  # 501 queries: ragged last warp for both group sizes
+    assert check(shim, oracle, pts, q, k, mode, 1.0, 0.2, coop=lanes) > 200
+
+
+@pytest.mark.parametrize("lanes", [4, 8])
+def test_coop_search_ties_caps_and_leaf_sizes(shim, oracle, lanes):
+    # lattice: exact distance ties across buckets handled by different lanes must resolve by visiting order
+    g = np.arange(-6, 6) * 0.5
+    pts = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    rng = np.random.default_rng(5)
+    pts = pts[rng.permutation(pts.shape[0])]
+    q = np.concatenate([pts[:300].astype(np.float64) + 0.25, pts[:300].astype(np.float64), np.round(rng.uniform(-3, 3, (200, 3)))])
+    for mode, k in ((19, 5), (27, 8), (7, 5)):
+        check(shim, oracle, pts, q, k, mode, 1.0, 0.0, coop=lanes)
+    # volumetric cloud (every neighbour occupied, several rounds of survivors), other leaf sizes, prefetch radii
+    vol = rng.uniform(-5, 5, (30000, 3)).astype(np.float32)
+    qv = rng.uniform(-5.5, 5.5, (600, 3))
+    for leaf, md, pref in ((0.5, 0.15, 0.0), (2.0, 0.0, 0.4), (0.25, 0.05, 2.0)):
+        assert check(shim, oracle, vol, qv, 5, 19, leaf, md, pref, coop=lanes) > 200
+    assert check(shim, oracle, vol, qv, 5, 27, 1.0, 0.0, coop=lanes) > 200
+    # caps: not a multiple of four; more than 4 * 4 points per bucket (second round of own-voxel chunks at G = 4)
+    dense = rng.uniform(-2, 2, (20000, 3)).astype(np.float32)
+    qd = rng.uniform(-2, 2, (500, 3))
+    check(shim, oracle, dense, qd, 5, 19, 1.0, 0.0, cap=7, coop=lanes)
+    check(shim, oracle, dense, qd, 5, 19, 1.0, 0.0, cap=31, coop=lanes)
+    # sparse: own voxel mostly empty, fewer than k neighbours
+    sparse = rng.uniform(-20, 20, (3000, 3)).astype(np.float32)
+    check(shim, oracle, sparse, rng.uniform(-20, 20, (600, 3)), 5, 27, 1.0, 0.0, coop=lanes)
