@@ -418,8 +418,8 @@ __global__ void __launch_bounds__(kKnnThreads, 7)
 
 // EXPERIMENTAL restricted k-NN with G lanes per query (mb_search_coop.cuh); MB_KNN_VARIANT=coop4 / coop8 selects it.
 // 128 threads = 128 / G queries per block; winner j of a query is resolved and written by group lane j % G.
-template <int K, int G>
-__global__ void __launch_bounds__(kKnnThreads, 5)
+template <int K, int G, int MINB, int STEP, int MODE>
+__global__ void __launch_bounds__(kKnnThreads, MINB)
     k_knn_coop(MapView mv, const double* __restrict__ q, size_t nq, int k, uint64_t* __restrict__ idx,
                double* __restrict__ d2, uint8_t* __restrict__ ok) {
   constexpr int kQ = kKnnThreads / G;  // queries per block
@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(kKnnThreads, 5)
   }
   double bd[K];
   uint32_t bs[K];
-  knn_group<K, G>(mv, s_ctab, s_pk, s_blk_all + grp * kCoopBlk, s_q_all + grp * kCoopQueue, s_st_all + threadIdx.x, kKnnThreads, qx,
+  knn_group<K, G, STEP, MODE>(mv, s_ctab, s_pk, s_blk_all + grp * kCoopBlk, s_q_all + grp * kCoopQueue, s_st_all + threadIdx.x, kKnnThreads, qx,
                   qy, qz, k, active, bd, bs);
   if (!active) return;
   uint64_t* const idx_q = idx + i * (size_t)k;
@@ -664,32 +664,60 @@ int ensure_mirror(mb_map* m) {
 int launch_knn(mb_map* m, const double* d_q, size_t nq, int k, uint64_t* d_idx, double* d_d2, uint8_t* d_ok) {
   if (nq == 0) return MB_OK;
   MB_TRY(ensure_mirror(m));
-  // development switch: MB_KNN_VARIANT=coop4 / coop8 runs the experimental lanes-per-query search instead
-  // (read at every launch so that one process can compare the variants; an unknown value is an error, not a fallback)
-  int coop = 0;
+  // development switch: MB_KNN_VARIANT = thread (default) | coop<G>[p][b<min blocks per SM>][s<points per step>], e.g.
+  // coop4, coop8, coop4b8, coop4b7s4 (a bucket per lane), coop4p, coop8p, coop4pb8 (a point per lane) — the experimental
+  // lanes-per-query search (read at every launch so that one process can compare the variants; an unknown value is an
+  // error, not a fallback)
+  int coop = 0, minb = 5, step = 8, mode = 0;
   if (const char* e = getenv("MB_KNN_VARIANT")) {
-    if (!strcmp(e, "coop4"))
-      coop = 4;
-    else if (!strcmp(e, "coop8"))
-      coop = 8;
-    else if (strcmp(e, "thread") && e[0]) {
-      set_error("MB_KNN_VARIANT=%s: expected thread, coop4 or coop8", e);
-      return MB_ERR_INVALID_ARG;
+    if (e[0] && strcmp(e, "thread")) {
+      bool ok = !strncmp(e, "coop", 4) && (e[4] == '4' || e[4] == '8');
+      const char* c = e + 5;
+      if (ok) {
+        coop = e[4] - '0';
+        if (*c == 'p') mode = 1, ++c;
+        if (*c == 'b' && c[1] >= '4' && c[1] <= '8') minb = c[1] - '0', c += 2;
+        if (*c == 's' && (c[1] == '4' || c[1] == '8')) step = c[1] - '0', c += 2;
+        ok = *c == 0;
+      }
+      if (ok) {
+        if (mode == 1)
+          ok = step == 8 && (minb == 5 || minb == 6 || minb == 8);
+        else if (coop == 8)
+          ok = minb == 5 && step == 8;
+        else
+          ok = (step == 8 && (minb == 5 || minb == 6 || minb == 8)) || (step == 4 && (minb == 7 || minb == 8));
+      }
+      if (!ok) {
+        set_error("MB_KNN_VARIANT=%s: expected thread, coop8, coop4[b6|b8], coop4b7s4, coop4b8s4 or coop{4,8}p[b6|b8]", e);
+        return MB_ERR_INVALID_ARG;
+      }
     }
   }
   cudaStream_t st = m->ctx->stream;
-  if (coop == 4) {
-    const unsigned grid = blocks_for(nq, kKnnThreads / 4);
-    if (k == 5)
-      k_knn_coop<5, 4><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
-    else
-      k_knn_coop<MB_MAX_K, 4><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
+#define MB_COOP_LAUNCH(G, MINB, STEP, MODE)                                                                          \
+  do {                                                                                                               \
+    const unsigned grid = blocks_for(nq, kKnnThreads / G);                                                           \
+    if (k == 5)                                                                                                      \
+      k_knn_coop<5, G, MINB, STEP, MODE><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);    \
+    else                                                                                                             \
+      k_knn_coop<MB_MAX_K, G, 4, 8, MODE><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);   \
+  } while (0)
+  if (coop && mode == 1) {
+    if (coop == 4 && minb == 5) MB_COOP_LAUNCH(4, 5, 8, 1);
+    if (coop == 4 && minb == 6) MB_COOP_LAUNCH(4, 6, 8, 1);
+    if (coop == 4 && minb == 8) MB_COOP_LAUNCH(4, 8, 8, 1);
+    if (coop == 8 && minb == 5) MB_COOP_LAUNCH(8, 5, 8, 1);
+    if (coop == 8 && minb == 6) MB_COOP_LAUNCH(8, 6, 8, 1);
+    if (coop == 8 && minb == 8) MB_COOP_LAUNCH(8, 8, 8, 1);
   } else if (coop == 8) {
-    const unsigned grid = blocks_for(nq, kKnnThreads / 8);
-    if (k == 5)
-      k_knn_coop<5, 8><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
-    else
-      k_knn_coop<MB_MAX_K, 8><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
+    MB_COOP_LAUNCH(8, 5, 8, 0);
+  } else if (coop == 4) {
+    if (step == 8 && minb == 5) MB_COOP_LAUNCH(4, 5, 8, 0);
+    if (step == 8 && minb == 6) MB_COOP_LAUNCH(4, 6, 8, 0);
+    if (step == 8 && minb == 8) MB_COOP_LAUNCH(4, 8, 8, 0);
+    if (step == 4 && minb == 7) MB_COOP_LAUNCH(4, 7, 4, 0);
+    if (step == 4 && minb == 8) MB_COOP_LAUNCH(4, 8, 4, 0);
   } else {
     const unsigned grid = blocks_for(nq, kKnnThreads);
     if (k == 5)
@@ -697,6 +725,7 @@ int launch_knn(mb_map* m, const double* d_q, size_t nq, int k, uint64_t* d_idx, 
     else
       k_knn<MB_MAX_K><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
   }
+#undef MB_COOP_LAUNCH
   ++m->ctx->launches;
   MB_CUDA(cudaGetLastError());
   return MB_OK;

@@ -37,6 +37,22 @@ __device__ __forceinline__ int coop_lane() { return (int)(threadIdx.x & 31u); }
 inline int coop_lane() { return lane_id(); }
 #endif
 
+// Both halves of a block-table entry (32 bytes, 32-byte aligned) with ONE load instruction: an LDG whose lanes touch
+// 32 different lines occupies the SM's L1 wavefront queue for ~66 cycles, so the instruction count of scattered loads
+// is what the search is bound by (profiles/r1_experiments.md, "coop" section).
+#if defined(__CUDACC__)
+__device__ __forceinline__ void ld_block_entry(const int4* p, int4& e, int4& m) {
+  asm volatile("ld.global.nc.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w), "=r"(m.x), "=r"(m.y), "=r"(m.z), "=r"(m.w)
+               : "l"(p));
+}
+#else
+inline void ld_block_entry(const int4* p, int4& e, int4& m) {
+  e = p[0];
+  m = p[1];
+}
+#endif
+
 constexpr int kCoopQueue = 26;   // survivors per query
 constexpr int kCoopStack = 8;    // candidates a lane can push per step
 constexpr int kCoopBlk = 44;     // {mask_lo, mask_hi, base, base + popc(mask_lo)} of the 8 blocks around a query + 3 x 4 gap words
@@ -51,11 +67,15 @@ MB_HDC inline uint32_t coop_tab_entry(uint16_t scan_e) {
 // (valid afterwards for the winners' resolution); s_blk: this group's [kCoopBlk] block / gap words; s_q: this group's
 // [kCoopQueue]; s_st: this THREAD's column of a [3 * kCoopStack][st_stride] array.  Every lane of the warp must call; all lanes of a group pass the same query.  On return every lane of the
 // group holds the same (bd, bs): the K best in (d2, sequence) order, +inf / 0xffffffff where fewer exist.
-template <int K, int G>
+template <int K, int G, int STEP = 8, int MODE = 0>
 MB_DEV void knn_group(const MapView& mv, const uint32_t* __restrict__ s_ctab, uint32_t* s_pk, uint32_t* s_blk, uint32_t* s_q,
                       uint32_t* s_st, int st_stride, double qx, double qy, double qz, int k, bool active,
                       double (&bd)[K], uint32_t (&bs)[K]) {
   static_assert(G == 4 || G == 8, "4 or 8 lanes per query");
+  static_assert(STEP == 4 || STEP == 8, "4 or 8 points per neighbour step");
+  static_assert(MODE == 0 || MODE == 1, "0: a bucket per lane, 1: a point per lane");
+  constexpr int NOWN = MODE == 0 ? 4 : (20 + G - 1) / G;  // own-bucket loads per lane in the first round
+  constexpr int PPL = 8 / G;                               // MODE 1: loads per lane that cover a bucket's first 8 points
   constexpr int NP = 8 / G;                // block probes per lane
   constexpr int T = (kScan + G - 1) / G;   // neighbour cells per lane
   const double kInf = __longlong_as_double(0x7ff0000000000000ll);
@@ -147,10 +167,7 @@ MB_UNROLL
       h[u] = hash_coord(bx[u], by[u], bz[u]) & mv.bmask;
       e[u] = make_int4(0, 0, 0, (int)kEmpty);
       m[u] = make_int4(0, 0, 0, 0);
-      if (active && (combo & dup_bits) == 0u) {
-        e[u] = __ldg(mv.btab + 2 * (size_t)h[u]);
-        m[u] = __ldg(mv.btab + 2 * (size_t)h[u] + 1);
-      }
+      if (active && (combo & dup_bits) == 0u) ld_block_entry(mv.btab + 2 * (size_t)h[u], e[u], m[u]);
     }
     // while the entries are in flight: group lane a < 3 leaves the squared gaps from the query to the lower / upper
     // neighbour slab of axis a (float, rounded towards zero at every step, shrunk by 1e-6 voxel: never above the true
@@ -180,8 +197,7 @@ MB_UNROLL
       for (int u = 0; u < NP; ++u) {
         if (miss[u]) {
           h[u] = (h[u] + 1) & mv.bmask;
-          e[u] = __ldg(mv.btab + 2 * (size_t)h[u]);
-          m[u] = __ldg(mv.btab + 2 * (size_t)h[u] + 1);
+          ld_block_entry(mv.btab + 2 * (size_t)h[u], e[u], m[u]);
           miss[u] = (uint32_t)e[u].w != kEmpty && !(e[u].x == bx[u] && e[u].y == by[u] && e[u].z == bz[u]);
         }
         any_miss |= miss[u];
@@ -211,12 +227,18 @@ MB_UNROLL
   }
   const float4* own_bucket = mv.pts + (size_t)(own_slot != kEmpty ? own_slot : 0u) * cap;
   const int n_chunks = (cap + 3) >> 2;
-  float4 p0[4];
+  float4 p0[NOWN];
 MB_UNROLL
-  for (int u = 0; u < 4; ++u) p0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (own_slot != kEmpty && gl < n_chunks) {
+  for (int u = 0; u < NOWN; ++u) p0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if constexpr (MODE == 0) {  // lane gl: the four points of chunk gl
+    if (own_slot != kEmpty && gl < n_chunks) {
 MB_UNROLL
-    for (int u = 0; u < 4; ++u) p0[u] = __ldg(own_bucket + min(4 * gl + u, cap - 1));
+      for (int u = 0; u < 4; ++u) p0[u] = __ldg(own_bucket + min(4 * gl + u, cap - 1));
+    }
+  } else {  // lane gl: points gl, gl + G, ... — every load instruction reads G consecutive points per group
+MB_UNROLL
+    for (int u = 0; u < NOWN; ++u)
+      if (own_slot != kEmpty && G * u + gl < cap) p0[u] = __ldg(own_bucket + G * u + gl);
   }
 
   // ---- 3: neighbour cells: lane gl takes scan positions gl, gl + G, ... ---------------------------------------------
@@ -258,21 +280,22 @@ MB_UNROLL
   }
   __syncwarp();
 
-  // the own voxel's candidates: the first round's four per lane go through a sorting network straight into the
-  // (empty) list; a second round of chunks only happens when some bucket holds more than 4 * G points
+  // the own voxel's candidates: the first round's NOWN per lane go through a sorting network straight into the
+  // (empty) list; further rounds only happen for buckets larger than the first round covers
   {
     int cnt = 0;
     {  // the fill count rides in the .w of the first point: group lane 0 has it
       const uint32_t w0 = __shfl_sync(kFull, (uint32_t)__float_as_int(p0[0].w), gbase);
       if (own_slot != kEmpty) cnt = (int)(w0 & kCntMask);
     }
-    double d[4];
-    uint32_t sq[4];
+    double d[NOWN];
+    uint32_t sq[NOWN];
 MB_UNROLL
-    for (int u = 0; u < 4; ++u) {
-      const bool ok = 4 * gl + u < cnt;
+    for (int u = 0; u < NOWN; ++u) {
+      const int j = MODE == 0 ? 4 * gl + u : G * u + gl;
+      const bool ok = j < cnt;
       d[u] = ok ? sqdist4((double)p0[u].x, (double)p0[u].y, (double)p0[u].z, qx, qy, qz) : kInf;
-      sq[u] = ok ? (rk_own << kSeqShift) | (uint32_t)(4 * gl + u) : 0xffffffffu;
+      sq[u] = ok ? (rk_own << kSeqShift) | (uint32_t)j : 0xffffffffu;
     }
     auto cswap = [&](int x, int y) {  // x < y: afterwards entry x <= entry y in (d2, sequence) order
       const bool sw = (d[y] < d[x]) | ((d[y] == d[x]) & (sq[y] < sq[x]));
@@ -281,17 +304,35 @@ MB_UNROLL
       d[x] = sw ? dy : dx, d[y] = sw ? dx : dy;
       sq[x] = sw ? sy : sx, sq[y] = sw ? sx : sy;
     };
-    cswap(0, 1), cswap(2, 3), cswap(0, 2), cswap(1, 3), cswap(1, 2);
+    if constexpr (NOWN == 3) {
+      cswap(0, 1), cswap(1, 2), cswap(0, 1);
+    } else if constexpr (NOWN == 4) {
+      cswap(0, 1), cswap(2, 3), cswap(0, 2), cswap(1, 3), cswap(1, 2);
+    } else {
+      static_assert(NOWN == 5, "sorting networks for 3, 4 and 5 entries");
+      cswap(0, 1), cswap(3, 4), cswap(2, 4), cswap(2, 3), cswap(1, 4), cswap(0, 3), cswap(0, 2), cswap(1, 3), cswap(1, 2);
+    }
+    static_assert(NOWN <= K, "the first round fits the list");
 MB_UNROLL
-    for (int u = 0; u < 4; ++u) bd[u] = d[u], bs[u] = sq[u];
-    for (int c0 = G; __any_sync(kFull, 4 * c0 < cnt); c0 += G) {
-      const int j = 4 * (c0 + gl);
-      if (c0 + gl < n_chunks && j < cnt) {
+    for (int u = 0; u < NOWN; ++u) bd[u] = d[u], bs[u] = sq[u];
+    if constexpr (MODE == 0) {
+      for (int c0 = G; __any_sync(kFull, 4 * c0 < cnt); c0 += G) {
+        const int j = 4 * (c0 + gl);
+        if (c0 + gl < n_chunks && j < cnt) {
 MB_UNROLL
-        for (int u = 0; u < 4; ++u) p0[u] = __ldg(own_bucket + min(j + u, cap - 1));
+          for (int u = 0; u < 4; ++u) p0[u] = __ldg(own_bucket + min(j + u, cap - 1));
 MB_UNROLL
-        for (int u = 0; u < 4; ++u)
-          if (j + u < cnt) offer(sqdist4((double)p0[u].x, (double)p0[u].y, (double)p0[u].z, qx, qy, qz), (rk_own << kSeqShift) | (uint32_t)(j + u));
+          for (int u = 0; u < 4; ++u)
+            if (j + u < cnt) offer(sqdist4((double)p0[u].x, (double)p0[u].y, (double)p0[u].z, qx, qy, qz), (rk_own << kSeqShift) | (uint32_t)(j + u));
+        }
+      }
+    } else {
+      for (int j0 = NOWN * G; __any_sync(kFull, j0 < cnt); j0 += G) {
+        const int j = j0 + gl;
+        if (j < cnt) {
+          const float4 p = __ldg(own_bucket + j);
+          offer(sqdist4((double)p.x, (double)p.y, (double)p.z, qx, qy, qz), (rk_own << kSeqShift) | (uint32_t)j);
+        }
       }
     }
   }
@@ -316,42 +357,110 @@ MB_UNROLL
   __syncwarp();
   const bool any_surv = __any_sync(kFull, n_surv > 0);
   int n_st = 0;
-  for (int r0 = 0; __any_sync(kFull, r0 < n_surv); r0 += G) {
-    const int item = r0 + gl;
-    bool has = item < n_surv;
-    const uint32_t w = has ? s_q[item] : 0u;
-    const uint32_t rk = w & 31u;
-    if (has && r0 > 0 && __int_as_float((int)(w & ~31u)) > wq_f) has = false;  // the radius has tightened since
-    const float4* bucket = mv.pts + (size_t)(has ? s_pk[rk] : 0u) * cap;
-    int cnt = has ? 1 : 0;  // the real count arrives with the first chunk
-    for (int j = 0; __any_sync(kFull, j < cnt); j += 8) {
-      if (j < cnt) {
-        float4 p[8];
+  auto push = [&](double d, uint32_t seq) {
+    s_st[(3 * n_st) * st_stride] = (uint32_t)__double2loint(d);
+    s_st[(3 * n_st + 1) * st_stride] = (uint32_t)__double2hiint(d);
+    s_st[(3 * n_st + 2) * st_stride] = seq;
+    ++n_st;
+  };
+  auto drain = [&]() {
+    while (__any_sync(kFull, n_st > 0)) {
+      if (n_st > 0) {
+        --n_st;
+        // volatile: the three words are read together, before offer()'s gate (see the note in knn_thread)
+        const volatile uint32_t* ent = s_st + (3 * n_st) * st_stride;
+        const uint32_t lo = ent[0], hi = ent[st_stride], sq = ent[2 * st_stride];
+        offer(__hiloint2double((int)hi, (int)lo), sq);
+      }
+    }
+    wq = worst_of();  // this lane's radius: replicated list + its own candidates
+    wq_f = __double2float_ru(wq);
+  };
+  if constexpr (MODE == 1) {
+    // The whole group works on the same two buckets per round: lane gl reads points gl, gl + G, ... so that every load
+    // instruction covers G consecutive points (one line) per group; a lane keeps the candidates it computed.
+    for (int b0 = 0; __any_sync(kFull, b0 < n_surv); b0 += 2) {
+      const uint32_t wa = b0 < n_surv ? s_q[b0] : 0u, wb = b0 + 1 < n_surv ? s_q[b0 + 1] : 0u;
+      const uint32_t rka = wa & 31u, rkb = wb & 31u;
+      // (the radius may have tightened since the queue was formed; lanes of a group may disagree, which is fine:
+      // a lane only skips work its own radius rules out)
+      const bool ha = b0 < n_surv && !(__int_as_float((int)(wa & ~31u)) > wq_f);
+      const bool hb = b0 + 1 < n_surv && !(__int_as_float((int)(wb & ~31u)) > wq_f);
+      const float4* ba = mv.pts + (size_t)(b0 < n_surv ? s_pk[rka] : 0u) * cap;
+      const float4* bb = mv.pts + (size_t)(b0 + 1 < n_surv ? s_pk[rkb] : 0u) * cap;
+      float4 pa[PPL], pb[PPL];
 MB_UNROLL
-        for (int u = 0; u < 8; ++u) p[u] = __ldg(bucket + min(j + u, cap - 1));
-        if (j == 0) cnt = (int)((uint32_t)__float_as_int(p[0].w) & kCntMask);
+      for (int u = 0; u < PPL; ++u) {
+        pa[u] = pb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // group lane 0 always fetches the first point of a bucket the group visits: it carries the fill count
+        if ((ha || (gl == 0 && u == 0 && b0 < n_surv)) && G * u + gl < cap) pa[u] = __ldg(ba + G * u + gl);
+        if ((hb || (gl == 0 && u == 0 && b0 + 1 < n_surv)) && G * u + gl < cap) pb[u] = __ldg(bb + G * u + gl);
+      }
+      const uint32_t ca = __shfl_sync(kFull, (uint32_t)__float_as_int(pa[0].w), gbase) & kCntMask;
+      const uint32_t cb = __shfl_sync(kFull, (uint32_t)__float_as_int(pb[0].w), gbase) & kCntMask;
+      const int cnta = ha ? (int)ca : 0, cntb = hb ? (int)cb : 0;
 MB_UNROLL
-        for (int u = 0; u < 8; ++u) {
-          const double d = sqdist4((double)p[u].x, (double)p[u].y, (double)p[u].z, qx, qy, qz);
-          if (j + u < cnt && d <= wq) {
-            s_st[(3 * n_st) * st_stride] = (uint32_t)__double2loint(d);
-            s_st[(3 * n_st + 1) * st_stride] = (uint32_t)__double2hiint(d);
-            s_st[(3 * n_st + 2) * st_stride] = (rk << kSeqShift) | (uint32_t)(j + u);
-            ++n_st;
+      for (int u = 0; u < PPL; ++u) {
+        const int j = G * u + gl;
+        const double da = sqdist4((double)pa[u].x, (double)pa[u].y, (double)pa[u].z, qx, qy, qz);
+        if (j < cnta && da <= wq) push(da, (rka << kSeqShift) | (uint32_t)j);
+        const double db = sqdist4((double)pb[u].x, (double)pb[u].y, (double)pb[u].z, qx, qy, qz);
+        if (j < cntb && db <= wq) push(db, (rkb << kSeqShift) | (uint32_t)j);
+      }
+      drain();
+      for (int j0 = 8; __any_sync(kFull, (j0 < cnta) | (j0 < cntb)); j0 += G) {  // buckets with more than 8 points
+        const int j = j0 + gl;
+        if (j < cnta) {
+          const float4 p = __ldg(ba + j);
+          const double d = sqdist4((double)p.x, (double)p.y, (double)p.z, qx, qy, qz);
+          if (d <= wq) push(d, (rka << kSeqShift) | (uint32_t)j);
+        }
+        if (j < cntb) {
+          const float4 p = __ldg(bb + j);
+          const double d = sqdist4((double)p.x, (double)p.y, (double)p.z, qx, qy, qz);
+          if (d <= wq) push(d, (rkb << kSeqShift) | (uint32_t)j);
+        }
+        drain();
+      }
+    }
+  } else {
+    for (int r0 = 0; __any_sync(kFull, r0 < n_surv); r0 += G) {
+      const int item = r0 + gl;
+      bool has = item < n_surv;
+      const uint32_t w = has ? s_q[item] : 0u;
+      const uint32_t rk = w & 31u;
+      if (has && r0 > 0 && __int_as_float((int)(w & ~31u)) > wq_f) has = false;  // the radius has tightened since
+      const float4* bucket = mv.pts + (size_t)(has ? s_pk[rk] : 0u) * cap;
+      int cnt = has ? 1 : 0;  // the real count arrives with the first chunk
+      for (int j = 0; __any_sync(kFull, j < cnt); j += STEP) {
+        if (j < cnt) {
+          float4 p[STEP];
+  MB_UNROLL
+          for (int u = 0; u < STEP; ++u) p[u] = __ldg(bucket + min(j + u, cap - 1));
+          if (j == 0) cnt = (int)((uint32_t)__float_as_int(p[0].w) & kCntMask);
+  MB_UNROLL
+          for (int u = 0; u < STEP; ++u) {
+            const double d = sqdist4((double)p[u].x, (double)p[u].y, (double)p[u].z, qx, qy, qz);
+            if (j + u < cnt && d <= wq) {
+              s_st[(3 * n_st) * st_stride] = (uint32_t)__double2loint(d);
+              s_st[(3 * n_st + 1) * st_stride] = (uint32_t)__double2hiint(d);
+              s_st[(3 * n_st + 2) * st_stride] = (rk << kSeqShift) | (uint32_t)(j + u);
+              ++n_st;
+            }
           }
         }
-      }
-      while (__any_sync(kFull, n_st > 0)) {  // drain
-        if (n_st > 0) {
-          --n_st;
-          // volatile: the three words are read together, before offer()'s gate (see the note in knn_thread)
-          const volatile uint32_t* ent = s_st + (3 * n_st) * st_stride;
-          const uint32_t lo = ent[0], hi = ent[st_stride], sq = ent[2 * st_stride];
-          offer(__hiloint2double((int)hi, (int)lo), sq);
+        while (__any_sync(kFull, n_st > 0)) {  // drain
+          if (n_st > 0) {
+            --n_st;
+            // volatile: the three words are read together, before offer()'s gate (see the note in knn_thread)
+            const volatile uint32_t* ent = s_st + (3 * n_st) * st_stride;
+            const uint32_t lo = ent[0], hi = ent[st_stride], sq = ent[2 * st_stride];
+            offer(__hiloint2double((int)hi, (int)lo), sq);
+          }
         }
+        wq = worst_of();  // this lane's radius: replicated list + its own candidates
+        wq_f = __double2float_ru(wq);
       }
-      wq = worst_of();  // this lane's radius: replicated list + its own candidates
-      wq_f = __double2float_ru(wq);
     }
   }
   // ---- 6: final merge (nothing to do when no group of the warp had a surviving neighbour) ---------------------------

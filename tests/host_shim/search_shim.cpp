@@ -245,7 +245,7 @@ void run_warps(const HostMirror& M, const double* q, size_t nq, int k, uint64_t*
   }
 }
 // G lanes per query (mb_search_coop.cuh): 32 / G queries per emulated warp, shared arrays laid out as in k_knn_coop
-template <int K, int G>
+template <int K, int G, int MODE>
 void run_coop(const HostMirror& M, const double* q, size_t nq, int k, uint64_t* idx, double* d2, uint8_t* ok) {
   constexpr int QW = 32 / G;
   uint32_t s_ctab[mb::kTabEntries] = {0};
@@ -266,7 +266,7 @@ void run_coop(const HostMirror& M, const double* q, size_t nq, int k, uint64_t* 
         double bd[K];
         uint32_t bs[K];
         uint32_t* pk = s_pk.data() + grp * mb::kCube;
-        mb::knn_group<K, G>(M.view, s_ctab, pk, s_blk.data() + grp * mb::kCoopBlk, s_q.data() + grp * mb::kCoopQueue, s_st.data() + lane, 32, q[3 * qi], q[3 * qi + 1],
+        mb::knn_group<K, G, 8, MODE>(M.view, s_ctab, pk, s_blk.data() + grp * mb::kCoopBlk, s_q.data() + grp * mb::kCoopQueue, s_st.data() + lane, 32, q[3 * qi], q[3 * qi + 1],
                             q[3 * qi + 2], k, active, bd, bs);
         if (active) {
           // winner j is written by group lane j % G, as in the kernel
@@ -287,21 +287,21 @@ void run_coop(const HostMirror& M, const double* q, size_t nq, int k, uint64_t* 
 }  // namespace
 
 extern "C" int shim_knn_coop(const int32_t* coords, const int32_t* counts, const float* xyz, uint32_t n_vox, int cap, int nbr_mode,
-                             double leaf, double pref_frac, const double* q, size_t nq, int k, int lanes_per_query, uint64_t* idx,
-                             double* d2, uint8_t* ok) {
-  if (k < 1 || k > 8 || (lanes_per_query != 4 && lanes_per_query != 8)) return 1;
+                             double leaf, double pref_frac, const double* q, size_t nq, int k, int lanes_per_query, int mode,
+                             uint64_t* idx, double* d2, uint8_t* ok) {
+  if (k < 1 || k > 8 || (lanes_per_query != 4 && lanes_per_query != 8) || mode < 0 || mode > 1) return 1;
   HostMirror M;
   build_mirror(M, coords, counts, xyz, n_vox, cap, nbr_mode, leaf, pref_frac);
-  if (lanes_per_query == 4) {
-    if (k == 5)
-      run_coop<5, 4>(M, q, nq, k, idx, d2, ok);
-    else
-      run_coop<8, 4>(M, q, nq, k, idx, d2, ok);
-  } else {
-    if (k == 5)
-      run_coop<5, 8>(M, q, nq, k, idx, d2, ok);
-    else
-      run_coop<8, 8>(M, q, nq, k, idx, d2, ok);
+  const int sel = (lanes_per_query == 8 ? 4 : 0) | (mode ? 2 : 0) | (k == 5 ? 1 : 0);
+  switch (sel) {
+    case 0: run_coop<8, 4, 0>(M, q, nq, k, idx, d2, ok); break;
+    case 1: run_coop<5, 4, 0>(M, q, nq, k, idx, d2, ok); break;
+    case 2: run_coop<8, 4, 1>(M, q, nq, k, idx, d2, ok); break;
+    case 3: run_coop<5, 4, 1>(M, q, nq, k, idx, d2, ok); break;
+    case 4: run_coop<8, 8, 0>(M, q, nq, k, idx, d2, ok); break;
+    case 5: run_coop<5, 8, 0>(M, q, nq, k, idx, d2, ok); break;
+    case 6: run_coop<8, 8, 1>(M, q, nq, k, idx, d2, ok); break;
+    default: run_coop<5, 8, 1>(M, q, nq, k, idx, d2, ok); break;
   }
   return 0;
 }

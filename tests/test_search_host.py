@@ -33,10 +33,10 @@ def shim_knn(shim, m, q, k, nbr_mode, leaf, pref_frac=0.4, warp=False, coop=0):
     q = np.ascontiguousarray(q, np.float64).reshape(-1, 3)
     nq = q.shape[0]
     idx, d2, ok = np.empty((nq, k), np.uint64), np.empty((nq, k), np.float64), np.empty(nq, np.uint8)
-    if coop:  # G lanes per query (mb_search_coop.cuh), always as an emulated 32-lane warp
+    if coop:  # G lanes per query (mb_search_coop.cuh), always as an emulated 32-lane warp; coop = (G, mode)
         rc = shim.shim_knn_coop(_p(coords), _p(counts), _p(pts), C.c_uint32(coords.shape[0]), C.c_int(m.cap), C.c_int(nbr_mode),
-                                C.c_double(leaf), C.c_double(pref_frac), _p(q), C.c_size_t(nq), C.c_int(k), C.c_int(coop), _p(idx),
-                                _p(d2), _p(ok))
+                                C.c_double(leaf), C.c_double(pref_frac), _p(q), C.c_size_t(nq), C.c_int(k), C.c_int(coop[0]),
+                                C.c_int(coop[1]), _p(idx), _p(d2), _p(ok))
         assert rc == 0
         return idx, d2, ok.astype(bool)
     rc = (shim.shim_knn_warp if warp else shim.shim_knn)(_p(coords), _p(counts), _p(pts), C.c_uint32(coords.shape[0]), C.c_int(m.cap), C.c_int(nbr_mode),
@@ -120,7 +120,7 @@ def test_search_32_lane_warp_emulation(shim, oracle, mode, k):
 
 
 # ---- the cooperative variant (G lanes per query, mb_search_coop.cuh), run as emulated 32-lane warps -----------------
-@pytest.mark.parametrize("lanes", [4, 8])
+@pytest.mark.parametrize("lanes", [(4, 0), (8, 0), (4, 1), (8, 1)])  # (lanes per query, 0 = bucket per lane / 1 = point per lane)
 @pytest.mark.parametrize("mode,k", [(19, 5), (27, 8), (7, 3), (1, 5), (27, 1)])
 def test_coop_search_matches_oracle_world(shim, oracle, lanes, mode, k):
     import synth
@@ -133,7 +133,7 @@ def test_coop_search_matches_oracle_world(shim, oracle, lanes, mode, k):
     assert check(shim, oracle, pts, q, k, mode, 1.0, 0.2, coop=lanes) > 200
 
 
-@pytest.mark.parametrize("lanes", [4, 8])
+@pytest.mark.parametrize("lanes", [(4, 0), (8, 0), (4, 1), (8, 1)])
 def test_coop_search_ties_caps_and_leaf_sizes(shim, oracle, lanes):
     # lattice: exact distance ties across buckets handled by different lanes must resolve by visiting order
     g = np.arange(-6, 6) * 0.5
