@@ -1,9 +1,13 @@
 // Restricted k-NN, G LANES PER QUERY (G = 4 or 8): the cooperative variant of mb_search.cuh::knn_thread.
 //
-// EXPERIMENTAL — selected with MB_KNN_VARIANT=coop4 / coop8 (mb_map.cu::launch_knn); the default search is still
-// knn_thread.  Written at the end of round 1 from the measurements in profiles/r1_experiments.md, checked on the CPU
-// against the oracle through the 32-lane warp emulation (tests/host_shim/search_shim.cpp, tests/test_search_host.py),
-// compiled for sm_100a, NOT YET TIMED on a GPU.
+// EXPERIMENTAL — selected with MB_KNN_VARIANT=coop4 / coop8 / coop4p / ... (mb_map.cu::launch_knn); the default search
+// is still knn_thread.  Checked on the CPU against the oracle through the 32-lane warp emulation
+// (tests/host_shim/search_shim.cpp, tests/test_search_host.py::test_coop_*) and on a B200 against the default kernel
+// (tools/knn_variants.py: bit-exact on 3 x 131 072 queries).  MEASURED (profiles/r1_experiments.md, session 4): 2.2x
+// faster than knn_thread on a launch of 8 192 queries (28 vs 60 us: the dependent chain is that much shorter), 8-55 %
+// slower on the full 131 072 (86-99 us at G = 4, 117-126 us at G = 8, against 80 us): the per-query fixed work is
+// spread over G lanes instead of one, ~330 / ~600 warp-instructions per query against 207, and the full launch is
+// issue-bound.  Kept as the starting point for the next design (fewer lanes per query or a warp-wide bucket queue).
 //
 // Why: with one query per thread the launch is a single wave of warps and lasts as long as the slowest warp's serial
 // chain (~35 dependent memory steps, ~12 k dependent instructions); neither traffic nor occupancy nor the

@@ -1,8 +1,9 @@
 """The EXPERIMENTAL lanes-per-query k-NN kernels (mimosa_b200/csrc/mb_search_coop.cuh, MB_KNN_VARIANT=coop4 / coop8)
 through the C ABI against the oracle's iVox: indices, squared distances and found flags bit-exact, like the default
-kernel's tests in test_gpu_parity.py.  The variants are not the product path yet (not timed on a GPU when they were
-written), so this file only runs when MB_TEST_EXPERIMENTAL=1; their logic is covered on the CPU by
-tests/test_search_host.py::test_coop_*."""
+kernel's tests in test_gpu_parity.py.  The variants are not the product path (measured slower than the default at full
+load, profiles/r1_experiments.md session 4), so this file only runs when MB_TEST_EXPERIMENTAL=1; their logic is covered
+on the CPU by tests/test_search_host.py::test_coop_* and their k = 5 kernels were compared bit for bit with the default
+kernel on a B200 by tools/knn_variants.py."""
 import os
 
 import numpy as np
@@ -14,7 +15,7 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("MB_TEST_EXPERIMENTAL") != "1", reason="experimental k-NN variants: set MB_TEST_EXPERIMENTAL=1")]
 
 
-@pytest.fixture(params=["coop4", "coop8"])
+@pytest.fixture(params=["coop4", "coop8", "coop4p", "coop8p"])
 def variant(request):
     old = os.environ.get("MB_KNN_VARIANT")
     os.environ["MB_KNN_VARIANT"] = request.param
