@@ -124,6 +124,19 @@ typedef struct mb_input_filter {
   double header_ts; /* msg.header.stamp in seconds */
 } mb_input_filter;
 
+/* The two message re-orderings lidar::Manager::prepareInput applies before its filter loop (manager.cpp:179-243;
+ * ManagerConfig::transpose_pointcloud / organize_pointcloud_by_ring, manager.hpp:28-29).  width x height is the
+ * PointCloud2's organisation (height == 1: unorganised).  The reference transposes only PointRslidar and
+ * PointVelodyneAnybotics clouds and never re-orders Livox / OusterOdyssey clouds by ring (`if constexpr` on the
+ * point type): the adapter passes the flags accordingly. */
+typedef struct mb_cloud_order {
+  uint32_t width, height;
+  int32_t transpose_pointcloud;        /* index i of the transposed cloud = old row i % height, old column i / height */
+  int32_t organize_pointcloud_by_ring; /* stable re-ordering by ring number; applied only when the (transposed) cloud's
+                                          height is 1, as in the reference.  Ring numbers >= 128 index out of range in
+                                          the reference (manager.cpp:213-219); here any 16-bit ring is ordered */
+} mb_cloud_order;
+
 typedef struct mb_ctx mb_ctx;
 typedef struct mb_map mb_map;
 typedef struct mb_factor mb_factor;
@@ -257,11 +270,18 @@ MB_API int mb_scan_upload(mb_ctx* ctx, const void* pts, size_t n, size_t stride_
  * range); geometric_idx[0..*n_geometric) indexes points_full (geometric_point_idxs_); unique_ns[0..*n_unique) are
  * the distinct timestamps ascending and pose_index[j] the timestamp group of points_full[j] — what
  * mb_scan_deskew takes once the host has propagated one pose per timestamp.  Host arrays need room for n_points
- * entries.  transpose_pointcloud / organize_pointcloud_by_ring are not covered. */
+ * entries. */
 MB_API int mb_scan_from_cloud(mb_ctx* ctx, const void* data, size_t n_points, const mb_cloud_layout* layout,
                               const mb_input_filter* filter, mb_scan** points_full, uint32_t* geometric_idx,
                               size_t* n_geometric, uint32_t* pose_index, uint32_t* unique_ns, size_t* n_unique,
                               uint32_t* last_point_ns);
+/* Same with the message re-orderings of manager.cpp:179-243 in front (order == NULL: none).  The re-ordered cloud is
+ * never materialised: the decode kernel fetches record src(i) of the message for index i of the re-ordered cloud, and
+ * `idx` of the output points is i, as in the reference. */
+MB_API int mb_scan_from_cloud_ordered(mb_ctx* ctx, const void* data, size_t n_points, const mb_cloud_layout* layout,
+                                      const mb_input_filter* filter, const mb_cloud_order* order, mb_scan** points_full,
+                                      uint32_t* geometric_idx, size_t* n_geometric, uint32_t* pose_index,
+                                      uint32_t* unique_ns, size_t* n_unique, uint32_t* last_point_ns);
 MB_API int mb_scan_release(mb_scan* scan);
 MB_API int mb_scan_size(mb_scan* scan, size_t* n, size_t* stride_bytes);
 MB_API int mb_scan_download(mb_scan* scan, void* pts);

@@ -3,7 +3,7 @@
 The product is the C-ABI shared library (include/mimosa_b200.h, mimosa_b200/csrc/); `host` mirrors the
 reference's C++ interface for the Python test/benchmark harness.  No CPU fallback exists.
 """
-from .capi import CloudLayout, InputFilter  # noqa: F401
+from .capi import CloudLayout, CloudOrder, InputFilter  # noqa: F401
 from .host import (  # noqa: F401
     HORNBILL_MAP,
     Context,

@@ -67,6 +67,12 @@ class InputFilter(C.Structure):
                 ("create_full_res_pointcloud", C.c_int32), ("z_offset", C.c_float), ("header_ts", C.c_double)]
 
 
+class CloudOrder(C.Structure):
+    """mb_cloud_order: the message re-orderings of lidar::Manager::prepareInput (manager.cpp:179-243)."""
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("transpose_pointcloud", C.c_int32),
+                ("organize_pointcloud_by_ring", C.c_int32)]
+
+
 class Linearization(C.Structure):
     _fields_ = [
         ("H", C.c_double * 36),
@@ -149,6 +155,8 @@ SIGNATURES = {
     "mb_scan_upload": (C.c_int, [_P, _P, _SZ, _SZ, C.POINTER(_P)]),
     "mb_scan_from_cloud": (C.c_int, [_P, _P, _SZ, C.POINTER(CloudLayout), C.POINTER(InputFilter), C.POINTER(_P), _P,
                                     C.POINTER(_SZ), _P, _P, C.POINTER(_SZ), C.POINTER(C.c_uint32)]),
+    "mb_scan_from_cloud_ordered": (C.c_int, [_P, _P, _SZ, C.POINTER(CloudLayout), C.POINTER(InputFilter), C.POINTER(CloudOrder),
+                                            C.POINTER(_P), _P, C.POINTER(_SZ), _P, _P, C.POINTER(_SZ), C.POINTER(C.c_uint32)]),
     "mb_scan_gather": (C.c_int, [_P, _P, _SZ, C.POINTER(_P)]),
     "mb_scan_release": (C.c_int, [_P]),
     "mb_scan_size": (C.c_int, [_P, C.POINTER(_SZ), C.POINTER(_SZ)]),

@@ -10,8 +10,11 @@
 //   points_full <- (x, y, z + z_offset, intensity, t_ns, i, sqrt(range_sq))                      (:312-313)
 //   geometric idx <- new index when i % point_skip == 0 and ring % ring_skip == 0               (:317-335)
 //   unique_ns = sorted distinct t_ns; every kept point is mapped to its timestamp group          (:341-371)
-// Not covered: transpose_pointcloud (:179-198) and organize_pointcloud_by_ring (:204-243) — host-side
-// re-orderings of the message for two vendors.
+// transpose_pointcloud (:179-198) and organize_pointcloud_by_ring (:204-243) re-order the message before that loop;
+// here they are an index map in front of the record fetch (mb_scan_from_cloud_ordered): candidate i of the re-ordered
+// cloud reads record src(i) = T(perm[i]) of the message as received — T the transposition of the width x height grid,
+// perm the stable ordering by ring number (a radix sort of ring keys, which is what the reference's counting sort
+// computes) — so the message itself is never copied.
 #include <cub/cub.cuh>
 
 #include "mb_map.cuh"
@@ -35,13 +38,33 @@ __device__ __forceinline__ T load_unaligned(const unsigned char* p) {
   return v;
 }
 
+// Record of the message that sits at index i of the re-ordered cloud: perm (nullable) = ring ordering over the
+// (possibly transposed) cloud; t_h != 0: the cloud was transposed from t_w columns x t_h rows, so index j of the
+// transposed cloud (t_h columns) is old row j % t_h, old column j / t_h (manager.cpp:192-198).
+__device__ __forceinline__ size_t src_record(size_t i, const uint32_t* __restrict__ perm, uint32_t t_w, uint32_t t_h) {
+  size_t j = perm ? (size_t)perm[i] : i;
+  if (t_h) j = (j % t_h) * (size_t)t_w + j / t_h;
+  return j;
+}
+
+// ring number of every record of the (possibly transposed) cloud, as sort keys, and the identity permutation
+__global__ void k_ring_keys(const unsigned char* __restrict__ data, size_t n, mb_cloud_layout lay, uint32_t t_w, uint32_t t_h,
+                            uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned char* p = data + src_record(i, nullptr, t_w, t_h) * lay.point_step;
+  keys[i] = lay.ring_type == 0 ? (uint32_t)load_unaligned<uint16_t>(p + lay.off_ring) : (uint32_t)p[lay.off_ring];
+  vals[i] = (uint32_t)i;
+}
+
 __global__ void k_decode(const unsigned char* __restrict__ data, size_t n_cand, uint32_t stride_pts, mb_cloud_layout lay,
-                         mb_input_filter fl, float range_min_sq, float range_max_sq, OutRec* __restrict__ tmp,
-                         uint32_t* __restrict__ keep, uint32_t* __restrict__ geo) {
+                         mb_input_filter fl, float range_min_sq, float range_max_sq, const uint32_t* __restrict__ perm,
+                         uint32_t t_w, uint32_t t_h, OutRec* __restrict__ tmp, uint32_t* __restrict__ keep,
+                         uint32_t* __restrict__ geo) {
   const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_cand) return;
   const size_t i = c * stride_pts;
-  const unsigned char* p = data + i * lay.point_step;
+  const unsigned char* p = data + src_record(i, perm, t_w, t_h) * lay.point_step;
   uint32_t k = 0, g = 0;
   OutRec r;
   r.x = load_unaligned<float>(p + lay.off_x);
@@ -154,7 +177,29 @@ extern "C" int mb_scan_from_cloud(mb_ctx* ctx, const void* data, size_t n_points
                                   const mb_input_filter* filter, mb_scan** points_full, uint32_t* geometric_idx,
                                   size_t* n_geometric, uint32_t* pose_index, uint32_t* unique_ns, size_t* n_unique,
                                   uint32_t* last_point_ns) {
+  return mb_scan_from_cloud_ordered(ctx, data, n_points, layout, filter, nullptr, points_full, geometric_idx, n_geometric, pose_index,
+                                    unique_ns, n_unique, last_point_ns);
+}
+
+extern "C" int mb_scan_from_cloud_ordered(mb_ctx* ctx, const void* data, size_t n_points, const mb_cloud_layout* layout,
+                                          const mb_input_filter* filter, const mb_cloud_order* order, mb_scan** points_full,
+                                          uint32_t* geometric_idx, size_t* n_geometric, uint32_t* pose_index,
+                                          uint32_t* unique_ns, size_t* n_unique, uint32_t* last_point_ns) {
   MB_REQUIRE(ctx && layout && filter && points_full && n_geometric && n_unique, "null argument");
+  uint32_t t_w = 0, t_h = 0;  // transposition: the message's width / height
+  bool by_ring = false;
+  if (order) {
+    MB_REQUIRE((size_t)order->width * order->height == n_points, "width * height must equal the number of points");
+    uint32_t height_now = order->height;  // height of the cloud the ring re-ordering would see
+    if (order->transpose_pointcloud && n_points) {
+      t_w = order->width;
+      t_h = order->height;
+      height_now = order->width;
+    }
+    // manager.cpp:210: only an unorganised cloud (height == 1) is re-ordered
+    by_ring = order->organize_pointcloud_by_ring && height_now == 1 && n_points > 0;
+    MB_REQUIRE(!by_ring || layout->off_ring >= 0, "organize_pointcloud_by_ring needs a ring field");
+  }
   MB_REQUIRE(n_points == 0 || (data && geometric_idx && pose_index && unique_ns), "null buffer");
   MB_REQUIRE(layout->point_step >= 12 && filter->point_skip_divisor >= 1 && filter->ring_skip_divisor >= 1, "bad layout/filter");
   MB_REQUIRE(layout->intensity_type >= 0 && layout->intensity_type <= 1 && layout->time_type >= 0 && layout->time_type <= 3 &&
@@ -183,7 +228,11 @@ extern "C" int mb_scan_from_cloud(mb_ctx* ctx, const void* data, size_t n_points
   cub::DeviceScan::ExclusiveSum(nullptr, scan_temp, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n_cand, st);
   const size_t temp_bytes = std::max(sort_temp, scan_temp);
   const size_t raw_bytes = n_points * layout->point_step;
-  const size_t bytes = raw_bytes + n_cand * (sizeof(OutRec) + 4 * 12) + temp_bytes + 256 * 20;
+  size_t ring_temp = 0;
+  if (by_ring)
+    cub::DeviceRadixSort::SortPairs(nullptr, ring_temp, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (int)n_points, 0, 16, st);
+  const size_t bytes = raw_bytes + n_cand * (sizeof(OutRec) + 4 * 12) + temp_bytes + (by_ring ? n_points * 16 + ring_temp : 0) + 256 * 26;
   unsigned char* scratch = nullptr;
   MB_TRY(dev_alloc_t(ctx, &scratch, bytes));
   struct Free {
@@ -218,13 +267,31 @@ extern "C" int mb_scan_from_cloud(mb_ctx* ctx, const void* data, size_t n_points
   uint32_t* d_pose_index = (uint32_t*)take(n_cand * 4);
   uint32_t* counters = (uint32_t*)take(16);
   void* temp = take(temp_bytes);
+  uint32_t *ring_keys = nullptr, *ring_vals = nullptr, *ring_keys_s = nullptr, *perm = nullptr;
+  void* ring_tmp = nullptr;
+  if (by_ring) {
+    ring_keys = (uint32_t*)take(n_points * 4);
+    ring_vals = (uint32_t*)take(n_points * 4);
+    ring_keys_s = (uint32_t*)take(n_points * 4);
+    perm = (uint32_t*)take(n_points * 4);
+    ring_tmp = take(ring_temp);
+  }
   // keep_pos .. d_pose_index reuse: unique_ns goes into t_keys after the sort (no longer needed)
 
   MB_TRY(pinned_reserve(ctx, raw_bytes));
   std::memcpy(ctx->pinned, data, raw_bytes);
   MB_CUDA(cudaMemcpyAsync(raw, ctx->pinned, raw_bytes, cudaMemcpyHostToDevice, st));
   const float rmin2 = filter->range_min * filter->range_min, rmax2 = filter->range_max * filter->range_max;
-  k_decode<<<blocks_for(n_cand, 256), 256, 0, st>>>(raw, n_cand, stride_pts, *layout, *filter, rmin2, rmax2, tmp, keep, geo);
+  if (by_ring) {
+    // stable order by ring number = the reference's counting sort (ring counts -> offsets -> in-order placement,
+    // manager.cpp:216-239); 16 key bits cover both ring types
+    k_ring_keys<<<blocks_for(n_points, 256), 256, 0, st>>>(raw, n_points, *layout, t_w, t_h, ring_keys, ring_vals);
+    size_t rb = ring_temp;
+    MB_CUDA(cub::DeviceRadixSort::SortPairs(ring_tmp, rb, ring_keys, ring_keys_s, ring_vals, perm, (int)n_points, 0, 16, st));
+    ctx->launches += 4;
+  }
+  k_decode<<<blocks_for(n_cand, 256), 256, 0, st>>>(raw, n_cand, stride_pts, *layout, *filter, rmin2, rmax2, perm, t_w, t_h, tmp, keep,
+                                                    geo);
   size_t tb = temp_bytes;
   MB_CUDA(cub::DeviceScan::ExclusiveSum(temp, tb, keep, keep_pos, (int)n_cand, st));
   tb = temp_bytes;

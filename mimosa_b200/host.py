@@ -18,7 +18,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import capi
-from .capi import CloudLayout, IcpConfig, IcpTrace, InputFilter, Linearization, check
+from .capi import CloudLayout, CloudOrder, IcpConfig, IcpTrace, InputFilter, Linearization, check
 
 
 def _ptr(a):
@@ -174,11 +174,21 @@ class Scan:
         self.h, self.cols = _handle, _cols
 
     @staticmethod
-    def from_cloud(ctx: Context, data: np.ndarray, layout: CloudLayout, filt: InputFilter):
-        """lidar::Manager::prepareInput (manager.cpp:149-383).  `data`: (n, point_step) uint8 PointCloud2 payload.
+    def from_cloud(ctx: Context, data: np.ndarray, layout: CloudLayout, filt: InputFilter, width: int = 0, height: int = 0,
+                   transpose_pointcloud: bool = False, organize_pointcloud_by_ring: bool = False):
+        """lidar::Manager::prepareInput (manager.cpp:149-383).  `data`: (n, point_step) uint8 PointCloud2 payload;
+        width x height + the two ManagerConfig flags select the message re-orderings of manager.cpp:179-243.
         Returns (points_full Scan, geometric_idx, pose_index, unique_ns, last_point_ns)."""
         data = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1, layout.point_step)
         n = data.shape[0]
+        if transpose_pointcloud or organize_pointcloud_by_ring:
+            order = CloudOrder(width, height, int(transpose_pointcloud), int(organize_pointcloud_by_ring))
+            geo, pi, uns = (np.empty(max(n, 1), np.uint32) for _ in range(3))
+            h, n_geo, n_un, last = C.c_void_p(), C.c_size_t(), C.c_size_t(), C.c_uint32()
+            check(ctx.lib.mb_scan_from_cloud_ordered(ctx.h, _ptr(data), n, C.byref(layout), C.byref(filt), C.byref(order), C.byref(h),
+                                                     _ptr(geo), C.byref(n_geo), _ptr(pi), _ptr(uns), C.byref(n_un), C.byref(last)))
+            sc = Scan(ctx, _handle=h, _cols=8)
+            return sc, geo[: n_geo.value].copy(), pi[: sc.n].copy(), uns[: n_un.value].copy(), int(last.value)
         geo = np.empty(max(n, 1), np.uint32)
         pi = np.empty(max(n, 1), np.uint32)
         uns = np.empty(max(n, 1), np.uint32)

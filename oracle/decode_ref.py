@@ -7,9 +7,60 @@ candidates i = 0, s, 2s, ... with s = create_full_res ? 1 : point_skip_divisor (
 (:258-264), intensity (:267-278), range (:281-282) filters; time decode (:285-304); (float)t_ns > ns_max (:306);
 points_full row = (x, y, z + z_offset, intensity, t_ns, i, sqrt(range_sq)) (:312-313); geometric idx when
 i % point_skip == 0 and ring % ring_skip == 0 (:317-335); timestamps sorted and grouped (:341-371).
-transpose_pointcloud / organize_pointcloud_by_ring are not modelled.
+The two message re-orderings in front of that loop — transpose_pointcloud (:179-198) and
+organize_pointcloud_by_ring (:204-243) — are restated by reorder_cloud() (vectorised) and reorder_cloud_loops()
+(the reference's loops, literally, for small inputs); prepare_input() runs on the re-ordered message.
 """
 import numpy as np
+
+
+def reorder_cloud_loops(data, width, height, transpose_pointcloud, organize_pointcloud_by_ring, off_ring, ring_type):
+    """manager.cpp:179-243 loop by loop (pure Python: small inputs only).  data: (n, point_step) uint8 with
+    n == width * height.  Returns (re-ordered data, width, height)."""
+    data = np.ascontiguousarray(data, np.uint8)
+    n = data.shape[0]
+    assert n == width * height
+    if transpose_pointcloud:  # :186-199
+        out = np.empty_like(data)
+        t_width, t_height = height, width
+        for i in range(n):
+            current_row, current_col = i // width, i % width
+            new_row, new_col = current_col, current_row
+            out[new_row * t_width + new_col] = data[i]
+        data, width, height = out, t_width, t_height
+    if organize_pointcloud_by_ring and height == 1:  # :210-241
+        num_rings = 128
+        size = 2 if ring_type == 0 else 1
+        ring = [int.from_bytes(bytes(data[i, off_ring:off_ring + size]), "little") for i in range(n)]
+        ring_counts = [0] * num_rings
+        for r in ring:
+            ring_counts[r] += 1
+        ring_offsets, offset = [0] * num_rings, 0
+        for r in range(num_rings):
+            ring_offsets[r] = offset
+            offset += ring_counts[r]
+        out = np.empty_like(data)
+        cursors = list(ring_offsets)
+        for i in range(n):
+            out[cursors[ring[i]]] = data[i]
+            cursors[ring[i]] += 1
+        data = out
+    return data, width, height
+
+
+def reorder_cloud(data, width, height, transpose_pointcloud, organize_pointcloud_by_ring, off_ring, ring_type):
+    """Same as reorder_cloud_loops, vectorised: the transposition is a swap of the grid's axes, the counting sort a
+    stable sort by ring number."""
+    data = np.ascontiguousarray(data, np.uint8)
+    n, step = data.shape
+    assert n == width * height
+    if transpose_pointcloud and n:
+        data = np.ascontiguousarray(data.reshape(height, width, step).swapaxes(0, 1)).reshape(n, step)
+        width, height = height, width
+    if organize_pointcloud_by_ring and height == 1 and n:
+        ring = _field(data, off_ring, np.uint16 if ring_type == 0 else np.uint8)
+        data = data[np.argsort(ring, kind="stable")]
+    return data, width, height
 
 
 def _field(data, off, dtype):

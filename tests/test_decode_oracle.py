@@ -59,3 +59,39 @@ def test_livox_tag_and_reflectivity_layouts():
     data, lay = make_cloud("ouster_odyssey", 2000, np.random.default_rng(5))
     pts, geo, *_ = decode_ref.prepare_input(data, lay, default_filter(create_full_res_pointcloud=1))
     assert np.all(pts[:, 4] <= 250.0) and pts.shape[0] > 0
+
+
+def _shuffled_ring_cloud(name, n, rng, n_rings=32):
+    """A cloud whose records are NOT in row-major ring order (the Hesai JT128 case the ring re-ordering exists for)."""
+    data, lay = make_cloud(name, n, rng, n_rings=n_rings)
+    return data[rng.permutation(n)], lay
+
+
+def test_reorder_transposition_and_ring_order_hand_checked():
+    lay = LAYOUTS["ouster"][1]
+    # 2 rows x 3 columns, x = 10 * row + column, ring = column
+    rows = [(10.0 * r + c, 0.0, 0.0, 1.0, 0, 0, c) for r in range(2) for c in range(3)]
+    data = _ouster(rows)
+    t, w, h = decode_ref.reorder_cloud(data, 3, 2, True, False, lay.off_ring, lay.ring_type)
+    assert (w, h) == (2, 3)
+    assert t[:, :4].copy().view(np.float32).ravel().tolist() == [0.0, 10.0, 1.0, 11.0, 2.0, 12.0]  # column-major walk
+    # unorganised (height 1): stable by ring — equal rings keep the message order
+    flat, w, h = decode_ref.reorder_cloud(data, 6, 1, False, True, lay.off_ring, lay.ring_type)
+    assert flat[:, :4].copy().view(np.float32).ravel().tolist() == [0.0, 10.0, 1.0, 11.0, 2.0, 12.0]
+    # an organised cloud is left alone by the ring re-ordering (manager.cpp:210)
+    same, *_ = decode_ref.reorder_cloud(data, 3, 2, False, True, lay.off_ring, lay.ring_type)
+    assert np.array_equal(same, data)
+    # transposing an N x 1 cloud makes it unorganised, so both apply in sequence
+    both, w, h = decode_ref.reorder_cloud(data, 1, 6, True, True, lay.off_ring, lay.ring_type)
+    assert (w, h) == (6, 1) and np.array_equal(both, flat)
+
+
+def test_reorder_vectorised_equals_reference_loops():
+    rng = np.random.default_rng(8)
+    for name, w, h in (("ouster", 37, 16), ("hesai", 600, 1), ("velodyne", 1, 480), ("ouster", 1, 1)):
+        data, lay = _shuffled_ring_cloud(name, w * h, rng)
+        for tr in (False, True):
+            for org in (False, True):
+                a = decode_ref.reorder_cloud(data, w, h, tr, org, lay.off_ring, lay.ring_type)
+                b = decode_ref.reorder_cloud_loops(data, w, h, tr, org, lay.off_ring, lay.ring_type)
+                assert np.array_equal(a[0], b[0]) and a[1:] == b[1:]
