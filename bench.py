@@ -141,8 +141,12 @@ def knn_algorithmic_bytes(q: np.ndarray, coords: np.ndarray, counts: np.ndarray,
     bucket_bytes = int(counts[order][pos[hit]].astype(np.int64).sum()) * 16
     nq = q.shape[0]
     total = nq * 24 + blocks.size * 32 + int(hit.sum()) * 4 + bucket_bytes + nq * (k * 16 + 1)
+    # SURVEY.md 8(d) wrote the figure down for the layout it assumed (a per-voxel hash probe of 16 B, whole 336-byte
+    # buckets): B_knn = N_q 16 + U_hash 16 + U_vox 336 + N_q k 16.  Reported beside the figure above, never instead of
+    # it: this kernel reads only the occupied part of a bucket, so its DRAM traffic is BELOW that number.
+    survey = nq * 16 + int(probed.size) * 16 + int(hit.sum()) * 336 + nq * k * 16
     return total, {"queries": nq, "distinct_blocks": int(blocks.size), "distinct_buckets": int(hit.sum()),
-                   "bucket_bytes": bucket_bytes}
+                   "bucket_bytes": bucket_bytes, "survey_8d_bytes": int(survey)}
 
 
 def host_gn_step(L, R, t, lam):
@@ -193,6 +197,18 @@ def knn_roofline(ctx, mg, scan, R0, t0, synth):
             "whole map, L2 flushed before every launch", "algorithmic_bytes": int(bytes_alg),
             "us_per_launch": t_knn * 1e6, "us_min": float(np.min(knn_ms)) * 1e3, "peak_source": peak_src,
             "queries_per_s": N_SCAN / t_knn, **parts}
+    roof["survey_8d"] = {"bytes": parts["survey_8d_bytes"], "achieved": parts["survey_8d_bytes"] / t_knn / 1e9,
+                         "frac": parts["survey_8d_bytes"] / t_knn / 1e9 / peak,
+                         "note": "SURVEY 8(d)'s formula (whole 336-B buckets, per-voxel probes): an upper figure, the kernel "
+                                 "moves fewer bytes than this; `achieved` / `frac` above use the stricter count"}
+    try:  # the bare-gather ceiling measured for the same bucket bytes (tools/probe/gather_probe.py), for context
+        gp = json.load(open(os.path.join(ROOT, "profiles", "r1_gather_probe.json")))["results"]
+        best = min((r for r in gp if r["pattern"].startswith("ascending runs") and r["points_per_item"] == 8), key=lambda r: r["us"])
+        roof["bare_gather_ceiling"] = {"us": best["us"], "bytes": best["bytes"], "gbs": best["gbs"], "frac_of_peak": best["gbs"] / peak,
+                                       "what": "no-compute gather of 807 154 buckets x 128 B after the same 256 MiB write-flush "
+                                               "(profiles/r1_gather_probe.json): what any kernel could reach on this launch size"}
+    except (OSError, KeyError, ValueError):
+        pass
     # local regime for context: the scan's own first-iteration queries (working set << L2)
     q_loc = scan[:, :3].astype(np.float64) @ R0.T + t0
     b_loc, _ = knn_algorithmic_bytes(q_loc, coords, counts, K_NN)

@@ -67,3 +67,21 @@ def test_product_does_not_import_oracle():
                 assert "oracle_py" not in txt and "liboracle" not in txt, fn
                 assert not re.search(r"#\s*include[^\n]*(oracle|_ref\.hpp)", txt), fn
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, re.M), fn
+
+
+def test_bench_algorithmic_bytes_count():
+    """bench.py's compulsory-byte count of a k-NN launch on a hand-made map: two occupied voxels in one 4x4x4 block, one
+    query whose 19-voxel neighbourhood contains both."""
+    import numpy as np
+
+    import bench
+
+    coords = np.array([[0, 0, 0], [1, 0, 0], [9, 9, 9]], np.int32)
+    counts = np.array([3, 7, 20], np.int32)
+    q = np.array([[0.5, 0.5, 0.5]])
+    total, parts = bench.knn_algorithmic_bytes(q, coords, counts, 5, nbr_mode=19, leaf=1.0)
+    # neighbourhood cells -1..1 straddle blocks -1 and 0 on every axis, minus the all-(-1) corner block that only
+    # the excluded (-1,-1,-1) corner touches: 7 blocks
+    assert parts["distinct_buckets"] == 2 and parts["bucket_bytes"] == (3 + 7) * 16 and parts["distinct_blocks"] == 7
+    assert total == 24 + 7 * 32 + 2 * 4 + 160 + (5 * 16 + 1)
+    assert parts["survey_8d_bytes"] == 16 + 19 * 16 + 2 * 336 + 5 * 16
