@@ -33,6 +33,7 @@
 
 #include "mb_map.cuh"
 #include "mb_scan.cuh"
+#include "mb_search_coop.cuh"
 
 namespace mb {
 namespace {
@@ -192,15 +193,25 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 // ROWS = rows of the per-thread neighbour-slot table: 19 covers neighbourhood modes 1 / 7 / 19, 27 the full cube.
-template <int K, typename PoseT, int ROWS>
+// G = 0: phase B searches one query per thread (knn_thread).  G = 4: EXPERIMENTAL, four lanes per query (knn_group,
+// mb_search_coop.cuh; selected per factor with MB_LIN_SEARCH=coop4): measured faster than the per-thread search for
+// launches below ~100 k queries in the stand-alone k-NN kernel (profiles/r1_experiments.md, session 4) — the regime of
+// a rank's shard at N >= 2 and of downsampled streaming scans; this fused form has not run on a GPU yet.
+template <int K, typename PoseT, int ROWS, int G = 0>
 __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
     k_linearize(MapView mv, FactorView fv, DevState* ds, PoseT pa, const PeerTable* __restrict__ peer) {
   double* pose_dev = ds->pose;
-  __shared__ uint16_t s_tab[kTabEntries];
-  // s_pk (phase B: probed neighbour words, [n_off][thread]) is re-used as s_row (phase C: whitened
-  // [J (6), e] per point, [warp][32][7] doubles = 7168 B <= 19 * 128 * 4 B).
-  __shared__ __align__(16) uint32_t s_pk_all[ROWS * kLinThreads];
-  __shared__ uint32_t s_blk_all[24 * kLinThreads];  // per-thread {mask_lo, mask_hi, base} of the <= 8 blocks around a query
+  constexpr bool kCoop = G != 0;
+  constexpr int kGroupWords = kCube + kCoopBlk + kCoopQueue;  // per query group: bucket table, block / gap words, survivor queue
+  __shared__ uint16_t s_tab[kCoop ? 1 : kTabEntries];
+  __shared__ uint32_t s_ctab[kCoop ? kTabEntries : 1];
+  // s_pk (phase B: probed neighbour words, [n_off][thread]; cooperative search: the per-thread candidate stacks,
+  // [3 * kCoopStack][thread]) is re-used as s_row (phase C: whitened [J (6), e] per point, [warp][32][7] doubles =
+  // 7168 B <= 19 * 128 * 4 B).
+  __shared__ __align__(16) uint32_t s_pk_all[kCoop ? 3 * kCoopStack * kLinThreads : ROWS * kLinThreads];
+  // per-thread {mask_lo, mask_hi, base} of the <= 8 blocks around a query; cooperative search: kGroupWords per group
+  __shared__ uint32_t s_blk_all[kCoop ? kGroupWords * (kLinThreads / (kCoop ? G : 1)) : 24 * kLinThreads];
+  static_assert(sizeof(s_pk_all) >= sizeof(double) * 7 * kLinThreads, "s_row fits");
   __shared__ double s_pt[3][kLinThreads];          // transformed point of each tile member
   __shared__ uint8_t s_status[kLinThreads];
   __shared__ uint16_t s_queue[kLinThreads];
@@ -210,7 +221,11 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   pdl_launch_dependents();
-  fill_scan_table(mv, s_tab);
+  if constexpr (kCoop) {
+    if (tid < kScan) s_ctab[tid] = coop_tab_entry(mv.scan[tid]);
+  } else {
+    fill_scan_table(mv, s_tab);
+  }
   double(*s_row)[7] = reinterpret_cast<double(*)[7]>(s_pk_all) + warp * 32;
   // Lane a < 28 owns entry a of the packed upper triangle of [J e]^T [J e] (7x7): the 21 entries of
   // J^T J first (row-major, c >= r), then J^T e (6), then e^2.
@@ -301,23 +316,15 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
 
     MB_LIN_T(1);
     // ---- B: search + plane fit for the compacted points -------------------------------------------
-    for (int q0 = warp * 32; q0 < n_need; q0 += kLinThreads) {
-      const int qi = q0 + lane;
-      const bool on = qi < n_need;
-      const int li = on ? (int)s_queue[qi] : 0;
-      const double qx = s_pt[0][li], qy = s_pt[1][li], qz = s_pt[2][li];
-      double bd[K];
-      uint32_t bs[K];
-      uint32_t* s_pk = s_pk_all + tid;
-      knn_thread<K>(mv, s_tab, s_pk, s_blk_all + tid, kLinThreads, qx, qy, qz, k, on, bd, bs);
-      MB_LIN_T(2);
-      if (on) {
+    if constexpr (kCoop) {
+      // what follows a query's search: the winners' indices and points, the two distance gates, the plane fit
+      auto finish_query = [&](int li, const uint32_t* pk, int pk_stride, const double (&bd)[K], const uint32_t (&bs)[K]) {
         const size_t gi = tile * kLinThreads + li;
         float4 nb[K];
         uint64_t g[K];
-        const int found = knn_resolve_all<K, true>(mv, s_pk, kLinThreads, bs, k, g, nb);
+        const int found = knn_resolve_all<K, true>(mv, pk, pk_stride, bs, k, g, nb);
         double dk = 0.0;
-#pragma unroll
+  #pragma unroll
         for (int j = 0; j < K; ++j) {
           if (j < k) {
             if (j == k - 1) dk = bd[j];
@@ -340,6 +347,65 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
           if (normal_set) st3(fv.normal, fv.ld, gi, normal);
         }
         s_status[li] = rs;  // a fitted plane itself reaches its owner through fv.mean / fv.normal (same block, barrier below)
+      };
+      constexpr int QW = 32 / G;  // queries per warp and pass
+      const int grp = lane / G, gl = lane % G;
+      uint32_t* g_words = s_blk_all + (warp * QW + grp) * kGroupWords;
+      for (int q0 = warp * QW; q0 < n_need; q0 += kLinWarps * QW) {
+        const int qi = q0 + grp;
+        const bool on = qi < n_need;
+        const int li = on ? (int)s_queue[qi] : 0;
+        const double qx = s_pt[0][li], qy = s_pt[1][li], qz = s_pt[2][li];
+        double bd[K];
+        uint32_t bs[K];
+        knn_group<K, G, 8, 0>(mv, s_ctab, g_words, g_words + kCube, g_words + kCube + kCoopBlk, s_pk_all + tid, kLinThreads, qx, qy, qz,
+                              k, on, bd, bs);
+        MB_LIN_T(2);
+        if (on && gl == 0) finish_query(li, g_words, 1, bd, bs);  // every lane of the group holds the same merged list
+        __syncwarp();  // the group's bucket table is rewritten by the next pass
+      }
+    } else {
+      // (this branch is the GPU-verified code, kept verbatim)
+      for (int q0 = warp * 32; q0 < n_need; q0 += kLinThreads) {
+        const int qi = q0 + lane;
+        const bool on = qi < n_need;
+        const int li = on ? (int)s_queue[qi] : 0;
+        const double qx = s_pt[0][li], qy = s_pt[1][li], qz = s_pt[2][li];
+        double bd[K];
+        uint32_t bs[K];
+        uint32_t* s_pk = s_pk_all + tid;
+        knn_thread<K>(mv, s_tab, s_pk, s_blk_all + tid, kLinThreads, qx, qy, qz, k, on, bd, bs);
+        MB_LIN_T(2);
+        if (on) {
+          const size_t gi = tile * kLinThreads + li;
+          float4 nb[K];
+          uint64_t g[K];
+          const int found = knn_resolve_all<K, true>(mv, s_pk, kLinThreads, bs, k, g, nb);
+          double dk = 0.0;
+#pragma unroll
+          for (int j = 0; j < K; ++j) {
+            if (j < k) {
+              if (j == k - 1) dk = bd[j];
+              // indices are only meaningful when all k exist (the reference discards partial results)
+              if (fv.knn_idx) fv.knn_idx[gi * k + j] = g[j];
+            }
+          }
+          uint8_t rs = MB_UNPROCESSED;
+          d3 mean = mk3(0, 0, 0), normal = mk3(0, 0, 0);
+          if (found != k) {
+            rs = MB_INSUFFICIENT_CORRES_POINTS;
+            if (fv.knn_idx)
+              for (int j = 0; j < k; ++j) fv.knn_idx[gi * k + j] = ~0ull;
+          } else if (dk > fv.max_corr_sq) {
+            rs = MB_CORRES_MAX_DIST;
+          } else {
+            bool normal_set;
+            rs = fit_plane<K>(nb, k, T, fv.pvd, mean, normal, normal_set);
+            st3(fv.mean, fv.ld, gi, mean);
+            if (normal_set) st3(fv.normal, fv.ld, gi, normal);
+          }
+          s_status[li] = rs;  // a fitted plane itself reaches its owner through fv.mean / fv.normal (same block, barrier below)
+        }
       }
     }
     __syncthreads();
@@ -795,6 +861,7 @@ struct mb_factor {
   mb_icp_trace* d_trace = nullptr;
   int trace_cap = 0;
   int grid = 0, grid2 = 0, n_groups = 0;
+  int search_g = 0;  // 0: one query per thread; 4: four lanes per query (MB_LIN_SEARCH=coop4, experimental)
   int linearize_count = 0;
   uint32_t flags = 0;
   // cached CUDA graph of an mb_icp_run sequence
@@ -859,7 +926,12 @@ int enqueue_linearize(mb_factor* f, int do_step, int iter, mb_icp_trace* d_trace
   // mb_icp_run launches k_loc_comp once, after the last iteration); the host-facing single call runs it right away.
   fv.fold_loc = do_step ? 1 : 0;
   const PeerTable* peer = c->world > 1 ? c->d_peer : nullptr;  // nullptr: single rank, or NCCL all-reduce
-  if (pose_arg) {
+  const bool coop4 = f->search_g == 4 && fv.k == 5 && f->map->n_off <= 19;  // MB_LIN_SEARCH=coop4 (experimental)
+  if (coop4 && pose_arg) {
+    MB_CUDA(launch_pdl(k_linearize<5, PoseArg, 19, 4>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, f->ds, *pose_arg, peer));
+  } else if (coop4) {
+    MB_CUDA(launch_pdl(k_linearize<5, NoPose, 19, 4>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, f->ds, NoPose{}, peer));
+  } else if (pose_arg) {
     if (fv.k == 5 && f->map->n_off <= 19)  // the specialised kernel: k = 5 and at most 19 neighbour voxels
       MB_CUDA(launch_pdl(k_linearize<5, PoseArg, 19>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, f->ds, *pose_arg, peer));
     else
@@ -950,7 +1022,19 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
   const size_t k = cfg->num_corres_points;
   const size_t n_tiles = (f->n + kLinThreads - 1) / kLinThreads;
   int per_sm = 4;
-  if (k == 5 && map->n_off <= 19)
+  if (const char* e = getenv("MB_LIN_SEARCH")) {  // development switch, read when the factor is created
+    if (!strcmp(e, "coop4")) {
+      f->search_g = 4;
+    } else if (e[0] && strcmp(e, "thread")) {
+      set_error("MB_LIN_SEARCH=%s: expected thread or coop4", e);
+      map->refs.fetch_sub(1);
+      delete f;
+      return MB_ERR_INVALID_ARG;
+    }
+  }
+  if (f->search_g == 4 && k == 5 && map->n_off <= 19)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<5, NoPose, 19, 4>, kLinThreads, 0);
+  else if (k == 5 && map->n_off <= 19)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<5, NoPose, 19>, kLinThreads, 0);
   else
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<MB_MAX_K, NoPose, 27>, kLinThreads, 0);
