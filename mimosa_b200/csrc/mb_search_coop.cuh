@@ -9,21 +9,25 @@
 // spread over G lanes instead of one, ~330 / ~600 warp-instructions per query against 207, and the full launch is
 // issue-bound.  Kept as the starting point for the next design (fewer lanes per query or a warp-wide bucket queue).
 //
-// Why: with one query per thread the launch is a single wave of warps and lasts as long as the slowest warp's serial
-// chain (~35 dependent memory steps, ~12 k dependent instructions); neither traffic nor occupancy nor the
-// instruction count sets its time.  Here the lanes of a group work on the SAME query so that its dependent chain is
-// short and the launch runs as several waves of short-lived warps whose phases interleave:
-//   1  block probes     the <= 8 blocks around the query's voxel, 8 / G per lane, ONE round of loads;
+// The idea: with one query per thread the launch is a single wave of warps and lasts as long as the slowest warp's
+// serial chain (~35 dependent memory steps, ~12 k dependent instructions).  Here the lanes of a group work on the SAME
+// query so that its dependent chain is short and the launch runs as several waves of short-lived warps whose phases
+// interleave:
+//   1  block probes     the <= 8 blocks around the query's voxel, 8 / G per lane, ONE round of loads (one 256-bit
+//                       load per entry); masks, bases and the per-axis box gaps are left in shared memory;
 //   2  own voxel        every lane locates the query's own bucket (group lane 0 holds the own block's entry) and
 //                       requests a different four-point chunk of it — speculatively up to the cap, the fill count
 //                       arrives with the first chunk — so that the loads fly while step 3 computes;
 //   3  cube cells       the 26 neighbour cells in scan-position order (faces, edges, corners), ceil(26 / G) per
-//                       lane: occupancy bit, bucket index, lower bound of the box distance; masks travel by shuffle;
+//                       lane: occupancy bit, bucket index, lower bound of the box distance (byte-parallel arithmetic
+//                       on a packed cell table);
 //   4  merge            every lane keeps a private (d2, sequence)-ordered K-list; K rounds of "group minimum of the
 //                       list heads" leave the merged list in EVERY lane (replicated), whose k-th entry is the radius;
 //   5  neighbours       the surviving cells (box bound <= radius) are compacted into a per-group queue in scan order
-//                       and dealt out one bucket per lane and round, eight points per step, candidates within the
-//                       lane's radius pushed on a per-thread stack and inserted at the drains (as in knn_thread);
+//                       and — MODE 0 — dealt out one bucket per lane and round, STEP points per step, or — MODE 1 —
+//                       visited two at a time by the whole group, lane gl reading points gl, gl + G, ... (every load
+//                       instruction covers G consecutive points); candidates within the lane's radius are pushed on
+//                       a per-thread stack and inserted at the drains (as in knn_thread);
 //   6  merge            as 4; entries replicated in step 4 sit at the head of every list that holds them when they
 //                       are the minimum and are popped together, so the result has no duplicates.
 // The (d2, sequence) order is the reference's visiting order (KnnResult::push, oracle/ivox_ref.hpp), so the outcome
@@ -41,9 +45,9 @@ __device__ __forceinline__ int coop_lane() { return (int)(threadIdx.x & 31u); }
 inline int coop_lane() { return lane_id(); }
 #endif
 
-// Both halves of a block-table entry (32 bytes, 32-byte aligned) with ONE load instruction: an LDG whose lanes touch
-// 32 different lines occupies the SM's L1 wavefront queue for ~66 cycles, so the instruction count of scattered loads
-// is what the search is bound by (profiles/r1_experiments.md, "coop" section).
+// Both halves of a block-table entry (32 bytes, 32-byte aligned) with ONE load instruction (LDG.E.256 on sm_100a):
+// half the load instructions of the probe round.  (Measured neutral on the launch time, like the coalesced MODE 1
+// loads: the L1 wavefront queue is not what bounds these kernels; profiles/r1_experiments.md, session 4.)
 #if defined(__CUDACC__)
 __device__ __forceinline__ void ld_block_entry(const int4* p, int4& e, int4& m) {
   asm volatile("ld.global.nc.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -69,8 +73,9 @@ MB_HDC inline uint32_t coop_tab_entry(uint16_t scan_e) {
 
 // s_ctab: [kScan] coop_tab_entry() values (block-shared); s_pk: this GROUP's [kCube] bucket index by visiting rank
 // (valid afterwards for the winners' resolution); s_blk: this group's [kCoopBlk] block / gap words; s_q: this group's
-// [kCoopQueue]; s_st: this THREAD's column of a [3 * kCoopStack][st_stride] array.  Every lane of the warp must call; all lanes of a group pass the same query.  On return every lane of the
-// group holds the same (bd, bs): the K best in (d2, sequence) order, +inf / 0xffffffff where fewer exist.
+// [kCoopQueue]; s_st: this THREAD's column of a [3 * kCoopStack][st_stride] array.  Every lane of the warp must call;
+// all lanes of a group pass the same query.  On return every lane of the group holds the same (bd, bs): the K best in
+// (d2, sequence) order, +inf / 0xffffffff where fewer exist.
 template <int K, int G, int STEP = 8, int MODE = 0>
 MB_DEV void knn_group(const MapView& mv, const uint32_t* __restrict__ s_ctab, uint32_t* s_pk, uint32_t* s_blk, uint32_t* s_q,
                       uint32_t* s_st, int st_stride, double qx, double qy, double qz, int k, bool active,
