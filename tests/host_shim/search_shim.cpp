@@ -74,6 +74,9 @@ static inline double __shfl_sync(unsigned, double v, int src) {
   std::memcpy(&v, &u, 8);
   return v;
 }
+// shared-memory atomics of the emulated warp's lanes (host threads between two barriers really do race)
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 static inline void __syncwarp(unsigned = 0xffffffffu) {
   if (t_warp) {
     t_warp->bar.arrive_and_wait();
