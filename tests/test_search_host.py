@@ -33,6 +33,7 @@ def shim_knn(shim, m, q, k, nbr_mode, leaf, pref_frac=0.4, warp=False, coop=0):
     q = np.ascontiguousarray(q, np.float64).reshape(-1, 3)
     nq = q.shape[0]
     idx, d2, ok = np.empty((nq, k), np.uint64), np.empty((nq, k), np.float64), np.empty(nq, np.uint8)
+    leaf = float(np.float32(leaf))  # the map's leaf size is a float (mb_map_create, IVoxRef): 1 / (double)leaf_f32
     if coop:  # G lanes per query (mb_search_coop.cuh), always as an emulated 32-lane warp; coop = (G, mode)
         rc = shim.shim_knn_coop(_p(coords), _p(counts), _p(pts), C.c_uint32(coords.shape[0]), C.c_int(m.cap), C.c_int(nbr_mode),
                                 C.c_double(leaf), C.c_double(pref_frac), _p(q), C.c_size_t(nq), C.c_int(k), C.c_int(coop[0]),
@@ -157,3 +158,25 @@ def test_coop_search_ties_caps_and_leaf_sizes(shim, oracle, lanes):
     # sparse: own voxel mostly empty, fewer than k neighbours
     sparse = rng.uniform(-20, 20, (3000, 3)).astype(np.float32)
     check(shim, oracle, sparse, rng.uniform(-20, 20, (600, 3)), 5, 27, 1.0, 0.0, coop=lanes)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_coop_search_randomized_configurations(shim, oracle, seed):
+    """Random neighbourhood mode, k, cap, leaf (including sizes a float does not represent exactly, with queries on voxel
+    faces), density and group shape per seed: the cooperative and the default search must agree with the oracle bit for
+    bit whatever the combination."""
+    rng = np.random.default_rng(5000 + seed)
+    mode = int(rng.choice([1, 7, 19, 27]))
+    k = int(rng.integers(1, 9))
+    cap = int(rng.choice([3, 8, 20, 31]))
+    leaf = float(rng.choice([0.3, 1.0, 2.0]))
+    lanes = [(4, 0), (8, 0), (4, 1), (8, 1)][seed % 4]
+    extent = float(rng.choice([2.0, 6.0, 15.0])) * leaf
+    n = int(rng.choice([500, 5000, 30000]))
+    pts = rng.uniform(-extent, extent, (n, 3)).astype(np.float32)
+    if seed % 3 == 0:  # snap some points to a lattice: exact ties
+        pts[: n // 2] = np.round(pts[: n // 2] / (leaf / 4)) * (leaf / 4)
+    q = np.concatenate([rng.uniform(-extent * 1.1, extent * 1.1, (300, 3)), pts[rng.integers(0, n, 150)].astype(np.float64)])
+    min_dist, pref = 0.0 if seed % 2 else 0.05 * leaf, float(rng.choice([0.0, 0.4, 1.5]))
+    check(shim, oracle, pts, q, k, mode, leaf, min_dist, pref_frac=pref, cap=cap, coop=lanes)
+    check(shim, oracle, pts, q, k, mode, leaf, min_dist, pref_frac=pref, cap=cap, warp=True)  # the default search, same configuration
