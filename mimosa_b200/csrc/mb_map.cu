@@ -416,6 +416,45 @@ __global__ void __launch_bounds__(kKnnThreads, 7)
 #endif
 }
 
+// EXPERIMENTAL: k_knn with the warp-wide chunk queue in the neighbour phase (knn_thread<K, true>, mb_search.cuh);
+// MB_KNN_VARIANT=threadq selects it.  Same launch shape as k_knn, 4.9 KB more shared memory per warp.
+template <int K>
+__global__ void __launch_bounds__(kKnnThreads, 4)
+    k_knn_queue(MapView mv, const double* __restrict__ q, size_t nq, int k, uint64_t* __restrict__ idx,
+                double* __restrict__ d2, uint8_t* __restrict__ ok) {
+  __shared__ uint16_t s_tab[kTabEntries];
+  __shared__ uint32_t s_pk_all[kMaxNbr * kKnnThreads];
+  __shared__ uint32_t s_blk_all[24 * kKnnThreads];
+  __shared__ WarpQueue s_wq[kKnnThreads / 32];
+  fill_scan_table(mv, s_tab);
+  __syncthreads();
+  uint32_t* s_pk = s_pk_all + threadIdx.x;
+  uint32_t* s_blk = s_blk_all + threadIdx.x;
+  const size_t i = (size_t)blockIdx.x * kKnnThreads + threadIdx.x;
+  const bool active = i < nq;
+  double qx = 0, qy = 0, qz = 0;
+  if (active) {
+    qx = q[3 * i];
+    qy = q[3 * i + 1];
+    qz = q[3 * i + 2];
+  }
+  double bd[K];
+  uint32_t bs[K];
+  knn_thread<K, true>(mv, s_tab, s_pk, s_blk, kKnnThreads, qx, qy, qz, k, active, bd, bs, s_wq + threadIdx.x / 32);
+  if (!active) return;
+  uint64_t g[K];
+  float4 pts_unused[K];
+  const int found = knn_resolve_all<K, false>(mv, s_pk, kKnnThreads, bs, k, g, pts_unused);
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    if (j < k) {
+      idx[i * k + j] = g[j];
+      d2[i * k + j] = g[j] != ~0ull ? bd[j] : DBL_MAX;
+    }
+  }
+  ok[i] = found == k;
+}
+
 // EXPERIMENTAL restricted k-NN with G lanes per query (mb_search_coop.cuh); MB_KNN_VARIANT=coop4 / coop8 selects it.
 // 128 threads = 128 / G queries per block; winner j of a query is resolved and written by group lane j % G.
 template <int K, int G, int MINB, int STEP, int MODE>
@@ -669,8 +708,11 @@ int launch_knn(mb_map* m, const double* d_q, size_t nq, int k, uint64_t* d_idx, 
   // lanes-per-query search (read at every launch so that one process can compare the variants; an unknown value is an
   // error, not a fallback)
   int coop = 0, minb = 5, step = 8, mode = 0;
+  bool queue = false;
   if (const char* e = getenv("MB_KNN_VARIANT")) {
-    if (e[0] && strcmp(e, "thread")) {
+    if (!strcmp(e, "threadq")) {
+      queue = true;  // one query per thread, warp-wide chunk queue in the neighbour phase
+    } else if (e[0] && strcmp(e, "thread")) {
       bool ok = !strncmp(e, "coop", 4) && (e[4] == '4' || e[4] == '8');
       const char* c = e + 5;
       if (ok) {
@@ -689,7 +731,7 @@ int launch_knn(mb_map* m, const double* d_q, size_t nq, int k, uint64_t* d_idx, 
           ok = (step == 8 && (minb == 5 || minb == 6 || minb == 8)) || (step == 4 && (minb == 7 || minb == 8));
       }
       if (!ok) {
-        set_error("MB_KNN_VARIANT=%s: expected thread, coop8, coop4[b6|b8], coop4b7s4, coop4b8s4 or coop{4,8}p[b6|b8]", e);
+        set_error("MB_KNN_VARIANT=%s: expected thread, threadq, coop8, coop4[b6|b8], coop4b7s4, coop4b8s4 or coop{4,8}p[b6|b8]", e);
         return MB_ERR_INVALID_ARG;
       }
     }
@@ -703,7 +745,13 @@ int launch_knn(mb_map* m, const double* d_q, size_t nq, int k, uint64_t* d_idx, 
     else                                                                                                             \
       k_knn_coop<MB_MAX_K, G, 4, 8, MODE><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);   \
   } while (0)
-  if (coop && mode == 1) {
+  if (queue) {
+    const unsigned grid = blocks_for(nq, kKnnThreads);
+    if (k == 5)
+      k_knn_queue<5><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
+    else
+      k_knn_queue<MB_MAX_K><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
+  } else if (coop && mode == 1) {
     if (coop == 4 && minb == 5) MB_COOP_LAUNCH(4, 5, 8, 1);
     if (coop == 4 && minb == 6) MB_COOP_LAUNCH(4, 6, 8, 1);
     if (coop == 4 && minb == 8) MB_COOP_LAUNCH(4, 8, 8, 1);

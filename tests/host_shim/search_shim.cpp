@@ -213,13 +213,15 @@ void run(const HostMirror& M, const double* q, size_t nq, int k, uint64_t* idx, 
   }
 }
 // 32 queries per emulated warp, one host thread per lane, shared-memory columns laid out as on the device
-template <int K>
+template <int K, bool kQueue = false>
 void run_warps(const HostMirror& M, const double* q, size_t nq, int k, uint64_t* idx, double* d2, uint8_t* ok) {
   uint16_t s_tab[mb::kTabEntries] = {0};
   for (int p = 0; p < mb::kScan; ++p) s_tab[p] = M.view.scan[p];
   for (size_t w0 = 0; w0 < nq; w0 += 32) {
     WarpCtx ctx;
     std::vector<uint32_t> s_pk(mb::kMaxNbr * 32, 0xdeadbeefu), s_blk(24 * 32, 0xdeadbeefu);
+    mb::WarpQueue wq;
+    std::memset(&wq, 0xee, sizeof wq);  // stale contents must never be used
     std::vector<std::thread> lanes;
     for (int lane = 0; lane < 32; ++lane)
       lanes.emplace_back([&, lane] {
@@ -230,8 +232,8 @@ void run_warps(const HostMirror& M, const double* q, size_t nq, int k, uint64_t*
         const size_t qi = active ? i : 0;
         double bd[K];
         uint32_t bs[K];
-        mb::knn_thread<K>(M.view, s_tab, s_pk.data() + lane, s_blk.data() + lane, 32, q[3 * qi], q[3 * qi + 1], q[3 * qi + 2], k,
-                          active, bd, bs);
+        mb::knn_thread<K, kQueue>(M.view, s_tab, s_pk.data() + lane, s_blk.data() + lane, 32, q[3 * qi], q[3 * qi + 1], q[3 * qi + 2], k,
+                                  active, bd, bs, &wq);
         if (active) {
           uint64_t g[K];
           float4 pts[K];
@@ -332,5 +334,19 @@ extern "C" int shim_knn_warp(const int32_t* coords, const int32_t* counts, const
     run_warps<5>(M, q, nq, k, idx, d2, ok);
   else
     run_warps<8>(M, q, nq, k, idx, d2, ok);
+  return 0;
+}
+
+// same, with the warp-wide chunk queue in the neighbour phase (knn_thread<K, true>)
+extern "C" int shim_knn_warp_queue(const int32_t* coords, const int32_t* counts, const float* xyz, uint32_t n_vox, int cap,
+                                   int nbr_mode, double leaf, double pref_frac, const double* q, size_t nq, int k, uint64_t* idx,
+                                   double* d2, uint8_t* ok) {
+  if (k < 1 || k > 8) return 1;
+  HostMirror M;
+  build_mirror(M, coords, counts, xyz, n_vox, cap, nbr_mode, leaf, pref_frac);
+  if (k == 5)
+    run_warps<5, true>(M, q, nq, k, idx, d2, ok);
+  else
+    run_warps<8, true>(M, q, nq, k, idx, d2, ok);
   return 0;
 }

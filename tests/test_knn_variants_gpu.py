@@ -1,4 +1,5 @@
-"""The EXPERIMENTAL lanes-per-query k-NN kernels (mimosa_b200/csrc/mb_search_coop.cuh, MB_KNN_VARIANT=coop4 / coop8)
+"""The EXPERIMENTAL k-NN kernels (lanes per query: mimosa_b200/csrc/mb_search_coop.cuh, MB_KNN_VARIANT=coop4 / coop8 / ...;
+warp-wide chunk queue: knn_thread<K, true> in mb_search.cuh, MB_KNN_VARIANT=threadq — the latter has not run on a GPU yet)
 through the C ABI against the oracle's iVox: indices, squared distances and found flags bit-exact, like the default
 kernel's tests in test_gpu_parity.py.  The variants are not the product path (measured slower than the default at full
 load, profiles/r1_experiments.md session 4), so this file only runs when MB_TEST_EXPERIMENTAL=1; their logic is covered
@@ -15,7 +16,7 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("MB_TEST_EXPERIMENTAL") != "1", reason="experimental k-NN variants: set MB_TEST_EXPERIMENTAL=1")]
 
 
-@pytest.fixture(params=["coop4", "coop8", "coop4p", "coop8p"])
+@pytest.fixture(params=["coop4", "coop8", "coop4p", "coop8p", "threadq"])
 def variant(request):
     old = os.environ.get("MB_KNN_VARIANT")
     os.environ["MB_KNN_VARIANT"] = request.param

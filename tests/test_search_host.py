@@ -40,7 +40,7 @@ def shim_knn(shim, m, q, k, nbr_mode, leaf, pref_frac=0.4, warp=False, coop=0):
                                 C.c_int(coop[1]), _p(idx), _p(d2), _p(ok))
         assert rc == 0
         return idx, d2, ok.astype(bool)
-    rc = (shim.shim_knn_warp if warp else shim.shim_knn)(_p(coords), _p(counts), _p(pts), C.c_uint32(coords.shape[0]), C.c_int(m.cap), C.c_int(nbr_mode),
+    rc = (shim.shim_knn_warp_queue if warp == "queue" else shim.shim_knn_warp if warp else shim.shim_knn)(_p(coords), _p(counts), _p(pts), C.c_uint32(coords.shape[0]), C.c_int(m.cap), C.c_int(nbr_mode),
                        C.c_double(leaf), C.c_double(pref_frac), _p(q), C.c_size_t(nq), C.c_int(k), _p(idx), _p(d2), _p(ok))
     assert rc == 0
     return idx, d2, ok.astype(bool)
@@ -180,3 +180,34 @@ def test_coop_search_randomized_configurations(shim, oracle, seed):
     min_dist, pref = 0.0 if seed % 2 else 0.05 * leaf, float(rng.choice([0.0, 0.4, 1.5]))
     check(shim, oracle, pts, q, k, mode, leaf, min_dist, pref_frac=pref, cap=cap, coop=lanes)
     check(shim, oracle, pts, q, k, mode, leaf, min_dist, pref_frac=pref, cap=cap, warp=True)  # the default search, same configuration
+
+
+# ---- the warp-wide chunk queue in the neighbour phase (knn_thread<K, true>), as emulated 32-lane warps ---------------------
+@pytest.mark.parametrize("mode,k", [(19, 5), (27, 8), (7, 3), (27, 5)])
+def test_queue_search_matches_oracle_world(shim, oracle, mode, k):
+    import synth
+
+    rng = synth.rng_for(1500 + mode + k)
+    pts = np.concatenate([synth.sample_world(40000, 25.0, rng), rng.uniform(-25, 25, (3000, 3)).astype(np.float32)])
+    q = np.concatenate([pts[rng.integers(0, pts.shape[0], 500), :3].astype(np.float64) + rng.normal(0, 0.2, (500, 3)),
+                        rng.uniform(-30, 30, (141, 3))])
+    q = q[rng.permutation(q.shape[0])]
+    assert check(shim, oracle, pts, q, k, mode, 1.0, 0.2, warp="queue") > 300
+
+
+def test_queue_search_dense_ties_and_overflow(shim, oracle):
+    rng = np.random.default_rng(21)
+    # volumetric and dense: every neighbour occupied and full, queries with an empty own voxel (infinite radius: every
+    # neighbour point is a candidate, the 8 candidate slots overflow and producers must retry), lists longer than 256 items
+    vol = rng.uniform(-4, 4, (60000, 3)).astype(np.float32)
+    qv = np.concatenate([rng.uniform(-4.5, 4.5, (500, 3)), rng.uniform(-5.2, 5.2, (140, 3))])
+    for mode, k, cap in ((19, 5, 20), (27, 5, 31), (27, 8, 20), (7, 5, 7)):
+        assert check(shim, oracle, vol, qv, k, mode, 1.0, 0.0, cap=cap, warp="queue") > 300
+    g = np.arange(-6, 6) * 0.5
+    lat = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    lat = lat[rng.permutation(lat.shape[0])]
+    ql = np.concatenate([lat[:300].astype(np.float64) + 0.25, lat[:300].astype(np.float64), np.round(rng.uniform(-3, 3, (200, 3)))])
+    for mode, k in ((19, 5), (27, 8)):
+        check(shim, oracle, lat, ql, k, mode, 1.0, 0.0, warp="queue")
+    sparse = rng.uniform(-20, 20, (3000, 3)).astype(np.float32)
+    check(shim, oracle, sparse, rng.uniform(-20, 20, (600, 3)), 5, 27, 1.0, 0.0, warp="queue")

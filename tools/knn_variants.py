@@ -1,5 +1,5 @@
 """Development: the restricted k-NN launch under every MB_KNN_VARIANT (thread = the default one-query-per-thread
-search, coop4 / coop8 = mb_search_coop.cuh) on the bench's spread query set: results compared bit for bit with the
+search, threadq = the same with the warp-wide chunk queue, coop4 / coop8 / ... = mb_search_coop.cuh) on the bench's spread query set: results compared bit for bit with the
 default variant's, then CUDA-event times with the L2 flushed before every launch.  One process, one map build.
 Also timed: every 16th spread query alone (8192 queries: how long the launch lasts when throughput cannot matter).
 usage: python tools/knn_variants.py [n_timed [variant ...]]   (MB_BENCH_SMALL=1 for a dry run on a small map)"""
@@ -31,7 +31,7 @@ b_alg, _ = bench.knn_algorithmic_bytes(q_spread, coords, counts, bench.K_NN)
 peak, _ = bench.peaks()
 out = {"algorithmic_bytes": int(b_alg), "peak_gbs": peak, "variants": {}}
 ref = {}
-variants = ["thread"] + [v for v in (sys.argv[2:] or ["coop4", "coop8"]) if v != "thread"]
+variants = ["thread"] + [v for v in (sys.argv[2:] or ["threadq", "coop4b6", "coop8"]) if v != "thread"]
 for variant in variants:
     os.environ["MB_KNN_VARIANT"] = variant
     rec = {}
