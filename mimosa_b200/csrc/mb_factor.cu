@@ -193,7 +193,8 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 // ROWS = rows of the per-thread neighbour-slot table: 19 covers neighbourhood modes 1 / 7 / 19, 27 the full cube.
-// G = 0: phase B searches one query per thread (knn_thread).  G = 4: EXPERIMENTAL, four lanes per query (knn_group,
+// G = 0: phase B searches one query per thread (knn_thread).  G = 1: EXPERIMENTAL, the same with the warp-wide chunk
+// queue in its neighbour phase (knn_thread<K, true>; MB_LIN_SEARCH=queue).  G = 4: EXPERIMENTAL, four lanes per query (knn_group,
 // mb_search_coop.cuh; selected per factor with MB_LIN_SEARCH=coop4): measured faster than the per-thread search for
 // launches below ~100 k queries in the stand-alone k-NN kernel (profiles/r1_experiments.md, session 4) — the regime of
 // a rank's shard at N >= 2 and of downsampled streaming scans; this fused form has not run on a GPU yet.
@@ -201,7 +202,8 @@ template <int K, typename PoseT, int ROWS, int G = 0>
 __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
     k_linearize(MapView mv, FactorView fv, DevState* ds, PoseT pa, const PeerTable* __restrict__ peer) {
   double* pose_dev = ds->pose;
-  constexpr bool kCoop = G != 0;
+  constexpr bool kCoop = G >= 2;   // lanes per query
+  constexpr bool kQueue = G == 1;  // one query per thread, warp-wide chunk queue in the neighbour phase (mb_search.cuh)
   constexpr int kGroupWords = kCube + kCoopBlk + kCoopQueue;  // per query group: bucket table, block / gap words, survivor queue
   __shared__ uint16_t s_tab[kCoop ? 1 : kTabEntries];
   __shared__ uint32_t s_ctab[kCoop ? kTabEntries : 1];
@@ -211,6 +213,7 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
   __shared__ __align__(16) uint32_t s_pk_all[kCoop ? 3 * kCoopStack * kLinThreads : ROWS * kLinThreads];
   // per-thread {mask_lo, mask_hi, base} of the <= 8 blocks around a query; cooperative search: kGroupWords per group
   __shared__ uint32_t s_blk_all[kCoop ? kGroupWords * (kLinThreads / (kCoop ? G : 1)) : 24 * kLinThreads];
+  __shared__ WarpQueue s_wq[kQueue ? kLinWarps : 1];
   static_assert(sizeof(s_pk_all) >= sizeof(double) * 7 * kLinThreads, "s_row fits");
   __shared__ double s_pt[3][kLinThreads];          // transformed point of each tile member
   __shared__ uint8_t s_status[kLinThreads];
@@ -316,7 +319,7 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
 
     MB_LIN_T(1);
     // ---- B: search + plane fit for the compacted points -------------------------------------------
-    if constexpr (kCoop) {
+    if constexpr (G != 0) {
       // what follows a query's search: the winners' indices and points, the two distance gates, the plane fit
       auto finish_query = [&](int li, const uint32_t* pk, int pk_stride, const double (&bd)[K], const uint32_t (&bs)[K]) {
         const size_t gi = tile * kLinThreads + li;
@@ -348,21 +351,36 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
         }
         s_status[li] = rs;  // a fitted plane itself reaches its owner through fv.mean / fv.normal (same block, barrier below)
       };
-      constexpr int QW = 32 / G;  // queries per warp and pass
-      const int grp = lane / G, gl = lane % G;
-      uint32_t* g_words = s_blk_all + (warp * QW + grp) * kGroupWords;
-      for (int q0 = warp * QW; q0 < n_need; q0 += kLinWarps * QW) {
-        const int qi = q0 + grp;
-        const bool on = qi < n_need;
-        const int li = on ? (int)s_queue[qi] : 0;
-        const double qx = s_pt[0][li], qy = s_pt[1][li], qz = s_pt[2][li];
-        double bd[K];
-        uint32_t bs[K];
-        knn_group<K, G, 8, 0>(mv, s_ctab, g_words, g_words + kCube, g_words + kCube + kCoopBlk, s_pk_all + tid, kLinThreads, qx, qy, qz,
-                              k, on, bd, bs);
-        MB_LIN_T(2);
-        if (on && gl == 0) finish_query(li, g_words, 1, bd, bs);  // every lane of the group holds the same merged list
-        __syncwarp();  // the group's bucket table is rewritten by the next pass
+      if constexpr (kCoop) {
+        constexpr int QW = 32 / G;  // queries per warp and pass
+        const int grp = lane / G, gl = lane % G;
+        uint32_t* g_words = s_blk_all + (warp * QW + grp) * kGroupWords;
+        for (int q0 = warp * QW; q0 < n_need; q0 += kLinWarps * QW) {
+          const int qi = q0 + grp;
+          const bool on = qi < n_need;
+          const int li = on ? (int)s_queue[qi] : 0;
+          const double qx = s_pt[0][li], qy = s_pt[1][li], qz = s_pt[2][li];
+          double bd[K];
+          uint32_t bs[K];
+          knn_group<K, G, 8, 0>(mv, s_ctab, g_words, g_words + kCube, g_words + kCube + kCoopBlk, s_pk_all + tid, kLinThreads, qx, qy, qz,
+                                k, on, bd, bs);
+          MB_LIN_T(2);
+          if (on && gl == 0) finish_query(li, g_words, 1, bd, bs);  // every lane of the group holds the same merged list
+          __syncwarp();  // the group's bucket table is rewritten by the next pass
+        }
+      } else {  // kQueue: the per-thread search with the warp-wide chunk queue
+        for (int q0 = warp * 32; q0 < n_need; q0 += kLinThreads) {
+          const int qi = q0 + lane;
+          const bool on = qi < n_need;
+          const int li = on ? (int)s_queue[qi] : 0;
+          const double qx = s_pt[0][li], qy = s_pt[1][li], qz = s_pt[2][li];
+          double bd[K];
+          uint32_t bs[K];
+          uint32_t* s_pk = s_pk_all + tid;
+          knn_thread<K, true>(mv, s_tab, s_pk, s_blk_all + tid, kLinThreads, qx, qy, qz, k, on, bd, bs, s_wq + warp);
+          MB_LIN_T(2);
+          if (on) finish_query(li, s_pk, kLinThreads, bd, bs);
+        }
       }
     } else {
       // (this branch is the GPU-verified code, kept verbatim)
@@ -861,7 +879,7 @@ struct mb_factor {
   mb_icp_trace* d_trace = nullptr;
   int trace_cap = 0;
   int grid = 0, grid2 = 0, n_groups = 0;
-  int search_g = 0;  // 0: one query per thread; 4: four lanes per query (MB_LIN_SEARCH=coop4, experimental)
+  int search_g = 0;  // 0: one query per thread; 1: the same with the warp-wide chunk queue (MB_LIN_SEARCH=queue); 4: four lanes per query (MB_LIN_SEARCH=coop4); both experimental
   int linearize_count = 0;
   uint32_t flags = 0;
   // cached CUDA graph of an mb_icp_run sequence
@@ -927,7 +945,12 @@ int enqueue_linearize(mb_factor* f, int do_step, int iter, mb_icp_trace* d_trace
   fv.fold_loc = do_step ? 1 : 0;
   const PeerTable* peer = c->world > 1 ? c->d_peer : nullptr;  // nullptr: single rank, or NCCL all-reduce
   const bool coop4 = f->search_g == 4 && fv.k == 5 && f->map->n_off <= 19;  // MB_LIN_SEARCH=coop4 (experimental)
-  if (coop4 && pose_arg) {
+  const bool queue = f->search_g == 1 && fv.k == 5 && f->map->n_off <= 19;  // MB_LIN_SEARCH=queue (experimental)
+  if (queue && pose_arg) {
+    MB_CUDA(launch_pdl(k_linearize<5, PoseArg, 19, 1>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, f->ds, *pose_arg, peer));
+  } else if (queue) {
+    MB_CUDA(launch_pdl(k_linearize<5, NoPose, 19, 1>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, f->ds, NoPose{}, peer));
+  } else if (coop4 && pose_arg) {
     MB_CUDA(launch_pdl(k_linearize<5, PoseArg, 19, 4>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, f->ds, *pose_arg, peer));
   } else if (coop4) {
     MB_CUDA(launch_pdl(k_linearize<5, NoPose, 19, 4>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, f->ds, NoPose{}, peer));
@@ -1025,8 +1048,10 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
   if (const char* e = getenv("MB_LIN_SEARCH")) {  // development switch, read when the factor is created
     if (!strcmp(e, "coop4")) {
       f->search_g = 4;
+    } else if (!strcmp(e, "queue")) {
+      f->search_g = 1;
     } else if (e[0] && strcmp(e, "thread")) {
-      set_error("MB_LIN_SEARCH=%s: expected thread or coop4", e);
+      set_error("MB_LIN_SEARCH=%s: expected thread, queue or coop4", e);
       map->refs.fetch_sub(1);
       delete f;
       return MB_ERR_INVALID_ARG;
@@ -1034,6 +1059,8 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
   }
   if (f->search_g == 4 && k == 5 && map->n_off <= 19)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<5, NoPose, 19, 4>, kLinThreads, 0);
+  else if (f->search_g == 1 && k == 5 && map->n_off <= 19)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<5, NoPose, 19, 1>, kLinThreads, 0);
   else if (k == 5 && map->n_off <= 19)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<5, NoPose, 19>, kLinThreads, 0);
   else

@@ -1,4 +1,5 @@
-"""k_linearize with the EXPERIMENTAL four-lanes-per-query search in its phase B (MB_LIN_SEARCH=coop4, mb_factor.cu):
+"""k_linearize with an EXPERIMENTAL search in its phase B (MB_LIN_SEARCH=coop4: four lanes per query; MB_LIN_SEARCH=queue:
+one query per thread with the warp-wide chunk queue; mb_factor.cu):
 the factor parity tests of test_gpu_parity.py re-run with that variant — per-point state and correspondence indices
 bit-exact, H / g / f within 1e-9 of the oracle, poses as before.  The variant was wired in after this round's GPU
 budget was spent (its search routine, knn_group, is GPU-verified in the stand-alone k-NN kernel; the fused form only
@@ -13,10 +14,10 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("MB_TEST_EXPERIMENTAL") != "1", reason="not yet run on a GPU: set MB_TEST_EXPERIMENTAL=1")]
 
 
-@pytest.fixture(autouse=True)
-def coop_search():
+@pytest.fixture(autouse=True, params=["coop4", "queue"])
+def coop_search(request):
     old = os.environ.get("MB_LIN_SEARCH")
-    os.environ["MB_LIN_SEARCH"] = "coop4"  # read when a factor is created
+    os.environ["MB_LIN_SEARCH"] = request.param  # read when a factor is created
     yield
     if old is None:
         os.environ.pop("MB_LIN_SEARCH", None)
