@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
   __shared__ __align__(16) uint32_t s_pk_all[kCoop ? 3 * kCoopStack * kLinThreads : ROWS * kLinThreads];
   // per-thread {mask_lo, mask_hi, base} of the <= 8 blocks around a query; cooperative search: kGroupWords per group
   __shared__ uint32_t s_blk_all[kCoop ? kGroupWords * (kLinThreads / (kCoop ? G : 1)) : 24 * kLinThreads];
-  __shared__ WarpQueue s_wq[kQueue ? kLinWarps : 1];
+  __shared__ WarpQueueT<ROWS - 1> s_wq[kQueue ? kLinWarps : 1];
   static_assert(sizeof(s_pk_all) >= sizeof(double) * 7 * kLinThreads, "s_row fits");
   __shared__ double s_pt[3][kLinThreads];          // transformed point of each tile member
   __shared__ uint8_t s_status[kLinThreads];
@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
           double bd[K];
           uint32_t bs[K];
           uint32_t* s_pk = s_pk_all + tid;
-          knn_thread<K, true>(mv, s_tab, s_pk, s_blk_all + tid, kLinThreads, qx, qy, qz, k, on, bd, bs, s_wq + warp);
+          knn_thread<K, true, ROWS - 1>(mv, s_tab, s_pk, s_blk_all + tid, kLinThreads, qx, qy, qz, k, on, bd, bs, s_wq + warp);
           MB_LIN_T(2);
           if (on) finish_query(li, s_pk, kLinThreads, bd, bs);
         }

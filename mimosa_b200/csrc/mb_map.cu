@@ -417,15 +417,16 @@ __global__ void __launch_bounds__(kKnnThreads, 7)
 }
 
 // EXPERIMENTAL: k_knn with the warp-wide chunk queue in the neighbour phase (knn_thread<K, true>, mb_search.cuh);
-// MB_KNN_VARIANT=threadq selects it.  Same launch shape as k_knn, 4.9 KB more shared memory per warp.
-template <int K>
-__global__ void __launch_bounds__(kKnnThreads, 4)
+// MB_KNN_VARIANT=threadq selects it.  Same launch shape as k_knn; ROWS = 19 (neighbourhood modes up to 19) keeps the
+// shared memory at 28.6 KB so that seven blocks per SM still fit (one wave for 131 072 queries), ROWS = 27 is generic.
+template <int K, int ROWS>
+__global__ void __launch_bounds__(kKnnThreads, ROWS == 19 ? 7 : 6)
     k_knn_queue(MapView mv, const double* __restrict__ q, size_t nq, int k, uint64_t* __restrict__ idx,
                 double* __restrict__ d2, uint8_t* __restrict__ ok) {
   __shared__ uint16_t s_tab[kTabEntries];
-  __shared__ uint32_t s_pk_all[kMaxNbr * kKnnThreads];
+  __shared__ uint32_t s_pk_all[ROWS * kKnnThreads];
   __shared__ uint32_t s_blk_all[24 * kKnnThreads];
-  __shared__ WarpQueue s_wq[kKnnThreads / 32];
+  __shared__ WarpQueueT<ROWS - 1> s_wq[kKnnThreads / 32];
   fill_scan_table(mv, s_tab);
   __syncthreads();
   uint32_t* s_pk = s_pk_all + threadIdx.x;
@@ -440,7 +441,7 @@ __global__ void __launch_bounds__(kKnnThreads, 4)
   }
   double bd[K];
   uint32_t bs[K];
-  knn_thread<K, true>(mv, s_tab, s_pk, s_blk, kKnnThreads, qx, qy, qz, k, active, bd, bs, s_wq + threadIdx.x / 32);
+  knn_thread<K, true, ROWS - 1>(mv, s_tab, s_pk, s_blk, kKnnThreads, qx, qy, qz, k, active, bd, bs, s_wq + threadIdx.x / 32);
   if (!active) return;
   uint64_t g[K];
   float4 pts_unused[K];
@@ -747,10 +748,10 @@ int launch_knn(mb_map* m, const double* d_q, size_t nq, int k, uint64_t* d_idx, 
   } while (0)
   if (queue) {
     const unsigned grid = blocks_for(nq, kKnnThreads);
-    if (k == 5)
-      k_knn_queue<5><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
+    if (k == 5 && m->n_off <= 19)
+      k_knn_queue<5, 19><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
     else
-      k_knn_queue<MB_MAX_K><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
+      k_knn_queue<MB_MAX_K, 27><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
   } else if (coop && mode == 1) {
     if (coop == 4 && minb == 5) MB_COOP_LAUNCH(4, 5, 8, 1);
     if (coop == 4 && minb == 6) MB_COOP_LAUNCH(4, 6, 8, 1);

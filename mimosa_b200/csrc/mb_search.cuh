@@ -131,27 +131,27 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // lane drains its own query's slots into its (d2, sequence) list.  Same result as the per-lane loop by the same
 // argument: the list order does not depend on when or by whom a candidate is offered, a stale radius only admits more.
 // Checked against the oracle through the 32-lane emulation; NOT YET RUN on a GPU.
-constexpr int kWqItems = 256;   // items listed before the list is worked off
-constexpr int kWqSurv = 18;     // surviving neighbours per query (mode 19; the full cube uses 26)
-struct WarpQueue {
-  double q[3][32];               // the warp's queries
-  float rad[32];                 // their radii (k-th best, rounded up), refreshed at drains
-  uint32_t cn[32];               // candidate slots claimed per query since its last drain
-  uint32_t sv[kMaxNbr - 1][32];  // survivor r of lane l: visiting rank | fill count << 5
-  uint16_t items[kWqItems];      // lane | survivor << 5 | chunk << 10
+constexpr int kWqItems = 128;  // items listed before the list is worked off
+// The warp's scratch.  NSV = surviving neighbours a query can have: 18 for neighbourhood modes up to 19, 26 for the
+// full cube.  (The queries' coordinates travel by shuffle; 1.7 - 2.2 KB per warp keeps seven 128-thread blocks per SM.)
+template <int NSV>
+struct WarpQueueT {
+  float rad[32];             // the queries' radii (k-th best, rounded up), refreshed at drains
+  uint32_t cn[32];           // candidate slots claimed per query since its last drain
+  uint16_t sv[NSV][32];      // survivor r of lane l: visiting rank | fill count << 5
+  uint16_t items[kWqItems];  // lane | survivor << 5 | chunk << 10
 };
 
-template <int K, typename Offer, typename Worst>
+template <int K, int NSV, typename Offer, typename Worst>
 MB_DEV void knn_queue_phase(const MapView& mv, const uint16_t* __restrict__ s_tab, uint32_t* s_pk, uint32_t* s_blk,
                             int pk_stride, double qx, double qy, double qz, int k, uint32_t todo, float wq_f,
-                            Offer& offer, Worst& worst_of, WarpQueue* wqp) {
-  WarpQueue& W = *wqp;
+                            Offer& offer, Worst& worst_of, WarpQueueT<NSV>* wqp) {
+  WarpQueueT<NSV>& W = *wqp;
   const int lane = warp_lane();
   const int cap = mv.cap;
   const uint32_t kCntMask = (1u << kCountBits) - 1;
   uint32_t* const pk0 = s_pk - lane;    // column 0 of the warp in the [rank][thread] slot table
   uint32_t* const cand0 = s_blk - lane;  // column 0 of the warp in the [3 * 8][thread] candidate slots
-  W.q[0][lane] = qx, W.q[1][lane] = qy, W.q[2][lane] = qz;
   W.rad[lane] = wq_f;
   W.cn[lane] = 0u;
   // (a) fill counts of the surviving buckets, four loads in flight per lane
@@ -172,7 +172,7 @@ MB_UNROLL
       }
 MB_UNROLL
       for (int u = 0; u < 4; ++u)
-        if (r0 + u < n) W.sv[r0 + u][lane] = rk[u] | ((w[u] & kCntMask) << 5);
+        if (r0 + u < n) W.sv[r0 + u][lane] = (uint16_t)(rk[u] | ((w[u] & kCntMask) << 5));
     }
   }
   __syncwarp();
@@ -199,7 +199,7 @@ MB_UNROLL
       const bool has = i0 + lane < count;
       const uint32_t it = has ? (uint32_t)W.items[i0 + lane] : 0u;
       const uint32_t ql = it & 31u, r = (it >> 5) & 31u, c = it >> 10;
-      const uint32_t sv = has ? W.sv[r][ql] : 0u;
+      const uint32_t sv = has ? (uint32_t)W.sv[r][ql] : 0u;
       const uint32_t rk = sv & 31u;
       const int cnt = has ? (int)(sv >> 5) : 0, j = 4 * (int)c;
       const float4* bucket = mv.pts + (size_t)(has ? pk0[rk * pk_stride + ql] : 0u) * cap;
@@ -210,7 +210,7 @@ MB_UNROLL
 MB_UNROLL
         for (int u = 0; u < 4; ++u) p[u] = __ldg(bucket + min(j + u, cap - 1));
       }
-      const double ox = W.q[0][ql], oy = W.q[1][ql], oz = W.q[2][ql];
+      const double ox = __shfl_sync(kFull, qx, (int)ql), oy = __shfl_sync(kFull, qy, (int)ql), oz = __shfl_sync(kFull, qz, (int)ql);
       const double rad = (double)W.rad[ql];
       double d[4];
       uint32_t pending = 0u;
@@ -245,7 +245,7 @@ MB_UNROLL
   // (b) list the chunks in (survivor, chunk)-major order; work the list off whenever it could overflow
   int base = 0;
   for (int r = 0; r < max_n; ++r) {
-    const int nch = r < n ? (int)(((W.sv[r][lane] >> 5) + 3u) >> 2) : 0;
+    const int nch = r < n ? (int)((((uint32_t)W.sv[r][lane] >> 5) + 3u) >> 2) : 0;
     const int max_c = __reduce_max_sync(kFull, nch);
     for (int c = 0; c < max_c; ++c) {
       const unsigned b = __ballot_sync(kFull, c < nch);
@@ -296,12 +296,11 @@ __device__ long long g_knn_t[16];
 
 // kQueue (EXPERIMENTAL, see knn_queue_phase below): the surviving neighbours' four-point chunks of all 32 queries of
 // the warp go through one shared work list instead of every lane walking its own buckets; s_wq = the warp's scratch.
-struct WarpQueue;
-template <int K, bool kQueue = false>
+template <int K, bool kQueue = false, int NSV = kMaxNbr - 1>
 MB_DEV void knn_thread(const MapView& mv, const uint16_t* __restrict__ s_tab, uint32_t* s_pk,
                                            uint32_t* s_blk, int pk_stride, double qx, double qy, double qz, int k,
                                            bool active,
-                                           double (&bd)[K], uint32_t (&bs)[K], WarpQueue* s_wq = nullptr) {
+                                           double (&bd)[K], uint32_t (&bs)[K], WarpQueueT<NSV>* s_wq = nullptr) {
   const double kInf = __longlong_as_double(0x7ff0000000000000ll);
 MB_UNROLL
   for (int i = 0; i < K; ++i) {
@@ -530,7 +529,7 @@ MB_UNROLL
   // accepted candidate and not per candidate slot of the warp.  The list's (d2, sequence) order makes the result
   // independent of when a candidate is inserted; a stale radius only admits more candidates.
   if constexpr (kQueue) {
-    knn_queue_phase<K>(mv, s_tab, s_pk, s_blk, pk_stride, qx, qy, qz, k, todo, wq_f, offer, worst_of, s_wq);
+    knn_queue_phase<K, NSV>(mv, s_tab, s_pk, s_blk, pk_stride, qx, qy, qz, k, todo, wq_f, offer, worst_of, s_wq);
     return;
   }
   int j = 0, cnt = 0, n_st = 0;

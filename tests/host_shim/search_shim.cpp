@@ -220,7 +220,7 @@ void run_warps(const HostMirror& M, const double* q, size_t nq, int k, uint64_t*
   for (size_t w0 = 0; w0 < nq; w0 += 32) {
     WarpCtx ctx;
     std::vector<uint32_t> s_pk(mb::kMaxNbr * 32, 0xdeadbeefu), s_blk(24 * 32, 0xdeadbeefu);
-    mb::WarpQueue wq;
+    mb::WarpQueueT<mb::kMaxNbr - 1> wq;
     std::memset(&wq, 0xee, sizeof wq);  // stale contents must never be used
     std::vector<std::thread> lanes;
     for (int lane = 0; lane < 32; ++lane)
@@ -232,7 +232,7 @@ void run_warps(const HostMirror& M, const double* q, size_t nq, int k, uint64_t*
         const size_t qi = active ? i : 0;
         double bd[K];
         uint32_t bs[K];
-        mb::knn_thread<K, kQueue>(M.view, s_tab, s_pk.data() + lane, s_blk.data() + lane, 32, q[3 * qi], q[3 * qi + 1], q[3 * qi + 2], k,
+        mb::knn_thread<K, kQueue, mb::kMaxNbr - 1>(M.view, s_tab, s_pk.data() + lane, s_blk.data() + lane, 32, q[3 * qi], q[3 * qi + 1], q[3 * qi + 2], k,
                                   active, bd, bs, &wq);
         if (active) {
           uint64_t g[K];
