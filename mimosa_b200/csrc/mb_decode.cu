@@ -57,14 +57,10 @@ __global__ void k_ring_keys(const unsigned char* __restrict__ data, size_t n, mb
   vals[i] = (uint32_t)i;
 }
 
-__global__ void k_decode(const unsigned char* __restrict__ data, size_t n_cand, uint32_t stride_pts, mb_cloud_layout lay,
-                         mb_input_filter fl, float range_min_sq, float range_max_sq, const uint32_t* __restrict__ perm,
-                         uint32_t t_w, uint32_t t_h, OutRec* __restrict__ tmp, uint32_t* __restrict__ keep,
-                         uint32_t* __restrict__ geo) {
-  const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_cand) return;
-  const size_t i = c * stride_pts;
-  const unsigned char* p = data + src_record(i, perm, t_w, t_h) * lay.point_step;
+// Candidate c = index i of the (re-ordered) cloud, its record at p: the filters, the time decode and the output row.
+__device__ __forceinline__ void decode_record(const unsigned char* p, size_t i, size_t c, const mb_cloud_layout lay,
+                                              const mb_input_filter fl, float range_min_sq, float range_max_sq,
+                                              OutRec* __restrict__ tmp, uint32_t* __restrict__ keep, uint32_t* __restrict__ geo) {
   uint32_t k = 0, g = 0;
   OutRec r;
   r.x = load_unaligned<float>(p + lay.off_x);
@@ -125,6 +121,27 @@ __global__ void k_decode(const unsigned char* __restrict__ data, size_t n_cand, 
   tmp[c] = r;
   keep[c] = k;
   geo[c] = g;
+}
+
+// the message as received (mb_scan_from_cloud)
+__global__ void k_decode(const unsigned char* __restrict__ data, size_t n_cand, uint32_t stride_pts, mb_cloud_layout lay,
+                         mb_input_filter fl, float range_min_sq, float range_max_sq, OutRec* __restrict__ tmp,
+                         uint32_t* __restrict__ keep, uint32_t* __restrict__ geo) {
+  const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cand) return;
+  const size_t i = c * stride_pts;
+  decode_record(data + i * lay.point_step, i, c, lay, fl, range_min_sq, range_max_sq, tmp, keep, geo);
+}
+
+// the re-ordered message (mb_scan_from_cloud_ordered): index i of the re-ordered cloud reads record src_record(i)
+__global__ void k_decode_ordered(const unsigned char* __restrict__ data, size_t n_cand, uint32_t stride_pts, mb_cloud_layout lay,
+                                 mb_input_filter fl, float range_min_sq, float range_max_sq, const uint32_t* __restrict__ perm,
+                                 uint32_t t_w, uint32_t t_h, OutRec* __restrict__ tmp, uint32_t* __restrict__ keep,
+                                 uint32_t* __restrict__ geo) {
+  const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cand) return;
+  const size_t i = c * stride_pts;
+  decode_record(data + src_record(i, perm, t_w, t_h) * lay.point_step, i, c, lay, fl, range_min_sq, range_max_sq, tmp, keep, geo);
 }
 
 __global__ void k_compact(const OutRec* __restrict__ tmp, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ keep_pos,
@@ -290,8 +307,11 @@ extern "C" int mb_scan_from_cloud_ordered(mb_ctx* ctx, const void* data, size_t 
     MB_CUDA(cub::DeviceRadixSort::SortPairs(ring_tmp, rb, ring_keys, ring_keys_s, ring_vals, perm, (int)n_points, 0, 16, st));
     ctx->launches += 4;
   }
-  k_decode<<<blocks_for(n_cand, 256), 256, 0, st>>>(raw, n_cand, stride_pts, *layout, *filter, rmin2, rmax2, perm, t_w, t_h, tmp, keep,
-                                                    geo);
+  if (perm || t_h)
+    k_decode_ordered<<<blocks_for(n_cand, 256), 256, 0, st>>>(raw, n_cand, stride_pts, *layout, *filter, rmin2, rmax2, perm, t_w, t_h,
+                                                              tmp, keep, geo);
+  else
+    k_decode<<<blocks_for(n_cand, 256), 256, 0, st>>>(raw, n_cand, stride_pts, *layout, *filter, rmin2, rmax2, tmp, keep, geo);
   size_t tb = temp_bytes;
   MB_CUDA(cub::DeviceScan::ExclusiveSum(temp, tb, keep, keep_pos, (int)n_cand, st));
   tb = temp_bytes;
