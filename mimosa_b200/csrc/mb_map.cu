@@ -715,8 +715,8 @@ int launch_knn(mb_map* m, const double* d_q, size_t nq, int k, uint64_t* d_idx, 
       queue = true;  // one query per thread, warp-wide chunk queue in the neighbour phase
     } else if (e[0] && strcmp(e, "thread")) {
       bool ok = !strncmp(e, "coop", 4) && (e[4] == '4' || e[4] == '8');
-      const char* c = e + 5;
       if (ok) {
+        const char* c = e + 5;
         coop = e[4] - '0';
         if (*c == 'p') mode = 1, ++c;
         if (*c == 'b' && c[1] >= '4' && c[1] <= '8') minb = c[1] - '0', c += 2;
