@@ -1050,8 +1050,12 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
       f->search_g = 4;
     } else if (!strcmp(e, "queue")) {
       f->search_g = 1;
+    } else if (!strcmp(e, "auto")) {
+      // by point count: the cooperative search wins below ~100 k queries per launch in the stand-alone kernel
+      // (profiles/r1_experiments.md, session 4) — a rank's shard at N >= 2, downsampled streaming scans
+      f->search_g = f->n <= 98304 ? 4 : 0;
     } else if (e[0] && strcmp(e, "thread")) {
-      set_error("MB_LIN_SEARCH=%s: expected thread, queue or coop4", e);
+      set_error("MB_LIN_SEARCH=%s: expected thread, queue, coop4 or auto", e);
       map->refs.fetch_sub(1);
       delete f;
       return MB_ERR_INVALID_ARG;
