@@ -26,6 +26,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <cub/cub.cuh>
+
 #include <type_traits>
 #if defined(__SSE2__)
 #include <emmintrin.h>
@@ -33,7 +35,7 @@
 
 #include "mb_map.cuh"
 #include "mb_scan.cuh"
-#include "mb_search_coop.cuh"
+#include "mb_search_group.cuh"
 
 namespace mb {
 namespace {
@@ -178,9 +180,16 @@ __device__ __forceinline__ void block_sum_rows(const double* rows, int count, in
   }
 }
 
-#ifndef MB_LIN_BLOCKS
-#define MB_LIN_BLOCKS 4  // measured: 4 x 128 threads at 128 registers (no spills) beat 5 x 96 and 3 x 156
-#endif
+// computeLocalizability (mimosa/include/mimosa/utils.hpp:308-313).  The closed-form solver (checked a posteriori,
+// iterative fallback) replaces the reference's iterative one here: its input, the reduced 6x6, already differs
+// from the CPU's in the last bits, so bit parity is not at stake, and it is 5x shorter as a single-thread chain.
+__device__ __forceinline__ void localizability(const m33& JtJ, double loc[3], m33& V) {
+  double lam[3];
+  eigh33_direct(JtJ, lam, V);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) loc[a] = sqrt(lam[a]);
+}
+
 // PoseT = PoseArg: host-facing single call (pose in the kernel parameters); PoseT = NoPose: device-resident loop.
 struct NoPose {};
 
@@ -192,435 +201,19 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-// ROWS = rows of the per-thread neighbour-slot table: 19 covers neighbourhood modes 1 / 7 / 19, 27 the full cube.
-// G = 0: phase B searches one query per thread (knn_thread).  G = 1: EXPERIMENTAL, the same with the warp-wide chunk
-// queue in its neighbour phase (knn_thread<K, true>; MB_LIN_SEARCH=queue).  G = 4: EXPERIMENTAL, four lanes per query (knn_group,
-// mb_search_coop.cuh; selected per factor with MB_LIN_SEARCH=coop4): measured faster than the per-thread search for
-// launches below ~100 k queries in the stand-alone k-NN kernel (profiles/r1_experiments.md, session 4) — the regime of
-// a rank's shard at N >= 2 and of downsampled streaming scans; this fused form has not run on a GPU yet.
-template <int K, typename PoseT, int ROWS, int G = 0>
-__global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
-    k_linearize(MapView mv, FactorView fv, DevState* ds, PoseT pa, const PeerTable* __restrict__ peer) {
-  double* pose_dev = ds->pose;
-  constexpr bool kCoop = G >= 2;   // lanes per query
-  constexpr bool kQueue = G == 1;  // one query per thread, warp-wide chunk queue in the neighbour phase (mb_search.cuh)
-  constexpr int kGroupWords = kCube + kCoopBlk + kCoopQueue;  // per query group: bucket table, block / gap words, survivor queue
-  __shared__ uint16_t s_tab[kCoop ? 1 : kTabEntries];
-  __shared__ uint32_t s_ctab[kCoop ? kTabEntries : 1];
-  // s_pk (phase B: probed neighbour words, [n_off][thread]; cooperative search: the per-thread candidate stacks,
-  // [3 * kCoopStack][thread]) is re-used as s_row (phase C: whitened [J (6), e] per point, [warp][32][7] doubles =
-  // 7168 B <= 19 * 128 * 4 B).
-  __shared__ __align__(16) uint32_t s_pk_all[kCoop ? 3 * kCoopStack * kLinThreads : ROWS * kLinThreads];
-  // per-thread {mask_lo, mask_hi, base} of the <= 8 blocks around a query; cooperative search: kGroupWords per group
-  __shared__ uint32_t s_blk_all[kCoop ? kGroupWords * (kLinThreads / (kCoop ? G : 1)) : 24 * kLinThreads];
-  __shared__ WarpQueueT<ROWS - 1> s_wq[kQueue ? kLinWarps : 1];
-  static_assert(sizeof(s_pk_all) >= sizeof(double) * 7 * kLinThreads, "s_row fits");
-  __shared__ double s_pt[3][kLinThreads];          // transformed point of each tile member
-  __shared__ uint8_t s_status[kLinThreads];
-  __shared__ uint16_t s_queue[kLinThreads];
-  __shared__ int s_warp_need[kLinWarps];
-  __shared__ double s_red[kLinWarps][kPack];
-  __shared__ double s_tmp[(kLinThreads / kPack) * kPack];
-  __shared__ bool s_last;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  pdl_launch_dependents();
-  if constexpr (kCoop) {
-    if (tid < kScan) s_ctab[tid] = coop_tab_entry(mv.scan[tid]);
-  } else {
-    fill_scan_table(mv, s_tab);
-  }
-  double(*s_row)[7] = reinterpret_cast<double(*)[7]>(s_pk_all) + warp * 32;
-  // Lane a < 28 owns entry a of the packed upper triangle of [J e]^T [J e] (7x7): the 21 entries of
-  // J^T J first (row-major, c >= r), then J^T e (6), then e^2.
-  int pr = 0, pc = 0;
-  {
-    int u = 0;
-    for (int r = 0; r < 6; ++r)
-      for (int c = r; c < 6; ++c) {
-        if (u == lane) {
-          pr = r;
-          pc = c;
-        }
-        ++u;
-      }
-    if (lane >= 21 && lane < 27) {
-      pr = lane - 21;
-      pc = 6;
-    }
-    if (lane == 27) pr = pc = 6;
-  }
 
-  // everything above is independent of earlier kernels; from here on we read the pose the previous iteration's
-  // k_finalize wrote and overwrite per-point state the previous k_loc_comp may still be reading
-  pdl_wait();
-  m33 R;
-#pragma unroll
-  d3 T;
-  if constexpr (std::is_same<PoseT, PoseArg>::value) {
-    if (blockIdx.x == 0 && tid < 16) pose_dev[tid] = pa.v[tid];  // k_finalize reads pose / gravity / lambda there
-#pragma unroll
-    for (int a = 0; a < 9; ++a) R.m[a] = pa.v[a];
-    T = mk3(pa.v[9], pa.v[10], pa.v[11]);
-  } else {
-#pragma unroll
-    for (int a = 0; a < 9; ++a) R.m[a] = pose_dev[a];
-    T = mk3(pose_dev[9], pose_dev[10], pose_dev[11]);
-  }
-  const int k = fv.k;
-  const bool forced = (fv.flags & 1u) != 0;
+// What follows the reduction of one linearisation (arguments of the finalize roles).
+struct FinArgs {
+  int reg_4_dof, linearize_count, do_step, iter;
+  mb_icp_trace* trace;
+  int fuse;  // 1: the last block of k_linearize runs the roles itself (no k_finalize launch)
+};
 
-  double acc = 0.0, lacc = 0.0;  // lacc: lane a < 6 sums component a of the previous linearisation's localizability pass
-  int cnt = 0;  // lane s < 9: points with status s; lane 9: points searched
-  // Folded localizability pass (device-resident loop): before a point's status and localizability vectors are
-  // overwritten, its contribution |loc^T V| (entries below 0.5 dropped, geometric_factor.hpp:434-457) to the
-  // component localizabilities of the PREVIOUS linearisation is taken with that linearisation's eigenvectors, which
-  // the previous k_finalize left in ds->lin.  It saves a pass over the points and a kernel launch per iteration.
-  __shared__ double s_V[18];
-  if (fv.fold_loc && tid < 18) s_V[tid] = tid < 9 ? ds->lin.eigvec_trans[tid] : ds->lin.eigvec_rot[tid - 9];
-  __syncthreads();
-#if defined(MB_LIN_TIMING)
-  long long lt_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define MB_LIN_T(i) do { if (blockIdx.x == MB_LIN_TIMING && tid == 0 && tile == blockIdx.x) lt_[i] = clock64(); } while (0)
-#else
-#define MB_LIN_T(i) do { } while (0)
-#endif
-
-  const size_t n_tiles = (fv.n + kLinThreads - 1) / kLinThreads;
-  for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const size_t i = tile * kLinThreads + tid;
-    const bool act = i < fv.n;
-    MB_LIN_T(0);
-    // ---- A: transform, gate, compaction ------------------------------------------------------------
-    d3 ps = mk3(0, 0, 0), pt = mk3(0, 0, 0);
-    uint8_t st = MB_UNPROCESSED;
-    bool need = false;
-    if (act) {
-      const float4 s = __ldg(fv.src + i);
-      ps = mk3((double)s.x, (double)s.y, (double)s.z);
-      pt = add3(mul33v(R, ps), T);
-      st = fv.status[i];
-      const d3 da = ld3(fv.p_da, fv.ld, i);
-      need = forced || sqrt(sqnorm3(sub3(pt, da))) > fv.da_gate;
-    }
-    s_pt[0][tid] = pt.x;
-    s_pt[1][tid] = pt.y;
-    s_pt[2][tid] = pt.z;
-    const unsigned mask = __ballot_sync(kFull, need);
-    if (lane == 0) s_warp_need[warp] = __popc(mask);
-    __syncthreads();
-    int base = 0, n_need = 0;
-#pragma unroll
-    for (int w = 0; w < kLinWarps; ++w) {
-      if (w < warp) base += s_warp_need[w];
-      n_need += s_warp_need[w];
-    }
-    if (need) s_queue[base + __popc(mask & ((1u << lane) - 1))] = (uint16_t)tid;
-    __syncthreads();
-
-    MB_LIN_T(1);
-    // ---- B: search + plane fit for the compacted points -------------------------------------------
-    if constexpr (G != 0) {
-      // what follows a query's search: the winners' indices and points, the two distance gates, the plane fit
-      auto finish_query = [&](int li, const uint32_t* pk, int pk_stride, const double (&bd)[K], const uint32_t (&bs)[K]) {
-        const size_t gi = tile * kLinThreads + li;
-        float4 nb[K];
-        uint64_t g[K];
-        const int found = knn_resolve_all<K, true>(mv, pk, pk_stride, bs, k, g, nb);
-        double dk = 0.0;
-  #pragma unroll
-        for (int j = 0; j < K; ++j) {
-          if (j < k) {
-            if (j == k - 1) dk = bd[j];
-            // indices are only meaningful when all k exist (the reference discards partial results)
-            if (fv.knn_idx) fv.knn_idx[gi * k + j] = g[j];
-          }
-        }
-        uint8_t rs = MB_UNPROCESSED;
-        d3 mean = mk3(0, 0, 0), normal = mk3(0, 0, 0);
-        if (found != k) {
-          rs = MB_INSUFFICIENT_CORRES_POINTS;
-          if (fv.knn_idx)
-            for (int j = 0; j < k; ++j) fv.knn_idx[gi * k + j] = ~0ull;
-        } else if (dk > fv.max_corr_sq) {
-          rs = MB_CORRES_MAX_DIST;
-        } else {
-          bool normal_set;
-          rs = fit_plane<K>(nb, k, T, fv.pvd, mean, normal, normal_set);
-          st3(fv.mean, fv.ld, gi, mean);
-          if (normal_set) st3(fv.normal, fv.ld, gi, normal);
-        }
-        s_status[li] = rs;  // a fitted plane itself reaches its owner through fv.mean / fv.normal (same block, barrier below)
-      };
-      if constexpr (kCoop) {
-        constexpr int QW = 32 / G;  // queries per warp and pass
-        const int grp = lane / G, gl = lane % G;
-        uint32_t* g_words = s_blk_all + (warp * QW + grp) * kGroupWords;
-        for (int q0 = warp * QW; q0 < n_need; q0 += kLinWarps * QW) {
-          const int qi = q0 + grp;
-          const bool on = qi < n_need;
-          const int li = on ? (int)s_queue[qi] : 0;
-          const double qx = s_pt[0][li], qy = s_pt[1][li], qz = s_pt[2][li];
-          double bd[K];
-          uint32_t bs[K];
-          knn_group<K, G, 8, 0>(mv, s_ctab, g_words, g_words + kCube, g_words + kCube + kCoopBlk, s_pk_all + tid, kLinThreads, qx, qy, qz,
-                                k, on, bd, bs);
-          MB_LIN_T(2);
-          if (on && gl == 0) finish_query(li, g_words, 1, bd, bs);  // every lane of the group holds the same merged list
-          __syncwarp();  // the group's bucket table is rewritten by the next pass
-        }
-      } else {  // kQueue: the per-thread search with the warp-wide chunk queue
-        for (int q0 = warp * 32; q0 < n_need; q0 += kLinThreads) {
-          const int qi = q0 + lane;
-          const bool on = qi < n_need;
-          const int li = on ? (int)s_queue[qi] : 0;
-          const double qx = s_pt[0][li], qy = s_pt[1][li], qz = s_pt[2][li];
-          double bd[K];
-          uint32_t bs[K];
-          uint32_t* s_pk = s_pk_all + tid;
-          knn_thread<K, true, ROWS - 1>(mv, s_tab, s_pk, s_blk_all + tid, kLinThreads, qx, qy, qz, k, on, bd, bs, s_wq + warp);
-          MB_LIN_T(2);
-          if (on) finish_query(li, s_pk, kLinThreads, bd, bs);
-        }
-      }
-    } else {
-      // (this branch is the GPU-verified code, kept verbatim)
-      for (int q0 = warp * 32; q0 < n_need; q0 += kLinThreads) {
-        const int qi = q0 + lane;
-        const bool on = qi < n_need;
-        const int li = on ? (int)s_queue[qi] : 0;
-        const double qx = s_pt[0][li], qy = s_pt[1][li], qz = s_pt[2][li];
-        double bd[K];
-        uint32_t bs[K];
-        uint32_t* s_pk = s_pk_all + tid;
-        knn_thread<K>(mv, s_tab, s_pk, s_blk_all + tid, kLinThreads, qx, qy, qz, k, on, bd, bs);
-        MB_LIN_T(2);
-        if (on) {
-          const size_t gi = tile * kLinThreads + li;
-          float4 nb[K];
-          uint64_t g[K];
-          const int found = knn_resolve_all<K, true>(mv, s_pk, kLinThreads, bs, k, g, nb);
-          double dk = 0.0;
-#pragma unroll
-          for (int j = 0; j < K; ++j) {
-            if (j < k) {
-              if (j == k - 1) dk = bd[j];
-              // indices are only meaningful when all k exist (the reference discards partial results)
-              if (fv.knn_idx) fv.knn_idx[gi * k + j] = g[j];
-            }
-          }
-          uint8_t rs = MB_UNPROCESSED;
-          d3 mean = mk3(0, 0, 0), normal = mk3(0, 0, 0);
-          if (found != k) {
-            rs = MB_INSUFFICIENT_CORRES_POINTS;
-            if (fv.knn_idx)
-              for (int j = 0; j < k; ++j) fv.knn_idx[gi * k + j] = ~0ull;
-          } else if (dk > fv.max_corr_sq) {
-            rs = MB_CORRES_MAX_DIST;
-          } else {
-            bool normal_set;
-            rs = fit_plane<K>(nb, k, T, fv.pvd, mean, normal, normal_set);
-            st3(fv.mean, fv.ld, gi, mean);
-            if (normal_set) st3(fv.normal, fv.ld, gi, normal);
-          }
-          s_status[li] = rs;  // a fitted plane itself reaches its owner through fv.mean / fv.normal (same block, barrier below)
-        }
-      }
-    }
-    __syncthreads();
-
-    MB_LIN_T(3);
-    // ---- C: residual, Jacobian, accumulation (own point) --------------------------------------------
-    double row[7] = {0, 0, 0, 0, 0, 0, 0};
-    if (fv.fold_loc) {
-      double v[6] = {0, 0, 0, 0, 0, 0};
-      if (act && st == MB_VALID) {  // st is still the status the previous linearisation left
-        const d3 lt = ld3(fv.loc_trans, fv.ld, i), lr = ld3(fv.loc_rot, fv.ld, i);
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {  // column a of V: (V^T loc)_a, in mul33Tv's order of operations
-          const double tc = fabs(s_V[a] * lt.x + (s_V[3 + a] * lt.y + s_V[6 + a] * lt.z));
-          const double rc = fabs(s_V[9 + a] * lr.x + (s_V[12 + a] * lr.y + s_V[15 + a] * lr.z));
-          v[a] = tc >= 0.5 ? tc : 0.0;
-          v[3 + a] = rc >= 0.5 ? rc : 0.0;
-        }
-      }
-      if (__ballot_sync(kFull, act && st == MB_VALID)) {
-#pragma unroll
-        for (int a = 0; a < 6; ++a) s_row[lane][a] = v[a];
-        __syncwarp();
-        if (lane < 6) {
-#pragma unroll 8
-          for (int p = 0; p < 32; ++p) lacc += s_row[p][lane];
-        }
-        __syncwarp();
-      }
-    }
-    if (act) {
-      bool proceed = false;
-      d3 mean = mk3(0, 0, 0), normal = mk3(0, 0, 0);
-      if (need) {
-        st3(fv.p_da, fv.ld, i, pt);
-        st = s_status[tid];
-        if (st == MB_UNPROCESSED) {
-          mean = ld3(fv.mean, fv.ld, i);
-          normal = ld3(fv.normal, fv.ld, i);
-          proceed = true;
-        }
-      } else if (st > MB_CORRES_PLANE_INVALID) {
-        mean = ld3(fv.mean, fv.ld, i);
-        normal = ld3(fv.normal, fv.ld, i);
-        proceed = true;
-      }
-      if (proceed) {
-        double e = dot3(normal, sub3(mean, pt));
-        const double s_chk = 1 - 0.9 * fabs(e) / sqrt(sqrt(sqnorm3(ps)));
-        if (s_chk < 0.9) {
-          st = MB_MAX_ERROR;
-        } else {
-          double sqrt_w = 1.0;
-          if (fv.use_huber) {
-            const double we = e / fv.sigma;
-            if (fabs(we) > fv.kh) sqrt_w = sqrt(fv.kh / fabs(we));
-          }
-          const double scale = sqrt_w / fv.sigma;
-          e *= scale;
-          const d3 ns = mul33Tv(R, normal);
-          const d3 jr = cross3(ns, ps);
-          const double z = sqnorm3(jr);
-          st3(fv.loc_rot, fv.ld, i, z > 0 ? div3(jr, sqrt(z)) : jr);
-          st3(fv.loc_trans, fv.ld, i, mk3(-ns.x, -ns.y, -ns.z));
-          row[0] = jr.x * scale;
-          row[1] = jr.y * scale;
-          row[2] = jr.z * scale;
-          row[3] = -ns.x * scale;
-          row[4] = -ns.y * scale;
-          row[5] = -ns.z * scale;
-          row[6] = e;
-          st = MB_VALID;
-        }
-      }
-      fv.status[i] = st;
-    }
-    // [J e]^T [J e] over the warp's 32 points: lane a sums its entry over the rows in point order.
-    const unsigned any_valid = __ballot_sync(kFull, act && st == MB_VALID);
-    if (any_valid) {
-#pragma unroll
-      for (int a = 0; a < 7; ++a) s_row[lane][a] = row[a];
-      __syncwarp();
-#pragma unroll 8
-      for (int p = 0; p < 32; ++p) acc += s_row[p][pr] * s_row[p][pc];
-    }
-#pragma unroll
-    for (int s = 0; s < 9; ++s) {
-      const int c = __popc(__ballot_sync(kFull, act && st == s));
-      if (lane == s) cnt += c;
-    }
-    if (lane == 9) cnt += __popc(mask);
-    __syncthreads();  // s_row (= s_pk), s_queue, s_status ... are rewritten by the next tile
-    MB_LIN_T(4);
-#if defined(MB_LIN_TIMING)
-    if (blockIdx.x == MB_LIN_TIMING && tid == 0 && tile == blockIdx.x)
-      printf("lin timing: A %lld  knn %lld  resolve+fit(+wait other warps) %lld  C %lld  (cycles), n_need %d\n", lt_[1] - lt_[0],
-             lt_[2] - lt_[1], lt_[3] - lt_[2], lt_[4] - lt_[3], n_need);
-#endif
-  }
-
-  // ---- block partial -> group partial -> packet (two ticketed levels, fixed order) ------------------------
-  if (lane < 28) s_red[warp][lane] = acc;
-  if (lane >= 30) s_red[warp][lane + 8] = s_red[warp][lane + 16] = 0.0;  // pad entries 38, 39, 46, 47
-  if (lane < 10) s_red[warp][kPackCnt + lane] = (double)cnt;
-  if (lane < 6) s_red[warp][kPackLoc + lane] = lacc;
-  __syncthreads();
-  if (tid < kPack) {
-    double v = 0.0;
-#pragma unroll
-    for (int w = 0; w < kLinWarps; ++w) v += s_red[w][tid];
-    fv.partials[(size_t)blockIdx.x * kPack + tid] = v;
-  }
-  const int g = blockIdx.x / kGroup;
-  const int n_groups = (gridDim.x + kGroup - 1) / kGroup;
-  const int g_size = min(kGroup, (int)gridDim.x - g * kGroup);
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = atomicAdd(fv.gtickets + g, 1u) == (unsigned)g_size - 1;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  block_sum_rows(fv.partials + (size_t)g * kGroup * kPack, g_size, kPack, s_tmp, fv.gpartials + (size_t)g * kPack,
-                 kLinThreads);
-  if (tid == 0) fv.gtickets[g] = 0u;
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = atomicAdd(fv.ticket, 1u) == (unsigned)n_groups - 1;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  block_sum_rows(fv.gpartials, n_groups, kPack, s_tmp, fv.packed, kLinThreads);
-  if (tid == 0) *fv.ticket = 0u;
-  if (peer) {
-    // Several ranks: this rank's packet goes straight into every rank's mailbox (peer stores over NVLink),
-    // then the flags are raised — k_finalize on each rank sums the mailbox in rank order (mb_internal.cuh).
-    __syncthreads();  // the packet written by this block's first kPack threads is visible to all of them
-    const int world = peer->world, rank = peer->rank;
-    const unsigned long long seq = *peer->xseq + 1ull;
-    const size_t slot = (size_t)((seq & 1ull) * kMaxRanks + (unsigned)rank);
-    for (int x = tid; x < world * kPack; x += kLinThreads) {
-      const int dst = x / kPack, e = x - dst * kPack;
-      peer->mbox[dst][slot * kXchgDoubles + e] = fv.packed[e];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < world) st_release_sys(peer->flag[tid] + slot, seq);
-  }
-}
-
-// computeLocalizability (mimosa/include/mimosa/utils.hpp:308-313).  The closed-form solver (checked a posteriori,
-// iterative fallback) replaces the reference's iterative one here: its input, the reduced 6x6, already differs
-// from the CPU's in the last bits, so bit parity is not at stake, and it is 5x shorter as a single-thread chain.
-__device__ __forceinline__ void localizability(const m33& JtJ, double loc[3], m33& V) {
-  double lam[3];
-  eigh33_direct(JtJ, lam, V);
-#pragma unroll
-  for (int a = 0; a < 3; ++a) loc[a] = sqrt(lam[a]);
-}
-
-// Everything after the per-point loop of ICPFactor::linearize, plus the harness GN step.  Lane 0 of warp w
-// plays role w: 0/1 localizability of the rotational / translational block, 2/3 Schur-complement degeneracy
-// info, 4 projection + packing + solve + retract.
-__global__ void __launch_bounds__(160) k_finalize(const double* packed_in, DevState* ds, int reg_4_dof,
-                                                  int linearize_count, int do_step, int iter, mb_icp_trace* trace,
-                                                  unsigned role_mask, const PeerTable* __restrict__ peer,
-                                                  double* packed_out) {
-  __shared__ double s_packed[kXchgDoubles];
-  pdl_launch_dependents();
-  const double* packed = packed_in;
-  if (peer) {
-    // wait for every rank's packet of this exchange, add them in rank order (identical on every rank)
-    pdl_wait();
-    const int world = peer->world, rank = peer->rank;
-    const unsigned long long seq = *peer->xseq + 1ull;
-    const size_t base = (size_t)((seq & 1ull) * kMaxRanks);
-    if ((int)threadIdx.x < world) {
-      const unsigned long long* fl = peer->flag[rank] + base + threadIdx.x;
-      while (ld_acquire_sys(fl) != seq) {
-      }
-      __threadfence_system();
-    }
-    __syncthreads();
-    if (threadIdx.x < kPack) {
-      const double* mb = peer->mbox[rank] + base * kXchgDoubles + threadIdx.x;
-      double v = 0.0;
-      for (int r = 0; r < world; ++r) v += __ldcg(mb + (size_t)r * kXchgDoubles);
-      s_packed[threadIdx.x] = v;
-      packed_out[threadIdx.x] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) *peer->xseq = seq;
-    packed = s_packed;
-  }
-  if ((threadIdx.x & 31) != 0) return;
-  const int role = threadIdx.x >> 5;
-  if (((role_mask >> role) & 1u) == 0) return;  // role_mask != 31 only in the timing diagnostic
-  if (!peer) pdl_wait();
+// Everything after the per-point loop of ICPFactor::linearize (geometric_factor.hpp:405-428, 464-475, 559-560), plus
+// the harness GN step that ISAM2 performs in the reference (mimosa/src/graph/manager.cpp:585-588).  One THREAD per
+// role: 0/1 localizability of the rotational / translational block, 2/3 Schur-complement degeneracy info,
+// 4 projection + packing + solve + retract.  `packed` = the reduced 48-double packet (all ranks summed).
+__device__ __noinline__ void finalize_role(const double* packed, DevState* ds, const FinArgs& fa, int role) {
   double H[36];
   {
     int u = 0;
@@ -679,7 +272,7 @@ __global__ void __launch_bounds__(160) k_finalize(const double* packed_in, DevSt
 #pragma unroll
     for (int a = 0; a < 9; ++a) R.m[a] = ds->pose[a];
     d3 T = mk3(ds->pose[9], ds->pose[10], ds->pose[11]);
-    if (reg_4_dof) {
+    if (fa.reg_4_dof) {
       const d3 gz = mk3(-ds->gravity[0], -ds->gravity[1], -ds->gravity[2]);
       const d3 lz = mul33Tv(R, gz);
       const double l[3] = {lz.x, lz.y, lz.z};
@@ -709,9 +302,9 @@ __global__ void __launch_bounds__(160) k_finalize(const double* packed_in, DevSt
     for (int a = 0; a < 6; ++a) L.g[a] = g[a];
     L.f = f;
     for (int a = 0; a < 9; ++a) L.counts[a] = (int64_t)packed[kPackCnt + a];
-    L.linearize_count = linearize_count;
+    L.linearize_count = fa.linearize_count;
     L.n_searched = (int32_t)packed[kPackSearched];
-    if (do_step) {
+    if (fa.do_step) {
       double delta[6] = {0, 0, 0, 0, 0, 0};
       const bool ok = solve6_ldlt(H, ds->lambda, g, delta);
       if (ok) {
@@ -722,8 +315,8 @@ __global__ void __launch_bounds__(160) k_finalize(const double* packed_in, DevSt
         ds->pose[10] = T.y;
         ds->pose[11] = T.z;
       }
-      if (trace) {
-        mb_icp_trace& tr = trace[iter];
+      if (fa.trace) {
+        mb_icp_trace& tr = fa.trace[fa.iter];
 #pragma unroll
         for (int a = 0; a < 36; ++a) tr.H[a] = H[a];
         for (int a = 0; a < 6; ++a) {
@@ -741,15 +334,375 @@ __global__ void __launch_bounds__(160) k_finalize(const double* packed_in, DevSt
         tr.n_searched = (int32_t)packed[kPackSearched];
         tr.solve_ok = ok ? 1 : 0;
         // the packet also carries the component localizabilities of the PREVIOUS linearisation (folded pass)
-        if (iter > 0) {
+        if (fa.iter > 0) {
           for (int a = 0; a < 3; ++a) {
-            trace[iter - 1].loc_trans_comp[a] = packed[kPackLoc + a];
-            trace[iter - 1].loc_rot_comp[a] = packed[kPackLoc + 3 + a];
+            fa.trace[fa.iter - 1].loc_trans_comp[a] = packed[kPackLoc + a];
+            fa.trace[fa.iter - 1].loc_rot_comp[a] = packed[kPackLoc + 3 + a];
           }
         }
       }
     }
   }
+}
+
+// Several ranks: wait for every rank's packet of this exchange in this rank's mailbox and add them in rank order
+// (identical on every rank).  Called by all threads of a block with >= kPack threads; s_packed receives the sum.
+__device__ __forceinline__ void peer_gather(const PeerTable* __restrict__ peer, double* s_packed, double* packed_out) {
+  const int world = peer->world, rank = peer->rank;
+  const unsigned long long seq = *peer->xseq + 1ull;
+  const size_t base = (size_t)((seq & 1ull) * kMaxRanks);
+  if ((int)threadIdx.x < world) {
+    const unsigned long long* fl = peer->flag[rank] + base + threadIdx.x;
+    while (ld_acquire_sys(fl) != seq) {
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x < kPack) {
+    const double* mb = peer->mbox[rank] + base * kXchgDoubles + threadIdx.x;
+    double v = 0.0;
+    for (int r = 0; r < world; ++r) v += __ldcg(mb + (size_t)r * kXchgDoubles);
+    s_packed[threadIdx.x] = v;
+    packed_out[threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *peer->xseq = seq;
+}
+
+// Stand-alone finalize: only when an NCCL all-reduce sits between the reduction and the roles (fallback exchange)
+// and for the timing diagnostic; otherwise the last block of k_linearize runs the roles itself.
+__global__ void __launch_bounds__(160) k_finalize(const double* packed_in, DevState* ds, FinArgs fa, unsigned role_mask,
+                                                  const PeerTable* __restrict__ peer, double* packed_out) {
+  __shared__ double s_packed[kXchgDoubles];
+  pdl_launch_dependents();
+  pdl_wait();
+  const double* packed = packed_in;
+  if (peer) {
+    peer_gather(peer, s_packed, packed_out);
+    packed = s_packed;
+  }
+  if ((threadIdx.x & 31) != 0) return;
+  const int role = threadIdx.x >> 5;
+  if (((role_mask >> role) & 1u) == 0) return;  // role_mask != 31 only in the timing diagnostic
+  finalize_role(packed, ds, fa, role);
+}
+
+#ifndef MB_LIN_BLOCKS
+#define MB_LIN_BLOCKS 4
+#endif
+#if defined(MB_LIN_TIMING)  // development build: %globaltimer stamps of one k_linearize launch (mb_debug_lin_timeline)
+__device__ unsigned long long g_lin_t[64][8];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define MB_LT_SET(slot) do { if (threadIdx.x == 0) g_lin_t[fa.linearize_count & 63][slot] = gtime(); } while (0)
+#define MB_LT_MAX(slot) do { if (threadIdx.x == 0) atomicMax(&g_lin_t[fa.linearize_count & 63][slot], gtime()); } while (0)
+#else
+#define MB_LT_SET(slot) do { } while (0)
+#define MB_LT_MAX(slot) do { } while (0)
+#endif
+// Shared memory of one warp of k_linearize: the group-search scratch, then its staging pool.
+template <int ROWS>
+__host__ __device__ constexpr size_t lin_warp_bytes(int pool_buckets, int cap) {
+  return ((sizeof(GroupScratch<ROWS>) + 15) / 16) * 16 + (size_t)pool_buckets * cap * sizeof(float4);
+}
+
+// One linearisation.  Every WARP owns tiles of 32 consecutive points of the voxel-sorted scan and does everything
+// for them — A transform + data-association gate (:276-287), B the voxel-grouped restricted k-NN (mb_search_group.cuh),
+// the two distance gates (:296-302) and the plane fit (:176-229) for the points that must re-associate, C residual,
+// s-check, Huber, Jacobian, localizability vectors (:319-355) and its share of [J e]^T [J e] (:364-366) — without
+// ever waiting for another warp; a point's data stay in its lane's registers from A to C.  Then block partial ->
+// group partial -> packet (two ticketed levels, fixed order: bitwise repeatable), and the LAST block exchanges the
+// packet with the other ranks (peer mailboxes) and runs the finalize roles (fa.fuse).
+template <int K, typename PoseT, int ROWS>
+__global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
+    k_linearize(MapView mv, FactorView fv, DevState* ds, PoseT pa, const PeerTable* __restrict__ peer, FinArgs fa,
+                int pool_buckets) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  __shared__ uint16_t s_rank[32];
+  __shared__ double s_red[kLinWarps][kPack];
+  __shared__ double s_tmp[(kLinThreads / kPack) * kPack];
+  __shared__ double s_V[18];
+  __shared__ double s_packed[kXchgDoubles];
+  __shared__ bool s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* pose_dev = ds->pose;
+  pdl_launch_dependents();
+#if defined(MB_LIN_TIMING)
+  if (blockIdx.x == 0 && tid == 0) {
+    g_lin_t[fa.linearize_count & 63][0] = gtime();
+    g_lin_t[fa.linearize_count & 63][2] = 0ull;
+    g_lin_t[fa.linearize_count & 63][3] = 0ull;
+    g_lin_t[fa.linearize_count & 63][6] = 0ull;
+    g_lin_t[fa.linearize_count & 63][7] = 0ull;
+  }
+#endif
+  GroupScratch<ROWS>& S = *reinterpret_cast<GroupScratch<ROWS>*>(s_dyn + (size_t)warp * lin_warp_bytes<ROWS>(pool_buckets, mv.cap));
+  float4* const pool = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(&S) + ((sizeof(GroupScratch<ROWS>) + 15) / 16) * 16);
+  // the whitened [J (6), e] rows of the warp's 32 points (phase C) share the candidate stacks' memory (phase B)
+  double(*s_row)[7] = reinterpret_cast<double(*)[7]>(S.stack);
+  static_assert(sizeof(S.stack) >= sizeof(double) * 7 * 32, "s_row fits");
+  if (tid < 32) s_rank[tid] = 0xffffu;
+  __syncthreads();
+  if (tid < kCube && mv.rank[tid] != 0xffu) s_rank[mv.rank[tid]] = rank_entry(tid);
+  if (lane == 0) mbar_init(&S.mbar, 1);
+  uint32_t mbar_parity = 0u;
+  // Lane a < 28 owns entry a of the packed upper triangle of [J e]^T [J e] (7x7): the 21 entries of
+  // J^T J first (row-major, c >= r), then J^T e (6), then e^2.
+  int pr = 0, pc = 0;
+  {
+    int u = 0;
+    for (int r = 0; r < 6; ++r)
+      for (int c = r; c < 6; ++c) {
+        if (u == lane) {
+          pr = r;
+          pc = c;
+        }
+        ++u;
+      }
+    if (lane >= 21 && lane < 27) {
+      pr = lane - 21;
+      pc = 6;
+    }
+    if (lane == 27) pr = pc = 6;
+  }
+
+  // everything above is independent of earlier kernels; from here on we read the pose the previous linearisation
+  // left and overwrite per-point state the previous k_loc_comp may still be reading
+  pdl_wait();
+  if (blockIdx.x == 0) MB_LT_SET(1);
+  m33 R;
+  d3 T;
+  if constexpr (std::is_same<PoseT, PoseArg>::value) {
+    if (blockIdx.x == 0 && tid < 16) pose_dev[tid] = pa.v[tid];  // the finalize roles read pose / gravity / lambda there
+#pragma unroll
+    for (int a = 0; a < 9; ++a) R.m[a] = pa.v[a];
+    T = mk3(pa.v[9], pa.v[10], pa.v[11]);
+  } else {
+#pragma unroll
+    for (int a = 0; a < 9; ++a) R.m[a] = pose_dev[a];
+    T = mk3(pose_dev[9], pose_dev[10], pose_dev[11]);
+  }
+  const int k = fv.k;
+  const bool forced = (fv.flags & 1u) != 0;
+
+  double acc = 0.0, lacc = 0.0;  // lacc: lane a < 6 sums component a of the previous linearisation's localizability pass
+  int cnt = 0;  // lane s < 9: points with status s; lane 9: points searched
+  // Folded localizability pass (device-resident loop): before a point's status and localizability vectors are
+  // overwritten, its contribution |loc^T V| (entries below 0.5 dropped, geometric_factor.hpp:434-457) to the
+  // component localizabilities of the PREVIOUS linearisation is taken with that linearisation's eigenvectors, which
+  // the previous finalize left in ds->lin.  It saves a pass over the points and a kernel launch per iteration.
+  if (fv.fold_loc && tid < 18) s_V[tid] = tid < 9 ? ds->lin.eigvec_trans[tid] : ds->lin.eigvec_rot[tid - 9];
+  __syncthreads();
+
+  const size_t n_tiles = (fv.n + 31) / 32;
+  const size_t n_warps = (size_t)gridDim.x * kLinWarps;
+  for (size_t tile = (size_t)blockIdx.x * kLinWarps + warp; tile < n_tiles; tile += n_warps) {
+    const size_t i = tile * 32 + lane;
+    const bool act = i < fv.n;
+    // ---- A: transform, gate ---------------------------------------------------------------------------------
+    d3 ps = mk3(0, 0, 0), pt = mk3(0, 0, 0);
+    uint8_t st = MB_UNPROCESSED;
+    bool need = false;
+    if (act) {
+      const float4 s = __ldg(fv.src + i);
+      ps = mk3((double)s.x, (double)s.y, (double)s.z);
+      pt = add3(mul33v(R, ps), T);
+      st = fv.status[i];
+      const d3 da = ld3(fv.p_da, fv.ld, i);
+      need = forced || sqrt(sqnorm3(sub3(pt, da))) > fv.da_gate;
+    }
+    const uint8_t st_prev = st;  // the status the previous linearisation left (folded localizability pass)
+    const unsigned need_mask = __ballot_sync(kFull, need);
+    // ---- B: search + plane fit for the points that re-associate ------------------------------------------------
+    bool proceed = false;
+    d3 mean = mk3(0, 0, 0), normal = mk3(0, 0, 0);
+    if (need_mask) {
+      double bd[K];
+      uint32_t bs[K];
+      const GroupLane gl = knn_warp_groups<K, ROWS>(mv, s_rank, S, pool, pool_buckets, mbar_parity, pt.x, pt.y, pt.z, k, need, bd, bs);
+      if (need) {
+        float4 nb[K];
+        uint64_t g[K];
+        const int found = group_resolve_all<K, ROWS>(mv, S, pool, gl, bs, k, g, nb);
+        double dk = 0.0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          if (j < k) {
+            if (j == k - 1) dk = bd[j];
+            // indices are only meaningful when all k exist (the reference discards partial results)
+            if (fv.knn_idx) fv.knn_idx[i * k + j] = found == k ? g[j] : ~0ull;
+          }
+        }
+        st3(fv.p_da, fv.ld, i, pt);
+        st = MB_UNPROCESSED;
+        if (found != k) {
+          st = MB_INSUFFICIENT_CORRES_POINTS;
+        } else if (dk > fv.max_corr_sq) {
+          st = MB_CORRES_MAX_DIST;
+        } else {
+          bool normal_set;
+          st = fit_plane<K>(nb, k, T, fv.pvd, mean, normal, normal_set);
+          st3(fv.mean, fv.ld, i, mean);
+          if (normal_set) st3(fv.normal, fv.ld, i, normal);
+          proceed = st == MB_UNPROCESSED;
+        }
+      }
+      __syncwarp();  // the stacks become s_row below; the pool may be refilled by the next tile
+    }
+    if (act && !need && st > MB_CORRES_PLANE_INVALID) {
+      mean = ld3(fv.mean, fv.ld, i);
+      normal = ld3(fv.normal, fv.ld, i);
+      proceed = true;
+    }
+
+    // ---- C: residual, Jacobian, accumulation -------------------------------------------------------------------
+    double row[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (fv.fold_loc) {
+      double v[6] = {0, 0, 0, 0, 0, 0};
+      if (act && st_prev == MB_VALID) {
+        const d3 lt = ld3(fv.loc_trans, fv.ld, i), lr = ld3(fv.loc_rot, fv.ld, i);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {  // column a of V: (V^T loc)_a, in mul33Tv's order of operations
+          const double tc = fabs(s_V[a] * lt.x + (s_V[3 + a] * lt.y + s_V[6 + a] * lt.z));
+          const double rc = fabs(s_V[9 + a] * lr.x + (s_V[12 + a] * lr.y + s_V[15 + a] * lr.z));
+          v[a] = tc >= 0.5 ? tc : 0.0;
+          v[3 + a] = rc >= 0.5 ? rc : 0.0;
+        }
+      }
+      if (__ballot_sync(kFull, act && st_prev == MB_VALID)) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) s_row[lane][a] = v[a];
+        __syncwarp();
+        if (lane < 6) {
+#pragma unroll 8
+          for (int p = 0; p < 32; ++p) lacc += s_row[p][lane];
+        }
+        __syncwarp();
+      }
+    }
+    if (act) {
+      if (proceed) {
+        double e = dot3(normal, sub3(mean, pt));
+        const double s_chk = 1 - 0.9 * fabs(e) / sqrt(sqrt(sqnorm3(ps)));
+        if (s_chk < 0.9) {
+          st = MB_MAX_ERROR;
+        } else {
+          double sqrt_w = 1.0;
+          if (fv.use_huber) {
+            const double we = e / fv.sigma;
+            if (fabs(we) > fv.kh) sqrt_w = sqrt(fv.kh / fabs(we));
+          }
+          const double scale = sqrt_w / fv.sigma;
+          e *= scale;
+          const d3 ns = mul33Tv(R, normal);
+          const d3 jr = cross3(ns, ps);
+          const double z = sqnorm3(jr);
+          st3(fv.loc_rot, fv.ld, i, z > 0 ? div3(jr, sqrt(z)) : jr);
+          st3(fv.loc_trans, fv.ld, i, mk3(-ns.x, -ns.y, -ns.z));
+          row[0] = jr.x * scale;
+          row[1] = jr.y * scale;
+          row[2] = jr.z * scale;
+          row[3] = -ns.x * scale;
+          row[4] = -ns.y * scale;
+          row[5] = -ns.z * scale;
+          row[6] = e;
+          st = MB_VALID;
+        }
+      }
+      if (st != st_prev) fv.status[i] = st;
+    }
+    // [J e]^T [J e] over the warp's 32 points: lane a sums its entry over the rows in point order.
+    const unsigned any_valid = __ballot_sync(kFull, act && st == MB_VALID);
+    if (any_valid) {
+#pragma unroll
+      for (int a = 0; a < 7; ++a) s_row[lane][a] = row[a];
+      __syncwarp();
+#pragma unroll 8
+      for (int p = 0; p < 32; ++p) acc += s_row[p][pr] * s_row[p][pc];
+      __syncwarp();
+    }
+#pragma unroll
+    for (int s = 0; s < 9; ++s) {
+      const int c = __popc(__ballot_sync(kFull, act && st == s));
+      if (lane == s) cnt += c;
+    }
+    if (lane == 9) cnt += __popc(need_mask);
+  }
+
+  // ---- block partial -> group partial -> packet (two ticketed levels, fixed order) ------------------------
+  MB_LT_MAX(2);
+  if (lane < 28) s_red[warp][lane] = acc;
+  if (lane >= 30) s_red[warp][lane + 8] = s_red[warp][lane + 16] = 0.0;  // pad entries 38, 39, 46, 47
+  if (lane < 10) s_red[warp][kPackCnt + lane] = (double)cnt;
+  if (lane < 6) s_red[warp][kPackLoc + lane] = lacc;
+  __syncthreads();
+  if (tid < kPack) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kLinWarps; ++w) v += s_red[w][tid];
+    fv.partials[(size_t)blockIdx.x * kPack + tid] = v;
+  }
+  const int g = blockIdx.x / kGroup;
+  const int n_groups = (gridDim.x + kGroup - 1) / kGroup;
+  const int g_size = min(kGroup, (int)gridDim.x - g * kGroup);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(fv.gtickets + g, 1u) == (unsigned)g_size - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  block_sum_rows(fv.partials + (size_t)g * kGroup * kPack, g_size, kPack, s_tmp, fv.gpartials + (size_t)g * kPack,
+                 kLinThreads);
+  if (tid == 0) fv.gtickets[g] = 0u;
+  MB_LT_MAX(3);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(fv.ticket, 1u) == (unsigned)n_groups - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  MB_LT_SET(4);
+  block_sum_rows(fv.gpartials, n_groups, kPack, s_tmp, fv.packed, kLinThreads);
+  if (tid == 0) *fv.ticket = 0u;
+  __syncthreads();  // the packet written by this block's first kPack threads is visible to all of them
+  MB_LT_SET(5);
+  const double* packed = fv.packed;
+  if (peer) {
+    // Several ranks: this rank's packet goes straight into every rank's mailbox (peer stores over NVLink),
+    // then the flags are raised — the finalize roles on each rank sum their mailbox in rank order (mb_internal.cuh).
+    const int world = peer->world, rank = peer->rank;
+    const unsigned long long seq = *peer->xseq + 1ull;
+    const size_t slot = (size_t)((seq & 1ull) * kMaxRanks + (unsigned)rank);
+    for (int x = tid; x < world * kPack; x += kLinThreads) {
+      const int dst = x / kPack, e = x - dst * kPack;
+      peer->mbox[dst][slot * kXchgDoubles + e] = fv.packed[e];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < world) st_release_sys(peer->flag[tid] + slot, seq);
+    if (!fa.fuse) return;
+    peer_gather(peer, s_packed, fv.packed);
+    __syncthreads();
+    packed = s_packed;
+  }
+  if (!fa.fuse) return;
+  // the finalize roles: the solve / retract chain alone on warp 0, the four eigen-decompositions on the other warps
+  if (lane == 0) {
+    if (warp == 0) {
+      finalize_role(packed, ds, fa, 4);
+    } else if (warp == 1) {
+      finalize_role(packed, ds, fa, 0);
+      finalize_role(packed, ds, fa, 1);
+    } else {
+      finalize_role(packed, ds, fa, warp);
+    }
+  }
+#if defined(MB_LIN_TIMING)
+  if (lane == 0) atomicMax(&g_lin_t[fa.linearize_count & 63][6 + (warp == 0 ? 0 : 1)], gtime());
+#endif
 }
 
 // Component localizabilities (geometric_factor.hpp:434-457): sum over Valid points of |loc_i^T V| with
@@ -853,6 +806,53 @@ __global__ void k_pack_src(const unsigned char* __restrict__ data, size_t stride
   src[i] = v;
 }
 
+// ---- voxel order of the scan --------------------------------------------------------------------------------
+// k_linearize wants the 32 points of a warp in as few map voxels as possible (mb_search_group.cuh).  Before a
+// factor's FIRST linearisation its points are sorted by the Morton code of the map voxel they fall into under that
+// call's pose (10 bits per axis around the sensor's voxel; farther points clamp, which only costs grouping); later
+// poses differ by centimetres, so the order stays good.  All per-point state lives in sorted order; `perm` (sorted
+// position -> index in the caller's scan) brings it back to reference order in mb_factor_download_state
+// (geometric_factor.hpp:79-84: the reference's arrays are indexed like the source cloud).
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {  // 10 bits -> every third bit
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+template <typename PoseT>
+__global__ void k_sort_keys(const float4* __restrict__ src_raw, size_t n, const DevState* __restrict__ ds, PoseT pa,
+                            double inv_leaf, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  m33 R;
+  d3 T;
+  if constexpr (std::is_same<PoseT, PoseArg>::value) {
+#pragma unroll
+    for (int a = 0; a < 9; ++a) R.m[a] = pa.v[a];
+    T = mk3(pa.v[9], pa.v[10], pa.v[11]);
+  } else {
+#pragma unroll
+    for (int a = 0; a < 9; ++a) R.m[a] = ds->pose[a];
+    T = mk3(ds->pose[9], ds->pose[10], ds->pose[11]);
+  }
+  const float4 s = src_raw[i];
+  const d3 pt = add3(mul33v(R, mk3((double)s.x, (double)s.y, (double)s.z)), T);
+  const int vx = fast_floor(pt.x * inv_leaf) - fast_floor(T.x * inv_leaf) + 512;
+  const int vy = fast_floor(pt.y * inv_leaf) - fast_floor(T.y * inv_leaf) + 512;
+  const int vz = fast_floor(pt.z * inv_leaf) - fast_floor(T.z * inv_leaf) + 512;
+  const uint32_t cx = (uint32_t)min(max(vx, 0), 1023), cy = (uint32_t)min(max(vy, 0), 1023), cz = (uint32_t)min(max(vz, 0), 1023);
+  keys[i] = spread10(cx) | (spread10(cy) << 1) | (spread10(cz) << 2);
+  vals[i] = (uint32_t)i;
+}
+__global__ void k_apply_perm(const float4* __restrict__ src_raw, const uint32_t* __restrict__ perm, size_t n,
+                             float4* __restrict__ src) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) src[i] = src_raw[perm[i]];
+}
+constexpr int kSortBits = 30;
+
 }  // namespace
 }  // namespace mb
 
@@ -879,7 +879,16 @@ struct mb_factor {
   mb_icp_trace* d_trace = nullptr;
   int trace_cap = 0;
   int grid = 0, grid2 = 0, n_groups = 0;
-  int search_g = 0;  // 0: one query per thread; 1: the same with the warp-wide chunk queue (MB_LIN_SEARCH=queue); 4: four lanes per query (MB_LIN_SEARCH=coop4); both experimental
+  // k_linearize launch shape: kernel variant (k == 5 and <= 19 neighbour voxels, or generic), staging pool per warp
+  bool lin_small = true;
+  int pool_buckets = 0;
+  size_t lin_smem = 0;
+  // voxel order (see k_sort_keys): the caller's points, the sort's buffers, sorted position -> caller's index
+  float4* src_raw = nullptr;
+  uint32_t *sort_keys = nullptr, *sort_keys_out = nullptr, *sort_vals = nullptr, *perm = nullptr;
+  void* sort_temp = nullptr;
+  size_t sort_temp_bytes = 0;
+  bool sorted = false;
   int linearize_count = 0;
   uint32_t flags = 0;
   // cached CUDA graph of an mb_icp_run sequence
@@ -931,6 +940,59 @@ int reset_state(mb_factor* f) {
     MB_CUDA(cudaMemsetAsync(f->knn_idx, 0xff, f->n * f->cfg.num_corres_points * sizeof(uint64_t), st));
   }
   f->linearize_count = 0;
+  f->sorted = false;  // the next first linearisation re-sorts under its own pose (all state is zero again)
+  return MB_OK;
+}
+
+// k_linearize needs more dynamic shared memory than the default limit: opt every instantiation in, once.
+template <typename Kern>
+int lin_opt_in(Kern kern, size_t bytes) {
+  MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return MB_OK;
+}
+int lin_opt_in_all(const mb_factor* f) {
+  if (f->lin_small) {
+    MB_TRY(lin_opt_in(k_linearize<5, PoseArg, 19>, f->lin_smem));
+    MB_TRY(lin_opt_in(k_linearize<5, NoPose, 19>, f->lin_smem));
+  } else {
+    MB_TRY(lin_opt_in(k_linearize<MB_MAX_K, PoseArg, 27>, f->lin_smem));
+    MB_TRY(lin_opt_in(k_linearize<MB_MAX_K, NoPose, 27>, f->lin_smem));
+  }
+  return MB_OK;
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl_smem(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// Before the first linearisation: bring the scan into voxel order under that call's pose (k_sort_keys).
+int enqueue_sort(mb_factor* f, const PoseArg* pose_arg) {
+  if (f->n == 0) return MB_OK;
+  mb_ctx* c = f->ctx;
+  cudaStream_t st = c->stream;
+  const unsigned blocks = (unsigned)((f->n + 255) / 256);
+  if (pose_arg)
+    k_sort_keys<PoseArg><<<blocks, 256, 0, st>>>(f->src_raw, f->n, f->ds, *pose_arg, f->map->inv_leaf, f->sort_keys, f->sort_vals);
+  else
+    k_sort_keys<NoPose><<<blocks, 256, 0, st>>>(f->src_raw, f->n, f->ds, NoPose{}, f->map->inv_leaf, f->sort_keys, f->sort_vals);
+  size_t tb = f->sort_temp_bytes;
+  MB_CUDA(cub::DeviceRadixSort::SortPairs(f->sort_temp, tb, f->sort_keys, f->sort_keys_out, f->sort_vals, f->perm, (int)f->n, 0,
+                                          kSortBits, st));
+  k_apply_perm<<<blocks, 256, 0, st>>>(f->src_raw, f->perm, f->n, f->src);
+  c->launches += 2 + 6;  // keys, gather + the radix sort's kernels (histogram, scan, four onesweep passes)
+  f->sorted = true;
+  MB_CUDA(cudaGetLastError());
   return MB_OK;
 }
 
@@ -939,59 +1001,65 @@ int enqueue_linearize(mb_factor* f, int do_step, int iter, mb_icp_trace* d_trace
                       const PoseArg* pose_arg = nullptr, const HostOut* host_out = nullptr) {
   mb_ctx* c = f->ctx;
   cudaStream_t st = c->stream;
+  if (linearize_count == 1) MB_TRY(enqueue_sort(f, pose_arg));  // first linearisation since construction / reset
   FactorView fv = f->view();
   // Device-resident loop: the localizability pass of this linearisation is folded into the NEXT k_linearize (and
   // mb_icp_run launches k_loc_comp once, after the last iteration); the host-facing single call runs it right away.
   fv.fold_loc = do_step ? 1 : 0;
   const PeerTable* peer = c->world > 1 ? c->d_peer : nullptr;  // nullptr: single rank, or NCCL all-reduce
-  const bool coop4 = f->search_g == 4 && fv.k == 5 && f->map->n_off <= 19;  // MB_LIN_SEARCH=coop4 (experimental)
-  const bool queue = f->search_g == 1 && fv.k == 5 && f->map->n_off <= 19;  // MB_LIN_SEARCH=queue (experimental)
-  if (queue && pose_arg) {
-    MB_CUDA(launch_pdl(k_linearize<5, PoseArg, 19, 1>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, f->ds, *pose_arg, peer));
-  } else if (queue) {
-    MB_CUDA(launch_pdl(k_linearize<5, NoPose, 19, 1>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, f->ds, NoPose{}, peer));
-  } else if (coop4 && pose_arg) {
-    MB_CUDA(launch_pdl(k_linearize<5, PoseArg, 19, 4>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, f->ds, *pose_arg, peer));
-  } else if (coop4) {
-    MB_CUDA(launch_pdl(k_linearize<5, NoPose, 19, 4>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, f->ds, NoPose{}, peer));
-  } else if (pose_arg) {
-    if (fv.k == 5 && f->map->n_off <= 19)  // the specialised kernel: k = 5 and at most 19 neighbour voxels
-      MB_CUDA(launch_pdl(k_linearize<5, PoseArg, 19>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, f->ds, *pose_arg, peer));
+  const bool nccl = c->world > 1 && !peer;
+  FinArgs fa;
+  fa.reg_4_dof = (int)f->cfg.reg_4_dof;
+  fa.linearize_count = linearize_count;
+  fa.do_step = do_step;
+  fa.iter = iter;
+  fa.trace = d_trace;
+  fa.fuse = nccl ? 0 : 1;  // the last block of k_linearize runs the finalize roles unless NCCL sits in between
+  const dim3 grid(f->grid), block(kLinThreads);
+  if (pose_arg) {
+    if (f->lin_small)  // the specialised kernel: k = 5 and at most 19 neighbour voxels
+      MB_CUDA(launch_pdl_smem(k_linearize<5, PoseArg, 19>, grid, block, f->lin_smem, st, f->map->view(), fv, f->ds, *pose_arg, peer, fa, f->pool_buckets));
     else
-      MB_CUDA(launch_pdl(k_linearize<MB_MAX_K, PoseArg, 27>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, f->ds, *pose_arg, peer));
+      MB_CUDA(launch_pdl_smem(k_linearize<MB_MAX_K, PoseArg, 27>, grid, block, f->lin_smem, st, f->map->view(), fv, f->ds, *pose_arg, peer, fa, f->pool_buckets));
   } else {
-    if (fv.k == 5 && f->map->n_off <= 19)
-      MB_CUDA(launch_pdl(k_linearize<5, NoPose, 19>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, f->ds, NoPose{}, peer));
+    if (f->lin_small)
+      MB_CUDA(launch_pdl_smem(k_linearize<5, NoPose, 19>, grid, block, f->lin_smem, st, f->map->view(), fv, f->ds, NoPose{}, peer, fa, f->pool_buckets));
     else
-      MB_CUDA(launch_pdl(k_linearize<MB_MAX_K, NoPose, 27>, dim3(f->grid), dim3(kLinThreads), st, f->map->view(), fv, f->ds, NoPose{}, peer));
+      MB_CUDA(launch_pdl_smem(k_linearize<MB_MAX_K, NoPose, 27>, grid, block, f->lin_smem, st, f->map->view(), fv, f->ds, NoPose{}, peer, fa, f->pool_buckets));
   }
-  if (c->world > 1 && !peer) MB_NCCL(ncclAllReduce(f->packed, f->packed, kPack, ncclDouble, ncclSum, c->comm, st));
-  MB_CUDA(launch_pdl(k_finalize, dim3(1), dim3(160), st, (const double*)f->packed, f->ds, (int)f->cfg.reg_4_dof,
-                     linearize_count, do_step, iter, d_trace, 31u, peer, f->packed));
+  ++c->launches;
+  if (nccl) {
+    MB_NCCL(ncclAllReduce(f->packed, f->packed, kPack, ncclDouble, ncclSum, c->comm, st));
+    MB_CUDA(launch_pdl(k_finalize, dim3(1), dim3(160), st, (const double*)f->packed, f->ds, fa, 31u, (const PeerTable*)nullptr, f->packed));
+    ++c->launches;
+  }
   if (host_out) {
     MB_CUDA(launch_pdl(k_loc_comp<true>, dim3(f->grid2), dim3(kLocThreads), st, fv, (const DevState*)f->ds, *host_out, peer));
+    ++c->launches;
   } else if (!do_step) {
     HostOut none;
     none.out = nullptr, none.flag = nullptr, none.seq = 0;
     MB_CUDA(launch_pdl(k_loc_comp<false>, dim3(f->grid2), dim3(kLocThreads), st, fv, (const DevState*)f->ds, none, peer));
+    ++c->launches;
   }
   // The cross-rank sum of the six component localizabilities is only needed when they are handed out
   // (mb_factor_linearize): through the peer mailboxes inside k_loc_comp, or with NCCL as the fallback.
-  if (c->world > 1 && !do_step && !peer)
-    MB_NCCL(ncclAllReduce(f->packed + kPack, f->packed + kPack, 6, ncclDouble, ncclSum, c->comm, st));
-  if (do_step) --c->launches;  // no k_loc_comp in this sequence
-  c->launches += 3;
+  if (nccl && !do_step) MB_NCCL(ncclAllReduce(f->packed + kPack, f->packed + kPack, 6, ncclDouble, ncclSum, c->comm, st));
   MB_CUDA(cudaGetLastError());
   return MB_OK;
 }
 
 // The localizability pass of the loop's LAST linearisation (the earlier ones were folded into their successors).
 int enqueue_last_loc_comp(mb_factor* f) {
+  mb_ctx* c = f->ctx;
   HostOut none;
   none.out = nullptr, none.flag = nullptr, none.seq = 0;
-  MB_CUDA(launch_pdl(k_loc_comp<false>, dim3(f->grid2), dim3(kLocThreads), f->ctx->stream, f->view(), (const DevState*)f->ds,
-                     none, (const PeerTable*)nullptr));
-  ++f->ctx->launches;
+  // several ranks: the six sums cover every rank's shard, like the folded sums of the earlier iterations
+  const PeerTable* peer = c->world > 1 ? c->d_peer : nullptr;
+  MB_CUDA(launch_pdl(k_loc_comp<false>, dim3(f->grid2), dim3(kLocThreads), c->stream, f->view(), (const DevState*)f->ds, none, peer));
+  if (c->world > 1 && !peer)
+    MB_NCCL(ncclAllReduce(f->packed + kPack, f->packed + kPack, 6, ncclDouble, ncclSum, c->comm, c->stream));
+  ++c->launches;
   return MB_OK;
 }
 
@@ -1044,38 +1112,41 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
   f->ld = std::max<size_t>(align_up(f->n, 32), 32);
   const size_t k = cfg->num_corres_points;
   const size_t n_tiles = (f->n + kLinThreads - 1) / kLinThreads;
-  int per_sm = 4;
-  if (const char* e = getenv("MB_LIN_SEARCH")) {  // development switch, read when the factor is created
-    if (!strcmp(e, "coop4")) {
-      f->search_g = 4;
-    } else if (!strcmp(e, "queue")) {
-      f->search_g = 1;
-    } else if (!strcmp(e, "auto")) {
-      // by point count: the cooperative search wins below ~100 k queries per launch in the stand-alone kernel
-      // (profiles/r1_experiments.md, session 4) — a rank's shard at N >= 2, downsampled streaming scans
-      f->search_g = f->n <= 98304 ? 4 : 0;
-    } else if (e[0] && strcmp(e, "thread")) {
-      set_error("MB_LIN_SEARCH=%s: expected thread, queue, coop4 or auto", e);
-      map->refs.fetch_sub(1);
-      delete f;
-      return MB_ERR_INVALID_ARG;
+  // k_linearize: one warp per 32-point tile; per warp the group-search scratch plus a staging pool sized so that
+  // MB_LIN_BLOCKS blocks share an SM's shared memory
+  f->lin_small = k == 5 && map->n_off <= 19;
+  {
+    int smem_sm = 0, smem_blk = 0;
+    MB_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device));
+    MB_CUDA(cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    const size_t fixed = f->lin_small ? lin_warp_bytes<19>(0, map->cap) : lin_warp_bytes<27>(0, map->cap);
+    const size_t per_block = std::min<size_t>((size_t)smem_blk, (size_t)smem_sm / MB_LIN_BLOCKS) - 1024 /* reserved */ - 4096 /* static */;
+    const size_t per_warp = per_block / kLinWarps;
+    const size_t bucket = (size_t)map->cap * sizeof(float4);
+    f->pool_buckets = per_warp > fixed ? (int)((per_warp - fixed) / bucket) : 0;
+    if (const char* e = getenv("MB_LIN_POOL")) f->pool_buckets = std::min(f->pool_buckets, atoi(e));  // development: 0 = never stage
+    f->lin_smem = kLinWarps * (f->lin_small ? lin_warp_bytes<19>(f->pool_buckets, map->cap) : lin_warp_bytes<27>(f->pool_buckets, map->cap));
+    const int orc = lin_opt_in_all(f);
+    if (orc != MB_OK) {
+      mb_factor_release(f);
+      return orc;
     }
   }
-  if (f->search_g == 4 && k == 5 && map->n_off <= 19)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<5, NoPose, 19, 4>, kLinThreads, 0);
-  else if (f->search_g == 1 && k == 5 && map->n_off <= 19)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<5, NoPose, 19, 1>, kLinThreads, 0);
-  else if (k == 5 && map->n_off <= 19)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<5, NoPose, 19>, kLinThreads, 0);
+  int per_sm = MB_LIN_BLOCKS;
+  if (f->lin_small)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<5, NoPose, 19>, kLinThreads, f->lin_smem);
   else
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<MB_MAX_K, NoPose, 27>, kLinThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<MB_MAX_K, NoPose, 27>, kLinThreads, f->lin_smem);
   per_sm = std::max(per_sm, 1);
-  f->grid = (int)std::max<size_t>(1, std::min<size_t>(n_tiles, (size_t)ctx->sm_count * per_sm));
+  const size_t n_wtiles = (f->n + 31) / 32;
+  f->grid = (int)std::max<size_t>(1, std::min<size_t>((n_wtiles + kLinWarps - 1) / kLinWarps, (size_t)ctx->sm_count * per_sm));
   f->n_groups = (f->grid + kGroup - 1) / kGroup;
   f->grid2 = (int)std::max<size_t>(1, std::min<size_t>((f->n + kLocThreads - 1) / kLocThreads, (size_t)ctx->sm_count * 4));
+  if (f->n) cub::DeviceRadixSort::SortPairs(nullptr, f->sort_temp_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                            (uint32_t*)nullptr, (int)f->n, 0, kSortBits, st);
 
-  // carve one block: [src | vecs (15 ld doubles) | status (ld bytes) | knn_idx | partials | gpartials |
-  //                   partials2 | packed | tickets | DevState]
+  // carve one block: [src | src_raw | sort buffers | vecs (15 ld doubles) | status (ld bytes) | knn_idx | partials |
+  //                   gpartials | partials2 | packed | tickets | DevState]
   size_t off = 0;
   auto take = [&](size_t bytes) {
     const size_t o = off;
@@ -1083,6 +1154,10 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
     return o;
   };
   const size_t o_src = take(f->ld * sizeof(float4));
+  const size_t o_raw = take(f->ld * sizeof(float4));
+  const size_t o_sk = take(f->ld * sizeof(uint32_t)), o_sko = take(f->ld * sizeof(uint32_t));
+  const size_t o_sv = take(f->ld * sizeof(uint32_t)), o_perm = take(f->ld * sizeof(uint32_t));
+  const size_t o_stemp = take(f->sort_temp_bytes);
   const size_t o_vecs = take(15 * f->ld * sizeof(double) + f->ld);  // status follows the vectors directly
   const size_t o_idx = take(f->ld * k * sizeof(uint64_t));
   const size_t o_par = take((size_t)f->grid * kPack * sizeof(double));
@@ -1099,6 +1174,12 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
   }
   char* base = (char*)f->block;
   f->src = (float4*)(base + o_src);
+  f->src_raw = (float4*)(base + o_raw);
+  f->sort_keys = (uint32_t*)(base + o_sk);
+  f->sort_keys_out = (uint32_t*)(base + o_sko);
+  f->sort_vals = (uint32_t*)(base + o_sv);
+  f->perm = (uint32_t*)(base + o_perm);
+  f->sort_temp = base + o_stemp;
   f->vecs = (double*)(base + o_vecs);
   f->status = (uint8_t*)(base + o_vecs + 15 * f->ld * sizeof(double));
   f->knn_idx = (uint64_t*)(base + o_idx);
@@ -1114,7 +1195,7 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
   if (dscan) {
     staged = false;
     // device-resident scan: pack xyz straight into the factor's float4 array
-    k_pack_src<<<(unsigned)((f->ld + 255) / 256), 256, 0, st>>>(dscan->data, dscan->stride, shard_begin, f->n, f->ld, f->src);
+    k_pack_src<<<(unsigned)((f->ld + 255) / 256), 256, 0, st>>>(dscan->data, dscan->stride, shard_begin, f->n, f->ld, f->src_raw);
     ++ctx->launches;
   } else if (f->n > 0 && host_is_page_locked(pts)) {
     // The caller's records are page-locked (cudaHostAlloc / mb_host_register): the copy engine takes this
@@ -1129,7 +1210,7 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
     }
     MB_CUDA(cudaMemcpyAsync(raw, (const char*)pts + shard_begin * stride_bytes, raw_bytes, cudaMemcpyHostToDevice, st));
     MB_CUDA(cudaEventRecord(ctx->ev1, st));  // the caller's buffer is free again once this copy has run (below)
-    k_pack_src<<<(unsigned)((f->ld + 255) / 256), 256, 0, st>>>(raw, stride_bytes, 0, f->n, f->ld, f->src);
+    k_pack_src<<<(unsigned)((f->ld + 255) / 256), 256, 0, st>>>(raw, stride_bytes, 0, f->n, f->ld, f->src_raw);
     ++ctx->launches;
     dev_free(ctx, raw, raw_bytes);  // pooled: only ever handed out again to work on this same stream
     staged = false;
@@ -1160,7 +1241,7 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
       h[i] = make_float4(p[0], p[1], p[2], 0.f);
     }
     for (size_t z = f->n; z < f->ld; ++z) h[z] = make_float4(0.f, 0.f, 0.f, 0.f);
-    MB_CUDA(cudaMemcpyAsync(f->src, h, f->ld * sizeof(float4), cudaMemcpyHostToDevice, st));
+    MB_CUDA(cudaMemcpyAsync(f->src_raw, h, f->ld * sizeof(float4), cudaMemcpyHostToDevice, st));
   }
   // everything from `packed` to the end of the block (packet, tickets, DevState) starts at zero
   MB_CUDA(cudaMemsetAsync(base + o_packed, 0, f->block_bytes - o_packed, st));
@@ -1200,20 +1281,22 @@ MB_API int mb_debug_time_finalize(mb_factor* f, unsigned role_mask, int reps, fl
   cudaStream_t st = f->ctx->stream;
   const FactorView fv = f->view();
   // role_mask < 32: k_finalize with those roles; 32: k_linearize at the current pose (fully cached after one
-  // call); 64: k_loc_comp.  Plain launches, back to back.
+  // call), reduction only; 33: the same with the fused finalize roles; 64: k_loc_comp.  Plain launches, back to back.
   const NoPose no_pose{};
   HostOut no_out;
   no_out.out = nullptr, no_out.flag = nullptr, no_out.seq = 0;
+  FinArgs fa;
+  fa.reg_4_dof = (int)f->cfg.reg_4_dof, fa.linearize_count = 0, fa.do_step = 0, fa.iter = 0, fa.trace = nullptr, fa.fuse = role_mask == 33u;
   auto one = [&]() {
-    if (role_mask == 32u) {
-      if (fv.k == 5 && f->map->n_off <= 19)
-        k_linearize<5, NoPose, 19><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds, no_pose, nullptr);
+    if (role_mask == 32u || role_mask == 33u) {
+      if (f->lin_small)
+        k_linearize<5, NoPose, 19><<<f->grid, kLinThreads, f->lin_smem, st>>>(f->map->view(), fv, f->ds, no_pose, nullptr, fa, f->pool_buckets);
       else
-        k_linearize<MB_MAX_K, NoPose, 27><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds, no_pose, nullptr);
+        k_linearize<MB_MAX_K, NoPose, 27><<<f->grid, kLinThreads, f->lin_smem, st>>>(f->map->view(), fv, f->ds, no_pose, nullptr, fa, f->pool_buckets);
     } else if (role_mask == 64u) {
       k_loc_comp<false><<<f->grid2, kLocThreads, 0, st>>>(fv, f->ds, no_out, nullptr);
     } else {
-      k_finalize<<<1, 160, 0, st>>>(f->packed, f->ds, f->cfg.reg_4_dof, 0, 0, 0, nullptr, role_mask, nullptr, f->packed);
+      k_finalize<<<1, 160, 0, st>>>(f->packed, f->ds, fa, role_mask, nullptr, f->packed);
     }
   };
   for (int w = 0; w < 3; ++w) one();
@@ -1225,6 +1308,21 @@ MB_API int mb_debug_time_finalize(mb_factor* f, unsigned role_mask, int reps, fl
   MB_CUDA(cudaEventElapsedTime(&ms, f->ctx->ev0, f->ctx->ev1));
   *us_per_launch = ms * 1e3f / reps;
   return MB_OK;
+}
+
+// Development (built with -DMB_LIN_TIMING only): the %globaltimer stamps of the last 64 k_linearize launches, 8 per
+// launch: entry, after the dependency wait, last tile loop end, last group reduction, final ticket, packet, solve /
+// retract done, eigen roles done.
+MB_API int mb_debug_lin_timeline(unsigned long long* out512) {
+#if defined(MB_LIN_TIMING)
+  MB_CUDA(cudaDeviceSynchronize());
+  MB_CUDA(cudaMemcpyFromSymbol(out512, g_lin_t, sizeof(unsigned long long) * 512));
+  return MB_OK;
+#else
+  (void)out512;
+  set_error("mb_debug_lin_timeline: library built without -DMB_LIN_TIMING");
+  return MB_ERR_UNSUPPORTED;
+#endif
 }
 
 int mb_factor_release(mb_factor* f) {
@@ -1315,12 +1413,30 @@ int mb_factor_download_state(mb_factor* f, uint8_t* status, double* p_da, double
   MB_REQUIRE(f, "null factor");
   MB_CUDA(cudaSetDevice(f->ctx->device));
   cudaStream_t st = f->ctx->stream;
-  const size_t n = f->n;
+  const size_t n = f->n, k = f->cfg.num_corres_points;
   if (n == 0) return MB_OK;
-  if (status) MB_CUDA(cudaMemcpyAsync(status, f->status, n, cudaMemcpyDeviceToHost, st));
+  // the device arrays are in voxel order (k_sort_keys); perm[s] = index of sorted position s in the caller's scan
+  std::vector<uint32_t> perm(n);
+  if (f->sorted) {
+    MB_CUDA(cudaMemcpyAsync(perm.data(), f->perm, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  } else {
+    for (size_t i = 0; i < n; ++i) perm[i] = (uint32_t)i;
+  }
+  std::vector<uint8_t> st_s;
+  std::vector<uint64_t> idx_s;
+  if (status) {
+    st_s.resize(n);
+    MB_CUDA(cudaMemcpyAsync(st_s.data(), f->status, n, cudaMemcpyDeviceToHost, st));
+  }
+  if (knn_idx) {
+    idx_s.resize(n * k);
+    MB_CUDA(cudaMemcpyAsync(idx_s.data(), f->knn_idx, n * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  }
+  MB_CUDA(cudaStreamSynchronize(st));
+  if (status)
+    for (size_t s = 0; s < n; ++s) status[perm[s]] = st_s[s];
   if (knn_idx)
-    MB_CUDA(cudaMemcpyAsync(knn_idx, f->knn_idx, n * f->cfg.num_corres_points * sizeof(uint64_t),
-                            cudaMemcpyDeviceToHost, st));
+    for (size_t s = 0; s < n; ++s) std::memcpy(knn_idx + (size_t)perm[s] * k, idx_s.data() + s * k, k * sizeof(uint64_t));
   double* outs[5] = {p_da, mean, normal, loc_rot, loc_trans};
   std::vector<double> soa;
   for (int v = 0; v < 5; ++v) {
@@ -1329,10 +1445,9 @@ int mb_factor_download_state(mb_factor* f, uint8_t* status, double* p_da, double
     MB_CUDA(cudaMemcpyAsync(soa.data(), f->vecs + (size_t)v * 3 * f->ld, 3 * f->ld * sizeof(double),
                             cudaMemcpyDeviceToHost, st));
     MB_CUDA(cudaStreamSynchronize(st));
-    for (size_t i = 0; i < n; ++i)
-      for (int c = 0; c < 3; ++c) outs[v][3 * i + c] = soa[(size_t)c * f->ld + i];
+    for (size_t s = 0; s < n; ++s)
+      for (int c = 0; c < 3; ++c) outs[v][3 * (size_t)perm[s] + c] = soa[(size_t)c * f->ld + s];
   }
-  MB_CUDA(cudaStreamSynchronize(st));
   return MB_OK;
 }
 
@@ -1381,7 +1496,7 @@ int mb_icp_run(mb_factor* f, double R[9], double t[3], int iters, double lambda,
       f->graph_iters = iters;
       f->graph_count0 = f->linearize_count;
     } else {
-      f->ctx->launches += 2ull * iters + 1ull;
+      f->ctx->launches += 1ull * iters + 1ull + (f->graph_count0 == 0 && f->n ? 8ull : 0ull);
     }
     MB_CUDA(cudaGraphLaunch(f->graph, st));
     f->linearize_count += iters;

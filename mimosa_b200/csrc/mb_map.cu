@@ -17,7 +17,6 @@
 #include <vector>
 
 #include "mb_map.cuh"
-#include "mb_search_coop.cuh"
 
 namespace mb {
 
@@ -416,105 +415,6 @@ __global__ void __launch_bounds__(kKnnThreads, 7)
 #endif
 }
 
-// EXPERIMENTAL: k_knn with the warp-wide chunk queue in the neighbour phase (knn_thread<K, true>, mb_search.cuh);
-// MB_KNN_VARIANT=threadq selects it.  Same launch shape as k_knn; ROWS = 19 (neighbourhood modes up to 19) keeps the
-// shared memory at 28.6 KB so that seven blocks per SM still fit (one wave for 131 072 queries), ROWS = 27 is generic.
-template <int K, int ROWS>
-__global__ void __launch_bounds__(kKnnThreads, ROWS == 19 ? 7 : 6)
-    k_knn_queue(MapView mv, const double* __restrict__ q, size_t nq, int k, uint64_t* __restrict__ idx,
-                double* __restrict__ d2, uint8_t* __restrict__ ok) {
-  __shared__ uint16_t s_tab[kTabEntries];
-  __shared__ uint32_t s_pk_all[ROWS * kKnnThreads];
-  __shared__ uint32_t s_blk_all[24 * kKnnThreads];
-  __shared__ WarpQueueT<ROWS - 1> s_wq[kKnnThreads / 32];
-  fill_scan_table(mv, s_tab);
-  __syncthreads();
-  uint32_t* s_pk = s_pk_all + threadIdx.x;
-  uint32_t* s_blk = s_blk_all + threadIdx.x;
-  const size_t i = (size_t)blockIdx.x * kKnnThreads + threadIdx.x;
-  const bool active = i < nq;
-  double qx = 0, qy = 0, qz = 0;
-  if (active) {
-    qx = q[3 * i];
-    qy = q[3 * i + 1];
-    qz = q[3 * i + 2];
-  }
-  double bd[K];
-  uint32_t bs[K];
-  knn_thread<K, true, ROWS - 1>(mv, s_tab, s_pk, s_blk, kKnnThreads, qx, qy, qz, k, active, bd, bs, s_wq + threadIdx.x / 32);
-  if (!active) return;
-  uint64_t g[K];
-  float4 pts_unused[K];
-  const int found = knn_resolve_all<K, false>(mv, s_pk, kKnnThreads, bs, k, g, pts_unused);
-#pragma unroll
-  for (int j = 0; j < K; ++j) {
-    if (j < k) {
-      idx[i * k + j] = g[j];
-      d2[i * k + j] = g[j] != ~0ull ? bd[j] : DBL_MAX;
-    }
-  }
-  ok[i] = found == k;
-}
-
-// EXPERIMENTAL restricted k-NN with G lanes per query (mb_search_coop.cuh); MB_KNN_VARIANT=coop4 / coop8 selects it.
-// 128 threads = 128 / G queries per block; winner j of a query is resolved and written by group lane j % G.
-template <int K, int G, int MINB, int STEP, int MODE>
-__global__ void __launch_bounds__(kKnnThreads, MINB)
-    k_knn_coop(MapView mv, const double* __restrict__ q, size_t nq, int k, uint64_t* __restrict__ idx,
-               double* __restrict__ d2, uint8_t* __restrict__ ok) {
-  constexpr int kQ = kKnnThreads / G;  // queries per block
-  __shared__ uint32_t s_ctab[kTabEntries];
-  __shared__ uint32_t s_pk_all[kCube * kQ];
-  __shared__ uint32_t s_blk_all[kCoopBlk * kQ];
-  __shared__ uint32_t s_q_all[kCoopQueue * kQ];
-  __shared__ uint32_t s_st_all[3 * kCoopStack * kKnnThreads];
-  if (threadIdx.x < kScan) s_ctab[threadIdx.x] = coop_tab_entry(mv.scan[threadIdx.x]);
-  __syncthreads();
-  const int grp = threadIdx.x / G, gl = threadIdx.x % G;
-  uint32_t* s_pk = s_pk_all + grp * kCube;
-  const size_t i = (size_t)blockIdx.x * kQ + grp;
-  const bool active = i < nq;
-  double qx = 0, qy = 0, qz = 0;
-  if (active) {
-    qx = q[3 * i];
-    qy = q[3 * i + 1];
-    qz = q[3 * i + 2];
-  }
-  double bd[K];
-  uint32_t bs[K];
-  knn_group<K, G, STEP, MODE>(mv, s_ctab, s_pk, s_blk_all + grp * kCoopBlk, s_q_all + grp * kCoopQueue, s_st_all + threadIdx.x, kKnnThreads, qx,
-                  qy, qz, k, active, bd, bs);
-  if (!active) return;
-  uint64_t* const idx_q = idx + i * (size_t)k;
-  double* const d2_q = d2 + i * (size_t)k;
-#pragma unroll
-  for (int r = 0; r < (K + G - 1) / G; ++r) {
-    const int j = gl + G * r;
-    if (j < k) {
-      double dj = 0.0;
-      uint32_t sj = 0xffffffffu;
-#pragma unroll
-      for (int a = 0; a < K; ++a)
-        if (a == j) dj = bd[a], sj = bs[a];
-      uint64_t g = ~0ull;
-      if (sj != 0xffffffffu) {
-        const float4* bucket = mv.pts + (size_t)s_pk[sj >> kSeqShift] * mv.cap;
-        const uint32_t w = (uint32_t)__float_as_int(__ldg(&bucket->w));  // (voxel id << 5) | count
-        g = ((uint64_t)(w >> kCountBits) << 32) | (uint64_t)(sj & ((1u << kSeqShift) - 1));
-      }
-      idx_q[j] = g;
-      d2_q[j] = g != ~0ull ? dj : DBL_MAX;
-    }
-  }
-  if (gl == 0) {  // the list is ordered: all k exist iff the k-th does
-    uint32_t sk = 0xffffffffu;
-#pragma unroll
-    for (int a = 0; a < K; ++a)
-      if (a == k - 1) sk = bs[a];
-    ok[i] = sk != 0xffffffffu;
-  }
-}
-
 __global__ void k_gather_points(const float4* __restrict__ pts, int cap, const uint64_t* __restrict__ idx, size_t n,
                                 double* __restrict__ out) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -704,77 +604,12 @@ int ensure_mirror(mb_map* m) {
 int launch_knn(mb_map* m, const double* d_q, size_t nq, int k, uint64_t* d_idx, double* d_d2, uint8_t* d_ok) {
   if (nq == 0) return MB_OK;
   MB_TRY(ensure_mirror(m));
-  // development switch: MB_KNN_VARIANT = thread (default) | coop<G>[p][b<min blocks per SM>][s<points per step>], e.g.
-  // coop4, coop8, coop4b8, coop4b7s4 (a bucket per lane), coop4p, coop8p, coop4pb8 (a point per lane) — the experimental
-  // lanes-per-query search (read at every launch so that one process can compare the variants; an unknown value is an
-  // error, not a fallback)
-  int coop = 0, minb = 5, step = 8, mode = 0;
-  bool queue = false;
-  if (const char* e = getenv("MB_KNN_VARIANT")) {
-    if (!strcmp(e, "threadq")) {
-      queue = true;  // one query per thread, warp-wide chunk queue in the neighbour phase
-    } else if (e[0] && strcmp(e, "thread")) {
-      bool ok = !strncmp(e, "coop", 4) && (e[4] == '4' || e[4] == '8');
-      if (ok) {
-        const char* c = e + 5;
-        coop = e[4] - '0';
-        if (*c == 'p') mode = 1, ++c;
-        if (*c == 'b' && c[1] >= '4' && c[1] <= '8') minb = c[1] - '0', c += 2;
-        if (*c == 's' && (c[1] == '4' || c[1] == '8')) step = c[1] - '0', c += 2;
-        ok = *c == 0;
-      }
-      if (ok) {
-        if (mode == 1)
-          ok = step == 8 && (minb == 5 || minb == 6 || minb == 8);
-        else if (coop == 8)
-          ok = minb == 5 && step == 8;
-        else
-          ok = (step == 8 && (minb == 5 || minb == 6 || minb == 8)) || (step == 4 && (minb == 7 || minb == 8));
-      }
-      if (!ok) {
-        set_error("MB_KNN_VARIANT=%s: expected thread, threadq, coop8, coop4[b6|b8], coop4b7s4, coop4b8s4 or coop{4,8}p[b6|b8]", e);
-        return MB_ERR_INVALID_ARG;
-      }
-    }
-  }
   cudaStream_t st = m->ctx->stream;
-#define MB_COOP_LAUNCH(G, MINB, STEP, MODE)                                                                          \
-  do {                                                                                                               \
-    const unsigned grid = blocks_for(nq, kKnnThreads / G);                                                           \
-    if (k == 5)                                                                                                      \
-      k_knn_coop<5, G, MINB, STEP, MODE><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);    \
-    else                                                                                                             \
-      k_knn_coop<MB_MAX_K, G, 4, 8, MODE><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);   \
-  } while (0)
-  if (queue) {
-    const unsigned grid = blocks_for(nq, kKnnThreads);
-    if (k == 5 && m->n_off <= 19)
-      k_knn_queue<5, 19><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
-    else
-      k_knn_queue<MB_MAX_K, 27><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
-  } else if (coop && mode == 1) {
-    if (coop == 4 && minb == 5) MB_COOP_LAUNCH(4, 5, 8, 1);
-    if (coop == 4 && minb == 6) MB_COOP_LAUNCH(4, 6, 8, 1);
-    if (coop == 4 && minb == 8) MB_COOP_LAUNCH(4, 8, 8, 1);
-    if (coop == 8 && minb == 5) MB_COOP_LAUNCH(8, 5, 8, 1);
-    if (coop == 8 && minb == 6) MB_COOP_LAUNCH(8, 6, 8, 1);
-    if (coop == 8 && minb == 8) MB_COOP_LAUNCH(8, 8, 8, 1);
-  } else if (coop == 8) {
-    MB_COOP_LAUNCH(8, 5, 8, 0);
-  } else if (coop == 4) {
-    if (step == 8 && minb == 5) MB_COOP_LAUNCH(4, 5, 8, 0);
-    if (step == 8 && minb == 6) MB_COOP_LAUNCH(4, 6, 8, 0);
-    if (step == 8 && minb == 8) MB_COOP_LAUNCH(4, 8, 8, 0);
-    if (step == 4 && minb == 7) MB_COOP_LAUNCH(4, 7, 4, 0);
-    if (step == 4 && minb == 8) MB_COOP_LAUNCH(4, 8, 4, 0);
-  } else {
-    const unsigned grid = blocks_for(nq, kKnnThreads);
-    if (k == 5)
-      k_knn<5><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
-    else
-      k_knn<MB_MAX_K><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
-  }
-#undef MB_COOP_LAUNCH
+  const unsigned grid = blocks_for(nq, kKnnThreads);
+  if (k == 5)
+    k_knn<5><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
+  else
+    k_knn<MB_MAX_K><<<grid, kKnnThreads, 0, st>>>(m->view(), d_q, nq, k, d_idx, d_d2, d_ok);
   ++m->ctx->launches;
   MB_CUDA(cudaGetLastError());
   return MB_OK;

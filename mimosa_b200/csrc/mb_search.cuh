@@ -120,146 +120,6 @@ __device__ __forceinline__ void fill_scan_table(const MapView& mv, uint16_t* s_t
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #endif
 
-// ---- EXPERIMENTAL: warp-wide chunk queue for the neighbour phase of knn_thread (kQueue = true) --------------------------
-// Today a warp's neighbour loop runs max-over-lanes iterations (26-30 in the heaviest warps against a mean of 9.75
-// four-point chunks per query).  Here the surviving buckets' chunks of ALL 32 queries of the warp are listed in shared
-// memory — fill counts fetched first (from the .w of each bucket's first point, which also brings its first sector in),
-// items placed by ballots in (survivor, chunk)-major order so that a step of 32 items holds different queries — and every
-// lane takes one (query, bucket, chunk) item per step: 4 loads, the owning query's coordinates and radius from shared
-// memory, four distances; candidates within the radius go into the OWNING query's candidate slots (the s_blk column
-// of its lane, 8 entries, claimed with atomicAdd; a producer that finds them full retries after the drain) and every
-// lane drains its own query's slots into its (d2, sequence) list.  Same result as the per-lane loop by the same
-// argument: the list order does not depend on when or by whom a candidate is offered, a stale radius only admits more.
-// Checked against the oracle through the 32-lane emulation; NOT YET RUN on a GPU.
-constexpr int kWqItems = 128;  // items listed before the list is worked off
-// The warp's scratch.  NSV = surviving neighbours a query can have: 18 for neighbourhood modes up to 19, 26 for the
-// full cube.  (The queries' coordinates travel by shuffle; 1.7 - 2.2 KB per warp keeps seven 128-thread blocks per SM.)
-template <int NSV>
-struct WarpQueueT {
-  float rad[32];             // the queries' radii (k-th best, rounded up), refreshed at drains
-  uint32_t cn[32];           // candidate slots claimed per query since its last drain
-  uint16_t sv[NSV][32];      // survivor r of lane l: visiting rank | fill count << 5
-  uint16_t items[kWqItems];  // lane | survivor << 5 | chunk << 10
-};
-
-template <int K, int NSV, typename Offer, typename Worst>
-MB_DEV void knn_queue_phase(const MapView& mv, const uint16_t* __restrict__ s_tab, uint32_t* s_pk, uint32_t* s_blk,
-                            int pk_stride, double qx, double qy, double qz, int k, uint32_t todo, float wq_f,
-                            Offer& offer, Worst& worst_of, WarpQueueT<NSV>* wqp) {
-  WarpQueueT<NSV>& W = *wqp;
-  const int lane = warp_lane();
-  const int cap = mv.cap;
-  const uint32_t kCntMask = (1u << kCountBits) - 1;
-  uint32_t* const pk0 = s_pk - lane;    // column 0 of the warp in the [rank][thread] slot table
-  uint32_t* const cand0 = s_blk - lane;  // column 0 of the warp in the [3 * 8][thread] candidate slots
-  W.rad[lane] = wq_f;
-  W.cn[lane] = 0u;
-  // (a) fill counts of the surviving buckets, four loads in flight per lane
-  const int n = __popc(todo);
-  const int max_n = __reduce_max_sync(kFull, n);
-  {
-    uint32_t t = todo;
-    for (int r0 = 0; r0 < max_n; r0 += 4) {
-      uint32_t rk[4], w[4];
-MB_UNROLL
-      for (int u = 0; u < 4; ++u) {
-        rk[u] = 0u, w[u] = 0u;
-        if (r0 + u < n) {
-          rk[u] = (uint32_t)s_tab[__ffs(t) - 1] >> 11;
-          t &= t - 1;
-          w[u] = (uint32_t)__float_as_int(__ldg(&(mv.pts + (size_t)s_pk[rk[u] * pk_stride] * cap)->w));
-        }
-      }
-MB_UNROLL
-      for (int u = 0; u < 4; ++u)
-        if (r0 + u < n) W.sv[r0 + u][lane] = (uint16_t)(rk[u] | ((w[u] & kCntMask) << 5));
-    }
-  }
-  __syncwarp();
-  // drain: every lane inserts the candidates its query has received
-  auto drain = [&]() {
-    __syncwarp();
-    int m = (int)min(W.cn[lane], 8u);
-    while (__any_sync(kFull, m > 0)) {
-      if (m > 0) {
-        --m;
-        const volatile uint32_t* ent = s_blk + (3 * m) * pk_stride;
-        const uint32_t lo = ent[0], hi = ent[pk_stride], sq = ent[2 * pk_stride];
-        offer(__hiloint2double((int)hi, (int)lo), sq);
-      }
-    }
-    W.cn[lane] = 0u;
-    W.rad[lane] = __double2float_ru(worst_of());
-    __syncwarp();
-  };
-  // (c) work off `count` listed items, 32 per step
-  auto process = [&](int count) {
-    __syncwarp();
-    for (int i0 = 0; i0 < count; i0 += 32) {
-      const bool has = i0 + lane < count;
-      const uint32_t it = has ? (uint32_t)W.items[i0 + lane] : 0u;
-      const uint32_t ql = it & 31u, r = (it >> 5) & 31u, c = it >> 10;
-      const uint32_t sv = has ? (uint32_t)W.sv[r][ql] : 0u;
-      const uint32_t rk = sv & 31u;
-      const int cnt = has ? (int)(sv >> 5) : 0, j = 4 * (int)c;
-      const float4* bucket = mv.pts + (size_t)(has ? pk0[rk * pk_stride + ql] : 0u) * cap;
-      float4 p[4];
-MB_UNROLL
-      for (int u = 0; u < 4; ++u) p[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (has) {
-MB_UNROLL
-        for (int u = 0; u < 4; ++u) p[u] = __ldg(bucket + min(j + u, cap - 1));
-      }
-      const double ox = __shfl_sync(kFull, qx, (int)ql), oy = __shfl_sync(kFull, qy, (int)ql), oz = __shfl_sync(kFull, qz, (int)ql);
-      const double rad = (double)W.rad[ql];
-      double d[4];
-      uint32_t pending = 0u;
-MB_UNROLL
-      for (int u = 0; u < 4; ++u) {
-        d[u] = sqdist4((double)p[u].x, (double)p[u].y, (double)p[u].z, ox, oy, oz);
-        if (j + u < cnt && d[u] <= rad) pending |= 1u << u;
-      }
-      // claim slots of the owning query; whoever finds them full tries again after the drain
-      bool again = __any_sync(kFull, pending != 0u);
-      while (again) {
-MB_UNROLL
-        for (int u = 0; u < 4; ++u) {
-          if (pending & (1u << u)) {
-            const uint32_t pos = atomicAdd(&W.cn[ql], 1u);
-            if (pos < 8u) {
-              uint32_t* ent = cand0 + (3 * pos) * pk_stride + ql;
-              ent[0] = (uint32_t)__double2loint(d[u]);
-              ent[pk_stride] = (uint32_t)__double2hiint(d[u]);
-              ent[2 * pk_stride] = (rk << kSeqShift) | (uint32_t)(j + u);
-              pending &= ~(1u << u);
-            }
-          }
-        }
-        __syncwarp();
-        again = __any_sync(kFull, pending != 0u);
-        if (again || __any_sync(kFull, W.cn[lane] > 4u)) drain();
-      }
-    }
-    drain();
-  };
-  // (b) list the chunks in (survivor, chunk)-major order; work the list off whenever it could overflow
-  int base = 0;
-  for (int r = 0; r < max_n; ++r) {
-    const int nch = r < n ? (int)((((uint32_t)W.sv[r][lane] >> 5) + 3u) >> 2) : 0;
-    const int max_c = __reduce_max_sync(kFull, nch);
-    for (int c = 0; c < max_c; ++c) {
-      const unsigned b = __ballot_sync(kFull, c < nch);
-      if (c < nch) W.items[base + __popc(b & ((1u << lane) - 1u))] = (uint16_t)((uint32_t)lane | ((uint32_t)r << 5) | ((uint32_t)c << 10));
-      base += __popc(b);
-      if (base > kWqItems - 32) {
-        process(base);
-        base = 0;
-      }
-    }
-  }
-  process(base);
-}
-
 // Restricted k-NN, ONE QUERY PER THREAD (every lane of the warp must call; `active` = false idles a lane).
 //
 // The reference (gtsam_points KnnResult::push over the neighbour voxels, restated in oracle/ivox_ref.hpp) scans
@@ -294,13 +154,10 @@ __device__ long long g_knn_t[16];
 #define MB_KNN_T(i) do { } while (0)
 #endif
 
-// kQueue (EXPERIMENTAL, see knn_queue_phase below): the surviving neighbours' four-point chunks of all 32 queries of
-// the warp go through one shared work list instead of every lane walking its own buckets; s_wq = the warp's scratch.
-template <int K, bool kQueue = false, int NSV = kMaxNbr - 1>
-MB_DEV void knn_thread(const MapView& mv, const uint16_t* __restrict__ s_tab, uint32_t* s_pk,
-                                           uint32_t* s_blk, int pk_stride, double qx, double qy, double qz, int k,
-                                           bool active,
-                                           double (&bd)[K], uint32_t (&bs)[K], WarpQueueT<NSV>* s_wq = nullptr) {
+template <int K>
+MB_DEV void knn_thread(const MapView& mv, const uint16_t* __restrict__ s_tab, uint32_t* s_pk, uint32_t* s_blk,
+                       int pk_stride, double qx, double qy, double qz, int k, bool active, double (&bd)[K],
+                       uint32_t (&bs)[K]) {
   const double kInf = __longlong_as_double(0x7ff0000000000000ll);
 MB_UNROLL
   for (int i = 0; i < K; ++i) {
@@ -528,10 +385,6 @@ MB_UNROLL
   // insertion runs when a stack could overflow and at the end ("drain"), so its ~50 instructions are paid per
   // accepted candidate and not per candidate slot of the warp.  The list's (d2, sequence) order makes the result
   // independent of when a candidate is inserted; a stale radius only admits more candidates.
-  if constexpr (kQueue) {
-    knn_queue_phase<K, NSV>(mv, s_tab, s_pk, s_blk, pk_stride, qx, qy, qz, k, todo, wq_f, offer, worst_of, s_wq);
-    return;
-  }
   int j = 0, cnt = 0, n_st = 0;
   uint32_t rk = 0;
   const float4* bucket = mv.pts;

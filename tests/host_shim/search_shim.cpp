@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -74,6 +75,22 @@ static inline double __shfl_sync(unsigned, double v, int src) {
   std::memcpy(&v, &u, 8);
   return v;
 }
+static inline int __shfl_up_sync(unsigned, int v, int delta) {
+  if (!t_warp) return v;
+  const int lane = t_lane;
+  return warp_exchange((unsigned long long)(unsigned)v, [lane, delta](const unsigned long long* s) {
+    return (int)(unsigned)s[lane >= delta ? lane - delta : lane];
+  });
+}
+static inline unsigned __match_any_sync(unsigned, unsigned long long v) {
+  if (!t_warp) return 1u;
+  return warp_exchange(v, [v](const unsigned long long* s) {
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l)
+      if (s[l] == v) m |= 1u << l;
+    return m;
+  });
+}
 // shared-memory atomics of the emulated warp's lanes (host threads between two barriers really do race)
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
@@ -127,7 +144,7 @@ static inline void prefetch_l2(const void*) {}
 using std::min;
 
 #include "../../mimosa_b200/csrc/mb_search.cuh"
-#include "../../mimosa_b200/csrc/mb_search_coop.cuh"
+#include "../../mimosa_b200/csrc/mb_search_group.cuh"
 
 namespace {
 struct HostMirror {
@@ -213,15 +230,13 @@ void run(const HostMirror& M, const double* q, size_t nq, int k, uint64_t* idx, 
   }
 }
 // 32 queries per emulated warp, one host thread per lane, shared-memory columns laid out as on the device
-template <int K, bool kQueue = false>
+template <int K>
 void run_warps(const HostMirror& M, const double* q, size_t nq, int k, uint64_t* idx, double* d2, uint8_t* ok) {
   uint16_t s_tab[mb::kTabEntries] = {0};
   for (int p = 0; p < mb::kScan; ++p) s_tab[p] = M.view.scan[p];
   for (size_t w0 = 0; w0 < nq; w0 += 32) {
     WarpCtx ctx;
     std::vector<uint32_t> s_pk(mb::kMaxNbr * 32, 0xdeadbeefu), s_blk(24 * 32, 0xdeadbeefu);
-    mb::WarpQueueT<mb::kMaxNbr - 1> wq;
-    std::memset(&wq, 0xee, sizeof wq);  // stale contents must never be used
     std::vector<std::thread> lanes;
     for (int lane = 0; lane < 32; ++lane)
       lanes.emplace_back([&, lane] {
@@ -232,8 +247,7 @@ void run_warps(const HostMirror& M, const double* q, size_t nq, int k, uint64_t*
         const size_t qi = active ? i : 0;
         double bd[K];
         uint32_t bs[K];
-        mb::knn_thread<K, kQueue, mb::kMaxNbr - 1>(M.view, s_tab, s_pk.data() + lane, s_blk.data() + lane, 32, q[3 * qi], q[3 * qi + 1], q[3 * qi + 2], k,
-                                  active, bd, bs, &wq);
+        mb::knn_thread<K>(M.view, s_tab, s_pk.data() + lane, s_blk.data() + lane, 32, q[3 * qi], q[3 * qi + 1], q[3 * qi + 2], k, active, bd, bs);
         if (active) {
           uint64_t g[K];
           float4 pts[K];
@@ -249,40 +263,49 @@ void run_warps(const HostMirror& M, const double* q, size_t nq, int k, uint64_t*
     for (auto& t : lanes) t.join();
   }
 }
-// G lanes per query (mb_search_coop.cuh): 32 / G queries per emulated warp, shared arrays laid out as in k_knn_coop
-template <int K, int G, int MODE>
-void run_coop(const HostMirror& M, const double* q, size_t nq, int k, uint64_t* idx, double* d2, uint8_t* ok) {
-  constexpr int QW = 32 / G;
-  uint32_t s_ctab[mb::kTabEntries] = {0};
-  for (int p = 0; p < mb::kScan; ++p) s_ctab[p] = mb::coop_tab_entry(M.view.scan[p]);
-  for (size_t w0 = 0; w0 < nq; w0 += QW) {
+// The voxel-grouped warp search of k_linearize (mb_search_group.cuh): 32 queries per emulated warp in the order
+// given (the caller sorts them by voxel or not), scratch laid out as in the kernel; pool_buckets = 0: never staged.
+// `mask` selects which lanes are active in each warp (bit per query, nullptr = all): inactive lanes must not disturb.
+template <int K, int ROWS>
+void run_groups(const HostMirror& M, const double* q, size_t nq, int k, int pool_buckets, const uint8_t* on, uint64_t* idx, double* d2,
+                uint8_t* ok) {
+  uint16_t s_rank[32];
+  for (int r = 0; r < 32; ++r) s_rank[r] = 0xffff;
+  for (int c = 0; c < mb::kCube; ++c)
+    if (M.view.rank[c] != 0xff) s_rank[M.view.rank[c]] = mb::rank_entry(c);
+  std::vector<float4> pool((size_t)std::max(pool_buckets, 1) * M.view.cap);
+  for (size_t w0 = 0; w0 < nq; w0 += 32) {
     WarpCtx ctx;
-    std::vector<uint32_t> s_pk(mb::kCube * QW, 0xdeadbeefu), s_q(mb::kCoopQueue * QW, 0xdeadbeefu),
-        s_blk(mb::kCoopBlk * QW, 0xdeadbeefu), s_st(3 * mb::kCoopStack * 32, 0xdeadbeefu);
+    auto S = std::make_unique<mb::GroupScratch<ROWS>>();
+    std::memset(S.get(), 0xee, sizeof *S);  // stale contents must never be used
+    for (auto& p : pool) p = make_float4(1e30f, 1e30f, 1e30f, 0.f);
     std::vector<std::thread> lanes;
     for (int lane = 0; lane < 32; ++lane)
       lanes.emplace_back([&, lane] {
         t_warp = &ctx;
         t_lane = lane;
-        const int grp = lane / G, gl = lane % G;
-        const size_t i = w0 + grp;
-        const bool active = i < nq;
-        const size_t qi = active ? i : 0;
+        const size_t i = w0 + lane;
+        const bool active = i < nq && (!on || on[i]);
+        const size_t qi = i < nq ? i : 0;
         double bd[K];
         uint32_t bs[K];
-        uint32_t* pk = s_pk.data() + grp * mb::kCube;
-        mb::knn_group<K, G, 8, MODE>(M.view, s_ctab, pk, s_blk.data() + grp * mb::kCoopBlk, s_q.data() + grp * mb::kCoopQueue, s_st.data() + lane, 32, q[3 * qi], q[3 * qi + 1],
-                            q[3 * qi + 2], k, active, bd, bs);
+        uint32_t parity = 0;
+        const mb::GroupLane gl = mb::knn_warp_groups<K, ROWS>(M.view, s_rank, *S, pool.data(), pool_buckets, parity, q[3 * qi],
+                                                              q[3 * qi + 1], q[3 * qi + 2], k, active, bd, bs);
         if (active) {
-          // winner j is written by group lane j % G, as in the kernel
           uint64_t g[K];
           float4 pts[K];
-          const int found = mb::knn_resolve_all<K, true>(M.view, pk, 1, bs, k, g, pts);
-          for (int j = gl; j < k; j += G) {
+          const int found = mb::group_resolve_all<K, ROWS>(M.view, *S, pool.data(), gl, bs, k, g, pts);
+          for (int j = 0; j < k; ++j) {
             idx[i * k + j] = g[j];
             d2[i * k + j] = g[j] != ~0ull ? bd[j] : 1.7976931348623157e308;
+            // the stored point handed to the plane fit must be the indexed one
+            if (g[j] != ~0ull) {
+              const double dd = mb::sqdist4((double)pts[j].x, (double)pts[j].y, (double)pts[j].z, q[3 * qi], q[3 * qi + 1], q[3 * qi + 2]);
+              if (dd != bd[j]) d2[i * k + j] = -1.0;
+            }
           }
-          if (gl == 0) ok[i] = found == k;
+          ok[i] = found == k;
         }
         t_warp = nullptr;
       });
@@ -291,23 +314,16 @@ void run_coop(const HostMirror& M, const double* q, size_t nq, int k, uint64_t* 
 }
 }  // namespace
 
-extern "C" int shim_knn_coop(const int32_t* coords, const int32_t* counts, const float* xyz, uint32_t n_vox, int cap, int nbr_mode,
-                             double leaf, double pref_frac, const double* q, size_t nq, int k, int lanes_per_query, int mode,
-                             uint64_t* idx, double* d2, uint8_t* ok) {
-  if (k < 1 || k > 8 || (lanes_per_query != 4 && lanes_per_query != 8) || mode < 0 || mode > 1) return 1;
+extern "C" int shim_knn_groups(const int32_t* coords, const int32_t* counts, const float* xyz, uint32_t n_vox, int cap, int nbr_mode,
+                               double leaf, const double* q, size_t nq, int k, int pool_buckets, const uint8_t* on, uint64_t* idx,
+                               double* d2, uint8_t* ok) {
+  if (k < 1 || k > 8) return 1;
   HostMirror M;
-  build_mirror(M, coords, counts, xyz, n_vox, cap, nbr_mode, leaf, pref_frac);
-  const int sel = (lanes_per_query == 8 ? 4 : 0) | (mode ? 2 : 0) | (k == 5 ? 1 : 0);
-  switch (sel) {
-    case 0: run_coop<8, 4, 0>(M, q, nq, k, idx, d2, ok); break;
-    case 1: run_coop<5, 4, 0>(M, q, nq, k, idx, d2, ok); break;
-    case 2: run_coop<8, 4, 1>(M, q, nq, k, idx, d2, ok); break;
-    case 3: run_coop<5, 4, 1>(M, q, nq, k, idx, d2, ok); break;
-    case 4: run_coop<8, 8, 0>(M, q, nq, k, idx, d2, ok); break;
-    case 5: run_coop<5, 8, 0>(M, q, nq, k, idx, d2, ok); break;
-    case 6: run_coop<8, 8, 1>(M, q, nq, k, idx, d2, ok); break;
-    default: run_coop<5, 8, 1>(M, q, nq, k, idx, d2, ok); break;
-  }
+  build_mirror(M, coords, counts, xyz, n_vox, cap, nbr_mode, leaf, 0.0);
+  if (k == 5 && M.view.n_off <= 19)
+    run_groups<5, 19>(M, q, nq, k, pool_buckets, on, idx, d2, ok);
+  else
+    run_groups<8, 27>(M, q, nq, k, pool_buckets, on, idx, d2, ok);
   return 0;
 }
 
@@ -337,16 +353,3 @@ extern "C" int shim_knn_warp(const int32_t* coords, const int32_t* counts, const
   return 0;
 }
 
-// same, with the warp-wide chunk queue in the neighbour phase (knn_thread<K, true>)
-extern "C" int shim_knn_warp_queue(const int32_t* coords, const int32_t* counts, const float* xyz, uint32_t n_vox, int cap,
-                                   int nbr_mode, double leaf, double pref_frac, const double* q, size_t nq, int k, uint64_t* idx,
-                                   double* d2, uint8_t* ok) {
-  if (k < 1 || k > 8) return 1;
-  HostMirror M;
-  build_mirror(M, coords, counts, xyz, n_vox, cap, nbr_mode, leaf, pref_frac);
-  if (k == 5)
-    run_warps<5, true>(M, q, nq, k, idx, d2, ok);
-  else
-    run_warps<8, true>(M, q, nq, k, idx, d2, ok);
-  return 0;
-}

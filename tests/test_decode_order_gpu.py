@@ -1,15 +1,10 @@
 """mb_scan_from_cloud_ordered: the message re-orderings of lidar::Manager::prepareInput (transpose_pointcloud,
 organize_pointcloud_by_ring; manager.cpp:179-243) as an index map in front of the device decode, against the oracle
-(oracle/decode_ref.py: re-order the message, then decode).  Written after this round's GPU budget was spent: compiled
-for sm_100a and covered on the CPU side (oracle KATs, ABI export), but not yet run on a GPU — so it only runs when
-MB_TEST_EXPERIMENTAL=1 until it has been seen green once."""
-import os
-
+(oracle/decode_ref.py: re-order the message, then decode).  First run on a B200 in round 2 (profiles/r2_experiments.md)."""
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MB_TEST_EXPERIMENTAL") != "1", reason="not yet run on a GPU: set MB_TEST_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("name,width,height,transpose,by_ring", [

@@ -1,6 +1,7 @@
 """The search code the kernels run (mimosa_b200/csrc/mb_search.cuh: block probes, occupancy masks, pruning
 bounds, deferred ordered insertion, tie order) compiled for the HOST, one emulated lane per query
-(tests/host_shim/search_shim.cpp), against the oracle's iVox k-NN: indices and squared distances bit-exact for
+(tests/host_shim/search_shim.cpp) and the voxel-grouped warp search k_linearize runs (mb_search_group.cuh, as an
+emulated 32-lane warp), against the oracle's iVox k-NN: indices and squared distances bit-exact for
 every neighbourhood mode, k, leaf size and early-prefetch radius.  CPU-only coverage of the hot path's logic;
 the GPU parity tests check the same kernels through the C ABI."""
 import ctypes as C
@@ -17,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def shim():
     src = os.path.join(HERE, "host_shim", "search_shim.cpp")
     out = os.path.join(HERE, "host_shim", "libsearch_shim.so")
-    hdrs = [os.path.join(HERE, "..", "mimosa_b200", "csrc", h) for h in ("mb_search.cuh", "mb_search_coop.cuh", "mb_math.cuh")]
+    hdrs = [os.path.join(HERE, "..", "mimosa_b200", "csrc", h) for h in ("mb_search.cuh", "mb_search_group.cuh", "mb_math.cuh")]
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(p) for p in [src] + hdrs):
         subprocess.run(["g++", "-O2", "-std=c++20", "-ffp-contract=off", "-frounding-math", "-fPIC", "-shared", "-pthread", src,
                         "-o", out], check=True)
@@ -28,29 +29,32 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def shim_knn(shim, m, q, k, nbr_mode, leaf, pref_frac=0.4, warp=False, coop=0):
+def shim_knn(shim, m, q, k, nbr_mode, leaf, pref_frac=0.4, warp=False, groups=None, on=None):
     coords, counts, _, pts, _ = m.download()
     q = np.ascontiguousarray(q, np.float64).reshape(-1, 3)
     nq = q.shape[0]
     idx, d2, ok = np.empty((nq, k), np.uint64), np.empty((nq, k), np.float64), np.empty(nq, np.uint8)
     leaf = float(np.float32(leaf))  # the map's leaf size is a float (mb_map_create, IVoxRef): 1 / (double)leaf_f32
-    if coop:  # G lanes per query (mb_search_coop.cuh), always as an emulated 32-lane warp; coop = (G, mode)
-        rc = shim.shim_knn_coop(_p(coords), _p(counts), _p(pts), C.c_uint32(coords.shape[0]), C.c_int(m.cap), C.c_int(nbr_mode),
-                                C.c_double(leaf), C.c_double(pref_frac), _p(q), C.c_size_t(nq), C.c_int(k), C.c_int(coop[0]),
-                                C.c_int(coop[1]), _p(idx), _p(d2), _p(ok))
+    if groups is not None:  # the voxel-grouped warp search (always an emulated 32-lane warp); groups = pool buckets per warp
+        on_p = _p(np.ascontiguousarray(on, np.uint8)) if on is not None else None
+        rc = shim.shim_knn_groups(_p(coords), _p(counts), _p(pts), C.c_uint32(coords.shape[0]), C.c_int(m.cap), C.c_int(nbr_mode),
+                                  C.c_double(leaf), _p(q), C.c_size_t(nq), C.c_int(k), C.c_int(groups), on_p, _p(idx), _p(d2), _p(ok))
         assert rc == 0
         return idx, d2, ok.astype(bool)
-    rc = (shim.shim_knn_warp_queue if warp == "queue" else shim.shim_knn_warp if warp else shim.shim_knn)(_p(coords), _p(counts), _p(pts), C.c_uint32(coords.shape[0]), C.c_int(m.cap), C.c_int(nbr_mode),
+    rc = (shim.shim_knn_warp if warp else shim.shim_knn)(_p(coords), _p(counts), _p(pts), C.c_uint32(coords.shape[0]), C.c_int(m.cap), C.c_int(nbr_mode),
                        C.c_double(leaf), C.c_double(pref_frac), _p(q), C.c_size_t(nq), C.c_int(k), _p(idx), _p(d2), _p(ok))
     assert rc == 0
     return idx, d2, ok.astype(bool)
 
 
-def check(shim, oracle, pts, q, k, mode, leaf, min_dist, pref_frac=0.4, cap=20, warp=False, coop=0):
+def check(shim, oracle, pts, q, k, mode, leaf, min_dist, pref_frac=0.4, cap=20, warp=False, groups=None, on=None):
     m = oracle.IVoxRef(leaf, min_dist, cap, mode, 1000)
     m.insert(pts)
     io, do, oo = m.knn_search(q, k)
-    ih, dh, oh = shim_knn(shim, m, q, k, mode, leaf, pref_frac, warp, coop)
+    ih, dh, oh = shim_knn(shim, m, q, k, mode, leaf, pref_frac, warp, groups, on)
+    if on is not None:  # lanes switched off must not have been written; compare the active ones
+        sel = np.asarray(on, bool)
+        io, do, oo, ih, dh, oh = io[sel], do[sel], oo[sel], ih[sel], dh[sel], oh[sel]
     assert np.array_equal(oo, oh)
     assert np.array_equal(io[oo], ih[oo]), f"indices differ (mode {mode}, k {k})"
     assert np.array_equal(do[oo], dh[oo]), "squared distances differ"
@@ -120,94 +124,57 @@ def test_search_32_lane_warp_emulation(shim, oracle, mode, k):
     assert check(shim, oracle, pts, q, k, mode, 1.0, 0.2, warp=True) > 300
 
 
-# ---- the cooperative variant (G lanes per query, mb_search_coop.cuh), run as emulated 32-lane warps -----------------
-@pytest.mark.parametrize("lanes", [(4, 0), (8, 0), (4, 1), (8, 1)])  # (lanes per query, 0 = bucket per lane / 1 = point per lane)
-@pytest.mark.parametrize("mode,k", [(19, 5), (27, 8), (7, 3), (1, 5), (27, 1)])
-def test_coop_search_matches_oracle_world(shim, oracle, lanes, mode, k):
+# ---- the voxel-grouped warp search of k_linearize (mb_search_group.cuh), run as emulated 32-lane warps ----------------
+def voxel_sorted(q, leaf):
+    c = np.floor(q / leaf).astype(np.int64)
+    return q[np.lexsort((c[:, 2], c[:, 1], c[:, 0]))]
+
+
+@pytest.mark.parametrize("pool", [0, 22, 400])  # never staged / the kernel's pool / everything staged
+@pytest.mark.parametrize("mode,k", [(19, 5), (27, 8), (7, 3), (1, 5), (27, 5), (19, 1)])
+def test_group_search_matches_oracle_world(shim, oracle, pool, mode, k):
     import synth
 
-    rng = synth.rng_for(1200 + mode + k)
+    rng = synth.rng_for(1700 + mode + k)
     pts = np.concatenate([synth.sample_world(40000, 25.0, rng), rng.uniform(-25, 25, (3000, 3)).astype(np.float32)])
-    q = np.concatenate([pts[rng.integers(0, pts.shape[0], 400), :3].astype(np.float64) + rng.normal(0, 0.2, (400, 3)),
-                        rng.uniform(-30, 30, (101, 3))])
-    q = q[rng.permutation(q.shape[0])]  # 501 queries: ragged last warp for both group sizes
-    assert check(shim, oracle, pts, q, k, mode, 1.0, 0.2, coop=lanes) > 200
+    q = np.concatenate([pts[rng.integers(0, pts.shape[0], 900), :3].astype(np.float64) + rng.normal(0, 0.2, (900, 3)),
+                        rng.uniform(-30, 30, (125, 3))])  # 1025 queries: 32 full warps + one lane
+    # voxel-sorted (few groups per warp, lock-step lanes) and shuffled (up to 32 groups per warp)
+    assert check(shim, oracle, pts, voxel_sorted(q, 1.0), k, mode, 1.0, 0.2, groups=pool) > 500
+    assert check(shim, oracle, pts, q[rng.permutation(q.shape[0])], k, mode, 1.0, 0.2, groups=pool) > 500
 
 
-@pytest.mark.parametrize("lanes", [(4, 0), (8, 0), (4, 1), (8, 1)])
-def test_coop_search_ties_caps_and_leaf_sizes(shim, oracle, lanes):
-    # lattice: exact distance ties across buckets handled by different lanes must resolve by visiting order
-    g = np.arange(-6, 6) * 0.5
+@pytest.mark.parametrize("pool", [0, 22])
+def test_group_search_dense_voxels_ties_and_caps(shim, oracle, pool):
+    # many queries per voxel (the benchmark scan's regime), lattice ties, caps that are not a multiple of four
+    g = np.arange(-8, 8) * 0.5
     pts = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
     rng = np.random.default_rng(5)
     pts = pts[rng.permutation(pts.shape[0])]
-    q = np.concatenate([pts[:300].astype(np.float64) + 0.25, pts[:300].astype(np.float64), np.round(rng.uniform(-3, 3, (200, 3)))])
+    q = np.concatenate([pts[:700].astype(np.float64) + 0.25, pts[:700].astype(np.float64), np.round(rng.uniform(-4, 4, (300, 3))),
+                        rng.uniform(-0.5, 1.5, (900, 3))])  # the last 900 share eight voxels
     for mode, k in ((19, 5), (27, 8), (7, 5)):
-        check(shim, oracle, pts, q, k, mode, 1.0, 0.0, coop=lanes)
-    # volumetric cloud (every neighbour occupied, several rounds of survivors), other leaf sizes, prefetch radii
-    vol = rng.uniform(-5, 5, (30000, 3)).astype(np.float32)
-    qv = rng.uniform(-5.5, 5.5, (600, 3))
-    for leaf, md, pref in ((0.5, 0.15, 0.0), (2.0, 0.0, 0.4), (0.25, 0.05, 2.0)):
-        assert check(shim, oracle, vol, qv, 5, 19, leaf, md, pref, coop=lanes) > 200
-    assert check(shim, oracle, vol, qv, 5, 27, 1.0, 0.0, coop=lanes) > 200
-    # caps: not a multiple of four; more than 4 * 4 points per bucket (second round of own-voxel chunks at G = 4)
+        check(shim, oracle, pts, voxel_sorted(q, 1.0), k, mode, 1.0, 0.0, groups=pool)
     dense = rng.uniform(-2, 2, (20000, 3)).astype(np.float32)
-    qd = rng.uniform(-2, 2, (500, 3))
-    check(shim, oracle, dense, qd, 5, 19, 1.0, 0.0, cap=7, coop=lanes)
-    check(shim, oracle, dense, qd, 5, 19, 1.0, 0.0, cap=31, coop=lanes)
-    # sparse: own voxel mostly empty, fewer than k neighbours
-    sparse = rng.uniform(-20, 20, (3000, 3)).astype(np.float32)
-    check(shim, oracle, sparse, rng.uniform(-20, 20, (600, 3)), 5, 27, 1.0, 0.0, coop=lanes)
+    qd = voxel_sorted(rng.uniform(-2, 2, (1500, 3)), 1.0)
+    check(shim, oracle, dense, qd, 5, 19, 1.0, 0.0, cap=7, groups=pool)
+    check(shim, oracle, dense, qd, 5, 19, 1.0, 0.0, cap=31, groups=pool)
+    for leaf, md in ((0.5, 0.15), (2.0, 0.0), (0.25, 0.05)):
+        vol = rng.uniform(-6, 6, (40000, 3)).astype(np.float32)
+        check(shim, oracle, vol, voxel_sorted(rng.uniform(-6.5, 6.5, (1500, 3)), leaf), 5, 19, leaf, md, groups=pool)
 
 
-@pytest.mark.parametrize("seed", range(10))
-def test_coop_search_randomized_configurations(shim, oracle, seed):
-    """Random neighbourhood mode, k, cap, leaf (including sizes a float does not represent exactly, with queries on voxel
-    faces), density and group shape per seed: the cooperative and the default search must agree with the oracle bit for
-    bit whatever the combination."""
-    rng = np.random.default_rng(5000 + seed)
-    mode = int(rng.choice([1, 7, 19, 27]))
-    k = int(rng.integers(1, 9))
-    cap = int(rng.choice([3, 8, 20, 31]))
-    leaf = float(rng.choice([0.3, 1.0, 2.0]))
-    lanes = [(4, 0), (8, 0), (4, 1), (8, 1)][seed % 4]
-    extent = float(rng.choice([2.0, 6.0, 15.0])) * leaf
-    n = int(rng.choice([500, 5000, 30000]))
-    pts = rng.uniform(-extent, extent, (n, 3)).astype(np.float32)
-    if seed % 3 == 0:  # snap some points to a lattice: exact ties
-        pts[: n // 2] = np.round(pts[: n // 2] / (leaf / 4)) * (leaf / 4)
-    q = np.concatenate([rng.uniform(-extent * 1.1, extent * 1.1, (300, 3)), pts[rng.integers(0, n, 150)].astype(np.float64)])
-    min_dist, pref = 0.0 if seed % 2 else 0.05 * leaf, float(rng.choice([0.0, 0.4, 1.5]))
-    check(shim, oracle, pts, q, k, mode, leaf, min_dist, pref_frac=pref, cap=cap, coop=lanes)
-    check(shim, oracle, pts, q, k, mode, leaf, min_dist, pref_frac=pref, cap=cap, warp=True)  # the default search, same configuration
-
-
-# ---- the warp-wide chunk queue in the neighbour phase (knn_thread<K, true>), as emulated 32-lane warps ---------------------
-@pytest.mark.parametrize("mode,k", [(19, 5), (27, 8), (7, 3), (27, 5)])
-def test_queue_search_matches_oracle_world(shim, oracle, mode, k):
+@pytest.mark.parametrize("pool", [0, 22])
+def test_group_search_partially_active_warps(shim, oracle, pool):
+    """Later search iterations re-associate only some points of a warp: idle lanes must neither join a group nor
+    disturb the others (k_linearize passes need = false for them)."""
     import synth
 
-    rng = synth.rng_for(1500 + mode + k)
-    pts = np.concatenate([synth.sample_world(40000, 25.0, rng), rng.uniform(-25, 25, (3000, 3)).astype(np.float32)])
-    q = np.concatenate([pts[rng.integers(0, pts.shape[0], 500), :3].astype(np.float64) + rng.normal(0, 0.2, (500, 3)),
-                        rng.uniform(-30, 30, (141, 3))])
-    q = q[rng.permutation(q.shape[0])]
-    assert check(shim, oracle, pts, q, k, mode, 1.0, 0.2, warp="queue") > 300
-
-
-def test_queue_search_dense_ties_and_overflow(shim, oracle):
-    rng = np.random.default_rng(21)
-    # volumetric and dense: every neighbour occupied and full, queries with an empty own voxel (infinite radius: every
-    # neighbour point is a candidate, the 8 candidate slots overflow and producers must retry), lists longer than 256 items
-    vol = rng.uniform(-4, 4, (60000, 3)).astype(np.float32)
-    qv = np.concatenate([rng.uniform(-4.5, 4.5, (500, 3)), rng.uniform(-5.2, 5.2, (140, 3))])
-    for mode, k, cap in ((19, 5, 20), (27, 5, 31), (27, 8, 20), (7, 5, 7)):
-        assert check(shim, oracle, vol, qv, k, mode, 1.0, 0.0, cap=cap, warp="queue") > 300
-    g = np.arange(-6, 6) * 0.5
-    lat = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
-    lat = lat[rng.permutation(lat.shape[0])]
-    ql = np.concatenate([lat[:300].astype(np.float64) + 0.25, lat[:300].astype(np.float64), np.round(rng.uniform(-3, 3, (200, 3)))])
-    for mode, k in ((19, 5), (27, 8)):
-        check(shim, oracle, lat, ql, k, mode, 1.0, 0.0, warp="queue")
-    sparse = rng.uniform(-20, 20, (3000, 3)).astype(np.float32)
-    check(shim, oracle, sparse, rng.uniform(-20, 20, (600, 3)), 5, 27, 1.0, 0.0, warp="queue")
+    rng = synth.rng_for(1900)
+    pts = synth.sample_world(40000, 25.0, rng)
+    q = voxel_sorted(pts[rng.integers(0, pts.shape[0], 1024), :3].astype(np.float64) + rng.normal(0, 0.2, (1024, 3)), 1.0)
+    for frac in (0.5, 0.1, 0.02):
+        on = rng.uniform(size=q.shape[0]) < frac
+        on[32:64] = False  # a warp with nobody active
+        on[64] = True      # a single active lane
+        assert check(shim, oracle, pts, q, 5, 19, 1.0, 0.2, groups=pool, on=on) > 0
