@@ -51,6 +51,21 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def host_threads() -> int:
+    """Cores this process may run on.  NOT omp_get_max_threads(): torch.distributed.run exports OMP_NUM_THREADS=1, which
+    made the round-1 CPU arm single-threaded at N >= 2; the oracle takes its thread count explicitly (num_threads clause)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def config_object(n_pts, n_vox, n_scan, parallelism, l2, cuda_graph, workload=None):
+    """The `config` object of a JSON line: the same key set in both arms (the driver compares them)."""
+    return {"workload": workload or WORKLOAD, "iters_per_step": ITERS, "map_points": int(n_pts), "map_voxels": int(n_vox),
+            "scan_points": int(n_scan), "parallelism": parallelism, "l2": l2, "cuda_graph": bool(cuda_graph)}
+
+
 def make_inputs():
     """Deterministic inputs shared by every arm: the chunk sequence fed to the map and the scan."""
     import synth
@@ -239,7 +254,7 @@ def run_reference(args, rank, world):
     mo = orc.IVoxRef(**HORNBILL_MAP)
     synth.build_map(mo.insert, MAP_POINTS, MAP_HALF_EXTENT, rng, size_fn=lambda: mo.size()[1])
     log(f"[reference] oracle map built: {mo.size()} in {time.time() - t_build:.1f}s")
-    cores = orc.max_threads()
+    cores = host_threads()
     f = orc.IcpFactorRef(mo, scan, hornbill_config())
 
     def step(nt):
@@ -256,8 +271,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "iters_per_step": ITERS, "map_points": mo.size()[1], "map_voxels": mo.size()[0],
-                   "scan_points": int(scan.shape[0])},
+        "config": config_object(mo.size()[1], mo.size()[0], scan.shape[0], f"CPU oracle, OpenMP {cores} host threads",
+                                "not applicable (CPU arm; every step starts from a reset factor)", False),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{args.steps} full scans x {ITERS} iterations, OpenMP {cores} threads "
                                    f"(the reference hard-codes 4: {faithful:.1f} it/s at 4 threads)",
@@ -537,13 +552,13 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "iters_per_step": ITERS, "map_points": n_pts, "map_voxels": n_vox,
-                   "scan_points": int(scan.shape[0]), "parallelism": (f"scan-block shard x{world}, map replicated, 48-double packet per iteration "
-                                   + ("all-reduced with NCCL" if os.environ.get("MB_BENCH_NCCL") else
-                                      "exchanged through peer memory (NVLink stores + flags), summed in rank order"))
-                   if world > 1 else "1 GPU",
-                   "l2": "flushed (256 MiB write) before every timed step, outside the event bracket",
-                   "cuda_graph": not args.no_graph, "final_pose_err_m": pose_err},
+        "config": config_object(n_pts, n_vox, scan.shape[0],
+                                (f"scan-block shard x{world}, map replicated, 48-double packet per iteration "
+                                 + ("all-reduced with NCCL" if os.environ.get("MB_BENCH_NCCL") else
+                                    "exchanged through peer memory (NVLink stores + flags), summed in rank order"))
+                                if world > 1 else "1 GPU",
+                                "flushed (256 MiB write) before every timed step, outside the event bracket", not args.no_graph),
+        "check": {"final_pose_err_m": pose_err},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_total / args.steps,
                 "what": "C++ caller over the C ABI (host/e2e_caller.cpp): mb_factor_create(host scan) + 20 x [mb_factor_linearize("
@@ -563,7 +578,7 @@ def main():
             mo = orc.IVoxRef(**HORNBILL_MAP)
             mo.load_raw(coords, counts, None, pts, lru_counter)
             fo = orc.IcpFactorRef(mo, scan, cfg)
-            cores = orc.max_threads()
+            cores = host_threads()
 
             def cpu_step(nt):
                 fo.reset()

@@ -6,10 +6,13 @@
  * CUDA/torch type crosses this boundary.  All host buffers are caller-owned.  There is NO CPU fallback:
  * without a usable sm_100 device mb_init() fails with MB_ERR_NO_DEVICE.
  *
- * Threading: handles are thread-compatible — one caller at a time per handle, different handles may be
- * used concurrently (ICPFactor::linearize is `const` but mutates per-point caches,
- * mimosa/include/mimosa/lidar/geometric_factor.hpp:79-116; instances are serialised by graph_mutex_,
- * mimosa/src/graph/manager.cpp:574).
+ * Threading: ONE CALLER AT A TIME PER CONTEXT.  Every map, factor and scan handle created from an mb_ctx shares
+ * that context's stream, device-block pool, page-locked staging buffers and completion flag, so calls on any handles
+ * of one context must be serialised by the caller (the reference already serialises them: ICPFactor::linearize is
+ * `const` but mutates per-point caches, mimosa/include/mimosa/lidar/geometric_factor.hpp:79-116, and instances in the
+ * smoother are linearised under graph_mutex_, mimosa/src/graph/manager.cpp:574; the one call outside that mutex,
+ * geometric.cpp:196, runs on the LiDAR callback thread, which an adapter guards with the same lock).  Handles of
+ * DIFFERENT contexts (one per thread, or one per GPU) may be used concurrently.
  */
 #ifndef MIMOSA_B200_H_
 #define MIMOSA_B200_H_
@@ -109,9 +112,12 @@ typedef struct mb_cloud_layout {
   int32_t off_time;
   int32_t time_type; /* 0: uint32 ns since header (Ouster t, LivoxFromCustom2 t); 1: float32 s since header (Velodyne time);
                         2: float64 absolute s (Hesai / Rslidar timestamp); 3: float64 absolute ns (Livox timestamp) */
-  int32_t off_ring;  /* -1: no ring filter (Livox, OusterOdyssey, VelodyneAnybotics) */
-  int32_t ring_type; /* 0: uint16; 1: uint8 */
+  int32_t off_ring;  /* -1: no ring field (Livox, OusterOdyssey) */
+  int32_t ring_type; /* 0: uint16; 1: uint8 (PointOusterR8); 2: float32 (PointVelodyneAnybotics) */
   int32_t off_tag;   /* Livox tag byte, -1 otherwise */
+  int32_t ring_filter; /* 1: drop geometric points with ring % ring_skip_divisor != 0 (manager.cpp:318-330); 0: the ring
+                          field only serves organize_pointcloud_by_ring — the reference skips the filter for
+                          PointVelodyneAnybotics ("unreliable ring numbers") although it re-orders that cloud by ring */
 } mb_cloud_layout;
 
 /* lidar::ManagerConfig's input filters (mimosa/include/mimosa/lidar/manager.hpp:30-34) + the two skip divisors of

@@ -58,7 +58,7 @@ class IcpConfig(C.Structure):
 class CloudLayout(C.Structure):
     _fields_ = [("point_step", C.c_uint32), ("off_x", C.c_int32), ("off_y", C.c_int32), ("off_z", C.c_int32),
                 ("off_intensity", C.c_int32), ("intensity_type", C.c_int32), ("off_time", C.c_int32), ("time_type", C.c_int32),
-                ("off_ring", C.c_int32), ("ring_type", C.c_int32), ("off_tag", C.c_int32)]
+                ("off_ring", C.c_int32), ("ring_type", C.c_int32), ("off_tag", C.c_int32), ("ring_filter", C.c_int32)]
 
 
 class InputFilter(C.Structure):

@@ -47,13 +47,27 @@ __device__ __forceinline__ size_t src_record(size_t i, const uint32_t* __restric
   return j;
 }
 
+// the ring number of a record: uint16 / uint8 / float32 (`++ring_counts[point.ring]`, manager.cpp:218, converts
+// PointVelodyneAnybotics' float ring to an index by truncation)
+__device__ __forceinline__ uint32_t load_ring(const unsigned char* p, const mb_cloud_layout& lay) {
+  if (lay.ring_type == 0) return (uint32_t)load_unaligned<uint16_t>(p + lay.off_ring);
+  if (lay.ring_type == 1) return (uint32_t)p[lay.off_ring];
+  return (uint32_t)(int)load_unaligned<float>(p + lay.off_ring);
+}
+
+// The reference assigns a double expression to `uint32_t t_ns` (manager.cpp:285-304).  For values outside [0, 2^32)
+// that conversion is what x86-64 compilers emit for it: truncate to a 64-bit integer, keep the low 32 bits — a point
+// stamped BEFORE the header (negative offset) wraps to ~4.29e9 ns and is then dropped by the ns_max test (:306).
+// Reproduced here (a saturating conversion would keep such points with t_ns = 0).
+__device__ __forceinline__ uint32_t wrap_u32(double v) { return (uint32_t)(unsigned long long)__double2ll_rz(v); }
+
 // ring number of every record of the (possibly transposed) cloud, as sort keys, and the identity permutation
 __global__ void k_ring_keys(const unsigned char* __restrict__ data, size_t n, mb_cloud_layout lay, uint32_t t_w, uint32_t t_h,
                             uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned char* p = data + src_record(i, nullptr, t_w, t_h) * lay.point_step;
-  keys[i] = lay.ring_type == 0 ? (uint32_t)load_unaligned<uint16_t>(p + lay.off_ring) : (uint32_t)p[lay.off_ring];
+  keys[i] = load_ring(p, lay);
   vals[i] = (uint32_t)i;
 }
 
@@ -98,11 +112,11 @@ __device__ __forceinline__ void decode_record(const unsigned char* p, size_t i, 
     if (lay.time_type == 0) {
       t_ns = load_unaligned<uint32_t>(p + lay.off_time);
     } else if (lay.time_type == 1) {
-      t_ns = (uint32_t)((double)load_unaligned<float>(p + lay.off_time) * 1e9);
+      t_ns = wrap_u32((double)load_unaligned<float>(p + lay.off_time) * 1e9);
     } else if (lay.time_type == 2) {
-      t_ns = (uint32_t)((load_unaligned<double>(p + lay.off_time) - fl.header_ts) * 1e9);
+      t_ns = wrap_u32((load_unaligned<double>(p + lay.off_time) - fl.header_ts) * 1e9);
     } else {
-      t_ns = (uint32_t)(load_unaligned<double>(p + lay.off_time) - fl.header_ts * 1e9);
+      t_ns = wrap_u32(load_unaligned<double>(p + lay.off_time) - fl.header_ts * 1e9);
     }
     ok = !((float)t_ns > fl.ns_max);
     r.t = t_ns;
@@ -112,10 +126,7 @@ __device__ __forceinline__ void decode_record(const unsigned char* p, size_t i, 
     r.z = r.z + fl.z_offset;
     r.range = sqrtf(range_sq);
     bool gk = i % (size_t)fl.point_skip_divisor == 0;
-    if (gk && lay.off_ring >= 0) {
-      const uint32_t ring = lay.ring_type == 0 ? (uint32_t)load_unaligned<uint16_t>(p + lay.off_ring) : (uint32_t)p[lay.off_ring];
-      gk = ring % (uint32_t)fl.ring_skip_divisor == 0;
-    }
+    if (gk && lay.ring_filter) gk = load_ring(p, lay) % (uint32_t)fl.ring_skip_divisor == 0;
     g = gk ? 1u : 0u;
   }
   tmp[c] = r;
@@ -220,8 +231,18 @@ extern "C" int mb_scan_from_cloud_ordered(mb_ctx* ctx, const void* data, size_t 
   MB_REQUIRE(n_points == 0 || (data && geometric_idx && pose_index && unique_ns), "null buffer");
   MB_REQUIRE(layout->point_step >= 12 && filter->point_skip_divisor >= 1 && filter->ring_skip_divisor >= 1, "bad layout/filter");
   MB_REQUIRE(layout->intensity_type >= 0 && layout->intensity_type <= 1 && layout->time_type >= 0 && layout->time_type <= 3 &&
-                 layout->ring_type >= 0 && layout->ring_type <= 1,
+                 layout->ring_type >= 0 && layout->ring_type <= 2,
              "unknown field type");
+  MB_REQUIRE(!layout->ring_filter || (layout->off_ring >= 0 && layout->ring_type != 2), "ring_filter needs an integer ring field");
+  {
+    // every field must lie inside a record
+    auto inside = [&](int32_t off, size_t size) { return off >= 0 && (size_t)off + size <= (size_t)layout->point_step; };
+    const size_t time_size = layout->time_type <= 1 ? 4 : 8, ring_size = layout->ring_type == 0 ? 2 : layout->ring_type == 1 ? 1 : 4;
+    MB_REQUIRE(inside(layout->off_x, 4) && inside(layout->off_y, 4) && inside(layout->off_z, 4) &&
+                   inside(layout->off_intensity, layout->intensity_type == 0 ? 4 : 2) && inside(layout->off_time, time_size) &&
+                   (layout->off_ring < 0 || inside(layout->off_ring, ring_size)) && (layout->off_tag < 0 || inside(layout->off_tag, 1)),
+               "a field of the layout lies outside the record (offset + size > point_step)");
+  }
   MB_REQUIRE(n_points < 0x7fffffffull, "too many points");
   MB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;

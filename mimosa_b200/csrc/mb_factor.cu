@@ -24,9 +24,9 @@
 // factor handle as structure-of-arrays, mirroring the `mutable` vectors at geometric_factor.hpp:79-106.
 // Every reduction has a fixed order, so results are bitwise repeatable for a given launch shape.
 #include <algorithm>
+#include <chrono>
+#include <thread>
 #include <vector>
-
-#include <cub/cub.cuh>
 
 #include <type_traits>
 #if defined(__SSE2__)
@@ -48,7 +48,12 @@ constexpr int kPack = 48;
 constexpr int kPackB = 21, kPackF = 27, kPackCnt = 28, kPackSearched = 37, kPackLoc = 40;
 constexpr int kGroup = 32;  // blocks per first-level reduction group
 constexpr int kLocThreads = 256;
+// packed upper triangle of [J e]^T [J e] (7x7), entry a = (kTriRow[a], kTriCol[a]): the 21 entries of J^T J row-major
+// (c >= r), then J^T e (6), then e^2; entries 28..31 unused
+__constant__ int8_t kTriRow[32] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5, 0, 1, 2, 3, 4, 5, 6, 0, 0, 0, 0};
+__constant__ int8_t kTriCol[32] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5, 6, 6, 6, 6, 6, 6, 6, 0, 0, 0, 0};
 
+struct LoopCtl;
 struct FactorView {
   const float4* src;
   uint8_t* status;
@@ -58,7 +63,11 @@ struct FactorView {
   int k, use_huber;
   uint32_t flags;
   int fold_loc;  // 1: also sum the component localizabilities of the previous linearisation (device-resident loop)
-  double da_gate, max_corr_sq, sigma, kh, pvd;
+  double da_gate_sq, max_corr_sq, sigma, kh, pvd;  // da_gate_sq: smallest d2 with sqrt(d2) > the gate (host: da_gate_sq_min)
+  const double* rroot;  // sqrt(||p_src||) per point (geometric_factor.hpp:323), constant per scan
+  LoopCtl* ctl;         // grid barrier and re-association queue control words
+  uint32_t* queue;      // [n] points queued for re-association in this launch (sorted positions)
+  uint32_t* need_mask;  // [tiles] lanes of each 32-point tile that re-associate in this launch
   double* partials;    // [grid][kPack]
   double* gpartials;   // [n_groups][kPack]
   unsigned* gtickets;  // [n_groups]
@@ -196,6 +205,14 @@ struct NoPose {};
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -206,14 +223,13 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 struct FinArgs {
   int reg_4_dof, linearize_count, do_step, iter;
   mb_icp_trace* trace;
-  int fuse;  // 1: the last block of k_linearize runs the roles itself (no k_finalize launch)
 };
 
 // Everything after the per-point loop of ICPFactor::linearize (geometric_factor.hpp:405-428, 464-475, 559-560), plus
 // the harness GN step that ISAM2 performs in the reference (mimosa/src/graph/manager.cpp:585-588).  One THREAD per
 // role: 0/1 localizability of the rotational / translational block, 2/3 Schur-complement degeneracy info,
 // 4 projection + packing + solve + retract.  `packed` = the reduced 48-double packet (all ranks summed).
-__device__ __noinline__ void finalize_role(const double* packed, DevState* ds, const FinArgs& fa, int role) {
+__device__ __noinline__ void finalize_role(const double* packed, const DevState* in, DevState* out, const FinArgs& fa, int role) {
   double H[36];
   {
     int u = 0;
@@ -226,7 +242,7 @@ __device__ __noinline__ void finalize_role(const double* packed, DevState* ds, c
         ++u;
       }
   }
-  mb_linearization& L = ds->lin;
+  mb_linearization& L = out->lin;
   m33 Hrr, Hrt, Htr, Htt;
 #pragma unroll
   for (int r = 0; r < 3; ++r)
@@ -270,10 +286,10 @@ __device__ __noinline__ void finalize_role(const double* packed, DevState* ds, c
     const double f = packed[kPackF];
     m33 R;
 #pragma unroll
-    for (int a = 0; a < 9; ++a) R.m[a] = ds->pose[a];
-    d3 T = mk3(ds->pose[9], ds->pose[10], ds->pose[11]);
+    for (int a = 0; a < 9; ++a) R.m[a] = in->pose[a];
+    d3 T = mk3(in->pose[9], in->pose[10], in->pose[11]);
     if (fa.reg_4_dof) {
-      const d3 gz = mk3(-ds->gravity[0], -ds->gravity[1], -ds->gravity[2]);
+      const d3 gz = mk3(-in->gravity[0], -in->gravity[1], -in->gravity[2]);
       const d3 lz = mul33Tv(R, gz);
       const double l[3] = {lz.x, lz.y, lz.z};
       m33 P;
@@ -306,14 +322,14 @@ __device__ __noinline__ void finalize_role(const double* packed, DevState* ds, c
     L.n_searched = (int32_t)packed[kPackSearched];
     if (fa.do_step) {
       double delta[6] = {0, 0, 0, 0, 0, 0};
-      const bool ok = solve6_ldlt(H, ds->lambda, g, delta);
+      const bool ok = solve6_ldlt(H, in->lambda, g, delta);
       if (ok) {
         se3_retract(R, T, delta);
 #pragma unroll
-        for (int a = 0; a < 9; ++a) ds->pose[a] = R.m[a];
-        ds->pose[9] = T.x;
-        ds->pose[10] = T.y;
-        ds->pose[11] = T.z;
+        for (int a = 0; a < 9; ++a) out->pose[a] = R.m[a];
+        out->pose[9] = T.x;
+        out->pose[10] = T.y;
+        out->pose[11] = T.z;
       }
       if (fa.trace) {
         mb_icp_trace& tr = fa.trace[fa.iter];
@@ -369,8 +385,9 @@ __device__ __forceinline__ void peer_gather(const PeerTable* __restrict__ peer, 
   if (threadIdx.x == 0) *peer->xseq = seq;
 }
 
-// Stand-alone finalize: only when an NCCL all-reduce sits between the reduction and the roles (fallback exchange)
-// and for the timing diagnostic; otherwise the last block of k_linearize runs the roles itself.
+// What follows the reduction, in its own small kernel (five warps, one role each).  Running the roles inside
+// k_linearize's last block was built and measured (profiles/r2_experiments.md): under k_linearize's register cap and
+// next to three blocks streaming through its instruction cache the same chain takes 10-13 us instead of 4.
 __global__ void __launch_bounds__(160) k_finalize(const double* packed_in, DevState* ds, FinArgs fa, unsigned role_mask,
                                                   const PeerTable* __restrict__ peer, double* packed_out) {
   __shared__ double s_packed[kXchgDoubles];
@@ -384,7 +401,7 @@ __global__ void __launch_bounds__(160) k_finalize(const double* packed_in, DevSt
   if ((threadIdx.x & 31) != 0) return;
   const int role = threadIdx.x >> 5;
   if (((role_mask >> role) & 1u) == 0) return;  // role_mask != 31 only in the timing diagnostic
-  finalize_role(packed, ds, fa, role);
+  finalize_role(packed, ds, ds, fa, role);
 }
 
 #ifndef MB_LIN_BLOCKS
@@ -392,6 +409,8 @@ __global__ void __launch_bounds__(160) k_finalize(const double* packed_in, DevSt
 #endif
 #if defined(MB_LIN_TIMING)  // development build: %globaltimer stamps of one k_linearize launch (mb_debug_lin_timeline)
 __device__ unsigned long long g_lin_t[64][8];
+__device__ unsigned long long g_lin_blk[2][1024][2];  // launches 1 and 2: per tile block, [start, end] of its tile loop
+__device__ unsigned g_lin_warp[2][4096];              // per TILE: duration in ns << 6 | voxel groups
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -409,46 +428,31 @@ __host__ __device__ constexpr size_t lin_warp_bytes(int pool_buckets, int cap) {
   return ((sizeof(GroupScratch<ROWS>) + 15) / 16) * 16 + (size_t)pool_buckets * cap * sizeof(float4);
 }
 
-// One linearisation.  Every WARP owns tiles of 32 consecutive points of the voxel-sorted scan and does everything
-// for them — A transform + data-association gate (:276-287), B the voxel-grouped restricted k-NN (mb_search_group.cuh),
-// the two distance gates (:296-302) and the plane fit (:176-229) for the points that must re-associate, C residual,
-// s-check, Huber, Jacobian, localizability vectors (:319-355) and its share of [J e]^T [J e] (:364-366) — without
-// ever waiting for another warp; a point's data stay in its lane's registers from A to C.  Then block partial ->
-// group partial -> packet (two ticketed levels, fixed order: bitwise repeatable), and the LAST block exchanges the
-// packet with the other ranks (peer mailboxes) and runs the finalize roles (fa.fuse).
+// ---- round-1 kernel, kept for A/B measurement (MB_LIN_KERNEL=v1): block tiles of 128 points, block-level compaction
+// of the points that re-associate, one query per thread (mb_search.cuh::knn_thread) -------------------------------
 template <int K, typename PoseT, int ROWS>
 __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
-    k_linearize(MapView mv, FactorView fv, DevState* ds, PoseT pa, const PeerTable* __restrict__ peer, FinArgs fa,
-                int pool_buckets) {
-  extern __shared__ __align__(16) unsigned char s_dyn[];
-  __shared__ uint16_t s_rank[32];
+    k_linearize_v1(MapView mv, FactorView fv, DevState* ds, PoseT pa, const PeerTable* __restrict__ peer) {
+  double* pose_dev = ds->pose;
+  __shared__ uint16_t s_tab[kTabEntries];
+  // s_pk (phase B: probed neighbour words, [n_off][thread]; cooperative search: the per-thread candidate stacks,
+  // [3 * kCoopStack][thread]) is re-used as s_row (phase C: whitened [J (6), e] per point, [warp][32][7] doubles =
+  // 7168 B <= 19 * 128 * 4 B).
+  __shared__ __align__(16) uint32_t s_pk_all[ROWS * kLinThreads];
+  // per-thread {mask_lo, mask_hi, base} of the <= 8 blocks around a query; cooperative search: kGroupWords per group
+  __shared__ uint32_t s_blk_all[24 * kLinThreads];
+  static_assert(sizeof(s_pk_all) >= sizeof(double) * 7 * kLinThreads, "s_row fits");
+  __shared__ double s_pt[3][kLinThreads];          // transformed point of each tile member
+  __shared__ uint8_t s_status[kLinThreads];
+  __shared__ uint16_t s_queue[kLinThreads];
+  __shared__ int s_warp_need[kLinWarps];
   __shared__ double s_red[kLinWarps][kPack];
   __shared__ double s_tmp[(kLinThreads / kPack) * kPack];
-  __shared__ double s_V[18];
-  __shared__ double s_packed[kXchgDoubles];
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double* pose_dev = ds->pose;
   pdl_launch_dependents();
-#if defined(MB_LIN_TIMING)
-  if (blockIdx.x == 0 && tid == 0) {
-    g_lin_t[fa.linearize_count & 63][0] = gtime();
-    g_lin_t[fa.linearize_count & 63][2] = 0ull;
-    g_lin_t[fa.linearize_count & 63][3] = 0ull;
-    g_lin_t[fa.linearize_count & 63][6] = 0ull;
-    g_lin_t[fa.linearize_count & 63][7] = 0ull;
-  }
-#endif
-  GroupScratch<ROWS>& S = *reinterpret_cast<GroupScratch<ROWS>*>(s_dyn + (size_t)warp * lin_warp_bytes<ROWS>(pool_buckets, mv.cap));
-  float4* const pool = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(&S) + ((sizeof(GroupScratch<ROWS>) + 15) / 16) * 16);
-  // the whitened [J (6), e] rows of the warp's 32 points (phase C) share the candidate stacks' memory (phase B)
-  double(*s_row)[7] = reinterpret_cast<double(*)[7]>(S.stack);
-  static_assert(sizeof(S.stack) >= sizeof(double) * 7 * 32, "s_row fits");
-  if (tid < 32) s_rank[tid] = 0xffffu;
-  __syncthreads();
-  if (tid < kCube && mv.rank[tid] != 0xffu) s_rank[mv.rank[tid]] = rank_entry(tid);
-  if (lane == 0) mbar_init(&S.mbar, 1);
-  uint32_t mbar_parity = 0u;
+  fill_scan_table(mv, s_tab);
+  double(*s_row)[7] = reinterpret_cast<double(*)[7]>(s_pk_all) + warp * 32;
   // Lane a < 28 owns entry a of the packed upper triangle of [J e]^T [J e] (7x7): the 21 entries of
   // J^T J first (row-major, c >= r), then J^T e (6), then e^2.
   int pr = 0, pc = 0;
@@ -469,14 +473,14 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
     if (lane == 27) pr = pc = 6;
   }
 
-  // everything above is independent of earlier kernels; from here on we read the pose the previous linearisation
-  // left and overwrite per-point state the previous k_loc_comp may still be reading
+  // everything above is independent of earlier kernels; from here on we read the pose the previous iteration's
+  // k_finalize wrote and overwrite per-point state the previous k_loc_comp may still be reading
   pdl_wait();
-  if (blockIdx.x == 0) MB_LT_SET(1);
   m33 R;
+#pragma unroll
   d3 T;
   if constexpr (std::is_same<PoseT, PoseArg>::value) {
-    if (blockIdx.x == 0 && tid < 16) pose_dev[tid] = pa.v[tid];  // the finalize roles read pose / gravity / lambda there
+    if (blockIdx.x == 0 && tid < 16) pose_dev[tid] = pa.v[tid];  // k_finalize reads pose / gravity / lambda there
 #pragma unroll
     for (int a = 0; a < 9; ++a) R.m[a] = pa.v[a];
     T = mk3(pa.v[9], pa.v[10], pa.v[11]);
@@ -493,16 +497,16 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
   // Folded localizability pass (device-resident loop): before a point's status and localizability vectors are
   // overwritten, its contribution |loc^T V| (entries below 0.5 dropped, geometric_factor.hpp:434-457) to the
   // component localizabilities of the PREVIOUS linearisation is taken with that linearisation's eigenvectors, which
-  // the previous finalize left in ds->lin.  It saves a pass over the points and a kernel launch per iteration.
+  // the previous k_finalize left in ds->lin.  It saves a pass over the points and a kernel launch per iteration.
+  __shared__ double s_V[18];
   if (fv.fold_loc && tid < 18) s_V[tid] = tid < 9 ? ds->lin.eigvec_trans[tid] : ds->lin.eigvec_rot[tid - 9];
   __syncthreads();
 
-  const size_t n_tiles = (fv.n + 31) / 32;
-  const size_t n_warps = (size_t)gridDim.x * kLinWarps;
-  for (size_t tile = (size_t)blockIdx.x * kLinWarps + warp; tile < n_tiles; tile += n_warps) {
-    const size_t i = tile * 32 + lane;
+  const size_t n_tiles = (fv.n + kLinThreads - 1) / kLinThreads;
+  for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const size_t i = tile * kLinThreads + tid;
     const bool act = i < fv.n;
-    // ---- A: transform, gate ---------------------------------------------------------------------------------
+    // ---- A: transform, gate, compaction ------------------------------------------------------------
     d3 ps = mk3(0, 0, 0), pt = mk3(0, 0, 0);
     uint8_t st = MB_UNPROCESSED;
     bool need = false;
@@ -512,57 +516,69 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
       pt = add3(mul33v(R, ps), T);
       st = fv.status[i];
       const d3 da = ld3(fv.p_da, fv.ld, i);
-      need = forced || sqrt(sqnorm3(sub3(pt, da))) > fv.da_gate;
+      need = forced || sqnorm3(sub3(pt, da)) >= fv.da_gate_sq;
     }
-    const uint8_t st_prev = st;  // the status the previous linearisation left (folded localizability pass)
-    const unsigned need_mask = __ballot_sync(kFull, need);
-    // ---- B: search + plane fit for the points that re-associate ------------------------------------------------
-    bool proceed = false;
-    d3 mean = mk3(0, 0, 0), normal = mk3(0, 0, 0);
-    if (need_mask) {
-      double bd[K];
-      uint32_t bs[K];
-      const GroupLane gl = knn_warp_groups<K, ROWS>(mv, s_rank, S, pool, pool_buckets, mbar_parity, pt.x, pt.y, pt.z, k, need, bd, bs);
-      if (need) {
-        float4 nb[K];
-        uint64_t g[K];
-        const int found = group_resolve_all<K, ROWS>(mv, S, pool, gl, bs, k, g, nb);
-        double dk = 0.0;
+    s_pt[0][tid] = pt.x;
+    s_pt[1][tid] = pt.y;
+    s_pt[2][tid] = pt.z;
+    const unsigned mask = __ballot_sync(kFull, need);
+    if (lane == 0) s_warp_need[warp] = __popc(mask);
+    __syncthreads();
+    int base = 0, n_need = 0;
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-          if (j < k) {
-            if (j == k - 1) dk = bd[j];
-            // indices are only meaningful when all k exist (the reference discards partial results)
-            if (fv.knn_idx) fv.knn_idx[i * k + j] = found == k ? g[j] : ~0ull;
+    for (int w = 0; w < kLinWarps; ++w) {
+      if (w < warp) base += s_warp_need[w];
+      n_need += s_warp_need[w];
+    }
+    if (need) s_queue[base + __popc(mask & ((1u << lane) - 1))] = (uint16_t)tid;
+    __syncthreads();
+    // ---- B: search + plane fit for the compacted points -------------------------------------------
+      for (int q0 = warp * 32; q0 < n_need; q0 += kLinThreads) {
+        const int qi = q0 + lane;
+        const bool on = qi < n_need;
+        const int li = on ? (int)s_queue[qi] : 0;
+        const double qx = s_pt[0][li], qy = s_pt[1][li], qz = s_pt[2][li];
+        double bd[K];
+        uint32_t bs[K];
+        uint32_t* s_pk = s_pk_all + tid;
+        knn_thread<K>(mv, s_tab, s_pk, s_blk_all + tid, kLinThreads, qx, qy, qz, k, on, bd, bs);
+        if (on) {
+          const size_t gi = tile * kLinThreads + li;
+          float4 nb[K];
+          uint64_t g[K];
+          const int found = knn_resolve_all<K, true>(mv, s_pk, kLinThreads, bs, k, g, nb);
+          double dk = 0.0;
+#pragma unroll
+          for (int j = 0; j < K; ++j) {
+            if (j < k) {
+              if (j == k - 1) dk = bd[j];
+              // indices are only meaningful when all k exist (the reference discards partial results)
+              if (fv.knn_idx) fv.knn_idx[gi * k + j] = g[j];
+            }
           }
-        }
-        st3(fv.p_da, fv.ld, i, pt);
-        st = MB_UNPROCESSED;
-        if (found != k) {
-          st = MB_INSUFFICIENT_CORRES_POINTS;
-        } else if (dk > fv.max_corr_sq) {
-          st = MB_CORRES_MAX_DIST;
-        } else {
-          bool normal_set;
-          st = fit_plane<K>(nb, k, T, fv.pvd, mean, normal, normal_set);
-          st3(fv.mean, fv.ld, i, mean);
-          if (normal_set) st3(fv.normal, fv.ld, i, normal);
-          proceed = st == MB_UNPROCESSED;
+          uint8_t rs = MB_UNPROCESSED;
+          d3 mean = mk3(0, 0, 0), normal = mk3(0, 0, 0);
+          if (found != k) {
+            rs = MB_INSUFFICIENT_CORRES_POINTS;
+            if (fv.knn_idx)
+              for (int j = 0; j < k; ++j) fv.knn_idx[gi * k + j] = ~0ull;
+          } else if (dk > fv.max_corr_sq) {
+            rs = MB_CORRES_MAX_DIST;
+          } else {
+            bool normal_set;
+            rs = fit_plane<K>(nb, k, T, fv.pvd, mean, normal, normal_set);
+            st3(fv.mean, fv.ld, gi, mean);
+            if (normal_set) st3(fv.normal, fv.ld, gi, normal);
+          }
+          s_status[li] = rs;  // a fitted plane itself reaches its owner through fv.mean / fv.normal (same block, barrier below)
         }
       }
-      __syncwarp();  // the stacks become s_row below; the pool may be refilled by the next tile
-    }
-    if (act && !need && st > MB_CORRES_PLANE_INVALID) {
-      mean = ld3(fv.mean, fv.ld, i);
-      normal = ld3(fv.normal, fv.ld, i);
-      proceed = true;
-    }
-
-    // ---- C: residual, Jacobian, accumulation -------------------------------------------------------------------
+    __syncthreads();
+    // ---- C: residual, Jacobian, accumulation (own point) --------------------------------------------
     double row[7] = {0, 0, 0, 0, 0, 0, 0};
     if (fv.fold_loc) {
       double v[6] = {0, 0, 0, 0, 0, 0};
-      if (act && st_prev == MB_VALID) {
+      if (act && st == MB_VALID) {  // st is still the status the previous linearisation left
         const d3 lt = ld3(fv.loc_trans, fv.ld, i), lr = ld3(fv.loc_rot, fv.ld, i);
 #pragma unroll
         for (int a = 0; a < 3; ++a) {  // column a of V: (V^T loc)_a, in mul33Tv's order of operations
@@ -572,7 +588,7 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
           v[3 + a] = rc >= 0.5 ? rc : 0.0;
         }
       }
-      if (__ballot_sync(kFull, act && st_prev == MB_VALID)) {
+      if (__ballot_sync(kFull, act && st == MB_VALID)) {
 #pragma unroll
         for (int a = 0; a < 6; ++a) s_row[lane][a] = v[a];
         __syncwarp();
@@ -584,9 +600,24 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
       }
     }
     if (act) {
+      bool proceed = false;
+      d3 mean = mk3(0, 0, 0), normal = mk3(0, 0, 0);
+      if (need) {
+        st3(fv.p_da, fv.ld, i, pt);
+        st = s_status[tid];
+        if (st == MB_UNPROCESSED) {
+          mean = ld3(fv.mean, fv.ld, i);
+          normal = ld3(fv.normal, fv.ld, i);
+          proceed = true;
+        }
+      } else if (st > MB_CORRES_PLANE_INVALID) {
+        mean = ld3(fv.mean, fv.ld, i);
+        normal = ld3(fv.normal, fv.ld, i);
+        proceed = true;
+      }
       if (proceed) {
         double e = dot3(normal, sub3(mean, pt));
-        const double s_chk = 1 - 0.9 * fabs(e) / sqrt(sqrt(sqnorm3(ps)));
+        const double s_chk = 1 - 0.9 * fabs(e) / fv.rroot[i];
         if (s_chk < 0.9) {
           st = MB_MAX_ERROR;
         } else {
@@ -612,7 +643,7 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
           st = MB_VALID;
         }
       }
-      if (st != st_prev) fv.status[i] = st;
+      fv.status[i] = st;
     }
     // [J e]^T [J e] over the warp's 32 points: lane a sums its entry over the rows in point order.
     const unsigned any_valid = __ballot_sync(kFull, act && st == MB_VALID);
@@ -622,18 +653,17 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
       __syncwarp();
 #pragma unroll 8
       for (int p = 0; p < 32; ++p) acc += s_row[p][pr] * s_row[p][pc];
-      __syncwarp();
     }
 #pragma unroll
     for (int s = 0; s < 9; ++s) {
       const int c = __popc(__ballot_sync(kFull, act && st == s));
       if (lane == s) cnt += c;
     }
-    if (lane == 9) cnt += __popc(need_mask);
+    if (lane == 9) cnt += __popc(mask);
+    __syncthreads();  // s_row (= s_pk), s_queue, s_status ... are rewritten by the next tile
   }
 
   // ---- block partial -> group partial -> packet (two ticketed levels, fixed order) ------------------------
-  MB_LT_MAX(2);
   if (lane < 28) s_red[warp][lane] = acc;
   if (lane >= 30) s_red[warp][lane + 8] = s_red[warp][lane + 16] = 0.0;  // pad entries 38, 39, 46, 47
   if (lane < 10) s_red[warp][kPackCnt + lane] = (double)cnt;
@@ -657,22 +687,18 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
   block_sum_rows(fv.partials + (size_t)g * kGroup * kPack, g_size, kPack, s_tmp, fv.gpartials + (size_t)g * kPack,
                  kLinThreads);
   if (tid == 0) fv.gtickets[g] = 0u;
-  MB_LT_MAX(3);
   __threadfence();
   __syncthreads();
   if (tid == 0) s_last = atomicAdd(fv.ticket, 1u) == (unsigned)n_groups - 1;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  MB_LT_SET(4);
   block_sum_rows(fv.gpartials, n_groups, kPack, s_tmp, fv.packed, kLinThreads);
   if (tid == 0) *fv.ticket = 0u;
-  __syncthreads();  // the packet written by this block's first kPack threads is visible to all of them
-  MB_LT_SET(5);
-  const double* packed = fv.packed;
   if (peer) {
     // Several ranks: this rank's packet goes straight into every rank's mailbox (peer stores over NVLink),
-    // then the flags are raised — the finalize roles on each rank sum their mailbox in rank order (mb_internal.cuh).
+    // then the flags are raised — k_finalize on each rank sums the mailbox in rank order (mb_internal.cuh).
+    __syncthreads();  // the packet written by this block's first kPack threads is visible to all of them
     const int world = peer->world, rank = peer->rank;
     const unsigned long long seq = *peer->xseq + 1ull;
     const size_t slot = (size_t)((seq & 1ull) * kMaxRanks + (unsigned)rank);
@@ -683,26 +709,355 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
     __threadfence_system();
     __syncthreads();
     if (tid < world) st_release_sys(peer->flag[tid] + slot, seq);
-    if (!fa.fuse) return;
-    peer_gather(peer, s_packed, fv.packed);
-    __syncthreads();
-    packed = s_packed;
   }
-  if (!fa.fuse) return;
-  // the finalize roles: the solve / retract chain alone on warp 0, the four eigen-decompositions on the other warps
-  if (lane == 0) {
-    if (warp == 0) {
-      finalize_role(packed, ds, fa, 4);
-    } else if (warp == 1) {
-      finalize_role(packed, ds, fa, 0);
-      finalize_role(packed, ds, fa, 1);
+}
+
+// One linearisation, three phases separated by grid-wide barriers (every block is resident: the grid never exceeds
+// what the device holds, and the launch is cooperative):
+//   P1  every warp walks its tiles of 32 consecutive points of the voxel-sorted scan: transform + data-association
+//       gate (:276-287).  Points that keep their association finish here — residual, s-check, Huber, Jacobian,
+//       localizability vectors (:319-355), their share of [J e]^T [J e] (:364-366).  Points that must re-associate
+//       are appended to a queue (one reservation per warp).
+//   P2  (only when the queue is not empty) the queue is worked off in passes of 32 points which the warps PULL from a
+//       counter: the voxel-grouped restricted k-NN (mb_search_group.cuh), the two distance gates (:296-302) and the
+//       plane fit (:176-229); results go to the points' state.  Pulling balances the passes, whose cost varies 3x with
+//       the number of voxel groups (measured: 31 us for one group, 57-68 us for five to sixteen, at full occupancy),
+//       and compacting makes an iteration that re-associates 13 % of the points cost 13 % of a full search instead of
+//       all of it.  Which warp serves which point is not deterministic; what it writes for the point is.
+//   P3  the warps revisit their tiles and finish the re-associated points like P1 (same order every run).
+// Then block partial -> group partial -> packet (two ticketed levels, fixed order: bitwise repeatable); the last block
+// hands the packet to the other ranks' mailboxes.  k_finalize follows.
+struct LoopCtl {        // device-side control words of a factor's k_linearize launches
+  unsigned bar_count;   // grid barrier: arrivals
+  unsigned bar_gen;     //               generation
+  unsigned q_count;     // points queued for re-association in this launch
+  unsigned q_pass;      // next pass of 32 queue entries
+};
+
+__device__ __forceinline__ void grid_barrier(LoopCtl* ctl, unsigned n_blocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned g = ld_acquire_gpu(&ctl->bar_gen);
+    __threadfence();
+    if (atomicAdd(&ctl->bar_count, 1u) == n_blocks - 1u) {
+      ctl->bar_count = 0u;
+      __threadfence();
+      st_release_gpu(&ctl->bar_gen, g + 1u);
     } else {
-      finalize_role(packed, ds, fa, warp);
+      while (ld_acquire_gpu(&ctl->bar_gen) == g) {
+      }
     }
   }
+  __syncthreads();
+}
+
+template <int K, typename PoseT, int ROWS>
+__global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
+    k_linearize(MapView mv, FactorView fv, DevState* ds, PoseT pa, const PeerTable* __restrict__ peer, FinArgs fa,
+                int pool_buckets) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  __shared__ uint16_t s_rank[32];
+  __shared__ double s_red[kLinWarps][kPack];
+  __shared__ double s_tmp[(kLinThreads / kPack) * kPack];
+  __shared__ double s_V[18];
+  __shared__ bool s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* pose_dev = ds->pose;
+  LoopCtl* const ctl = fv.ctl;
 #if defined(MB_LIN_TIMING)
-  if (lane == 0) atomicMax(&g_lin_t[fa.linearize_count & 63][6 + (warp == 0 ? 0 : 1)], gtime());
+  if (blockIdx.x == 0 && tid == 0) {
+    g_lin_t[fa.linearize_count & 63][0] = gtime();
+    for (int a = 2; a < 8; ++a) g_lin_t[fa.linearize_count & 63][a] = 0ull;
+  }
 #endif
+  GroupScratch<ROWS>& S = *reinterpret_cast<GroupScratch<ROWS>*>(s_dyn + (size_t)warp * lin_warp_bytes<ROWS>(pool_buckets, mv.cap));
+  float4* const pool = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(&S) + ((sizeof(GroupScratch<ROWS>) + 15) / 16) * 16);
+  // the whitened [J (6), e] rows of the warp's 32 points share the candidate stacks' memory (P2 vs P1 / P3)
+  double(*s_row)[7] = reinterpret_cast<double(*)[7]>(S.stack);
+  static_assert(sizeof(S.stack) >= sizeof(double) * 7 * 32, "s_row fits");
+  if (tid < 32) s_rank[tid] = 0xffffu;
+  __syncthreads();
+  if (tid < kCube && mv.rank[tid] != 0xffu) s_rank[mv.rank[tid]] = rank_entry(tid);
+  if (lane == 0) mbar_init(&S.mbar, 1);
+  uint32_t mbar_parity = 0u;
+  // Lane a < 28 owns entry a of the packed upper triangle of [J e]^T [J e] (7x7): the 21 entries of
+  // J^T J first (row-major, c >= r), then J^T e (6), then e^2.
+  const int pr = kTriRow[lane], pc = kTriCol[lane];
+
+  // everything above is independent of earlier kernels; from here on we read the pose the previous linearisation
+  // left and overwrite per-point state the previous k_loc_comp may still be reading
+  pdl_wait();
+  if (blockIdx.x == 0) MB_LT_SET(1);
+  m33 R;
+  d3 T;
+  if constexpr (std::is_same<PoseT, PoseArg>::value) {
+    if (blockIdx.x == 0 && tid < 16) pose_dev[tid] = pa.v[tid];  // k_finalize reads pose / gravity / lambda there
+#pragma unroll
+    for (int a = 0; a < 9; ++a) R.m[a] = pa.v[a];
+    T = mk3(pa.v[9], pa.v[10], pa.v[11]);
+  } else {
+#pragma unroll
+    for (int a = 0; a < 9; ++a) R.m[a] = pose_dev[a];
+    T = mk3(pose_dev[9], pose_dev[10], pose_dev[11]);
+  }
+  const int k = fv.k;
+  const bool forced = (fv.flags & 1u) != 0;
+  const double inv_sigma = 1.0 / fv.sigma;  // = sqrt_w / sigma for the points Huber leaves alone (sqrt_w == 1)
+
+  double acc = 0.0, lacc = 0.0;  // lacc: lane a < 6 sums component a of the previous linearisation's localizability pass
+  int cnt = 0;  // lane s < 9: points with status s; lane 9: points searched
+  // Folded localizability pass (device-resident loop): before a point's status and localizability vectors are
+  // overwritten, its contribution |loc^T V| (entries below 0.5 dropped, geometric_factor.hpp:434-457) to the
+  // component localizabilities of the PREVIOUS linearisation is taken with that linearisation's eigenvectors, which
+  // the previous k_finalize left in ds->lin.  It saves a pass over the points and a kernel launch per iteration.
+  if (fv.fold_loc && tid < 18) s_V[tid] = tid < 9 ? ds->lin.eigvec_trans[tid] : ds->lin.eigvec_rot[tid - 9];
+  __syncthreads();
+
+  // Residual, s-check, Huber, Jacobian, localizability vectors of point i on plane (mean, normal); accumulates the
+  // warp's rows.  `go`: this lane takes part; st: in = the plane's status (Unprocessed after a fresh fit), out = final.
+  auto finish_points = [&](size_t i, bool go, d3 ps, d3 pt, d3 mean, d3 normal, uint8_t& st) {
+    double row[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (go) {
+      double e = dot3(normal, sub3(mean, pt));
+      const double s_chk = 1 - 0.9 * fabs(e) / fv.rroot[i];
+      if (s_chk < 0.9) {
+        st = MB_MAX_ERROR;
+      } else {
+        double sqrt_w = 1.0;
+        if (fv.use_huber) {
+          const double we = e / fv.sigma;
+          if (fabs(we) > fv.kh) sqrt_w = sqrt(fv.kh / fabs(we));
+        }
+        const double scale = sqrt_w == 1.0 ? inv_sigma : sqrt_w / fv.sigma;
+        e *= scale;
+        const d3 ns = mul33Tv(R, normal);
+        const d3 jr = cross3(ns, ps);
+        const double z = sqnorm3(jr);
+        st3(fv.loc_rot, fv.ld, i, z > 0 ? div3(jr, sqrt(z)) : jr);
+        st3(fv.loc_trans, fv.ld, i, mk3(-ns.x, -ns.y, -ns.z));
+        row[0] = jr.x * scale;
+        row[1] = jr.y * scale;
+        row[2] = jr.z * scale;
+        row[3] = -ns.x * scale;
+        row[4] = -ns.y * scale;
+        row[5] = -ns.z * scale;
+        row[6] = e;
+        st = MB_VALID;
+      }
+    }
+    // [J e]^T [J e] over the warp's points: lane a sums its entry over the rows in point order.
+    if (__ballot_sync(kFull, go && st == MB_VALID)) {
+#pragma unroll
+      for (int a = 0; a < 7; ++a) s_row[lane][a] = row[a];
+      __syncwarp();
+#pragma unroll 8
+      for (int p = 0; p < 32; ++p) acc += s_row[p][pr] * s_row[p][pc];
+      __syncwarp();
+    }
+  };
+
+  const size_t n_tiles = (fv.n + 31) / 32;
+  const size_t n_warps = (size_t)gridDim.x * kLinWarps;
+  const size_t first_tile = (size_t)blockIdx.x * kLinWarps + warp;
+  // ================================ P1: gate, cached points, queue =====================================
+  for (size_t tile = first_tile; tile < n_tiles; tile += n_warps) {
+    const size_t i = tile * 32 + lane;
+    const bool act = i < fv.n;
+    d3 ps = mk3(0, 0, 0), pt = mk3(0, 0, 0);
+    uint8_t st = MB_UNPROCESSED;
+    bool need = false;
+    if (act) {
+      const float4 s = __ldg(fv.src + i);
+      ps = mk3((double)s.x, (double)s.y, (double)s.z);
+      pt = add3(mul33v(R, ps), T);
+      st = fv.status[i];
+      const d3 da = ld3(fv.p_da, fv.ld, i);
+      need = forced || sqnorm3(sub3(pt, da)) >= fv.da_gate_sq;  // == sqrt(d2) > gate (:281-283), without the square root
+    }
+    const uint8_t st_prev = st;  // the status the previous linearisation left (folded localizability pass)
+    const unsigned need_mask = __ballot_sync(kFull, need);
+    if (lane == 0) fv.need_mask[tile] = need_mask;
+    if (need_mask) {
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(&ctl->q_count, (unsigned)__popc(need_mask));
+      base = __shfl_sync(kFull, base, 0);
+      if (need) fv.queue[base + __popc(need_mask & ((1u << lane) - 1u))] = (uint32_t)i;
+    }
+    if (fv.fold_loc) {
+      double v[6] = {0, 0, 0, 0, 0, 0};
+      if (act && st_prev == MB_VALID) {
+        const d3 lt = ld3(fv.loc_trans, fv.ld, i), lr = ld3(fv.loc_rot, fv.ld, i);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {  // column a of V: (V^T loc)_a, in mul33Tv's order of operations
+          const double tc = fabs(s_V[a] * lt.x + (s_V[3 + a] * lt.y + s_V[6 + a] * lt.z));
+          const double rc = fabs(s_V[9 + a] * lr.x + (s_V[12 + a] * lr.y + s_V[15 + a] * lr.z));
+          v[a] = tc >= 0.5 ? tc : 0.0;
+          v[3 + a] = rc >= 0.5 ? rc : 0.0;
+        }
+      }
+      if (__ballot_sync(kFull, act && st_prev == MB_VALID)) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) s_row[lane][a] = v[a];
+        __syncwarp();
+        if (lane < 6) {
+#pragma unroll 8
+          for (int p = 0; p < 32; ++p) lacc += s_row[p][lane];
+        }
+        __syncwarp();
+      }
+    }
+    // points that keep their association: skipped for good when the cached plane was rejected (:314-316)
+    const bool go = act && !need && st > MB_CORRES_PLANE_INVALID;
+    d3 mean = mk3(0, 0, 0), normal = mk3(0, 0, 0);
+    if (go) {
+      mean = ld3(fv.mean, fv.ld, i);
+      normal = ld3(fv.normal, fv.ld, i);
+    }
+    finish_points(i, go, ps, pt, mean, normal, st);
+    if (go && st != st_prev) fv.status[i] = st;
+#pragma unroll
+    for (int s = 0; s < 9; ++s) {
+      const int c = __popc(__ballot_sync(kFull, act && !need && st == s));
+      if (lane == s) cnt += c;
+    }
+    if (lane == 9) cnt += __popc(need_mask);
+  }
+  MB_LT_MAX(2);
+  grid_barrier(ctl, gridDim.x);
+  pdl_launch_dependents();  // from here on every block of this grid is known to be resident
+  const unsigned q_count = ld_acquire_gpu(&ctl->q_count);
+  if (q_count) {
+    // ================================ P2: search passes, pulled =========================================
+    for (;;) {
+      unsigned pass = 0;
+      if (lane == 0) pass = atomicAdd(&ctl->q_pass, 1u);
+      pass = __shfl_sync(kFull, pass, 0);
+      if ((size_t)pass * 32 >= q_count) break;
+      const unsigned e = pass * 32 + lane;
+      const bool on = e < q_count;
+      const size_t i = on ? (size_t)__ldcg(fv.queue + e) : 0;
+      const float4 s = __ldg(fv.src + i);
+      const d3 ps = mk3((double)s.x, (double)s.y, (double)s.z);
+      const d3 pt = add3(mul33v(R, ps), T);
+      double bd[K];
+      uint32_t bs[K];
+      const GroupLane gl = knn_warp_groups<K, ROWS>(mv, s_rank, S, pool, pool_buckets, mbar_parity, pt.x, pt.y, pt.z, k, on, bd, bs);
+      if (on) {
+        float4 nb[K];
+        uint64_t g[K];
+        const int found = group_resolve_all<K, ROWS>(mv, S, pool, gl, bs, k, g, nb);
+        double dk = 0.0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          if (j < k) {
+            if (j == k - 1) dk = bd[j];
+            // indices are only meaningful when all k exist (the reference discards partial results)
+            if (fv.knn_idx) fv.knn_idx[i * k + j] = found == k ? g[j] : ~0ull;
+          }
+        }
+        st3(fv.p_da, fv.ld, i, pt);
+        uint8_t st = MB_UNPROCESSED;  // :290
+        if (found != k) {
+          st = MB_INSUFFICIENT_CORRES_POINTS;
+        } else if (dk > fv.max_corr_sq) {
+          st = MB_CORRES_MAX_DIST;
+        } else {
+          bool normal_set;
+          d3 mean, normal;
+          st = fit_plane<K>(nb, k, T, fv.pvd, mean, normal, normal_set);
+          st3(fv.mean, fv.ld, i, mean);
+          if (normal_set) st3(fv.normal, fv.ld, i, normal);
+        }
+        fv.status[i] = st;  // Unprocessed = the plane stands: P3 takes the residual
+      }
+      __syncwarp();  // the group tables and the pool are rewritten by the next pass
+    }
+    MB_LT_MAX(3);
+    grid_barrier(ctl, gridDim.x);
+    // ================================ P3: the re-associated points =====================================
+    for (size_t tile = first_tile; tile < n_tiles; tile += n_warps) {
+      const unsigned need_mask = fv.need_mask[tile];
+      if (need_mask == 0u) continue;
+      const size_t i = tile * 32 + lane;
+      const bool need = (need_mask >> lane) & 1u;
+      d3 ps = mk3(0, 0, 0), pt = mk3(0, 0, 0), mean = mk3(0, 0, 0), normal = mk3(0, 0, 0);
+      uint8_t st = MB_UNPROCESSED;
+      bool go = false;
+      if (need) {
+        st = __ldcg(fv.status + i);
+        go = st == MB_UNPROCESSED;
+        if (go) {
+          const float4 s = __ldg(fv.src + i);
+          ps = mk3((double)s.x, (double)s.y, (double)s.z);
+          pt = add3(mul33v(R, ps), T);
+          mean = mk3(__ldcg(fv.mean + i), __ldcg(fv.mean + fv.ld + i), __ldcg(fv.mean + 2 * fv.ld + i));
+          normal = mk3(__ldcg(fv.normal + i), __ldcg(fv.normal + fv.ld + i), __ldcg(fv.normal + 2 * fv.ld + i));
+        }
+      }
+      finish_points(i, go, ps, pt, mean, normal, st);
+      if (go) fv.status[i] = st;
+#pragma unroll
+      for (int s = 0; s < 9; ++s) {
+        const int c = __popc(__ballot_sync(kFull, need && st == s));
+        if (lane == s) cnt += c;
+      }
+    }
+  }
+
+  // ---- block partial -> group partial -> packet (two ticketed levels, fixed order) ------------------------
+  MB_LT_MAX(4);
+  if (lane < 28) s_red[warp][lane] = acc;
+  if (lane >= 30) s_red[warp][lane + 8] = s_red[warp][lane + 16] = 0.0;  // pad entries 38, 39, 46, 47
+  if (lane < 10) s_red[warp][kPackCnt + lane] = (double)cnt;
+  if (lane < 6) s_red[warp][kPackLoc + lane] = lacc;
+  __syncthreads();
+  if (tid < kPack) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kLinWarps; ++w) v += s_red[w][tid];
+    fv.partials[(size_t)blockIdx.x * kPack + tid] = v;
+  }
+  const int g = blockIdx.x / kGroup;
+  const int n_groups = (gridDim.x + kGroup - 1) / kGroup;
+  const int g_size = min(kGroup, (int)gridDim.x - g * kGroup);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(fv.gtickets + g, 1u) == (unsigned)g_size - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  block_sum_rows(fv.partials + (size_t)g * kGroup * kPack, g_size, kPack, s_tmp, fv.gpartials + (size_t)g * kPack,
+                 kLinThreads);
+  if (tid == 0) fv.gtickets[g] = 0u;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(fv.ticket, 1u) == (unsigned)n_groups - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  MB_LT_SET(5);
+  block_sum_rows(fv.gpartials, n_groups, kPack, s_tmp, fv.packed, kLinThreads);
+  if (tid == 0) {
+    *fv.ticket = 0u;
+    ctl->q_count = 0u;  // every block has left P2 / P3: ready for the next launch
+    ctl->q_pass = 0u;
+  }
+  MB_LT_SET(6);
+  if (peer) {
+    // Several ranks: this rank's packet goes straight into every rank's mailbox (peer stores over NVLink),
+    // then the flags are raised — k_finalize on each rank sums its mailbox in rank order (mb_internal.cuh).
+    __syncthreads();  // the packet written by this block's first kPack threads is visible to all of them
+    const int world = peer->world, rank = peer->rank;
+    const unsigned long long seq = *peer->xseq + 1ull;
+    const size_t slot = (size_t)((seq & 1ull) * kMaxRanks + (unsigned)rank);
+    for (int x = tid; x < world * kPack; x += kLinThreads) {
+      const int dst = x / kPack, e = x - dst * kPack;
+      peer->mbox[dst][slot * kXchgDoubles + e] = fv.packed[e];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < world) st_release_sys(peer->flag[tid] + slot, seq);
+  }
 }
 
 // Component localizabilities (geometric_factor.hpp:434-457): sum over Valid points of |loc_i^T V| with
@@ -808,24 +1163,39 @@ __global__ void k_pack_src(const unsigned char* __restrict__ data, size_t stride
 
 // ---- voxel order of the scan --------------------------------------------------------------------------------
 // k_linearize wants the 32 points of a warp in as few map voxels as possible (mb_search_group.cuh).  Before a
-// factor's FIRST linearisation its points are sorted by the Morton code of the map voxel they fall into under that
-// call's pose (10 bits per axis around the sensor's voxel; farther points clamp, which only costs grouping); later
-// poses differ by centimetres, so the order stays good.  All per-point state lives in sorted order; `perm` (sorted
-// position -> index in the caller's scan) brings it back to reference order in mb_factor_download_state
-// (geometric_factor.hpp:79-84: the reference's arrays are indexed like the source cloud).
-__device__ __forceinline__ uint32_t spread10(uint32_t v) {  // 10 bits -> every third bit
-  v &= 0x3ffu;
-  v = (v | (v << 16)) & 0x030000ffu;
-  v = (v | (v << 8)) & 0x0300f00fu;
-  v = (v | (v << 4)) & 0x030c30c3u;
-  v = (v | (v << 2)) & 0x09249249u;
-  return v;
-}
-template <typename PoseT>
-__global__ void k_sort_keys(const float4* __restrict__ src_raw, size_t n, const DevState* __restrict__ ds, PoseT pa,
-                            double inv_leaf, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+// factor's FIRST linearisation (and after a reset) its points are grouped by the map voxel they fall into under that
+// call's pose; later poses differ by centimetres, so the grouping stays good.  Grouping, not ordering, is what
+// matters, and LiDAR scans arrive spatially coherent (consecutive records are neighbouring beams), so this is a
+// STABLE COUNTING SORT INSIDE CHUNKS of 4096 consecutive points on an 11-bit hash of the voxel coordinates: one
+// kernel, one block per chunk, no global passes (the benchmark scan: 2.1 voxels per warp against 1.9 for a global
+// sort and 11.8 unsorted; a 63-bit radix sort of the scan costs 130 us on a B200, this kernel a few).  Voxels whose
+// hashes collide merely interleave.  All per-point state lives in sorted order; `perm` (sorted position -> index in
+// the caller's scan) brings it back to reference order in mb_factor_download_state (geometric_factor.hpp:79-84: the
+// reference's arrays are indexed like the source cloud).  The result is a deterministic function of scan and pose.
+// development (MB_LIN_SORT=0): the caller's order, for A/B measurements of what the voxel order buys
+__global__ void k_copy_src(const float4* __restrict__ src_raw, size_t n, float4* __restrict__ src, double* __restrict__ rroot) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const float4 p = src_raw[i];
+  src[i] = p;
+  rroot[i] = sqrt(sqrt(sqnorm3(mk3((double)p.x, (double)p.y, (double)p.z))));
+}
+
+constexpr int kGsThreads = 1024, kGsWarps = kGsThreads / 32;
+constexpr int kGsRows = 4;                          // rows of 32 points per warp
+constexpr int kGsChunk = kGsThreads * kGsRows;      // points per block
+constexpr int kGsBins = 2048;
+constexpr size_t kGsSmem = (size_t)kGsWarps * kGsBins * sizeof(uint16_t) + kGsBins * sizeof(uint32_t) + 64 * sizeof(uint32_t);
+template <typename PoseT>
+__global__ void __launch_bounds__(kGsThreads, 1)
+    k_group_sort(const float4* __restrict__ src_raw, size_t n, const DevState* __restrict__ ds, PoseT pa, double inv_leaf,
+                 float4* __restrict__ src, uint32_t* __restrict__ perm, double* __restrict__ rroot) {
+  extern __shared__ __align__(16) unsigned char s_gs[];
+  uint16_t* hist = reinterpret_cast<uint16_t*>(s_gs);                                   // [warp][bin]
+  uint32_t* total = reinterpret_cast<uint32_t*>(s_gs + (size_t)kGsWarps * kGsBins * 2);  // [bin], then the exclusive scan
+  uint32_t* wsum = total + kGsBins;                                                     // [32] scan scratch
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int x = tid; x < kGsWarps * kGsBins / 2; x += kGsThreads) reinterpret_cast<uint32_t*>(hist)[x] = 0u;
   m33 R;
   d3 T;
   if constexpr (std::is_same<PoseT, PoseArg>::value) {
@@ -837,26 +1207,95 @@ __global__ void k_sort_keys(const float4* __restrict__ src_raw, size_t n, const 
     for (int a = 0; a < 9; ++a) R.m[a] = ds->pose[a];
     T = mk3(ds->pose[9], ds->pose[10], ds->pose[11]);
   }
-  const float4 s = src_raw[i];
-  const d3 pt = add3(mul33v(R, mk3((double)s.x, (double)s.y, (double)s.z)), T);
-  const int vx = fast_floor(pt.x * inv_leaf) - fast_floor(T.x * inv_leaf) + 512;
-  const int vy = fast_floor(pt.y * inv_leaf) - fast_floor(T.y * inv_leaf) + 512;
-  const int vz = fast_floor(pt.z * inv_leaf) - fast_floor(T.z * inv_leaf) + 512;
-  const uint32_t cx = (uint32_t)min(max(vx, 0), 1023), cy = (uint32_t)min(max(vy, 0), 1023), cz = (uint32_t)min(max(vz, 0), 1023);
-  keys[i] = spread10(cx) | (spread10(cy) << 1) | (spread10(cz) << 2);
-  vals[i] = (uint32_t)i;
+  __syncthreads();
+  const size_t chunk0 = (size_t)blockIdx.x * kGsChunk;
+  uint16_t* const my_hist = hist + (size_t)warp * kGsBins;
+  // 1. keys and the rank of every point among the earlier points of its warp with the same key
+  float4 pt[kGsRows];
+  uint32_t key[kGsRows], rank[kGsRows];
+#pragma unroll
+  for (int r = 0; r < kGsRows; ++r) {
+    const size_t i = chunk0 + (size_t)warp * (32 * kGsRows) + r * 32 + lane;
+    const bool on = i < n;
+    pt[r] = on ? src_raw[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const d3 w = add3(mul33v(R, mk3((double)pt[r].x, (double)pt[r].y, (double)pt[r].z)), T);
+    key[r] = on ? (hash_coord(fast_floor(w.x * inv_leaf), fast_floor(w.y * inv_leaf), fast_floor(w.z * inv_leaf)) & (kGsBins - 1)) : 0xffffffffu;
+    const unsigned peers = __match_any_sync(kFull, key[r]);
+    const int leader = __ffs(peers) - 1;
+    uint32_t before = 0u;
+    if (on && lane == leader) {
+      before = my_hist[key[r]];
+      my_hist[key[r]] = (uint16_t)(before + (uint32_t)__popc(peers));
+    }
+    rank[r] = __shfl_sync(kFull, before, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+    __syncwarp();
+  }
+  __syncthreads();
+  // 2. per bin: exclusive prefix over the warps, total
+  for (int b = tid; b < kGsBins; b += kGsThreads) {
+    uint32_t run = 0u;
+#pragma unroll 8
+    for (int w = 0; w < kGsWarps; ++w) {
+      const uint32_t c = hist[(size_t)w * kGsBins + b];
+      hist[(size_t)w * kGsBins + b] = (uint16_t)run;
+      run += c;
+    }
+    total[b] = run;
+  }
+  __syncthreads();
+  // 3. exclusive scan of the totals (two bins per thread)
+  {
+    const uint32_t a0 = total[2 * tid], a1 = total[2 * tid + 1];
+    uint32_t v = a0 + a1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(kFull, v, o);
+      if (lane >= o) v += u;
+    }
+    if (lane == 31) wsum[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t x = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(kFull, x, o);
+        if (lane >= o) x += u;
+      }
+      wsum[lane] = x - wsum[lane];  // exclusive
+    }
+    __syncthreads();
+    const uint32_t excl = wsum[warp] + v - (a0 + a1);
+    total[2 * tid] = excl;
+    total[2 * tid + 1] = excl + a0;
+  }
+  __syncthreads();
+  // 4. scatter
+#pragma unroll
+  for (int r = 0; r < kGsRows; ++r) {
+    const size_t i = chunk0 + (size_t)warp * (32 * kGsRows) + r * 32 + lane;
+    if (i < n) {
+      const size_t pos = chunk0 + total[key[r]] + my_hist[key[r]] + rank[r];
+      src[pos] = pt[r];
+      perm[pos] = (uint32_t)i;
+      rroot[pos] = sqrt(sqrt(sqnorm3(mk3((double)pt[r].x, (double)pt[r].y, (double)pt[r].z))));
+    }
+  }
 }
-__global__ void k_apply_perm(const float4* __restrict__ src_raw, const uint32_t* __restrict__ perm, size_t n,
-                             float4* __restrict__ src) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) src[i] = src_raw[perm[i]];
-}
-constexpr int kSortBits = 30;
 
 }  // namespace
 }  // namespace mb
 
 using namespace mb;
+
+// The reference gates on sqrt(d2) > g (geometric_factor.hpp:281-283).  sqrt is monotone and correctly rounded on both
+// sides, so there is a smallest double d2* with sqrt(d2*) > g and the test equals d2 >= d2*: found here once.
+static double da_gate_sq_min(double g) {
+  if (!(g >= 0.0)) return 0.0;  // sqrt(x) >= 0 > g for every x >= 0 (a NaN gate never fires either way: d2 >= NaN is false)
+  double x = g * g;
+  while (x > 0.0 && std::sqrt(x) > g) x = std::nextafter(x, 0.0);
+  while (!(std::sqrt(x) > g)) x = std::nextafter(x, INFINITY);
+  return x;
+}
 
 struct mb_factor {
   mb_ctx* ctx = nullptr;
@@ -881,14 +1320,19 @@ struct mb_factor {
   int grid = 0, grid2 = 0, n_groups = 0;
   // k_linearize launch shape: kernel variant (k == 5 and <= 19 neighbour voxels, or generic), staging pool per warp
   bool lin_small = true;
+  bool use_v1 = false;  // development (MB_LIN_KERNEL=v1): the round-1 kernel
   int pool_buckets = 0;
   size_t lin_smem = 0;
-  // voxel order (see k_sort_keys): the caller's points, the sort's buffers, sorted position -> caller's index
+  // voxel order (see k_group_sort): the caller's points, sorted position -> caller's index
   float4* src_raw = nullptr;
-  uint32_t *sort_keys = nullptr, *sort_keys_out = nullptr, *sort_vals = nullptr, *perm = nullptr;
-  void* sort_temp = nullptr;
-  size_t sort_temp_bytes = 0;
+  uint32_t* perm = nullptr;
+  double* rroot = nullptr;  // sqrt(||p||) per sorted point
+  LoopCtl* ctl = nullptr;       // k_linearize's barrier / queue control words
+  uint32_t* queue = nullptr;    // re-association queue
+  uint32_t* need_mask = nullptr;
   bool sorted = false;
+  void* raw = nullptr;  // the caller's records on the device while a factor is being built from page-locked memory
+  size_t raw_bytes = 0;
   int linearize_count = 0;
   uint32_t flags = 0;
   // cached CUDA graph of an mb_icp_run sequence
@@ -912,7 +1356,11 @@ struct mb_factor {
     v.flags = flags;
     v.fold_loc = 0;
     const float da_gate_f = cfg.target_ivox_map_min_dist_in_voxel / 4;          // geometric_factor.hpp:283
-    v.da_gate = (double)da_gate_f;
+    v.da_gate_sq = da_gate_sq_min((double)da_gate_f);
+    v.rroot = rroot;
+    v.ctl = ctl;
+    v.queue = queue;
+    v.need_mask = need_mask;
     const float max_corr_f = cfg.max_corres_distance * cfg.max_corres_distance;  // :299
     v.max_corr_sq = (double)max_corr_f;
     v.sigma = (double)cfg.lidar_point_noise_std_dev;
@@ -961,36 +1409,50 @@ int lin_opt_in_all(const mb_factor* f) {
   return MB_OK;
 }
 
+// k_linearize's launch: cooperative (its grid barriers need every block resident) and programmatically serialised
+// behind its predecessor like the other kernels of an iteration.
 template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl_smem(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+cudaError_t launch_lin(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[1].id = cudaLaunchAttributeCooperative;
+  attr[1].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
-// Before the first linearisation: bring the scan into voxel order under that call's pose (k_sort_keys).
+// Before the first linearisation: group the scan by map voxel under that call's pose (k_group_sort).
 int enqueue_sort(mb_factor* f, const PoseArg* pose_arg) {
   if (f->n == 0) return MB_OK;
   mb_ctx* c = f->ctx;
   cudaStream_t st = c->stream;
-  const unsigned blocks = (unsigned)((f->n + 255) / 256);
+  if (const char* e = getenv("MB_LIN_SORT")) {
+    if (atoi(e) == 0) {
+      k_copy_src<<<(unsigned)((f->n + 255) / 256), 256, 0, st>>>(f->src_raw, f->n, f->src, f->rroot);
+      ++c->launches;
+      f->sorted = false;
+      return MB_OK;
+    }
+  }
+  static bool opted_in = false;
+  if (!opted_in) {
+    MB_CUDA(cudaFuncSetAttribute(k_group_sort<PoseArg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGsSmem));
+    MB_CUDA(cudaFuncSetAttribute(k_group_sort<NoPose>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGsSmem));
+    opted_in = true;
+  }
+  const unsigned blocks = (unsigned)((f->n + kGsChunk - 1) / kGsChunk);
   if (pose_arg)
-    k_sort_keys<PoseArg><<<blocks, 256, 0, st>>>(f->src_raw, f->n, f->ds, *pose_arg, f->map->inv_leaf, f->sort_keys, f->sort_vals);
+    k_group_sort<PoseArg><<<blocks, kGsThreads, kGsSmem, st>>>(f->src_raw, f->n, f->ds, *pose_arg, f->map->inv_leaf, f->src, f->perm, f->rroot);
   else
-    k_sort_keys<NoPose><<<blocks, 256, 0, st>>>(f->src_raw, f->n, f->ds, NoPose{}, f->map->inv_leaf, f->sort_keys, f->sort_vals);
-  size_t tb = f->sort_temp_bytes;
-  MB_CUDA(cub::DeviceRadixSort::SortPairs(f->sort_temp, tb, f->sort_keys, f->sort_keys_out, f->sort_vals, f->perm, (int)f->n, 0,
-                                          kSortBits, st));
-  k_apply_perm<<<blocks, 256, 0, st>>>(f->src_raw, f->perm, f->n, f->src);
-  c->launches += 2 + 6;  // keys, gather + the radix sort's kernels (histogram, scan, four onesweep passes)
+    k_group_sort<NoPose><<<blocks, kGsThreads, kGsSmem, st>>>(f->src_raw, f->n, f->ds, NoPose{}, f->map->inv_leaf, f->src, f->perm, f->rroot);
+  ++c->launches;
   f->sorted = true;
   MB_CUDA(cudaGetLastError());
   return MB_OK;
@@ -1014,25 +1476,33 @@ int enqueue_linearize(mb_factor* f, int do_step, int iter, mb_icp_trace* d_trace
   fa.do_step = do_step;
   fa.iter = iter;
   fa.trace = d_trace;
-  fa.fuse = nccl ? 0 : 1;  // the last block of k_linearize runs the finalize roles unless NCCL sits in between
   const dim3 grid(f->grid), block(kLinThreads);
-  if (pose_arg) {
+  if (f->use_v1) {
+    if (pose_arg) {
+      if (f->lin_small)
+        MB_CUDA(launch_pdl(k_linearize_v1<5, PoseArg, 19>, grid, block, st, f->map->view(), fv, f->ds, *pose_arg, peer));
+      else
+        MB_CUDA(launch_pdl(k_linearize_v1<MB_MAX_K, PoseArg, 27>, grid, block, st, f->map->view(), fv, f->ds, *pose_arg, peer));
+    } else {
+      if (f->lin_small)
+        MB_CUDA(launch_pdl(k_linearize_v1<5, NoPose, 19>, grid, block, st, f->map->view(), fv, f->ds, NoPose{}, peer));
+      else
+        MB_CUDA(launch_pdl(k_linearize_v1<MB_MAX_K, NoPose, 27>, grid, block, st, f->map->view(), fv, f->ds, NoPose{}, peer));
+    }
+  } else if (pose_arg) {
     if (f->lin_small)  // the specialised kernel: k = 5 and at most 19 neighbour voxels
-      MB_CUDA(launch_pdl_smem(k_linearize<5, PoseArg, 19>, grid, block, f->lin_smem, st, f->map->view(), fv, f->ds, *pose_arg, peer, fa, f->pool_buckets));
+      MB_CUDA(launch_lin(k_linearize<5, PoseArg, 19>, grid, block, f->lin_smem, st, f->map->view(), fv, f->ds, *pose_arg, peer, fa, f->pool_buckets));
     else
-      MB_CUDA(launch_pdl_smem(k_linearize<MB_MAX_K, PoseArg, 27>, grid, block, f->lin_smem, st, f->map->view(), fv, f->ds, *pose_arg, peer, fa, f->pool_buckets));
+      MB_CUDA(launch_lin(k_linearize<MB_MAX_K, PoseArg, 27>, grid, block, f->lin_smem, st, f->map->view(), fv, f->ds, *pose_arg, peer, fa, f->pool_buckets));
   } else {
     if (f->lin_small)
-      MB_CUDA(launch_pdl_smem(k_linearize<5, NoPose, 19>, grid, block, f->lin_smem, st, f->map->view(), fv, f->ds, NoPose{}, peer, fa, f->pool_buckets));
+      MB_CUDA(launch_lin(k_linearize<5, NoPose, 19>, grid, block, f->lin_smem, st, f->map->view(), fv, f->ds, NoPose{}, peer, fa, f->pool_buckets));
     else
-      MB_CUDA(launch_pdl_smem(k_linearize<MB_MAX_K, NoPose, 27>, grid, block, f->lin_smem, st, f->map->view(), fv, f->ds, NoPose{}, peer, fa, f->pool_buckets));
+      MB_CUDA(launch_lin(k_linearize<MB_MAX_K, NoPose, 27>, grid, block, f->lin_smem, st, f->map->view(), fv, f->ds, NoPose{}, peer, fa, f->pool_buckets));
   }
-  ++c->launches;
-  if (nccl) {
-    MB_NCCL(ncclAllReduce(f->packed, f->packed, kPack, ncclDouble, ncclSum, c->comm, st));
-    MB_CUDA(launch_pdl(k_finalize, dim3(1), dim3(160), st, (const double*)f->packed, f->ds, fa, 31u, (const PeerTable*)nullptr, f->packed));
-    ++c->launches;
-  }
+  if (nccl) MB_NCCL(ncclAllReduce(f->packed, f->packed, kPack, ncclDouble, ncclSum, c->comm, st));
+  MB_CUDA(launch_pdl(k_finalize, dim3(1), dim3(160), st, (const double*)f->packed, f->ds, fa, 31u, peer, f->packed));
+  c->launches += 2;
   if (host_out) {
     MB_CUDA(launch_pdl(k_loc_comp<true>, dim3(f->grid2), dim3(kLocThreads), st, fv, (const DevState*)f->ds, *host_out, peer));
     ++c->launches;
@@ -1074,35 +1544,11 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
-static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const mb_scan* dscan, size_t n,
-                              size_t stride_bytes, const mb_icp_config* cfg, size_t shard_begin, size_t shard_end,
-                              mb_factor** out) {
-  MB_REQUIRE(ctx && map && cfg && out, "null argument");
-  MB_REQUIRE(n == 0 || pts || dscan, "null scan");
-  MB_REQUIRE(map->ctx == ctx, "map belongs to another context");
-  MB_REQUIRE(stride_bytes >= 12 && stride_bytes % 4 == 0, "stride must be >= 12 and a multiple of 4");
-  MB_REQUIRE(shard_begin <= shard_end && shard_end <= n, "bad shard range");
-  if (cfg->project_on_degneneracy) {
-    set_error("mb_factor_create: project_on_degneneracy=true is not supported (the reference branch at "
-              "geometric_factor.hpp:477-557 re-sums arrays that are never written)");
-    return MB_ERR_UNSUPPORTED;
-  }
-  if (cfg->num_corres_points < 3 || cfg->num_corres_points > MB_MAX_K) {
-    set_error("mb_factor_create: num_corres_points=%llu outside [3, %d] (geometric_config.cpp:32-48)",
-              (unsigned long long)cfg->num_corres_points, MB_MAX_K);
-    return MB_ERR_UNSUPPORTED;
-  }
-  MB_CUDA(cudaSetDevice(ctx->device));
+// Everything that can fail once the factor holds its map reference; on failure the caller releases the factor
+// (device block, raw-scan block, map reference) in one place.
+static int factor_init(mb_factor* f, mb_ctx* ctx, mb_map* map, const void* pts, const mb_scan* dscan, size_t n, size_t stride_bytes,
+                       const mb_icp_config* cfg, size_t shard_begin, size_t shard_end) {
   cudaStream_t st = ctx->stream;
-  mb_factor* f = new mb_factor;
-  f->ctx = ctx;
-  {
-    const int mrc = ensure_mirror(map);  // the map is immutable from here on (refs > 1): build its search mirror once
-    if (mrc != MB_OK) {
-      delete f;
-      return mrc;
-    }
-  }
   f->map = map;
   map->refs.fetch_add(1);
   f->cfg = *cfg;
@@ -1111,9 +1557,11 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
   f->n = shard_end - shard_begin;
   f->ld = std::max<size_t>(align_up(f->n, 32), 32);
   const size_t k = cfg->num_corres_points;
-  const size_t n_tiles = (f->n + kLinThreads - 1) / kLinThreads;
-  // k_linearize: one warp per 32-point tile; per warp the group-search scratch plus a staging pool sized so that
-  // MB_LIN_BLOCKS blocks share an SM's shared memory
+  // k_linearize: one warp per 32-point tile; per warp the group-search scratch and, optionally, a staging pool for the
+  // bulk-copy engine.  The pool is OFF by default: staged and direct reads were both measured on the benchmark scan
+  // (profiles/r2_experiments.md) and reading the buckets through L1 won (lock-step lanes of a voxel group read the
+  // same 16 bytes, one broadcast access per step, and the 52 KB of pools per block leave the SM 30 KB of L1);
+  // MB_LIN_POOL=<buckets per warp> turns staging on (development / the tests of the staged path).
   f->lin_small = k == 5 && map->n_off <= 19;
   {
     int smem_sm = 0, smem_blk = 0;
@@ -1123,12 +1571,13 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
     const size_t per_block = std::min<size_t>((size_t)smem_blk, (size_t)smem_sm / MB_LIN_BLOCKS) - 1024 /* reserved */ - 4096 /* static */;
     const size_t per_warp = per_block / kLinWarps;
     const size_t bucket = (size_t)map->cap * sizeof(float4);
-    f->pool_buckets = per_warp > fixed ? (int)((per_warp - fixed) / bucket) : 0;
-    if (const char* e = getenv("MB_LIN_POOL")) f->pool_buckets = std::min(f->pool_buckets, atoi(e));  // development: 0 = never stage
+    const int fit = per_warp > fixed ? (int)((per_warp - fixed) / bucket) : 0;
+    f->pool_buckets = 0;
+    if (const char* e = getenv("MB_LIN_POOL")) f->pool_buckets = std::max(0, std::min(fit, atoi(e)));
+    if (const char* e = getenv("MB_LIN_KERNEL")) f->use_v1 = !strcmp(e, "v1");
     f->lin_smem = kLinWarps * (f->lin_small ? lin_warp_bytes<19>(f->pool_buckets, map->cap) : lin_warp_bytes<27>(f->pool_buckets, map->cap));
     const int orc = lin_opt_in_all(f);
     if (orc != MB_OK) {
-      mb_factor_release(f);
       return orc;
     }
   }
@@ -1139,13 +1588,11 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<MB_MAX_K, NoPose, 27>, kLinThreads, f->lin_smem);
   per_sm = std::max(per_sm, 1);
   const size_t n_wtiles = (f->n + 31) / 32;
-  f->grid = (int)std::max<size_t>(1, std::min<size_t>((n_wtiles + kLinWarps - 1) / kLinWarps, (size_t)ctx->sm_count * per_sm));
+  f->grid = (int)std::max<size_t>(1, std::min<size_t>((n_wtiles + kLinWarps - 1) / kLinWarps, (size_t)ctx->sm_count * per_sm));  // all resident
   f->n_groups = (f->grid + kGroup - 1) / kGroup;
   f->grid2 = (int)std::max<size_t>(1, std::min<size_t>((f->n + kLocThreads - 1) / kLocThreads, (size_t)ctx->sm_count * 4));
-  if (f->n) cub::DeviceRadixSort::SortPairs(nullptr, f->sort_temp_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
-                                            (uint32_t*)nullptr, (int)f->n, 0, kSortBits, st);
 
-  // carve one block: [src | src_raw | sort buffers | vecs (15 ld doubles) | status (ld bytes) | knn_idx | partials |
+  // carve one block: [src | src_raw | perm | vecs (15 ld doubles) | status (ld bytes) | knn_idx | partials |
   //                   gpartials | partials2 | packed | tickets | DevState]
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -1155,31 +1602,31 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
   };
   const size_t o_src = take(f->ld * sizeof(float4));
   const size_t o_raw = take(f->ld * sizeof(float4));
-  const size_t o_sk = take(f->ld * sizeof(uint32_t)), o_sko = take(f->ld * sizeof(uint32_t));
-  const size_t o_sv = take(f->ld * sizeof(uint32_t)), o_perm = take(f->ld * sizeof(uint32_t));
-  const size_t o_stemp = take(f->sort_temp_bytes);
+  const size_t o_perm = take(f->ld * sizeof(uint32_t));
+  const size_t o_rroot = take(f->ld * sizeof(double));
+  const size_t o_queue = take(f->ld * sizeof(uint32_t));
+  const size_t o_nmask = take((f->ld / 32 + 1) * sizeof(uint32_t));
   const size_t o_vecs = take(15 * f->ld * sizeof(double) + f->ld);  // status follows the vectors directly
   const size_t o_idx = take(f->ld * k * sizeof(uint64_t));
   const size_t o_par = take((size_t)f->grid * kPack * sizeof(double));
   const size_t o_gpar = take((size_t)f->n_groups * kPack * sizeof(double));
   const size_t o_par2 = take((size_t)f->grid2 * 8 * sizeof(double));
   const size_t o_packed = take((kPack + 8) * sizeof(double));
-  const size_t o_tick = take((2 + (size_t)f->n_groups) * sizeof(unsigned));
+  const size_t o_tick = take((2 + (size_t)f->n_groups) * sizeof(unsigned));  // final, loc, groups...
+  const size_t o_ctl = take(sizeof(LoopCtl));
   const size_t o_ds = take(sizeof(DevState));
   f->block_bytes = off;
   int rc = dev_alloc(ctx, &f->block, f->block_bytes);
   if (rc != MB_OK) {
-    mb_factor_release(f);
     return rc;
   }
   char* base = (char*)f->block;
   f->src = (float4*)(base + o_src);
   f->src_raw = (float4*)(base + o_raw);
-  f->sort_keys = (uint32_t*)(base + o_sk);
-  f->sort_keys_out = (uint32_t*)(base + o_sko);
-  f->sort_vals = (uint32_t*)(base + o_sv);
   f->perm = (uint32_t*)(base + o_perm);
-  f->sort_temp = base + o_stemp;
+  f->rroot = (double*)(base + o_rroot);
+  f->queue = (uint32_t*)(base + o_queue);
+  f->need_mask = (uint32_t*)(base + o_nmask);
   f->vecs = (double*)(base + o_vecs);
   f->status = (uint8_t*)(base + o_vecs + 15 * f->ld * sizeof(double));
   f->knn_idx = (uint64_t*)(base + o_idx);
@@ -1188,6 +1635,7 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
   f->partials2 = (double*)(base + o_par2);
   f->packed = (double*)(base + o_packed);
   f->tickets = (unsigned*)(base + o_tick);
+  f->ctl = (LoopCtl*)(base + o_ctl);
   f->ds = (DevState*)(base + o_ds);
 
   bool staged = true;  // the context's pinned staging buffer was used: wait for the copy before returning
@@ -1202,17 +1650,18 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
     // rank's block of them as it is and a kernel extracts xyz — no CPU pass over the scan, and nothing here
     // has to wait for the copy (the first linearisation follows it in stream order).
     const size_t raw_bytes = f->n * stride_bytes;
-    unsigned char* raw = nullptr;
-    rc = dev_alloc(ctx, (void**)&raw, raw_bytes);
+    rc = dev_alloc(ctx, &f->raw, raw_bytes);
     if (rc != MB_OK) {
-      mb_factor_release(f);
       return rc;
     }
+    f->raw_bytes = raw_bytes;
+    unsigned char* raw = (unsigned char*)f->raw;
     MB_CUDA(cudaMemcpyAsync(raw, (const char*)pts + shard_begin * stride_bytes, raw_bytes, cudaMemcpyHostToDevice, st));
     MB_CUDA(cudaEventRecord(ctx->ev1, st));  // the caller's buffer is free again once this copy has run (below)
     k_pack_src<<<(unsigned)((f->ld + 255) / 256), 256, 0, st>>>(raw, stride_bytes, 0, f->n, f->ld, f->src_raw);
     ++ctx->launches;
     dev_free(ctx, raw, raw_bytes);  // pooled: only ever handed out again to work on this same stream
+    f->raw = nullptr;
     staged = false;
     copied_from_caller = true;
   } else {
@@ -1220,7 +1669,6 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
     // geometric_factor.hpp:277,323,346)
     rc = pinned_reserve(ctx, f->ld * sizeof(float4));
     if (rc != MB_OK) {
-      mb_factor_release(f);
       return rc;
     }
     float4* h = (float4*)ctx->pinned;
@@ -1255,6 +1703,42 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
     }
     MB_CUDA(q);
   }
+  return MB_OK;
+}
+
+static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const mb_scan* dscan, size_t n,
+                              size_t stride_bytes, const mb_icp_config* cfg, size_t shard_begin, size_t shard_end,
+                              mb_factor** out) {
+  MB_REQUIRE(ctx && map && cfg && out, "null argument");
+  MB_REQUIRE(n == 0 || pts || dscan, "null scan");
+  MB_REQUIRE(map->ctx == ctx, "map belongs to another context");
+  MB_REQUIRE(stride_bytes >= 12 && stride_bytes % 4 == 0, "stride must be >= 12 and a multiple of 4");
+  MB_REQUIRE(shard_begin <= shard_end && shard_end <= n, "bad shard range");
+  if (cfg->project_on_degneneracy) {
+    set_error("mb_factor_create: project_on_degneneracy=true is not supported (the reference branch at "
+              "geometric_factor.hpp:477-557 re-sums arrays that are never written)");
+    return MB_ERR_UNSUPPORTED;
+  }
+  if (cfg->num_corres_points < 3 || cfg->num_corres_points > MB_MAX_K) {
+    set_error("mb_factor_create: num_corres_points=%llu outside [3, %d] (geometric_config.cpp:32-48)",
+              (unsigned long long)cfg->num_corres_points, MB_MAX_K);
+    return MB_ERR_UNSUPPORTED;
+  }
+  MB_CUDA(cudaSetDevice(ctx->device));
+  mb_factor* f = new mb_factor;
+  f->ctx = ctx;
+  {
+    const int mrc = ensure_mirror(map);  // the map is immutable from here on (refs > 1): build its search mirror once
+    if (mrc != MB_OK) {
+      delete f;
+      return mrc;
+    }
+  }
+  const int rc = factor_init(f, ctx, map, pts, dscan, n, stride_bytes, cfg, shard_begin, shard_end);
+  if (rc != MB_OK) {
+    mb_factor_release(f);  // also gives the map reference back
+    return rc;
+  }
   *out = f;
   return MB_OK;
 }
@@ -1280,19 +1764,19 @@ MB_API int mb_debug_time_finalize(mb_factor* f, unsigned role_mask, int reps, fl
   MB_CUDA(cudaSetDevice(f->ctx->device));
   cudaStream_t st = f->ctx->stream;
   const FactorView fv = f->view();
-  // role_mask < 32: k_finalize with those roles; 32: k_linearize at the current pose (fully cached after one
-  // call), reduction only; 33: the same with the fused finalize roles; 64: k_loc_comp.  Plain launches, back to back.
+  // role_mask < 32: k_finalize with those roles; 32: k_linearize at the current pose (fully cached after one call);
+  // 64: k_loc_comp.  Back to back.
   const NoPose no_pose{};
   HostOut no_out;
   no_out.out = nullptr, no_out.flag = nullptr, no_out.seq = 0;
   FinArgs fa;
-  fa.reg_4_dof = (int)f->cfg.reg_4_dof, fa.linearize_count = 0, fa.do_step = 0, fa.iter = 0, fa.trace = nullptr, fa.fuse = role_mask == 33u;
+  fa.reg_4_dof = (int)f->cfg.reg_4_dof, fa.linearize_count = 0, fa.do_step = 0, fa.iter = 0, fa.trace = nullptr;
   auto one = [&]() {
-    if (role_mask == 32u || role_mask == 33u) {
+    if (role_mask == 32u) {
       if (f->lin_small)
-        k_linearize<5, NoPose, 19><<<f->grid, kLinThreads, f->lin_smem, st>>>(f->map->view(), fv, f->ds, no_pose, nullptr, fa, f->pool_buckets);
+        launch_lin(k_linearize<5, NoPose, 19>, dim3(f->grid), dim3(kLinThreads), f->lin_smem, st, f->map->view(), fv, f->ds, no_pose, (const PeerTable*)nullptr, fa, f->pool_buckets);
       else
-        k_linearize<MB_MAX_K, NoPose, 27><<<f->grid, kLinThreads, f->lin_smem, st>>>(f->map->view(), fv, f->ds, no_pose, nullptr, fa, f->pool_buckets);
+        launch_lin(k_linearize<MB_MAX_K, NoPose, 27>, dim3(f->grid), dim3(kLinThreads), f->lin_smem, st, f->map->view(), fv, f->ds, no_pose, (const PeerTable*)nullptr, fa, f->pool_buckets);
     } else if (role_mask == 64u) {
       k_loc_comp<false><<<f->grid2, kLocThreads, 0, st>>>(fv, f->ds, no_out, nullptr);
     } else {
@@ -1317,6 +1801,8 @@ MB_API int mb_debug_lin_timeline(unsigned long long* out512) {
 #if defined(MB_LIN_TIMING)
   MB_CUDA(cudaDeviceSynchronize());
   MB_CUDA(cudaMemcpyFromSymbol(out512, g_lin_t, sizeof(unsigned long long) * 512));
+  MB_CUDA(cudaMemcpyFromSymbol(out512 + 512, g_lin_blk, sizeof(unsigned long long) * 4096));
+  MB_CUDA(cudaMemcpyFromSymbol(out512 + 512 + 4096, g_lin_warp, sizeof(unsigned) * 8192));
   return MB_OK;
 #else
   (void)out512;
@@ -1331,6 +1817,7 @@ int mb_factor_release(mb_factor* f) {
   cudaStreamSynchronize(f->ctx->stream);
   drop_graph(f);
   dev_free(f->ctx, f->block, f->block_bytes);
+  dev_free(f->ctx, f->raw, f->raw_bytes);
   if (f->d_trace) dev_free(f->ctx, f->d_trace, (size_t)f->trace_cap * sizeof(mb_icp_trace));
   mb_map_release(f->map);
   delete f;
@@ -1377,16 +1864,33 @@ int mb_factor_linearize(mb_factor* f, const double R[9], const double t[3], cons
     ho.seq = ++f->ctx->host_seq;
     if (ho.seq == 0) ho.seq = ++f->ctx->host_seq;
     MB_TRY(enqueue_linearize(f, 0, 0, nullptr, f->linearize_count, &pa, &ho));
+    // Poll the completion flag: busy for the first ~100 us (a call normally ends well inside that), then yielding the
+    // core between polls; the stream is queried now and then so that a failed launch ends the wait with its error, and
+    // a kernel that never finishes ends it after kPollTimeoutS instead of hanging the caller (mimosa's node has three
+    // threads that may sit here, mimosa_node.cpp:28-43).
+    constexpr double kPollTimeoutS = 30.0;
+    const auto t_begin = std::chrono::steady_clock::now();
     unsigned spins = 0;
+    bool yielding = false;
     while (__atomic_load_n((const unsigned*)ho.flag, __ATOMIC_ACQUIRE) != ho.seq) {
-      if ((++spins & 0x3fffu) == 0) {  // every ~16k polls make sure the stream is still healthy
+      if ((++spins & 0x3ffu) == 0) {
         const cudaError_t q = cudaStreamQuery(st);
         if (q == cudaSuccess) break;
         if (q != cudaErrorNotReady) MB_CUDA(q);
+        const double waited = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+        yielding = waited > 100e-6;
+        if (waited > kPollTimeoutS) {
+          set_error("mb_factor_linearize: no result after %.0f s (kernel lost or device hung)", kPollTimeoutS);
+          return MB_ERR_CUDA;
+        }
       }
+      if (yielding) {
+        std::this_thread::yield();
+      } else {
 #if defined(__x86_64__)
-      __builtin_ia32_pause();
+        __builtin_ia32_pause();
 #endif
+      }
     }
   } else {
     std::memcpy(hin, R, 9 * sizeof(double));
@@ -1415,7 +1919,7 @@ int mb_factor_download_state(mb_factor* f, uint8_t* status, double* p_da, double
   cudaStream_t st = f->ctx->stream;
   const size_t n = f->n, k = f->cfg.num_corres_points;
   if (n == 0) return MB_OK;
-  // the device arrays are in voxel order (k_sort_keys); perm[s] = index of sorted position s in the caller's scan
+  // the device arrays are in voxel order (k_group_sort); perm[s] = index of sorted position s in the caller's scan
   std::vector<uint32_t> perm(n);
   if (f->sorted) {
     MB_CUDA(cudaMemcpyAsync(perm.data(), f->perm, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -1496,7 +2000,7 @@ int mb_icp_run(mb_factor* f, double R[9], double t[3], int iters, double lambda,
       f->graph_iters = iters;
       f->graph_count0 = f->linearize_count;
     } else {
-      f->ctx->launches += 1ull * iters + 1ull + (f->graph_count0 == 0 && f->n ? 8ull : 0ull);
+      f->ctx->launches += 2ull * iters + 1ull + (f->graph_count0 == 0 && f->n ? 1ull : 0ull);
     }
     MB_CUDA(cudaGraphLaunch(f->graph, st));
     f->linearize_count += iters;

@@ -83,6 +83,7 @@ struct GroupLane {
   int g;            // group ordinal inside the warp
   uint32_t exist;   // the group's existing neighbours, by rank
   int pool_base;    // first pool bucket of the group, -1 = buckets are read from global memory
+  int n_groups;     // voxel groups in the warp (telemetry)
 };
 
 template <int ROWS>
@@ -125,6 +126,7 @@ MB_UNROLL
   gl.g = __popc(leaders & ((1u << leader) - 1u));
   gl.exist = 0u;
   gl.pool_base = -1;
+  gl.n_groups = n_groups;
   S.exist[lane] = 0u;
   S.todo[lane] = 0u;
   if (is_leader) S.gc[gl.g] = make_int4(cx, cy, cz, 0);

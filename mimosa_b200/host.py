@@ -434,15 +434,72 @@ def gn_step(L: Linearization, R, t, lam: float = 0.0):
     return R.reshape(3, 3), t, delta, bool(ok.value)
 
 
-def degeneracy_flags(L: Linearization, config: RegistrationConfig):
-    """Geometric::getFactors' consumer of the localizabilities (geometric.cpp:218-228)."""
+def degeneracy_flags_from(loc_rot_comp, loc_trans_comp, eigvec_rot, eigvec_trans, degen_thresh_rot, degen_thresh_trans):
+    """Geometric::getFactors' consumer of the localizabilities (geometric.cpp:218-228): six booleans "component
+    localizability below its (float) threshold", rotations first, and blkdiag(V_rot, V_trans)."""
     ev = np.zeros((6, 6))
-    ev[:3, :3] = np.array(L.eigvec_rot).reshape(3, 3)
-    ev[3:, 3:] = np.array(L.eigvec_trans).reshape(3, 3)
-    d = np.zeros(6)
-    d[:3] = np.array(L.loc_rot_comp) < config.degen_thresh_rot
-    d[3:] = np.array(L.loc_trans_comp) < config.degen_thresh_trans
-    return ev, d
+    ev[:3, :3] = np.asarray(eigvec_rot, np.float64).reshape(3, 3)
+    ev[3:, 3:] = np.asarray(eigvec_trans, np.float64).reshape(3, 3)
+    d = np.zeros(6, dtype=bool)
+    d[:3] = np.asarray(loc_rot_comp, np.float64) < float(np.float32(degen_thresh_rot))
+    d[3:] = np.asarray(loc_trans_comp, np.float64) < float(np.float32(degen_thresh_trans))
+    return d, ev
+
+
+def degeneracy_flags(L: Linearization, config: RegistrationConfig):
+    """The same from a linearisation and the factor's configuration; returns (eigenvectors_block_matrix, degen_directions)."""
+    d, ev = degeneracy_flags_from(L.loc_rot_comp, L.loc_trans_comp, L.eigvec_rot, L.eigvec_trans, config.degen_thresh_rot,
+                                  config.degen_thresh_trans)
+    return ev, d.astype(np.float64)
+
+
+class KeyframeGate:
+    """The keyframe rule of Geometric::updateMap (mimosa/src/lidar/geometric.cpp:437-478), as in the C++ mirror
+    (mimosa_b200/host/mimosa_b200.hpp::KeyframeGate): nearest map pose by (float) translation distance, first minimum;
+    update when that distance exceeds map_keyframe_trans_thresh or the largest |yaw|, |pitch|, |roll| of
+    R_B_L^-1 (R_kf^-1 R_now) R_B_L exceeds DEG2RAD(map_keyframe_rot_thresh_deg); the first
+    initial_clouds_to_force_map_update calls always update.  Host logic; no compute."""
+
+    def __init__(self, trans_thresh, rot_thresh_deg, initial_clouds_to_force_map_update, R_B_L=None):
+        self.trans_thresh = np.float32(trans_thresh)
+        self.rot_thresh_deg = np.float32(rot_thresh_deg)
+        self.forced_left = int(initial_clouds_to_force_map_update)
+        self.R_B_L = np.eye(3) if R_B_L is None else np.asarray(R_B_L, np.float64).reshape(3, 3)
+        self.R = np.zeros((0, 3, 3))
+        self.t = np.zeros((0, 3))
+
+    @staticmethod
+    def _rq_abs_max(A):  # gtsam::RQ -> Rot3::ypr(), only max |angle| is consumed
+        x = -np.arctan2(-A[2, 1], A[2, 2])
+        cx, sx = np.cos(-x), np.sin(-x)
+        B = A @ np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+        y = -np.arctan2(B[2, 0], B[2, 2])
+        cy, sy = np.cos(-y), np.sin(-y)
+        Cm = B @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        z = -np.arctan2(-Cm[1, 0], Cm[1, 1])
+        return max(abs(x), abs(y), abs(z))
+
+    def should_update(self, R, t) -> bool:
+        R, t = np.asarray(R, np.float64).reshape(3, 3), np.asarray(t, np.float64).reshape(3)
+        update = True
+        if self.t.shape[0]:
+            d = np.sqrt(((self.t - t) ** 2).sum(1)).astype(np.float32)
+            i = int(np.argmin(d))  # first minimum, like the reference's strict '<'
+            rot_diff = self.R_B_L.T @ (self.R[i].T @ R) @ self.R_B_L
+            if d[i] > self.trans_thresh:
+                update = True
+            elif self._rq_abs_max(rot_diff) > float(self.rot_thresh_deg) * 0.017453293:
+                update = True
+            else:
+                update = False
+        if self.forced_left > 0:
+            update = True
+            self.forced_left -= 1
+        return update
+
+    def add_keyframe(self, R, t):
+        self.R = np.concatenate([self.R, np.asarray(R, np.float64).reshape(1, 3, 3)])
+        self.t = np.concatenate([self.t, np.asarray(t, np.float64).reshape(1, 3)])
 
 
 def shard_range(n: int, rank: int, world: int):

@@ -30,8 +30,11 @@ def reorder_cloud_loops(data, width, height, transpose_pointcloud, organize_poin
         data, width, height = out, t_width, t_height
     if organize_pointcloud_by_ring and height == 1:  # :210-241
         num_rings = 128
-        size = 2 if ring_type == 0 else 1
-        ring = [int.from_bytes(bytes(data[i, off_ring:off_ring + size]), "little") for i in range(n)]
+        if ring_type == 2:  # float ring (PointVelodyneAnybotics): `ring_counts[point.ring]` truncates to an index
+            ring = [int(np.frombuffer(bytes(data[i, off_ring:off_ring + 4]), "<f4")[0]) for i in range(n)]
+        else:
+            size = 2 if ring_type == 0 else 1
+            ring = [int.from_bytes(bytes(data[i, off_ring:off_ring + size]), "little") for i in range(n)]
         ring_counts = [0] * num_rings
         for r in ring:
             ring_counts[r] += 1
@@ -58,7 +61,7 @@ def reorder_cloud(data, width, height, transpose_pointcloud, organize_pointcloud
         data = np.ascontiguousarray(data.reshape(height, width, step).swapaxes(0, 1)).reshape(n, step)
         width, height = height, width
     if organize_pointcloud_by_ring and height == 1 and n:
-        ring = _field(data, off_ring, np.uint16 if ring_type == 0 else np.uint8)
+        ring = _ring(data, off_ring, ring_type)
         data = data[np.argsort(ring, kind="stable")]
     return data, width, height
 
@@ -67,6 +70,18 @@ def _field(data, off, dtype):
     n = data.shape[0]
     size = np.dtype(dtype).itemsize
     return np.ascontiguousarray(data[:, off:off + size]).view(dtype).reshape(n)
+
+
+def _ring(data, off_ring, ring_type):
+    if ring_type == 2:
+        return _field(data, off_ring, np.float32).astype(np.int64)
+    return _field(data, off_ring, np.uint16 if ring_type == 0 else np.uint8).astype(np.int64)
+
+
+def _wrap_u32(td):
+    """`uint32_t t_ns = <double>` as x86-64 compilers emit it (manager.cpp:285-304): truncate to int64, keep the low 32
+    bits — negative offsets wrap to ~4.29e9 and are then dropped by the ns_max test."""
+    return (np.trunc(td).astype(np.int64) & np.int64(0xFFFFFFFF)).astype(np.uint32)
 
 
 def prepare_input(data, layout, filt):
@@ -105,7 +120,7 @@ def prepare_input(data, layout, filt):
             else:
                 td = _field(d, layout.off_time, np.float64) - filt.header_ts * 1e9
             td = np.where(ok, td, 0.0)
-        t_ns = np.floor(np.clip(td, 0, 4294967295.0)).astype(np.uint32)  # valid inputs give 0 <= t_ns < 2^32
+        t_ns = _wrap_u32(td)
     ok &= ~(t_ns.astype(np.float32) > np.float32(filt.ns_max))
     kept = np.flatnonzero(ok)
     m = kept.size
@@ -118,8 +133,8 @@ def prepare_input(data, layout, filt):
     out[:, 6] = idx[kept].astype(np.uint32).view(np.float32)
     out[:, 7] = np.sqrt(range_sq[kept])
     gk = idx[kept] % filt.point_skip_divisor == 0
-    if layout.off_ring >= 0:
-        ring = _field(d, layout.off_ring, np.uint16 if layout.ring_type == 0 else np.uint8)[kept].astype(np.int64)
+    if layout.ring_filter:  # :318-330; PointVelodyneAnybotics carries a ring but is not filtered by it
+        ring = _ring(d, layout.off_ring, layout.ring_type)[kept]
         gk &= ring % filt.ring_skip_divisor == 0
     geometric_idx = np.flatnonzero(gk).astype(np.uint32)
     unique_ns, pose_index = np.unique(t_ns[kept], return_inverse=True)

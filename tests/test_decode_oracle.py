@@ -95,3 +95,36 @@ def test_reorder_vectorised_equals_reference_loops():
                 a = decode_ref.reorder_cloud(data, w, h, tr, org, lay.off_ring, lay.ring_type)
                 b = decode_ref.reorder_cloud_loops(data, w, h, tr, org, lay.off_ring, lay.ring_type)
                 assert np.array_equal(a[0], b[0]) and a[1:] == b[1:]
+
+
+def test_points_stamped_before_the_header_are_dropped_by_the_uint32_wrap():
+    """manager.cpp:291-306: `uint32_t t_ns = (timestamp - header) * 1e9` of a NEGATIVE offset wraps (x86-64 conversion) to
+    ~4.29e9 ns, which the ns_max test then rejects; a saturating conversion would keep the point with t_ns = 0."""
+    n = 4000
+    for name in ("hesai", "rslidar", "livox"):
+        clean, lay = make_cloud(name, n, np.random.default_rng(9), nan_frac=0.0)
+        dirty, _ = make_cloud(name, n, np.random.default_rng(9), nan_frac=0.0, early_frac=0.05)
+        f = default_filter(create_full_res_pointcloud=1)
+        a, *_ = decode_ref.prepare_input(clean, lay, f)
+        b, *_ = decode_ref.prepare_input(dirty, lay, f)
+        changed = np.flatnonzero((clean != dirty).any(1))
+        assert 100 < changed.size < 400
+        kept_a, kept_b = set(a[:, 6].view(np.uint32).tolist()), set(b[:, 6].view(np.uint32).tolist())
+        assert kept_b == kept_a - set(changed.tolist())  # exactly the early points disappear
+    assert decode_ref._wrap_u32(np.array([-5.0, 0.0, 7.9, 4294967296.0 + 3, -4294967296.0 * 3 - 2.5])).tolist() == [4294967291, 0, 7, 3, 4294967294]
+
+
+def test_anybotics_float_ring_orders_but_does_not_filter():
+    rng = np.random.default_rng(10)
+    data, lay = _shuffled_ring_cloud("velodyne_anybotics", 480, rng)
+    assert lay.ring_type == 2 and lay.ring_filter == 0
+    a = decode_ref.reorder_cloud(data, 480, 1, False, True, lay.off_ring, lay.ring_type)
+    b = decode_ref.reorder_cloud_loops(data, 480, 1, False, True, lay.off_ring, lay.ring_type)
+    assert np.array_equal(a[0], b[0])
+    rings = a[0][:, 20:24].copy().view(np.float32).ravel()
+    assert np.all(np.diff(rings) >= 0)
+    f1, f2 = default_filter(ring_skip_divisor=1), default_filter(ring_skip_divisor=4)
+    assert np.array_equal(decode_ref.prepare_input(a[0], lay, f1)[1], decode_ref.prepare_input(a[0], lay, f2)[1])
+    # the same cloud read as a plain Velodyne cloud (integer ring, filtered) does depend on the ring divisor
+    v, vlay = _shuffled_ring_cloud("velodyne", 480, np.random.default_rng(10))
+    assert decode_ref.prepare_input(v, vlay, f1)[1].size > decode_ref.prepare_input(v, vlay, f2)[1].size

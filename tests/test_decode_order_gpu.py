@@ -12,6 +12,9 @@ pytestmark = [pytest.mark.gpu]
     ("hesai", 60000, 1, False, True),      # JT128-style unorganised cloud, records in arbitrary ring order
     ("velodyne", 1, 60000, True, True),    # transposition yields height 1, so the ring re-ordering applies too
     ("ouster", 500, 120, False, True),     # organised: the ring flag must change nothing
+    ("rslidar", 96, 680, True, False),     # RSAiry: the sensor the transposition exists for (manager.cpp:179-198)
+    ("velodyne_anybotics", 1, 60000, True, True),  # float ring numbers: ordered by ring, NOT filtered by ring (:318-330)
+    ("ouster_r8", 60000, 1, False, True),  # uint8 ring numbers
 ])
 def test_ordered_decode_matches_oracle(ctx, name, width, height, transpose, by_ring):
     import decode_ref

@@ -562,16 +562,18 @@ def test_streaming_pipeline_matches_oracle(ctx, oracle, pattern, n_scans, n_pts)
     mg.release()
 
 
-@pytest.mark.parametrize("name", ["ouster", "ouster_odyssey", "velodyne", "hesai", "livox"])
+@pytest.mark.parametrize("name", ["ouster", "ouster_odyssey", "ouster_r8", "velodyne", "velodyne_anybotics", "hesai", "rslidar",
+                                  "livox", "livox_custom2"])
 def test_pointcloud2_decode_matches_oracle(ctx, name):
-    """lidar::Manager::prepareInput (manager.cpp:149-383) on the device vs the numpy restatement, for five vendor
-    layouts, full-resolution and skipped; then the decoded scan flows into deskew + gather like in the callback."""
+    """lidar::Manager::prepareInput (manager.cpp:149-383) on the device vs the numpy restatement, for the nine vendor
+    layouts of point.hpp:41-178, full-resolution and skipped (some points stamped before the header: dropped through the
+    reference's uint32 wrap); then the decoded scan flows into deskew + gather like in the callback."""
     import decode_ref
     from cloud_layouts import default_filter, make_cloud
     from mimosa_b200 import Scan
 
     rng = np.random.default_rng(200)
-    data, lay = make_cloud(name, 60000, rng)
+    data, lay = make_cloud(name, 60000, rng, early_frac=0.01)
     for full, skip, ring_skip in ((1, 4, 2), (0, 4, 1), (1, 1, 1)):
         f = default_filter(create_full_res_pointcloud=full, point_skip_divisor=skip, ring_skip_divisor=ring_skip)
         want = decode_ref.prepare_input(data, lay, f)

@@ -26,12 +26,14 @@ for rep in range(3):
     ctx.flush_l2()
     ctx.sync()
     f.icp_run(R0, t0, 20, 0.0, want_trace=False)
-buf = (C.c_ulonglong * 512)()
+buf = (C.c_ulonglong * (512 + 4096 + 4096))()
 assert ctx.lib.mb_debug_lin_timeline(buf) == 0
-t = np.array(buf, dtype=np.int64).reshape(64, 8)
-print("iter: entry->wait  wait->tiles  tiles->grp  grp->ticket  ticket->packet  packet->solve  (eigen roles)  | total  gap to next entry (us)")
+allb = np.array(buf, dtype=np.int64)
+t = allb[:512].reshape(64, 8)
+print("iter: entry->wait   P1 (gate+cached)   P2 (search passes)   P3 (re-associated)   reduce->ticket   packet | kernel total (us)")
 for it in range(1, 21):
     r = t[it]
-    d = lambda a, b: (r[b] - r[a]) / 1e3
-    nxt = (t[it + 1][0] - r[6]) / 1e3 if it < 20 else float("nan")
-    print(f"{it:3d}: {d(0,1):7.1f} {d(1,2):9.1f} {d(2,3):9.1f} {d(3,4):9.1f} {d(4,5):9.1f} {d(5,6):9.1f}   ({d(5,7):6.1f})  | {d(0,6):7.1f}  {nxt:7.1f}")
+    d = lambda a, b: (r[b] - r[a]) / 1e3 if r[a] and r[b] else float("nan")
+    p2 = d(2, 3) if r[3] else 0.0
+    p3 = d(3, 4) if r[3] else d(2, 4)
+    print(f"{it:3d}: {d(0,1):7.1f} {d(1,2):12.1f} {p2:18.1f} {p3:18.1f} {d(4,5):16.1f} {d(5,6):10.1f} | {d(0,6):8.1f}")
