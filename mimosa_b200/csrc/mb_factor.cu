@@ -35,7 +35,6 @@
 
 #include "mb_map.cuh"
 #include "mb_scan.cuh"
-#include "mb_search_group.cuh"
 
 namespace mb {
 namespace {
@@ -53,7 +52,6 @@ constexpr int kLocThreads = 256;
 __constant__ int8_t kTriRow[32] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5, 0, 1, 2, 3, 4, 5, 6, 0, 0, 0, 0};
 __constant__ int8_t kTriCol[32] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5, 6, 6, 6, 6, 6, 6, 6, 0, 0, 0, 0};
 
-struct LoopCtl;
 struct FactorView {
   const float4* src;
   uint8_t* status;
@@ -65,9 +63,6 @@ struct FactorView {
   int fold_loc;  // 1: also sum the component localizabilities of the previous linearisation (device-resident loop)
   double da_gate_sq, max_corr_sq, sigma, kh, pvd;  // da_gate_sq: smallest d2 with sqrt(d2) > the gate (host: da_gate_sq_min)
   const double* rroot;  // sqrt(||p_src||) per point (geometric_factor.hpp:323), constant per scan
-  LoopCtl* ctl;         // grid barrier and re-association queue control words
-  uint32_t* queue;      // [n] points queued for re-association in this launch (sorted positions)
-  uint32_t* need_mask;  // [tiles] lanes of each 32-point tile that re-associate in this launch
   double* partials;    // [grid][kPack]
   double* gpartials;   // [n_groups][kPack]
   unsigned* gtickets;  // [n_groups]
@@ -199,19 +194,14 @@ __device__ __forceinline__ void localizability(const m33& JtJ, double loc[3], m3
   for (int a = 0; a < 3; ++a) loc[a] = sqrt(lam[a]);
 }
 
+#ifndef MB_LIN_BLOCKS
+#define MB_LIN_BLOCKS 4  // measured: 4 x 128 threads at 128 registers beat 5 x 96 and 3 x 156
+#endif
 // PoseT = PoseArg: host-facing single call (pose in the kernel parameters); PoseT = NoPose: device-resident loop.
 struct NoPose {};
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
 }
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v;
@@ -253,32 +243,25 @@ __device__ __noinline__ void finalize_role(const double* packed, const DevState*
       Htr.m[3 * r + c] = H[6 * (r + 3) + c];
       Htt.m[3 * r + c] = H[6 * (r + 3) + 3 + c];
     }
-  if (role == 0) {
+  if (role < 4) {
+    // The four eigen roles run as four LANES of one warp: the same instruction stream for all of them (one trip
+    // through the instruction cache instead of four), selected inputs and outputs.  Lanes 2 / 3 first form their Schur
+    // complement  A - B C^-1 D  with (A, B, C, D) = (Hrr, Hrt, Htt, Htr) / (Htt, Htr, Hrr, Hrt), inverted (:413-422).
+    m33 M = role == 0 ? Hrr : Htt;
+    if (role >= 2) {
+      const m33& A = role == 2 ? Hrr : Htt;
+      const m33& B = role == 2 ? Hrt : Htr;
+      const m33& C = role == 2 ? Htt : Hrr;
+      const m33& D = role == 2 ? Htr : Hrt;
+      M = inv33(sub33(A, mul33(mul33(B, inv33(C)), D)));
+    }
     m33 V;
     double loc[3];
-    localizability(Hrr, loc, V);
-    for (int a = 0; a < 3; ++a) L.loc_rot_final[a] = loc[a];
-    for (int a = 0; a < 9; ++a) L.eigvec_rot[a] = V.m[a];
-  } else if (role == 1) {
-    m33 V;
-    double loc[3];
-    localizability(Htt, loc, V);
-    for (int a = 0; a < 3; ++a) L.loc_trans_final[a] = loc[a];
-    for (int a = 0; a < 9; ++a) L.eigvec_trans[a] = V.m[a];
-  } else if (role == 2) {
-    const m33 Srr = inv33(sub33(Hrr, mul33(mul33(Hrt, inv33(Htt)), Htr)));
-    m33 V;
-    double loc[3];
-    localizability(Srr, loc, V);
-    for (int a = 0; a < 3; ++a) L.degen_rot[a] = loc[a] * 57.29578;
-    for (int a = 0; a < 9; ++a) L.degen_eigvec_rot[a] = V.m[a];
-  } else if (role == 3) {
-    const m33 Stt = inv33(sub33(Htt, mul33(mul33(Htr, inv33(Hrr)), Hrt)));
-    m33 V;
-    double loc[3];
-    localizability(Stt, loc, V);
-    for (int a = 0; a < 3; ++a) L.degen_trans[a] = loc[a];
-    for (int a = 0; a < 9; ++a) L.degen_eigvec_trans[a] = V.m[a];
+    localizability(M, loc, V);
+    double* const loc_out = role == 0 ? L.loc_rot_final : role == 1 ? L.loc_trans_final : role == 2 ? L.degen_rot : L.degen_trans;
+    double* const vec_out = role == 0 ? L.eigvec_rot : role == 1 ? L.eigvec_trans : role == 2 ? L.degen_eigvec_rot : L.degen_eigvec_trans;
+    for (int a = 0; a < 3; ++a) loc_out[a] = role == 2 ? loc[a] * 57.29578 : loc[a];  // RAD2DEG (PCL's macro), :428
+    for (int a = 0; a < 9; ++a) vec_out[a] = V.m[a];
   } else {
     double b[6];
 #pragma unroll
@@ -385,11 +368,11 @@ __device__ __forceinline__ void peer_gather(const PeerTable* __restrict__ peer, 
   if (threadIdx.x == 0) *peer->xseq = seq;
 }
 
-// What follows the reduction, in its own small kernel (five warps, one role each).  Running the roles inside
-// k_linearize's last block was built and measured (profiles/r2_experiments.md): under k_linearize's register cap and
-// next to three blocks streaming through its instruction cache the same chain takes 10-13 us instead of 4.
-__global__ void __launch_bounds__(160) k_finalize(const double* packed_in, DevState* ds, FinArgs fa, unsigned role_mask,
-                                                  const PeerTable* __restrict__ peer, double* packed_out) {
+// What follows the reduction, in its own small kernel (two warps: the solve, and the four eigen roles as four lanes of
+// the other).  Running the roles inside k_linearize's last block was built and measured (profiles/r2_experiments.md):
+// under k_linearize's register cap the same chain takes 10-13 us instead of 4-6.
+__global__ void __launch_bounds__(64) k_finalize(const double* packed_in, DevState* ds, FinArgs fa, unsigned role_mask,
+                                                 const PeerTable* __restrict__ peer, double* packed_out) {
   __shared__ double s_packed[kXchgDoubles];
   pdl_launch_dependents();
   pdl_wait();
@@ -398,41 +381,21 @@ __global__ void __launch_bounds__(160) k_finalize(const double* packed_in, DevSt
     peer_gather(peer, s_packed, packed_out);
     packed = s_packed;
   }
-  if ((threadIdx.x & 31) != 0) return;
-  const int role = threadIdx.x >> 5;
-  if (((role_mask >> role) & 1u) == 0) return;  // role_mask != 31 only in the timing diagnostic
+  // warp 0, lane 0: projection + packing + solve + retract; warp 1, lanes 0..3: the four eigen roles in lock step
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int role = warp == 0 ? (lane == 0 ? 4 : -1) : (lane < 4 ? lane : -1);
+  if (role < 0 || ((role_mask >> role) & 1u) == 0) return;  // role_mask != 31 only in the timing diagnostic
   finalize_role(packed, ds, ds, fa, role);
 }
 
-#ifndef MB_LIN_BLOCKS
-#define MB_LIN_BLOCKS 4
-#endif
-#if defined(MB_LIN_TIMING)  // development build: %globaltimer stamps of one k_linearize launch (mb_debug_lin_timeline)
-__device__ unsigned long long g_lin_t[64][8];
-__device__ unsigned long long g_lin_blk[2][1024][2];  // launches 1 and 2: per tile block, [start, end] of its tile loop
-__device__ unsigned g_lin_warp[2][4096];              // per TILE: duration in ns << 6 | voxel groups
-__device__ __forceinline__ unsigned long long gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-#define MB_LT_SET(slot) do { if (threadIdx.x == 0) g_lin_t[fa.linearize_count & 63][slot] = gtime(); } while (0)
-#define MB_LT_MAX(slot) do { if (threadIdx.x == 0) atomicMax(&g_lin_t[fa.linearize_count & 63][slot], gtime()); } while (0)
-#else
-#define MB_LT_SET(slot) do { } while (0)
-#define MB_LT_MAX(slot) do { } while (0)
-#endif
-// Shared memory of one warp of k_linearize: the group-search scratch, then its staging pool.
-template <int ROWS>
-__host__ __device__ constexpr size_t lin_warp_bytes(int pool_buckets, int cap) {
-  return ((sizeof(GroupScratch<ROWS>) + 15) / 16) * 16 + (size_t)pool_buckets * cap * sizeof(float4);
-}
-
-// ---- round-1 kernel, kept for A/B measurement (MB_LIN_KERNEL=v1): block tiles of 128 points, block-level compaction
-// of the points that re-associate, one query per thread (mb_search.cuh::knn_thread) -------------------------------
+// One linearisation: block tiles of 128 points of the voxel-ordered scan, block-level compaction of the points that
+// re-associate, one query per thread (mb_search.cuh::knn_thread).  Two other shapes of this kernel were built and
+// measured in round 2 and lost (profiles/r2_experiments.md): one warp per 32-point tile with the neighbourhood
+// resolved once per voxel group and staged through the bulk-copy engine, and a three-phase form with grid barriers
+// and pulled, compacted search passes.
 template <int K, typename PoseT, int ROWS>
 __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
-    k_linearize_v1(MapView mv, FactorView fv, DevState* ds, PoseT pa, const PeerTable* __restrict__ peer) {
+    k_linearize(MapView mv, FactorView fv, DevState* ds, PoseT pa, const PeerTable* __restrict__ peer) {
   double* pose_dev = ds->pose;
   __shared__ uint16_t s_tab[kTabEntries];
   // s_pk (phase B: probed neighbour words, [n_off][thread]; cooperative search: the per-thread candidate stacks,
@@ -455,29 +418,12 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
   double(*s_row)[7] = reinterpret_cast<double(*)[7]>(s_pk_all) + warp * 32;
   // Lane a < 28 owns entry a of the packed upper triangle of [J e]^T [J e] (7x7): the 21 entries of
   // J^T J first (row-major, c >= r), then J^T e (6), then e^2.
-  int pr = 0, pc = 0;
-  {
-    int u = 0;
-    for (int r = 0; r < 6; ++r)
-      for (int c = r; c < 6; ++c) {
-        if (u == lane) {
-          pr = r;
-          pc = c;
-        }
-        ++u;
-      }
-    if (lane >= 21 && lane < 27) {
-      pr = lane - 21;
-      pc = 6;
-    }
-    if (lane == 27) pr = pc = 6;
-  }
+  const int pr = kTriRow[lane], pc = kTriCol[lane];
 
   // everything above is independent of earlier kernels; from here on we read the pose the previous iteration's
   // k_finalize wrote and overwrite per-point state the previous k_loc_comp may still be reading
   pdl_wait();
   m33 R;
-#pragma unroll
   d3 T;
   if constexpr (std::is_same<PoseT, PoseArg>::value) {
     if (blockIdx.x == 0 && tid < 16) pose_dev[tid] = pa.v[tid];  // k_finalize reads pose / gravity / lambda there
@@ -491,6 +437,7 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
   }
   const int k = fv.k;
   const bool forced = (fv.flags & 1u) != 0;
+  const double inv_sigma = 1.0 / fv.sigma;  // = sqrt_w / sigma for the points Huber leaves alone (sqrt_w == 1)
 
   double acc = 0.0, lacc = 0.0;  // lacc: lane a < 6 sums component a of the previous linearisation's localizability pass
   int cnt = 0;  // lane s < 9: points with status s; lane 9: points searched
@@ -626,7 +573,7 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
             const double we = e / fv.sigma;
             if (fabs(we) > fv.kh) sqrt_w = sqrt(fv.kh / fabs(we));
           }
-          const double scale = sqrt_w / fv.sigma;
+          const double scale = sqrt_w == 1.0 ? inv_sigma : sqrt_w / fv.sigma;
           e *= scale;
           const d3 ns = mul33Tv(R, normal);
           const d3 jr = cross3(ns, ps);
@@ -698,354 +645,6 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
   if (peer) {
     // Several ranks: this rank's packet goes straight into every rank's mailbox (peer stores over NVLink),
     // then the flags are raised — k_finalize on each rank sums the mailbox in rank order (mb_internal.cuh).
-    __syncthreads();  // the packet written by this block's first kPack threads is visible to all of them
-    const int world = peer->world, rank = peer->rank;
-    const unsigned long long seq = *peer->xseq + 1ull;
-    const size_t slot = (size_t)((seq & 1ull) * kMaxRanks + (unsigned)rank);
-    for (int x = tid; x < world * kPack; x += kLinThreads) {
-      const int dst = x / kPack, e = x - dst * kPack;
-      peer->mbox[dst][slot * kXchgDoubles + e] = fv.packed[e];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < world) st_release_sys(peer->flag[tid] + slot, seq);
-  }
-}
-
-// One linearisation, three phases separated by grid-wide barriers (every block is resident: the grid never exceeds
-// what the device holds, and the launch is cooperative):
-//   P1  every warp walks its tiles of 32 consecutive points of the voxel-sorted scan: transform + data-association
-//       gate (:276-287).  Points that keep their association finish here — residual, s-check, Huber, Jacobian,
-//       localizability vectors (:319-355), their share of [J e]^T [J e] (:364-366).  Points that must re-associate
-//       are appended to a queue (one reservation per warp).
-//   P2  (only when the queue is not empty) the queue is worked off in passes of 32 points which the warps PULL from a
-//       counter: the voxel-grouped restricted k-NN (mb_search_group.cuh), the two distance gates (:296-302) and the
-//       plane fit (:176-229); results go to the points' state.  Pulling balances the passes, whose cost varies 3x with
-//       the number of voxel groups (measured: 31 us for one group, 57-68 us for five to sixteen, at full occupancy),
-//       and compacting makes an iteration that re-associates 13 % of the points cost 13 % of a full search instead of
-//       all of it.  Which warp serves which point is not deterministic; what it writes for the point is.
-//   P3  the warps revisit their tiles and finish the re-associated points like P1 (same order every run).
-// Then block partial -> group partial -> packet (two ticketed levels, fixed order: bitwise repeatable); the last block
-// hands the packet to the other ranks' mailboxes.  k_finalize follows.
-struct LoopCtl {        // device-side control words of a factor's k_linearize launches
-  unsigned bar_count;   // grid barrier: arrivals
-  unsigned bar_gen;     //               generation
-  unsigned q_count;     // points queued for re-association in this launch
-  unsigned q_pass;      // next pass of 32 queue entries
-};
-
-__device__ __forceinline__ void grid_barrier(LoopCtl* ctl, unsigned n_blocks) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned g = ld_acquire_gpu(&ctl->bar_gen);
-    __threadfence();
-    if (atomicAdd(&ctl->bar_count, 1u) == n_blocks - 1u) {
-      ctl->bar_count = 0u;
-      __threadfence();
-      st_release_gpu(&ctl->bar_gen, g + 1u);
-    } else {
-      while (ld_acquire_gpu(&ctl->bar_gen) == g) {
-      }
-    }
-  }
-  __syncthreads();
-}
-
-template <int K, typename PoseT, int ROWS>
-__global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
-    k_linearize(MapView mv, FactorView fv, DevState* ds, PoseT pa, const PeerTable* __restrict__ peer, FinArgs fa,
-                int pool_buckets) {
-  extern __shared__ __align__(16) unsigned char s_dyn[];
-  __shared__ uint16_t s_rank[32];
-  __shared__ double s_red[kLinWarps][kPack];
-  __shared__ double s_tmp[(kLinThreads / kPack) * kPack];
-  __shared__ double s_V[18];
-  __shared__ bool s_last;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double* pose_dev = ds->pose;
-  LoopCtl* const ctl = fv.ctl;
-#if defined(MB_LIN_TIMING)
-  if (blockIdx.x == 0 && tid == 0) {
-    g_lin_t[fa.linearize_count & 63][0] = gtime();
-    for (int a = 2; a < 8; ++a) g_lin_t[fa.linearize_count & 63][a] = 0ull;
-  }
-#endif
-  GroupScratch<ROWS>& S = *reinterpret_cast<GroupScratch<ROWS>*>(s_dyn + (size_t)warp * lin_warp_bytes<ROWS>(pool_buckets, mv.cap));
-  float4* const pool = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(&S) + ((sizeof(GroupScratch<ROWS>) + 15) / 16) * 16);
-  // the whitened [J (6), e] rows of the warp's 32 points share the candidate stacks' memory (P2 vs P1 / P3)
-  double(*s_row)[7] = reinterpret_cast<double(*)[7]>(S.stack);
-  static_assert(sizeof(S.stack) >= sizeof(double) * 7 * 32, "s_row fits");
-  if (tid < 32) s_rank[tid] = 0xffffu;
-  __syncthreads();
-  if (tid < kCube && mv.rank[tid] != 0xffu) s_rank[mv.rank[tid]] = rank_entry(tid);
-  if (lane == 0) mbar_init(&S.mbar, 1);
-  uint32_t mbar_parity = 0u;
-  // Lane a < 28 owns entry a of the packed upper triangle of [J e]^T [J e] (7x7): the 21 entries of
-  // J^T J first (row-major, c >= r), then J^T e (6), then e^2.
-  const int pr = kTriRow[lane], pc = kTriCol[lane];
-
-  // everything above is independent of earlier kernels; from here on we read the pose the previous linearisation
-  // left and overwrite per-point state the previous k_loc_comp may still be reading
-  pdl_wait();
-  if (blockIdx.x == 0) MB_LT_SET(1);
-  m33 R;
-  d3 T;
-  if constexpr (std::is_same<PoseT, PoseArg>::value) {
-    if (blockIdx.x == 0 && tid < 16) pose_dev[tid] = pa.v[tid];  // k_finalize reads pose / gravity / lambda there
-#pragma unroll
-    for (int a = 0; a < 9; ++a) R.m[a] = pa.v[a];
-    T = mk3(pa.v[9], pa.v[10], pa.v[11]);
-  } else {
-#pragma unroll
-    for (int a = 0; a < 9; ++a) R.m[a] = pose_dev[a];
-    T = mk3(pose_dev[9], pose_dev[10], pose_dev[11]);
-  }
-  const int k = fv.k;
-  const bool forced = (fv.flags & 1u) != 0;
-  const double inv_sigma = 1.0 / fv.sigma;  // = sqrt_w / sigma for the points Huber leaves alone (sqrt_w == 1)
-
-  double acc = 0.0, lacc = 0.0;  // lacc: lane a < 6 sums component a of the previous linearisation's localizability pass
-  int cnt = 0;  // lane s < 9: points with status s; lane 9: points searched
-  // Folded localizability pass (device-resident loop): before a point's status and localizability vectors are
-  // overwritten, its contribution |loc^T V| (entries below 0.5 dropped, geometric_factor.hpp:434-457) to the
-  // component localizabilities of the PREVIOUS linearisation is taken with that linearisation's eigenvectors, which
-  // the previous k_finalize left in ds->lin.  It saves a pass over the points and a kernel launch per iteration.
-  if (fv.fold_loc && tid < 18) s_V[tid] = tid < 9 ? ds->lin.eigvec_trans[tid] : ds->lin.eigvec_rot[tid - 9];
-  __syncthreads();
-
-  // Residual, s-check, Huber, Jacobian, localizability vectors of point i on plane (mean, normal); accumulates the
-  // warp's rows.  `go`: this lane takes part; st: in = the plane's status (Unprocessed after a fresh fit), out = final.
-  auto finish_points = [&](size_t i, bool go, d3 ps, d3 pt, d3 mean, d3 normal, uint8_t& st) {
-    double row[7] = {0, 0, 0, 0, 0, 0, 0};
-    if (go) {
-      double e = dot3(normal, sub3(mean, pt));
-      const double s_chk = 1 - 0.9 * fabs(e) / fv.rroot[i];
-      if (s_chk < 0.9) {
-        st = MB_MAX_ERROR;
-      } else {
-        double sqrt_w = 1.0;
-        if (fv.use_huber) {
-          const double we = e / fv.sigma;
-          if (fabs(we) > fv.kh) sqrt_w = sqrt(fv.kh / fabs(we));
-        }
-        const double scale = sqrt_w == 1.0 ? inv_sigma : sqrt_w / fv.sigma;
-        e *= scale;
-        const d3 ns = mul33Tv(R, normal);
-        const d3 jr = cross3(ns, ps);
-        const double z = sqnorm3(jr);
-        st3(fv.loc_rot, fv.ld, i, z > 0 ? div3(jr, sqrt(z)) : jr);
-        st3(fv.loc_trans, fv.ld, i, mk3(-ns.x, -ns.y, -ns.z));
-        row[0] = jr.x * scale;
-        row[1] = jr.y * scale;
-        row[2] = jr.z * scale;
-        row[3] = -ns.x * scale;
-        row[4] = -ns.y * scale;
-        row[5] = -ns.z * scale;
-        row[6] = e;
-        st = MB_VALID;
-      }
-    }
-    // [J e]^T [J e] over the warp's points: lane a sums its entry over the rows in point order.
-    if (__ballot_sync(kFull, go && st == MB_VALID)) {
-#pragma unroll
-      for (int a = 0; a < 7; ++a) s_row[lane][a] = row[a];
-      __syncwarp();
-#pragma unroll 8
-      for (int p = 0; p < 32; ++p) acc += s_row[p][pr] * s_row[p][pc];
-      __syncwarp();
-    }
-  };
-
-  const size_t n_tiles = (fv.n + 31) / 32;
-  const size_t n_warps = (size_t)gridDim.x * kLinWarps;
-  const size_t first_tile = (size_t)blockIdx.x * kLinWarps + warp;
-  // ================================ P1: gate, cached points, queue =====================================
-  for (size_t tile = first_tile; tile < n_tiles; tile += n_warps) {
-    const size_t i = tile * 32 + lane;
-    const bool act = i < fv.n;
-    d3 ps = mk3(0, 0, 0), pt = mk3(0, 0, 0);
-    uint8_t st = MB_UNPROCESSED;
-    bool need = false;
-    if (act) {
-      const float4 s = __ldg(fv.src + i);
-      ps = mk3((double)s.x, (double)s.y, (double)s.z);
-      pt = add3(mul33v(R, ps), T);
-      st = fv.status[i];
-      const d3 da = ld3(fv.p_da, fv.ld, i);
-      need = forced || sqnorm3(sub3(pt, da)) >= fv.da_gate_sq;  // == sqrt(d2) > gate (:281-283), without the square root
-    }
-    const uint8_t st_prev = st;  // the status the previous linearisation left (folded localizability pass)
-    const unsigned need_mask = __ballot_sync(kFull, need);
-    if (lane == 0) fv.need_mask[tile] = need_mask;
-    if (need_mask) {
-      unsigned base = 0;
-      if (lane == 0) base = atomicAdd(&ctl->q_count, (unsigned)__popc(need_mask));
-      base = __shfl_sync(kFull, base, 0);
-      if (need) fv.queue[base + __popc(need_mask & ((1u << lane) - 1u))] = (uint32_t)i;
-    }
-    if (fv.fold_loc) {
-      double v[6] = {0, 0, 0, 0, 0, 0};
-      if (act && st_prev == MB_VALID) {
-        const d3 lt = ld3(fv.loc_trans, fv.ld, i), lr = ld3(fv.loc_rot, fv.ld, i);
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {  // column a of V: (V^T loc)_a, in mul33Tv's order of operations
-          const double tc = fabs(s_V[a] * lt.x + (s_V[3 + a] * lt.y + s_V[6 + a] * lt.z));
-          const double rc = fabs(s_V[9 + a] * lr.x + (s_V[12 + a] * lr.y + s_V[15 + a] * lr.z));
-          v[a] = tc >= 0.5 ? tc : 0.0;
-          v[3 + a] = rc >= 0.5 ? rc : 0.0;
-        }
-      }
-      if (__ballot_sync(kFull, act && st_prev == MB_VALID)) {
-#pragma unroll
-        for (int a = 0; a < 6; ++a) s_row[lane][a] = v[a];
-        __syncwarp();
-        if (lane < 6) {
-#pragma unroll 8
-          for (int p = 0; p < 32; ++p) lacc += s_row[p][lane];
-        }
-        __syncwarp();
-      }
-    }
-    // points that keep their association: skipped for good when the cached plane was rejected (:314-316)
-    const bool go = act && !need && st > MB_CORRES_PLANE_INVALID;
-    d3 mean = mk3(0, 0, 0), normal = mk3(0, 0, 0);
-    if (go) {
-      mean = ld3(fv.mean, fv.ld, i);
-      normal = ld3(fv.normal, fv.ld, i);
-    }
-    finish_points(i, go, ps, pt, mean, normal, st);
-    if (go && st != st_prev) fv.status[i] = st;
-#pragma unroll
-    for (int s = 0; s < 9; ++s) {
-      const int c = __popc(__ballot_sync(kFull, act && !need && st == s));
-      if (lane == s) cnt += c;
-    }
-    if (lane == 9) cnt += __popc(need_mask);
-  }
-  MB_LT_MAX(2);
-  grid_barrier(ctl, gridDim.x);
-  pdl_launch_dependents();  // from here on every block of this grid is known to be resident
-  const unsigned q_count = ld_acquire_gpu(&ctl->q_count);
-  if (q_count) {
-    // ================================ P2: search passes, pulled =========================================
-    for (;;) {
-      unsigned pass = 0;
-      if (lane == 0) pass = atomicAdd(&ctl->q_pass, 1u);
-      pass = __shfl_sync(kFull, pass, 0);
-      if ((size_t)pass * 32 >= q_count) break;
-      const unsigned e = pass * 32 + lane;
-      const bool on = e < q_count;
-      const size_t i = on ? (size_t)__ldcg(fv.queue + e) : 0;
-      const float4 s = __ldg(fv.src + i);
-      const d3 ps = mk3((double)s.x, (double)s.y, (double)s.z);
-      const d3 pt = add3(mul33v(R, ps), T);
-      double bd[K];
-      uint32_t bs[K];
-      const GroupLane gl = knn_warp_groups<K, ROWS>(mv, s_rank, S, pool, pool_buckets, mbar_parity, pt.x, pt.y, pt.z, k, on, bd, bs);
-      if (on) {
-        float4 nb[K];
-        uint64_t g[K];
-        const int found = group_resolve_all<K, ROWS>(mv, S, pool, gl, bs, k, g, nb);
-        double dk = 0.0;
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-          if (j < k) {
-            if (j == k - 1) dk = bd[j];
-            // indices are only meaningful when all k exist (the reference discards partial results)
-            if (fv.knn_idx) fv.knn_idx[i * k + j] = found == k ? g[j] : ~0ull;
-          }
-        }
-        st3(fv.p_da, fv.ld, i, pt);
-        uint8_t st = MB_UNPROCESSED;  // :290
-        if (found != k) {
-          st = MB_INSUFFICIENT_CORRES_POINTS;
-        } else if (dk > fv.max_corr_sq) {
-          st = MB_CORRES_MAX_DIST;
-        } else {
-          bool normal_set;
-          d3 mean, normal;
-          st = fit_plane<K>(nb, k, T, fv.pvd, mean, normal, normal_set);
-          st3(fv.mean, fv.ld, i, mean);
-          if (normal_set) st3(fv.normal, fv.ld, i, normal);
-        }
-        fv.status[i] = st;  // Unprocessed = the plane stands: P3 takes the residual
-      }
-      __syncwarp();  // the group tables and the pool are rewritten by the next pass
-    }
-    MB_LT_MAX(3);
-    grid_barrier(ctl, gridDim.x);
-    // ================================ P3: the re-associated points =====================================
-    for (size_t tile = first_tile; tile < n_tiles; tile += n_warps) {
-      const unsigned need_mask = fv.need_mask[tile];
-      if (need_mask == 0u) continue;
-      const size_t i = tile * 32 + lane;
-      const bool need = (need_mask >> lane) & 1u;
-      d3 ps = mk3(0, 0, 0), pt = mk3(0, 0, 0), mean = mk3(0, 0, 0), normal = mk3(0, 0, 0);
-      uint8_t st = MB_UNPROCESSED;
-      bool go = false;
-      if (need) {
-        st = __ldcg(fv.status + i);
-        go = st == MB_UNPROCESSED;
-        if (go) {
-          const float4 s = __ldg(fv.src + i);
-          ps = mk3((double)s.x, (double)s.y, (double)s.z);
-          pt = add3(mul33v(R, ps), T);
-          mean = mk3(__ldcg(fv.mean + i), __ldcg(fv.mean + fv.ld + i), __ldcg(fv.mean + 2 * fv.ld + i));
-          normal = mk3(__ldcg(fv.normal + i), __ldcg(fv.normal + fv.ld + i), __ldcg(fv.normal + 2 * fv.ld + i));
-        }
-      }
-      finish_points(i, go, ps, pt, mean, normal, st);
-      if (go) fv.status[i] = st;
-#pragma unroll
-      for (int s = 0; s < 9; ++s) {
-        const int c = __popc(__ballot_sync(kFull, need && st == s));
-        if (lane == s) cnt += c;
-      }
-    }
-  }
-
-  // ---- block partial -> group partial -> packet (two ticketed levels, fixed order) ------------------------
-  MB_LT_MAX(4);
-  if (lane < 28) s_red[warp][lane] = acc;
-  if (lane >= 30) s_red[warp][lane + 8] = s_red[warp][lane + 16] = 0.0;  // pad entries 38, 39, 46, 47
-  if (lane < 10) s_red[warp][kPackCnt + lane] = (double)cnt;
-  if (lane < 6) s_red[warp][kPackLoc + lane] = lacc;
-  __syncthreads();
-  if (tid < kPack) {
-    double v = 0.0;
-#pragma unroll
-    for (int w = 0; w < kLinWarps; ++w) v += s_red[w][tid];
-    fv.partials[(size_t)blockIdx.x * kPack + tid] = v;
-  }
-  const int g = blockIdx.x / kGroup;
-  const int n_groups = (gridDim.x + kGroup - 1) / kGroup;
-  const int g_size = min(kGroup, (int)gridDim.x - g * kGroup);
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = atomicAdd(fv.gtickets + g, 1u) == (unsigned)g_size - 1;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  block_sum_rows(fv.partials + (size_t)g * kGroup * kPack, g_size, kPack, s_tmp, fv.gpartials + (size_t)g * kPack,
-                 kLinThreads);
-  if (tid == 0) fv.gtickets[g] = 0u;
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = atomicAdd(fv.ticket, 1u) == (unsigned)n_groups - 1;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  MB_LT_SET(5);
-  block_sum_rows(fv.gpartials, n_groups, kPack, s_tmp, fv.packed, kLinThreads);
-  if (tid == 0) {
-    *fv.ticket = 0u;
-    ctl->q_count = 0u;  // every block has left P2 / P3: ready for the next launch
-    ctl->q_pass = 0u;
-  }
-  MB_LT_SET(6);
-  if (peer) {
-    // Several ranks: this rank's packet goes straight into every rank's mailbox (peer stores over NVLink),
-    // then the flags are raised — k_finalize on each rank sums its mailbox in rank order (mb_internal.cuh).
     __syncthreads();  // the packet written by this block's first kPack threads is visible to all of them
     const int world = peer->world, rank = peer->rank;
     const unsigned long long seq = *peer->xseq + 1ull;
@@ -1320,16 +919,10 @@ struct mb_factor {
   int grid = 0, grid2 = 0, n_groups = 0;
   // k_linearize launch shape: kernel variant (k == 5 and <= 19 neighbour voxels, or generic), staging pool per warp
   bool lin_small = true;
-  bool use_v1 = false;  // development (MB_LIN_KERNEL=v1): the round-1 kernel
-  int pool_buckets = 0;
-  size_t lin_smem = 0;
   // voxel order (see k_group_sort): the caller's points, sorted position -> caller's index
   float4* src_raw = nullptr;
   uint32_t* perm = nullptr;
   double* rroot = nullptr;  // sqrt(||p||) per sorted point
-  LoopCtl* ctl = nullptr;       // k_linearize's barrier / queue control words
-  uint32_t* queue = nullptr;    // re-association queue
-  uint32_t* need_mask = nullptr;
   bool sorted = false;
   void* raw = nullptr;  // the caller's records on the device while a factor is being built from page-locked memory
   size_t raw_bytes = 0;
@@ -1358,9 +951,6 @@ struct mb_factor {
     const float da_gate_f = cfg.target_ivox_map_min_dist_in_voxel / 4;          // geometric_factor.hpp:283
     v.da_gate_sq = da_gate_sq_min((double)da_gate_f);
     v.rroot = rroot;
-    v.ctl = ctl;
-    v.queue = queue;
-    v.need_mask = need_mask;
     const float max_corr_f = cfg.max_corres_distance * cfg.max_corres_distance;  // :299
     v.max_corr_sq = (double)max_corr_f;
     v.sigma = (double)cfg.lidar_point_noise_std_dev;
@@ -1390,42 +980,6 @@ int reset_state(mb_factor* f) {
   f->linearize_count = 0;
   f->sorted = false;  // the next first linearisation re-sorts under its own pose (all state is zero again)
   return MB_OK;
-}
-
-// k_linearize needs more dynamic shared memory than the default limit: opt every instantiation in, once.
-template <typename Kern>
-int lin_opt_in(Kern kern, size_t bytes) {
-  MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  return MB_OK;
-}
-int lin_opt_in_all(const mb_factor* f) {
-  if (f->lin_small) {
-    MB_TRY(lin_opt_in(k_linearize<5, PoseArg, 19>, f->lin_smem));
-    MB_TRY(lin_opt_in(k_linearize<5, NoPose, 19>, f->lin_smem));
-  } else {
-    MB_TRY(lin_opt_in(k_linearize<MB_MAX_K, PoseArg, 27>, f->lin_smem));
-    MB_TRY(lin_opt_in(k_linearize<MB_MAX_K, NoPose, 27>, f->lin_smem));
-  }
-  return MB_OK;
-}
-
-// k_linearize's launch: cooperative (its grid barriers need every block resident) and programmatically serialised
-// behind its predecessor like the other kernels of an iteration.
-template <typename... KArgs, typename... Args>
-cudaError_t launch_lin(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  attr[1].id = cudaLaunchAttributeCooperative;
-  attr[1].val.cooperative = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 2;
-  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 // Before the first linearisation: group the scan by map voxel under that call's pose (k_group_sort).
@@ -1477,31 +1031,19 @@ int enqueue_linearize(mb_factor* f, int do_step, int iter, mb_icp_trace* d_trace
   fa.iter = iter;
   fa.trace = d_trace;
   const dim3 grid(f->grid), block(kLinThreads);
-  if (f->use_v1) {
-    if (pose_arg) {
-      if (f->lin_small)
-        MB_CUDA(launch_pdl(k_linearize_v1<5, PoseArg, 19>, grid, block, st, f->map->view(), fv, f->ds, *pose_arg, peer));
-      else
-        MB_CUDA(launch_pdl(k_linearize_v1<MB_MAX_K, PoseArg, 27>, grid, block, st, f->map->view(), fv, f->ds, *pose_arg, peer));
-    } else {
-      if (f->lin_small)
-        MB_CUDA(launch_pdl(k_linearize_v1<5, NoPose, 19>, grid, block, st, f->map->view(), fv, f->ds, NoPose{}, peer));
-      else
-        MB_CUDA(launch_pdl(k_linearize_v1<MB_MAX_K, NoPose, 27>, grid, block, st, f->map->view(), fv, f->ds, NoPose{}, peer));
-    }
-  } else if (pose_arg) {
+  if (pose_arg) {
     if (f->lin_small)  // the specialised kernel: k = 5 and at most 19 neighbour voxels
-      MB_CUDA(launch_lin(k_linearize<5, PoseArg, 19>, grid, block, f->lin_smem, st, f->map->view(), fv, f->ds, *pose_arg, peer, fa, f->pool_buckets));
+      MB_CUDA(launch_pdl(k_linearize<5, PoseArg, 19>, grid, block, st, f->map->view(), fv, f->ds, *pose_arg, peer));
     else
-      MB_CUDA(launch_lin(k_linearize<MB_MAX_K, PoseArg, 27>, grid, block, f->lin_smem, st, f->map->view(), fv, f->ds, *pose_arg, peer, fa, f->pool_buckets));
+      MB_CUDA(launch_pdl(k_linearize<MB_MAX_K, PoseArg, 27>, grid, block, st, f->map->view(), fv, f->ds, *pose_arg, peer));
   } else {
     if (f->lin_small)
-      MB_CUDA(launch_lin(k_linearize<5, NoPose, 19>, grid, block, f->lin_smem, st, f->map->view(), fv, f->ds, NoPose{}, peer, fa, f->pool_buckets));
+      MB_CUDA(launch_pdl(k_linearize<5, NoPose, 19>, grid, block, st, f->map->view(), fv, f->ds, NoPose{}, peer));
     else
-      MB_CUDA(launch_lin(k_linearize<MB_MAX_K, NoPose, 27>, grid, block, f->lin_smem, st, f->map->view(), fv, f->ds, NoPose{}, peer, fa, f->pool_buckets));
+      MB_CUDA(launch_pdl(k_linearize<MB_MAX_K, NoPose, 27>, grid, block, st, f->map->view(), fv, f->ds, NoPose{}, peer));
   }
   if (nccl) MB_NCCL(ncclAllReduce(f->packed, f->packed, kPack, ncclDouble, ncclSum, c->comm, st));
-  MB_CUDA(launch_pdl(k_finalize, dim3(1), dim3(160), st, (const double*)f->packed, f->ds, fa, 31u, peer, f->packed));
+  MB_CUDA(launch_pdl(k_finalize, dim3(1), dim3(64), st, (const double*)f->packed, f->ds, fa, 31u, peer, f->packed));
   c->launches += 2;
   if (host_out) {
     MB_CUDA(launch_pdl(k_loc_comp<true>, dim3(f->grid2), dim3(kLocThreads), st, fv, (const DevState*)f->ds, *host_out, peer));
@@ -1557,38 +1099,16 @@ static int factor_init(mb_factor* f, mb_ctx* ctx, mb_map* map, const void* pts, 
   f->n = shard_end - shard_begin;
   f->ld = std::max<size_t>(align_up(f->n, 32), 32);
   const size_t k = cfg->num_corres_points;
-  // k_linearize: one warp per 32-point tile; per warp the group-search scratch and, optionally, a staging pool for the
-  // bulk-copy engine.  The pool is OFF by default: staged and direct reads were both measured on the benchmark scan
-  // (profiles/r2_experiments.md) and reading the buckets through L1 won (lock-step lanes of a voxel group read the
-  // same 16 bytes, one broadcast access per step, and the 52 KB of pools per block leave the SM 30 KB of L1);
-  // MB_LIN_POOL=<buckets per warp> turns staging on (development / the tests of the staged path).
+  // k_linearize: blocks of 128 threads, one 128-point tile at a time, as many blocks as the device holds
   f->lin_small = k == 5 && map->n_off <= 19;
-  {
-    int smem_sm = 0, smem_blk = 0;
-    MB_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device));
-    MB_CUDA(cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-    const size_t fixed = f->lin_small ? lin_warp_bytes<19>(0, map->cap) : lin_warp_bytes<27>(0, map->cap);
-    const size_t per_block = std::min<size_t>((size_t)smem_blk, (size_t)smem_sm / MB_LIN_BLOCKS) - 1024 /* reserved */ - 4096 /* static */;
-    const size_t per_warp = per_block / kLinWarps;
-    const size_t bucket = (size_t)map->cap * sizeof(float4);
-    const int fit = per_warp > fixed ? (int)((per_warp - fixed) / bucket) : 0;
-    f->pool_buckets = 0;
-    if (const char* e = getenv("MB_LIN_POOL")) f->pool_buckets = std::max(0, std::min(fit, atoi(e)));
-    if (const char* e = getenv("MB_LIN_KERNEL")) f->use_v1 = !strcmp(e, "v1");
-    f->lin_smem = kLinWarps * (f->lin_small ? lin_warp_bytes<19>(f->pool_buckets, map->cap) : lin_warp_bytes<27>(f->pool_buckets, map->cap));
-    const int orc = lin_opt_in_all(f);
-    if (orc != MB_OK) {
-      return orc;
-    }
-  }
   int per_sm = MB_LIN_BLOCKS;
   if (f->lin_small)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<5, NoPose, 19>, kLinThreads, f->lin_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<5, NoPose, 19>, kLinThreads, 0);
   else
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<MB_MAX_K, NoPose, 27>, kLinThreads, f->lin_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<MB_MAX_K, NoPose, 27>, kLinThreads, 0);
   per_sm = std::max(per_sm, 1);
-  const size_t n_wtiles = (f->n + 31) / 32;
-  f->grid = (int)std::max<size_t>(1, std::min<size_t>((n_wtiles + kLinWarps - 1) / kLinWarps, (size_t)ctx->sm_count * per_sm));  // all resident
+  const size_t n_tiles = (f->n + kLinThreads - 1) / kLinThreads;
+  f->grid = (int)std::max<size_t>(1, std::min<size_t>(n_tiles, (size_t)ctx->sm_count * per_sm));
   f->n_groups = (f->grid + kGroup - 1) / kGroup;
   f->grid2 = (int)std::max<size_t>(1, std::min<size_t>((f->n + kLocThreads - 1) / kLocThreads, (size_t)ctx->sm_count * 4));
 
@@ -1604,8 +1124,6 @@ static int factor_init(mb_factor* f, mb_ctx* ctx, mb_map* map, const void* pts, 
   const size_t o_raw = take(f->ld * sizeof(float4));
   const size_t o_perm = take(f->ld * sizeof(uint32_t));
   const size_t o_rroot = take(f->ld * sizeof(double));
-  const size_t o_queue = take(f->ld * sizeof(uint32_t));
-  const size_t o_nmask = take((f->ld / 32 + 1) * sizeof(uint32_t));
   const size_t o_vecs = take(15 * f->ld * sizeof(double) + f->ld);  // status follows the vectors directly
   const size_t o_idx = take(f->ld * k * sizeof(uint64_t));
   const size_t o_par = take((size_t)f->grid * kPack * sizeof(double));
@@ -1613,7 +1131,6 @@ static int factor_init(mb_factor* f, mb_ctx* ctx, mb_map* map, const void* pts, 
   const size_t o_par2 = take((size_t)f->grid2 * 8 * sizeof(double));
   const size_t o_packed = take((kPack + 8) * sizeof(double));
   const size_t o_tick = take((2 + (size_t)f->n_groups) * sizeof(unsigned));  // final, loc, groups...
-  const size_t o_ctl = take(sizeof(LoopCtl));
   const size_t o_ds = take(sizeof(DevState));
   f->block_bytes = off;
   int rc = dev_alloc(ctx, &f->block, f->block_bytes);
@@ -1625,8 +1142,6 @@ static int factor_init(mb_factor* f, mb_ctx* ctx, mb_map* map, const void* pts, 
   f->src_raw = (float4*)(base + o_raw);
   f->perm = (uint32_t*)(base + o_perm);
   f->rroot = (double*)(base + o_rroot);
-  f->queue = (uint32_t*)(base + o_queue);
-  f->need_mask = (uint32_t*)(base + o_nmask);
   f->vecs = (double*)(base + o_vecs);
   f->status = (uint8_t*)(base + o_vecs + 15 * f->ld * sizeof(double));
   f->knn_idx = (uint64_t*)(base + o_idx);
@@ -1635,7 +1150,6 @@ static int factor_init(mb_factor* f, mb_ctx* ctx, mb_map* map, const void* pts, 
   f->partials2 = (double*)(base + o_par2);
   f->packed = (double*)(base + o_packed);
   f->tickets = (unsigned*)(base + o_tick);
-  f->ctl = (LoopCtl*)(base + o_ctl);
   f->ds = (DevState*)(base + o_ds);
 
   bool staged = true;  // the context's pinned staging buffer was used: wait for the copy before returning
@@ -1774,13 +1288,13 @@ MB_API int mb_debug_time_finalize(mb_factor* f, unsigned role_mask, int reps, fl
   auto one = [&]() {
     if (role_mask == 32u) {
       if (f->lin_small)
-        launch_lin(k_linearize<5, NoPose, 19>, dim3(f->grid), dim3(kLinThreads), f->lin_smem, st, f->map->view(), fv, f->ds, no_pose, (const PeerTable*)nullptr, fa, f->pool_buckets);
+        k_linearize<5, NoPose, 19><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds, no_pose, nullptr);
       else
-        launch_lin(k_linearize<MB_MAX_K, NoPose, 27>, dim3(f->grid), dim3(kLinThreads), f->lin_smem, st, f->map->view(), fv, f->ds, no_pose, (const PeerTable*)nullptr, fa, f->pool_buckets);
+        k_linearize<MB_MAX_K, NoPose, 27><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds, no_pose, nullptr);
     } else if (role_mask == 64u) {
       k_loc_comp<false><<<f->grid2, kLocThreads, 0, st>>>(fv, f->ds, no_out, nullptr);
     } else {
-      k_finalize<<<1, 160, 0, st>>>(f->packed, f->ds, fa, role_mask, nullptr, f->packed);
+      k_finalize<<<1, 64, 0, st>>>(f->packed, f->ds, fa, role_mask, nullptr, f->packed);
     }
   };
   for (int w = 0; w < 3; ++w) one();
@@ -1792,23 +1306,6 @@ MB_API int mb_debug_time_finalize(mb_factor* f, unsigned role_mask, int reps, fl
   MB_CUDA(cudaEventElapsedTime(&ms, f->ctx->ev0, f->ctx->ev1));
   *us_per_launch = ms * 1e3f / reps;
   return MB_OK;
-}
-
-// Development (built with -DMB_LIN_TIMING only): the %globaltimer stamps of the last 64 k_linearize launches, 8 per
-// launch: entry, after the dependency wait, last tile loop end, last group reduction, final ticket, packet, solve /
-// retract done, eigen roles done.
-MB_API int mb_debug_lin_timeline(unsigned long long* out512) {
-#if defined(MB_LIN_TIMING)
-  MB_CUDA(cudaDeviceSynchronize());
-  MB_CUDA(cudaMemcpyFromSymbol(out512, g_lin_t, sizeof(unsigned long long) * 512));
-  MB_CUDA(cudaMemcpyFromSymbol(out512 + 512, g_lin_blk, sizeof(unsigned long long) * 4096));
-  MB_CUDA(cudaMemcpyFromSymbol(out512 + 512 + 4096, g_lin_warp, sizeof(unsigned) * 8192));
-  return MB_OK;
-#else
-  (void)out512;
-  set_error("mb_debug_lin_timeline: library built without -DMB_LIN_TIMING");
-  return MB_ERR_UNSUPPORTED;
-#endif
 }
 
 int mb_factor_release(mb_factor* f) {

@@ -144,7 +144,6 @@ static inline void prefetch_l2(const void*) {}
 using std::min;
 
 #include "../../mimosa_b200/csrc/mb_search.cuh"
-#include "../../mimosa_b200/csrc/mb_search_group.cuh"
 
 namespace {
 struct HostMirror {
@@ -263,69 +262,7 @@ void run_warps(const HostMirror& M, const double* q, size_t nq, int k, uint64_t*
     for (auto& t : lanes) t.join();
   }
 }
-// The voxel-grouped warp search of k_linearize (mb_search_group.cuh): 32 queries per emulated warp in the order
-// given (the caller sorts them by voxel or not), scratch laid out as in the kernel; pool_buckets = 0: never staged.
-// `mask` selects which lanes are active in each warp (bit per query, nullptr = all): inactive lanes must not disturb.
-template <int K, int ROWS>
-void run_groups(const HostMirror& M, const double* q, size_t nq, int k, int pool_buckets, const uint8_t* on, uint64_t* idx, double* d2,
-                uint8_t* ok) {
-  uint16_t s_rank[32];
-  for (int r = 0; r < 32; ++r) s_rank[r] = 0xffff;
-  for (int c = 0; c < mb::kCube; ++c)
-    if (M.view.rank[c] != 0xff) s_rank[M.view.rank[c]] = mb::rank_entry(c);
-  std::vector<float4> pool((size_t)std::max(pool_buckets, 1) * M.view.cap);
-  for (size_t w0 = 0; w0 < nq; w0 += 32) {
-    WarpCtx ctx;
-    auto S = std::make_unique<mb::GroupScratch<ROWS>>();
-    std::memset(S.get(), 0xee, sizeof *S);  // stale contents must never be used
-    for (auto& p : pool) p = make_float4(1e30f, 1e30f, 1e30f, 0.f);
-    std::vector<std::thread> lanes;
-    for (int lane = 0; lane < 32; ++lane)
-      lanes.emplace_back([&, lane] {
-        t_warp = &ctx;
-        t_lane = lane;
-        const size_t i = w0 + lane;
-        const bool active = i < nq && (!on || on[i]);
-        const size_t qi = i < nq ? i : 0;
-        double bd[K];
-        uint32_t bs[K];
-        uint32_t parity = 0;
-        const mb::GroupLane gl = mb::knn_warp_groups<K, ROWS>(M.view, s_rank, *S, pool.data(), pool_buckets, parity, q[3 * qi],
-                                                              q[3 * qi + 1], q[3 * qi + 2], k, active, bd, bs);
-        if (active) {
-          uint64_t g[K];
-          float4 pts[K];
-          const int found = mb::group_resolve_all<K, ROWS>(M.view, *S, pool.data(), gl, bs, k, g, pts);
-          for (int j = 0; j < k; ++j) {
-            idx[i * k + j] = g[j];
-            d2[i * k + j] = g[j] != ~0ull ? bd[j] : 1.7976931348623157e308;
-            // the stored point handed to the plane fit must be the indexed one
-            if (g[j] != ~0ull) {
-              const double dd = mb::sqdist4((double)pts[j].x, (double)pts[j].y, (double)pts[j].z, q[3 * qi], q[3 * qi + 1], q[3 * qi + 2]);
-              if (dd != bd[j]) d2[i * k + j] = -1.0;
-            }
-          }
-          ok[i] = found == k;
-        }
-        t_warp = nullptr;
-      });
-    for (auto& t : lanes) t.join();
-  }
-}
 }  // namespace
-
-extern "C" int shim_knn_groups(const int32_t* coords, const int32_t* counts, const float* xyz, uint32_t n_vox, int cap, int nbr_mode,
-                               double leaf, const double* q, size_t nq, int k, int pool_buckets, const uint8_t* on, uint64_t* idx,
-                               double* d2, uint8_t* ok) {
-  if (k < 1 || k > 8) return 1;
-  HostMirror M;
-  build_mirror(M, coords, counts, xyz, n_vox, cap, nbr_mode, leaf, 0.0);
-  if (k == 5 && M.view.n_off <= 19)
-    run_groups<5, 19>(M, q, nq, k, pool_buckets, on, idx, d2, ok);
-  else
-    run_groups<8, 27>(M, q, nq, k, pool_buckets, on, idx, d2, ok);
-  return 0;
-}
 
 extern "C" int shim_knn(const int32_t* coords, const int32_t* counts, const float* xyz, uint32_t n_vox, int cap, int nbr_mode,
                         double leaf, double pref_frac, const double* q, size_t nq, int k, uint64_t* idx, double* d2, uint8_t* ok) {

@@ -1,7 +1,6 @@
 """The search code the kernels run (mimosa_b200/csrc/mb_search.cuh: block probes, occupancy masks, pruning
 bounds, deferred ordered insertion, tie order) compiled for the HOST, one emulated lane per query
-(tests/host_shim/search_shim.cpp) and the voxel-grouped warp search k_linearize runs (mb_search_group.cuh, as an
-emulated 32-lane warp), against the oracle's iVox k-NN: indices and squared distances bit-exact for
+(tests/host_shim/search_shim.cpp), against the oracle's iVox k-NN: indices and squared distances bit-exact for
 every neighbourhood mode, k, leaf size and early-prefetch radius.  CPU-only coverage of the hot path's logic;
 the GPU parity tests check the same kernels through the C ABI."""
 import ctypes as C
@@ -18,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def shim():
     src = os.path.join(HERE, "host_shim", "search_shim.cpp")
     out = os.path.join(HERE, "host_shim", "libsearch_shim.so")
-    hdrs = [os.path.join(HERE, "..", "mimosa_b200", "csrc", h) for h in ("mb_search.cuh", "mb_search_group.cuh", "mb_math.cuh")]
+    hdrs = [os.path.join(HERE, "..", "mimosa_b200", "csrc", h) for h in ("mb_search.cuh", "mb_math.cuh")]
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(p) for p in [src] + hdrs):
         subprocess.run(["g++", "-O2", "-std=c++20", "-ffp-contract=off", "-frounding-math", "-fPIC", "-shared", "-pthread", src,
                         "-o", out], check=True)
@@ -29,32 +28,23 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def shim_knn(shim, m, q, k, nbr_mode, leaf, pref_frac=0.4, warp=False, groups=None, on=None):
+def shim_knn(shim, m, q, k, nbr_mode, leaf, pref_frac=0.4, warp=False):
     coords, counts, _, pts, _ = m.download()
     q = np.ascontiguousarray(q, np.float64).reshape(-1, 3)
     nq = q.shape[0]
     idx, d2, ok = np.empty((nq, k), np.uint64), np.empty((nq, k), np.float64), np.empty(nq, np.uint8)
     leaf = float(np.float32(leaf))  # the map's leaf size is a float (mb_map_create, IVoxRef): 1 / (double)leaf_f32
-    if groups is not None:  # the voxel-grouped warp search (always an emulated 32-lane warp); groups = pool buckets per warp
-        on_p = _p(np.ascontiguousarray(on, np.uint8)) if on is not None else None
-        rc = shim.shim_knn_groups(_p(coords), _p(counts), _p(pts), C.c_uint32(coords.shape[0]), C.c_int(m.cap), C.c_int(nbr_mode),
-                                  C.c_double(leaf), _p(q), C.c_size_t(nq), C.c_int(k), C.c_int(groups), on_p, _p(idx), _p(d2), _p(ok))
-        assert rc == 0
-        return idx, d2, ok.astype(bool)
     rc = (shim.shim_knn_warp if warp else shim.shim_knn)(_p(coords), _p(counts), _p(pts), C.c_uint32(coords.shape[0]), C.c_int(m.cap), C.c_int(nbr_mode),
                        C.c_double(leaf), C.c_double(pref_frac), _p(q), C.c_size_t(nq), C.c_int(k), _p(idx), _p(d2), _p(ok))
     assert rc == 0
     return idx, d2, ok.astype(bool)
 
 
-def check(shim, oracle, pts, q, k, mode, leaf, min_dist, pref_frac=0.4, cap=20, warp=False, groups=None, on=None):
+def check(shim, oracle, pts, q, k, mode, leaf, min_dist, pref_frac=0.4, cap=20, warp=False):
     m = oracle.IVoxRef(leaf, min_dist, cap, mode, 1000)
     m.insert(pts)
     io, do, oo = m.knn_search(q, k)
-    ih, dh, oh = shim_knn(shim, m, q, k, mode, leaf, pref_frac, warp, groups, on)
-    if on is not None:  # lanes switched off must not have been written; compare the active ones
-        sel = np.asarray(on, bool)
-        io, do, oo, ih, dh, oh = io[sel], do[sel], oo[sel], ih[sel], dh[sel], oh[sel]
+    ih, dh, oh = shim_knn(shim, m, q, k, mode, leaf, pref_frac, warp)
     assert np.array_equal(oo, oh)
     assert np.array_equal(io[oo], ih[oo]), f"indices differ (mode {mode}, k {k})"
     assert np.array_equal(do[oo], dh[oo]), "squared distances differ"
@@ -122,59 +112,3 @@ def test_search_32_lane_warp_emulation(shim, oracle, mode, k):
                         rng.uniform(-30, 30, (141, 3))])
     q = q[rng.permutation(q.shape[0])]  # 641 queries: 20 full warps + one lane
     assert check(shim, oracle, pts, q, k, mode, 1.0, 0.2, warp=True) > 300
-
-
-# ---- the voxel-grouped warp search of k_linearize (mb_search_group.cuh), run as emulated 32-lane warps ----------------
-def voxel_sorted(q, leaf):
-    c = np.floor(q / leaf).astype(np.int64)
-    return q[np.lexsort((c[:, 2], c[:, 1], c[:, 0]))]
-
-
-@pytest.mark.parametrize("pool", [0, 22, 400])  # never staged / the kernel's pool / everything staged
-@pytest.mark.parametrize("mode,k", [(19, 5), (27, 8), (7, 3), (1, 5), (27, 5), (19, 1)])
-def test_group_search_matches_oracle_world(shim, oracle, pool, mode, k):
-    import synth
-
-    rng = synth.rng_for(1700 + mode + k)
-    pts = np.concatenate([synth.sample_world(40000, 25.0, rng), rng.uniform(-25, 25, (3000, 3)).astype(np.float32)])
-    q = np.concatenate([pts[rng.integers(0, pts.shape[0], 900), :3].astype(np.float64) + rng.normal(0, 0.2, (900, 3)),
-                        rng.uniform(-30, 30, (125, 3))])  # 1025 queries: 32 full warps + one lane
-    # voxel-sorted (few groups per warp, lock-step lanes) and shuffled (up to 32 groups per warp)
-    assert check(shim, oracle, pts, voxel_sorted(q, 1.0), k, mode, 1.0, 0.2, groups=pool) > 500
-    assert check(shim, oracle, pts, q[rng.permutation(q.shape[0])], k, mode, 1.0, 0.2, groups=pool) > 500
-
-
-@pytest.mark.parametrize("pool", [0, 22])
-def test_group_search_dense_voxels_ties_and_caps(shim, oracle, pool):
-    # many queries per voxel (the benchmark scan's regime), lattice ties, caps that are not a multiple of four
-    g = np.arange(-8, 8) * 0.5
-    pts = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
-    rng = np.random.default_rng(5)
-    pts = pts[rng.permutation(pts.shape[0])]
-    q = np.concatenate([pts[:700].astype(np.float64) + 0.25, pts[:700].astype(np.float64), np.round(rng.uniform(-4, 4, (300, 3))),
-                        rng.uniform(-0.5, 1.5, (900, 3))])  # the last 900 share eight voxels
-    for mode, k in ((19, 5), (27, 8), (7, 5)):
-        check(shim, oracle, pts, voxel_sorted(q, 1.0), k, mode, 1.0, 0.0, groups=pool)
-    dense = rng.uniform(-2, 2, (20000, 3)).astype(np.float32)
-    qd = voxel_sorted(rng.uniform(-2, 2, (1500, 3)), 1.0)
-    check(shim, oracle, dense, qd, 5, 19, 1.0, 0.0, cap=7, groups=pool)
-    check(shim, oracle, dense, qd, 5, 19, 1.0, 0.0, cap=31, groups=pool)
-    for leaf, md in ((0.5, 0.15), (2.0, 0.0), (0.25, 0.05)):
-        vol = rng.uniform(-6, 6, (40000, 3)).astype(np.float32)
-        check(shim, oracle, vol, voxel_sorted(rng.uniform(-6.5, 6.5, (1500, 3)), leaf), 5, 19, leaf, md, groups=pool)
-
-
-@pytest.mark.parametrize("pool", [0, 22])
-def test_group_search_partially_active_warps(shim, oracle, pool):
-    """Later search iterations re-associate only some points of a warp: idle lanes must neither join a group nor
-    disturb the others (k_linearize passes need = false for them)."""
-    import synth
-
-    rng = synth.rng_for(1900)
-    pts = synth.sample_world(40000, 25.0, rng)
-    q = voxel_sorted(pts[rng.integers(0, pts.shape[0], 1024), :3].astype(np.float64) + rng.normal(0, 0.2, (1024, 3)), 1.0)
-    for frac in (0.5, 0.1, 0.02):
-        on = rng.uniform(size=q.shape[0]) < frac
-        on[32:64] = False  # a warp with nobody active
-        on[64] = True      # a single active lane
-        assert check(shim, oracle, pts, q, 5, 19, 1.0, 0.2, groups=pool, on=on) > 0
