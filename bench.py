@@ -7,6 +7,8 @@ registered against a ~10 M-point hashed voxel map, 20 Gauss-Newton iterations pe
 ICPFactor::linearize + 6x6 solve + SE(3) retract, data-association cache semantics on, as in the reference).
 
   value     device-resident loop (mb_icp_run, CUDA graph), scan + map already in HBM; per-step CUDA-event times
+  configs   (N = 1 only) BASELINE.json's other configurations as sub-objects, each with its own CPU-oracle baseline:
+            C2 (2 M-point map), C3 (Airy-style scan, deskewed on the device), C5 (10 Hz stream, scans/s end to end)
   e2e       the reference-facing call sequence with HOST buffers: ICPFactor(scan) [H2D], then 20 x
             { linearize(pose) -> H, g, f [D2H] ; 6x6 solve + retract on the host } — what mimosa's
             Geometric::getFactors + the smoother's update() loop would drive
@@ -25,6 +27,12 @@ import subprocess
 import sys
 import threading
 import time
+
+# The CPU oracle's OpenMP workers must SLEEP between parallel regions: libgomp's default lets them spin for a while on
+# every core, and the GPU arm's host thread (kernel launches, polling) then competes with 16 spinners — measured as
+# 100 ms outliers in the streaming config when it ran after a CPU leg.  Must be set before libgomp is loaded.
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+os.environ.setdefault("GOMP_SPINCOUNT", "0")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for _p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tools")):
@@ -201,17 +209,30 @@ def knn_roofline(ctx, mg, scan, R0, t0, synth):
         mg.knn_staged_run()
         knn_ms.append(ctx.timer_end())
     t_knn = float(np.mean(knn_ms)) * 1e-3
+    read_ms = []  # the same launches after a READ flush: the L2 holds clean lines, nothing is written back meanwhile
+    for _ in range(3 + 10):
+        ctx.flush_l2(by_reading=True)
+        ctx.sync()
+        ctx.timer_begin()
+        mg.knn_staged_run()
+        read_ms.append(ctx.timer_end())
+    t_read = float(np.mean(read_ms[3:])) * 1e-3
     peak, peak_src = peaks()
     achieved = bytes_alg / t_knn / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("k_knn_dram_bytes_per_launch")
+        tj = json.load(open(tp))
+        traffic = tj.get("k_knn_dram_bytes_per_launch")
+        traffic_src = {k: tj.get(k) for k in ("source", "build", "captured") if k in tj}
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "kernel": "k_knn (restricted 19-voxel k-NN, k=5), spread queries over the "
-            "whole map, L2 flushed before every launch", "algorithmic_bytes": int(bytes_alg),
+            "traffic": traffic, "traffic_source": traffic_src,
+            "kernel": "k_knn (restricted 19-voxel k-NN, k=5), spread queries over the "
+            "whole map, L2 flushed (256 MiB write) before every launch", "algorithmic_bytes": int(bytes_alg),
             "us_per_launch": t_knn * 1e6, "us_min": float(np.min(knn_ms)) * 1e3, "peak_source": peak_src,
-            "queries_per_s": N_SCAN / t_knn, **parts}
+            "queries_per_s": N_SCAN / t_knn,
+            "read_flush": {"us_per_launch": t_read * 1e6, "achieved": bytes_alg / t_read / 1e9, "frac": bytes_alg / t_read / 1e9 / peak,
+                           "note": "same launches with the L2 flushed by READING 256 MiB (clean lines)"}, **parts}
     roof["survey_8d"] = {"bytes": parts["survey_8d_bytes"], "achieved": parts["survey_8d_bytes"] / t_knn / 1e9,
                          "frac": parts["survey_8d_bytes"] / t_knn / 1e9 / peak,
                          "note": "SURVEY 8(d)'s formula (whole 336-B buckets, per-voxel probes): an upper figure, the kernel "
@@ -282,18 +303,21 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def run_stream(args, ctx, mg, cfg, synth):
+def run_stream(n_scans_arg, ctx, mg, cfg, synth, cpu_scans=0, coords_counts_pts=None):
     """Config C5 (BASELINE.json configs[4]): a 10 Hz scan sequence along a 2 m/s path; per scan the calls
     lidar::Manager::callback makes on this path — deskew (manager.cpp:494-509), preprocess = T_B_L + voxel
     downsample (geometric.cpp:128-183), getFactors = ICPFactor + first linearize (geometric.cpp:194-196), then the
     smoother's 1 + additional_update_iterations(5) linearize calls (graph/manager.cpp:585-588), each followed by a
-    host-side GN step standing in for ISAM2, then updateMap with the reference's keyframe gate (translation > 1 m
-    or any |ypr| > 10 deg, geometric.cpp:439-472): snapshot + float world transform + insert.  Everything enters
-    and leaves through host buffers; timing is host wall clock per scan."""
+    host-side GN step standing in for ISAM2, then updateMap with the reference's keyframe rule (nearest map pose:
+    translation > 1 m or any |ypr| > 10 deg, first 10 clouds forced; geometric.cpp:437-478, host.KeyframeGate):
+    snapshot + float world transform + insert.  Everything enters and leaves through host buffers; timing is host
+    wall clock per scan.  cpu_scans > 0: the same per-scan sequence on the CPU oracle for the first cpu_scans scans
+    (bounded sample) as this config's cpu_baseline.  Returns the config's result object."""
     from mimosa_b200 import ICPFactor, Scan, gn_step
+    from mimosa_b200.host import KeyframeGate
 
     rng = synth.rng_for(5)
-    n_scans = args.stream
+    n_scans = n_scans_arg
     R_B_L, t_B_L = np.eye(3, dtype=np.float32), np.zeros(3, np.float32)
     n_poses = 128
     poses = np.zeros((n_poses, 12), np.float32)
@@ -315,7 +339,8 @@ def run_stream(args, ctx, mg, cfg, synth):
         ctx.host_register(rec)  # the driver's scan buffer is page-locked: mb_scan_upload fetches it by DMA
     stages = {k: 0.0 for k in ("t_deskew", "t_preprocess", "t_get_factors", "t_updates", "t_update_map")}
     per_scan, n_key, errs, n_ds = [], 0, [], []
-    last_key_t, last_key_R = None, None
+    gate = KeyframeGate(1.0, 10.0, 10, np.eye(3))  # hornbill: map_keyframe_trans_thresh 1, rot 10 deg, 10 forced clouds
+    n_warm = 4 if n_scans > 8 else 0
     cur = mg
     for s, (rec, R_true, t_true) in enumerate(scans):
         ctx.sync()
@@ -334,15 +359,15 @@ def run_stream(args, ctx, mg, cfg, synth):
             R, t, _, _ = gn_step(L, R, t, 1e-6)
             L = f.linearize(R, t)
         t4 = time.perf_counter()
-        is_key = last_key_t is None or np.linalg.norm(t - last_key_t) > 1.0 or \
-            np.abs(np.arctan2((last_key_R.T @ R)[1, 0], (last_key_R.T @ R)[0, 0])) > np.deg2rad(10.0)
+        is_key = gate.should_update(R, t)
         if is_key:
             new = cur.snapshot()
             new.insert_scan(sc, R.astype(np.float32), t.astype(np.float32))
             if cur is not mg:
                 f.release()
                 cur.release()
-            cur, last_key_t, last_key_R = new, t.copy(), R.copy()
+            cur = new
+            gate.add_keyframe(R, t)
             n_key += 1
         f.release()
         sc.release()
@@ -350,19 +375,187 @@ def run_stream(args, ctx, mg, cfg, synth):
         ds.release()
         ctx.sync()
         t5 = time.perf_counter()
-        if s >= 2 or n_scans <= 4:  # same scans as `value`: the first two carry one-off allocations
+        if s >= n_warm:  # the first scans carry one-off allocations (two map buffers, search mirror, pooled blocks)
             for k, v in zip(stages, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
                 stages[k] += v
         per_scan.append(t5 - t0)
         errs.append(float(np.abs(t - t_true).max()))
-    warm = per_scan[2:] if len(per_scan) > 4 else per_scan
+        if os.environ.get("MB_BENCH_STREAM_VERBOSE"):
+            log(f"  scan {s:3d} key={int(is_key)} ms: deskew {1e3 * (t1 - t0):6.2f} preprocess {1e3 * (t2 - t1):6.2f} get_factors {1e3 * (t3 - t2):7.2f} "
+                f"updates {1e3 * (t4 - t3):6.2f} update_map {1e3 * (t5 - t4):7.2f}  total {1e3 * (t5 - t0):7.2f}")
+    warm = per_scan[n_warm:]
     line = {"metric": "stream_scans_per_sec", "value": len(warm) / float(np.sum(warm)), "unit": "scans/s",
             "config": {"workload": "C5: 131072-pt scans at 10 Hz vs rolling 10M-pt map; per scan deskew + T_B_L + downsample + "
-                       "7 linearize calls + keyframe-gated snapshot/insert; host buffers in and out",
+                       "7 linearize calls + keyframe rule (geometric.cpp:437-478) + snapshot/insert; host buffers in and out",
                        "n_scans": n_scans, "keyframes": n_key, "downsampled_points_mean": float(np.mean(n_ds))},
-            "ms_per_scan": 1e3 * float(np.mean(warm)), "stage_ms_per_scan": {k: 1e3 * v / len(warm) for k, v in stages.items()},
+            "ms_per_scan": 1e3 * float(np.mean(warm)), "ms_per_scan_median": 1e3 * float(np.median(warm)),
+            "ms_per_scan_max": 1e3 * float(np.max(warm)), "untimed_first_scans_ms": [1e3 * v for v in per_scan[:n_warm]],
+            "stage_ms_per_scan": {k: 1e3 * v / len(warm) for k, v in stages.items()},
             "max_pose_err_m": max(errs), "map_points_end": cur.size()[1]}
-    print(json.dumps(line), flush=True)
+    if cur is not mg:
+        cur.release()
+    for rec, _, _ in scans:
+        ctx.host_unregister(rec)
+    if cpu_scans and coords_counts_pts is not None:
+        line["cpu_baseline"] = oracle_stream(scans[:cpu_scans], pose_index, poses, cfg, coords_counts_pts, synth)
+    return line
+
+
+def oracle_stream(scans, pose_index, poses, cfg, coords_counts_pts, synth):
+    """C5's per-scan sequence on the CPU oracle (bounded sample: the first scans): deskew, T_B_L (identity), downsample,
+    ICPFactor + 7 linearize calls with host GN steps, keyframe rule, deep map copy + insertion of the full cloud."""
+    import oracle_py as orc
+    import geometric_ref as gref
+    from mimosa_b200.host import HORNBILL_MAP
+
+    coords, counts, pts, lru_counter = coords_counts_pts
+    mo = orc.IVoxRef(**HORNBILL_MAP)
+    mo.load_raw(coords, counts, None, pts, lru_counter)
+    cores = host_threads()
+    gate = gref.KeyframeGateRef(1.0, 10.0, 10, np.eye(3))
+    secs, n_key = [], 0
+    for rec, R_true, t_true in scans:
+        t0 = time.perf_counter()
+        full = np.ascontiguousarray(rec).copy()
+        orc.transform_f32(full, poses, pose_index)  # deskew
+        keep = orc.downsample(full[:, :3], cfg.source_voxel_grid_filter_leaf_size, 20, cfg.source_voxel_grid_min_dist_in_voxel)
+        ds = np.ascontiguousarray(full[keep])
+        f = orc.IcpFactorRef(mo, ds, cfg)
+        R, t = synth.perturbed_start(R_true, t_true, (0.002, -0.002, 0.003, 0.03, -0.02, 0.01))
+        L = f.linearize(R, t, n_threads=cores)
+        for _ in range(6):
+            R, t = host_gn_step(L, R, t, 1e-6)
+            L = f.linearize(R, t, n_threads=cores)
+        if gate.should_update(R, t):
+            new = mo.snapshot()
+            world = full.copy()
+            orc.transform_f32(world, np.concatenate([R.reshape(9), t]).astype(np.float32)[None, :])
+            new.insert(world[:, :3])
+            mo = new
+            gate.add_keyframe(R, t)
+            n_key += 1
+        secs.append(time.perf_counter() - t0)
+    return {"value": len(secs) / float(np.sum(secs)), "unit": "scans/s", "cores": cores, "kind": "port",
+            "sample": f"the first {len(secs)} scans of the same sequence on the CPU oracle ({n_key} keyframes: the 10M-point map is "
+                      f"deep-copied at each, geometric.cpp:494), linearize on {cores} OpenMP threads",
+            "ms_per_scan": 1e3 * float(np.mean(secs))}
+
+
+def device_loop_ms(ctx, f, R0, t0, steps, warmup, before_step=None):
+    """Per-step CUDA-event times of the device-resident 20-iteration loop (factor reset and L2 flush outside the bracket)."""
+    ms = []
+    for s in range(warmup + steps):
+        f.reset()
+        if before_step:
+            before_step()
+        ctx.flush_l2()
+        ctx.sync()
+        ctx.timer_begin()
+        R, t, _ = f.icp_run(R0, t0, ITERS, LAMBDA, want_trace=False)
+        v = ctx.timer_end()
+        if s >= warmup:
+            ms.append(v)
+    return ms, R, t
+
+
+def cpu_loop(mo, scan, cfg, R0, t0, budget_s=4.0):
+    """The oracle's 20-iteration loop on the same inputs, all host threads: (iterations/s, cores, scans timed, pose)."""
+    import oracle_py as orc
+
+    cores = host_threads()
+    fo = orc.IcpFactorRef(mo, scan, cfg)
+    fo.reset()
+    fo.icp_run(R0, t0, ITERS, LAMBDA, n_threads=cores)
+    reps, spent = 0, 0.0
+    while reps < 2 or (spent < budget_s and reps < 20):
+        fo.reset()
+        Rc, tc, _, secs = fo.icp_run(R0, t0, ITERS, LAMBDA, n_threads=cores)
+        spent += secs
+        reps += 1
+    return ITERS * reps / spent, cores, reps, tc
+
+
+def run_other_configs(ctx, mg, cfg, synth, coords_counts_pts, steps, warmup, with_cpu):
+    """BASELINE.json's other configurations, measured on one GPU in the same process (sub-objects of the C4 line):
+    C2  OS0-128 scan (131 072 rays) vs a 2 M-point map, 20 iterations
+    C3  Airy-style scan (65 280 rays, 96 beams x 680 azimuths, hemispherical) vs the 10 M-point map, motion-deskewed on
+        the device (mb_scan_deskew) inside the timed step, 20 iterations
+    C5  streaming: run_stream()"""
+    import oracle_py as orc
+    from mimosa_b200 import HORNBILL_MAP, ICPFactor, IncrementalVoxelMap, Scan
+
+    out = {}
+    coords, counts, pts, lru_counter = coords_counts_pts
+    # ---- C2 -------------------------------------------------------------------------------------------------
+    rng, scan, R0, t0, R_true, t_true = make_inputs()
+    m2 = IncrementalVoxelMap(ctx, **HORNBILL_MAP)
+    synth.build_map(m2.insert, 2_000_000, 224.0, synth.rng_for(6), size_fn=lambda: m2.size()[1])
+    f2 = ICPFactor(ctx, m2, scan, cfg)
+    f2.set_flags(cuda_graph=True)
+    ms, R, t = device_loop_ms(ctx, f2, R0, t0, steps, warmup)
+    nv2, np2, _ = m2.size()
+    c2 = {"workload": "C2: 131072-pt OS0-128 scan vs 2M-pt map, 20 ICP iters/scan, hornbill params", "value": ITERS / (float(np.mean(ms)) * 1e-3),
+          "unit": UNIT, "ms_per_step": float(np.mean(ms)), "map_points": int(np2), "map_voxels": int(nv2),
+          "final_pose_err_m": float(np.abs(np.asarray(t) - t_true).max())}
+    if with_cpu:
+        a2, b2, _, p2, l2 = m2.download()
+        mo2 = orc.IVoxRef(**HORNBILL_MAP)
+        mo2.load_raw(a2, b2, None, p2, l2)
+        v, cores, reps, tc = cpu_loop(mo2, scan, cfg, R0, t0)
+        c2["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"{reps} full scans x {ITERS} iterations (oracle)",
+                              "pose_agrees_with_gpu": bool(np.abs(np.asarray(tc) - np.asarray(t)).max() < 1e-6)}
+    f2.release()
+    m2.release()
+    out["C2"] = c2
+    # ---- C3 -------------------------------------------------------------------------------------------------
+    rng3 = synth.rng_for(7)
+    # the hemispherical sensor looks DOWN from 3 m (roll = pi): ground and box walls in view; looking up it sees nothing
+    R3, t3 = synth.rot_from_rpy(np.pi, 0.0, -0.4), np.array([3.0, 2.0, 3.0])
+    rec = synth.make_scan(R3, t3, 65280, rng3, pattern="airy")
+    n3 = rec.shape[0]
+    n_poses = 128
+    poses = np.zeros((n_poses, 12), np.float32)
+    for pz in range(n_poses):  # constant twist over the 100 ms sweep: 1 m/s, 0.5 rad/s (SURVEY 8d, C3)
+        a = (n_poses - 1 - pz) / (n_poses - 1) * 0.1
+        poses[pz, :9] = synth.rot_from_rpy(0, 0, -0.5 * a).reshape(9)
+        poses[pz, 9:] = [-1.0 * a, 0.0, 0.0]
+    pose_index = ((np.arange(n3, dtype=np.int64) * n_poses) // n3).astype(np.uint32)
+    Rk = poses[pose_index, :9].reshape(-1, 3, 3).astype(np.float64)
+    tk = poses[pose_index, 9:].astype(np.float64)
+    raw = rec.copy()
+    raw[:, :3] = np.einsum("nji,nj->ni", Rk, rec[:, :3].astype(np.float64) - tk).astype(np.float32)  # skewed as the sensor saw it
+    R03, t03 = synth.perturbed_start(R3, t3)
+    ms3 = []
+    for s3 in range(warmup + steps):
+        sc = Scan(ctx, raw)
+        ctx.flush_l2()
+        ctx.sync()
+        ctx.timer_begin()
+        sc.deskew(pose_index, poses)
+        f3 = ICPFactor(ctx, mg, sc, cfg)
+        R, t, _ = f3.icp_run(R03, t03, ITERS, LAMBDA, want_trace=False)
+        v = ctx.timer_end()
+        if s3 >= warmup:
+            ms3.append(v)
+        f3.release()
+        sc.release()
+    c3 = {"workload": "C3: 65280-pt Airy-style scan vs 10M-pt map, deskewed on the device inside the step, 20 ICP iters/scan",
+          "value": ITERS / (float(np.mean(ms3)) * 1e-3), "unit": UNIT, "ms_per_step": float(np.mean(ms3)), "scan_points": int(n3),
+          "final_pose_err_m": float(np.abs(np.asarray(t) - t3).max()),
+          "note": "the step also creates the factor from the device scan (no CUDA graph: the factor is new every scan)"}
+    if with_cpu:
+        mo = orc.IVoxRef(**HORNBILL_MAP)
+        mo.load_raw(coords, counts, None, pts, lru_counter)
+        desk = np.ascontiguousarray(raw).copy()
+        orc.transform_f32(desk, poses, pose_index)
+        v, cores, reps, tc = cpu_loop(mo, desk, cfg, R03, t03)
+        c3["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"{reps} full scans x {ITERS} iterations (oracle, scan deskewed beforehand)",
+                              "pose_agrees_with_gpu": bool(np.abs(np.asarray(tc) - np.asarray(t)).max() < 1e-6)}
+        del mo
+    out["C3"] = c3
+    # ---- C5 -------------------------------------------------------------------------------------------------
+    out["C5"] = run_stream(24, ctx, mg, cfg, synth, cpu_scans=3 if with_cpu else 0, coords_counts_pts=coords_counts_pts)
+    return out
 
 
 def main():
@@ -372,6 +565,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the C2 / C3 / C5 sub-objects of the line")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--profile-knn", action="store_true", help="only build inputs and run a few k-NN launches (for ncu)")
     ap.add_argument("--value-only", action="store_true", help="development: only the device-resident ICP loop timing")
@@ -429,7 +623,7 @@ def main():
     shard = shard_range(scan.shape[0], rank, world)
 
     if args.stream:
-        run_stream(args, ctx, mg, cfg, synth)
+        print(json.dumps(run_stream(args.stream, ctx, mg, cfg, synth)), flush=True)
         return
 
     if args.knn_only:
@@ -597,6 +791,10 @@ def main():
                 "sample": f"{reps} full scans x {ITERS} iterations of the same workload (oracle, OpenMP {cores} threads)",
                 "best_all_cores": ITERS / best_all, "faithful_4_threads": ITERS / best4,
                 "pose_agrees_with_gpu": bool(np.abs(np.asarray(tc) - np.asarray(t)).max() < 1e-6)}
+            del fo, mo
+        if not args.no_other_configs:
+            line["configs"] = run_other_configs(ctx, mg, cfg, synth, (coords, counts, pts, lru_counter), min(args.steps, 10), 3,
+                                                not args.no_cpu_baseline)
 
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -168,6 +168,9 @@ MB_API int mb_timer_end(mb_ctx* ctx, float* ms);
 MB_API int mb_launch_count(mb_ctx* ctx, uint64_t* out);
 /* Write `bytes` of device memory (L2 flush between timed iterations). */
 MB_API int mb_flush_l2(mb_ctx* ctx, size_t bytes);
+/* Same purpose by READING `bytes` of device memory: the L2 ends up full of clean lines (no write-back traffic during
+ * the timed kernel).  bench.py reports the k-NN roofline under both protocols. */
+MB_API int mb_flush_l2_read(mb_ctx* ctx, size_t bytes);
 /* Page-lock a caller-owned host buffer (cudaHostRegister) so that scans handed to mb_factor_create /
  * mb_scan_upload from it are fetched by DMA without a CPU staging pass; e.g. the point buffer a LiDAR driver
  * re-uses for every scan.  Purely an optimisation: pageable buffers work everywhere. */

@@ -124,6 +124,7 @@ SIGNATURES = {
     "mb_timer_end": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "mb_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "mb_flush_l2": (C.c_int, [_P, _SZ]),
+    "mb_flush_l2_read": (C.c_int, [_P, _SZ]),
     "mb_host_register": (C.c_int, [_P, C.c_size_t]),
     "mb_host_unregister": (C.c_int, [_P]),
     "mb_comm_unique_id": (C.c_int, [_P]),

@@ -118,8 +118,8 @@ class Context:
         check(self.lib.mb_launch_count(self.h, C.byref(v)))
         return int(v.value)
 
-    def flush_l2(self, nbytes: int = 256 << 20):
-        check(self.lib.mb_flush_l2(self.h, nbytes))
+    def flush_l2(self, nbytes: int = 256 << 20, by_reading: bool = False):
+        check((self.lib.mb_flush_l2_read if by_reading else self.lib.mb_flush_l2)(self.h, nbytes))
 
     def host_register(self, a: np.ndarray):
         """Page-lock a C-contiguous numpy array in place (mb_host_register); scans taken from it skip the CPU staging pass."""

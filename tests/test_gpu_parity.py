@@ -7,7 +7,7 @@ import pytest
 
 import synth
 from helpers import assert_linearization_close, assert_state_equal, g_err, load_golden, rel_err
-from mimosa_b200 import HORNBILL_MAP, ICPFactor, IncrementalVoxelMap, Scan, hornbill_config
+from mimosa_b200 import HORNBILL_MAP, ICPFactor, IncrementalVoxelMap, Scan, gn_step, hornbill_config
 from mimosa_b200.capi import MB_ERR_INVALID_ARG, MB_ERR_UNSUPPORTED, MimosaError
 
 pytestmark = pytest.mark.gpu
@@ -451,6 +451,40 @@ def test_full_size_properties(ctx, oracle):
     fg.set_flags()
     assert_linearization_close(fg.linearize(R0, t0), fo.linearize(R0, t0, n_threads=4), H_TOL)
     assert_state_equal(fg.download_state(), fo.download_state())
+    fg.release()
+    mg.release()
+
+
+def test_c4_size_parity(ctx, oracle):
+    """BASELINE.json's headline configuration at FULL size (131 072-point scan, ~10 M-point / 1.27 M-voxel map, bench.py's
+    inputs): restricted k-NN bit-exact against the oracle on 4 000 sampled queries, then two full linearisations (the second
+    after a Gauss-Newton step: data-association cache in play) with statuses, correspondence indices and per-point planes
+    bit-exact and H, g, f within 1e-9."""
+    import bench
+
+    rng, scan, R0, t0, R_true, t_true = bench.make_inputs()
+    mg = IncrementalVoxelMap(ctx, **HORNBILL_MAP)
+    synth.build_map(mg.insert, 10_000_000, 500.0, rng, size_fn=lambda: mg.size()[1])
+    nv, npts, _ = mg.size()
+    assert npts >= 10_000_000 and nv > 1_000_000
+    mo = oracle.IVoxRef(**HORNBILL_MAP)
+    mo.load_raw(*mg.download())
+    q = scan[:, :3].astype(np.float64) @ R0.T + t0
+    sel = synth.rng_for(77).choice(q.shape[0], 4000, replace=False)
+    ig, dg, og = mg.knn_search(q[sel], 5)
+    io, do, oo = mo.knn_search(q[sel], 5, n_threads=8)
+    assert np.array_equal(og, oo) and np.array_equal(ig, io) and np.array_equal(dg, do) and oo.mean() > 0.9
+    cfg = hornbill_config()
+    fg, fo = ICPFactor(ctx, mg, scan, cfg), oracle.IcpFactorRef(mo, scan, cfg)
+    Lg, Lo = fg.linearize(R0, t0), fo.linearize(R0, t0, n_threads=8)
+    assert_linearization_close(Lg, Lo, H_TOL)
+    assert_state_equal(fg.download_state(), fo.download_state())
+    R1, t1, _, ok = gn_step(Lg, R0, t0, 0.0)
+    assert ok
+    Lg, Lo = fg.linearize(R1, t1), fo.linearize(R1, t1, n_threads=8)
+    assert_linearization_close(Lg, Lo, H_TOL)
+    assert_state_equal(fg.download_state(), fo.download_state())
+    assert Lg.counts[8] > 60000
     fg.release()
     mg.release()
 
