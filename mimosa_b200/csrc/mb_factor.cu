@@ -59,6 +59,7 @@ struct FactorView {
   uint64_t* knn_idx;                                   // [i * k + j]
   size_t n, ld;
   int k, use_huber;
+  int tile;  // points per block tile of k_linearize: 128, 64 or 32
   uint32_t flags;
   int fold_loc;  // 1: also sum the component localizabilities of the previous linearisation (device-resident loop)
   double da_gate_sq, max_corr_sq, sigma, kh, pvd;  // da_gate_sq: smallest d2 with sqrt(d2) > the gate (host: da_gate_sq_min)
@@ -449,10 +450,13 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
   if (fv.fold_loc && tid < 18) s_V[tid] = tid < 9 ? ds->lin.eigvec_trans[tid] : ds->lin.eigvec_rot[tid - 9];
   __syncthreads();
 
-  const size_t n_tiles = (fv.n + kLinThreads - 1) / kLinThreads;
+  // Points per tile: 128 when the scan fills the device, 64 or 32 for shards that would otherwise leave SMs without a
+  // block (mb_factor: tile_points).  The threads beyond a tile's points idle in phases A and C.
+  const int tile_pts = fv.tile;
+  const size_t n_tiles = (fv.n + tile_pts - 1) / tile_pts;
   for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const size_t i = tile * kLinThreads + tid;
-    const bool act = i < fv.n;
+    const size_t i = tile * tile_pts + tid;
+    const bool act = tid < tile_pts && i < fv.n;
     // ---- A: transform, gate, compaction ------------------------------------------------------------
     d3 ps = mk3(0, 0, 0), pt = mk3(0, 0, 0);
     uint8_t st = MB_UNPROCESSED;
@@ -480,9 +484,14 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
     if (need) s_queue[base + __popc(mask & ((1u << lane) - 1))] = (uint16_t)tid;
     __syncthreads();
     // ---- B: search + plane fit for the compacted points -------------------------------------------
-      for (int q0 = warp * 32; q0 < n_need; q0 += kLinThreads) {
+      // Queries per warp and pass: a tile's re-associations are dealt out evenly over its four warps.  A warp's search
+      // time grows with the number of different queries it carries (every lane walks its own buckets and the warp
+      // follows the union: measured 7 us for two queries, 50 us for thirty-two), so a tile with 17 points to
+      // re-associate runs four warps of 5 instead of one warp of 17 — and a 32-point tile four warps of 8.
+      const int per_warp = min(32, max(1, (n_need + kLinWarps - 1) / kLinWarps));
+      for (int q0 = warp * per_warp; q0 < n_need; q0 += kLinWarps * per_warp) {
         const int qi = q0 + lane;
-        const bool on = qi < n_need;
+        const bool on = lane < per_warp && qi < n_need;
         const int li = on ? (int)s_queue[qi] : 0;
         const double qx = s_pt[0][li], qy = s_pt[1][li], qz = s_pt[2][li];
         double bd[K];
@@ -490,7 +499,7 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
         uint32_t* s_pk = s_pk_all + tid;
         knn_thread<K>(mv, s_tab, s_pk, s_blk_all + tid, kLinThreads, qx, qy, qz, k, on, bd, bs);
         if (on) {
-          const size_t gi = tile * kLinThreads + li;
+          const size_t gi = tile * tile_pts + li;
           float4 nb[K];
           uint64_t g[K];
           const int found = knn_resolve_all<K, true>(mv, s_pk, kLinThreads, bs, k, g, nb);
@@ -917,6 +926,7 @@ struct mb_factor {
   mb_icp_trace* d_trace = nullptr;
   int trace_cap = 0;
   int grid = 0, grid2 = 0, n_groups = 0;
+  int tile_points = 128;  // points per block tile of k_linearize
   // k_linearize launch shape: kernel variant (k == 5 and <= 19 neighbour voxels, or generic), staging pool per warp
   bool lin_small = true;
   // voxel order (see k_group_sort): the caller's points, sorted position -> caller's index
@@ -946,6 +956,7 @@ struct mb_factor {
     v.ld = ld;
     v.k = (int)cfg.num_corres_points;
     v.use_huber = cfg.use_huber;
+    v.tile = tile_points;
     v.flags = flags;
     v.fold_loc = 0;
     const float da_gate_f = cfg.target_ivox_map_min_dist_in_voxel / 4;          // geometric_factor.hpp:283
@@ -1107,8 +1118,18 @@ static int factor_init(mb_factor* f, mb_ctx* ctx, mb_map* map, const void* pts, 
   else
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<MB_MAX_K, NoPose, 27>, kLinThreads, 0);
   per_sm = std::max(per_sm, 1);
-  const size_t n_tiles = (f->n + kLinThreads - 1) / kLinThreads;
-  f->grid = (int)std::max<size_t>(1, std::min<size_t>(n_tiles, (size_t)ctx->sm_count * per_sm));
+  // Points per tile: the smallest of 32 / 64 / 128 whose tiles still fit the device in one round.  A full scan on one
+  // GPU needs 128 (and two rounds); a shard of a scan on 4 or 8 GPUs gets 64 or 32, which spreads its points over all
+  // SMs with fewer queries per warp — the only lever on the search's latency once every SM has a block.
+  const size_t capacity = (size_t)ctx->sm_count * per_sm;
+  f->tile_points = 128;
+  for (int tp : {32, 64})
+    if ((f->n + tp - 1) / tp <= capacity) {
+      f->tile_points = tp;
+      break;
+    }
+  const size_t n_tiles = (f->n + f->tile_points - 1) / f->tile_points;
+  f->grid = (int)std::max<size_t>(1, std::min<size_t>(n_tiles, capacity));
   f->n_groups = (f->grid + kGroup - 1) / kGroup;
   f->grid2 = (int)std::max<size_t>(1, std::min<size_t>((f->n + kLocThreads - 1) / kLocThreads, (size_t)ctx->sm_count * 4));
 

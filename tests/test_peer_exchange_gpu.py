@@ -65,8 +65,17 @@ def _worker(rank, world, port, use_peer, out):
     gathered = [torch.zeros(lin.size, dtype=torch.float64) for _ in range(world)]
     dist.all_gather(gathered, torch.tensor(lin))
     assert all(torch.equal(gathered[0], x) for x in gathered), "ranks disagree on the linearisation"
+    # the device loop WITH a trace: every iteration's component localizabilities — the folded ones of the earlier
+    # iterations and the trailing k_loc_comp's of the last — must be sums over ALL ranks' shards, identical on every rank
+    f.reset()
+    f.set_flags(cuda_graph=False)
+    _, _, tr = f.icp_run(R0, t0, ITERS, 0.0, want_trace=True)
+    comps = np.array([list(x.loc_trans_comp) + list(x.loc_rot_comp) for x in tr]).ravel()
+    gathered = [torch.zeros(comps.size, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(gathered, torch.tensor(comps))
+    assert all(torch.equal(gathered[0], x) for x in gathered), "ranks disagree on the traced component localizabilities"
     if rank == 0:
-        np.save(out, np.concatenate([poses[0], lin]))
+        np.save(out, np.concatenate([poses[0], lin, comps]))
     f.release()
     m.release()
     dist.barrier()
@@ -87,15 +96,19 @@ def test_peer_memory_exchange_two_gpus(tmp_path, ctx, oracle):
         mp.spawn(_worker, args=(2, port, use_peer, out), nprocs=2, join=True)
         got[use_peer] = np.load(out)
     assert np.array_equal(got[True], got[False]), "peer-memory sum (rank order) and NCCL sum differ"
-    lin2 = got[True][12:]
+    n_lin = 36 + 6 + 1 + 6 + 9
+    lin2, comps2 = got[True][12:12 + n_lin], got[True][12 + n_lin:].reshape(ITERS, 6)
     got = {k: v[:12] for k, v in got.items()}
     world_pts, scan, R0, t0 = _inputs()
     m = IncrementalVoxelMap(ctx, **HORNBILL_MAP)
     m.insert(world_pts)
     f = ICPFactor(ctx, m, scan, hornbill_config())
-    R1, t1, _ = f.icp_run(R0, t0, ITERS, 0.0, want_trace=False)
+    R1, t1, tr1 = f.icp_run(R0, t0, ITERS, 0.0, want_trace=True)
     one = np.concatenate([np.asarray(R1).ravel(), np.asarray(t1).ravel()])
     assert np.abs(got[True] - one).max() < 1e-10
+    comps1 = np.array([list(x.loc_trans_comp) + list(x.loc_rot_comp) for x in tr1])
+    # sums of |loc^T V| entries >= 0.5 over ~10^4 points: the LAST row used to cover one rank's shard only
+    assert np.allclose(comps2, comps1, rtol=1e-6, atol=1e-6 * comps1.max()) and comps1[-1].max() > 100
     f.reset()
     L = f.linearize(R0, t0)
     lin1 = np.concatenate([np.array(L.H), np.array(L.g), [L.f], np.array(L.loc_trans_comp), np.array(L.loc_rot_comp),

@@ -18,7 +18,9 @@ ctx = Context(0)
 rng, scan, R0, t0, _, _ = bench.make_inputs()
 mg = IncrementalVoxelMap(ctx, **HORNBILL_MAP)
 synth.build_map(mg.insert, bench.MAP_POINTS, bench.MAP_HALF_EXTENT, rng, size_fn=lambda: mg.size()[1])
-f = ICPFactor(ctx, mg, scan, hornbill_config())
+div = int(sys.argv[sys.argv.index("--shard") + 1]) if "--shard" in sys.argv else 1  # time one rank's share of the scan
+f = ICPFactor(ctx, mg, scan, hornbill_config(), (0, scan.shape[0] // div))
+print(f"points {scan.shape[0] // div}", flush=True)
 flush = "--no-flush" not in sys.argv
 prev = 0.0
 for iters in (1, 2, 3, 4, 5, 6, 10, 20):
