@@ -72,6 +72,10 @@ struct FactorView {
   double* partials2;   // [grid2][8]
   unsigned* ticket2;
   double* loc_out;     // [8]: trans comp (3), rot comp (3)
+  // persistent loop (k_icp_loop)
+  struct LoopCtl* ctl;
+  uint32_t* queue;       // [n] points that re-associate in the current linearisation
+  uint32_t* tile_stamp;  // [n_tiles] linearize_count of the last linearisation that deferred the tile to its second pass
 };
 
 // Pose handed to k_linearize BY VALUE (kernel parameter space) on the host-facing single-call path: no H2D copy
@@ -756,6 +760,472 @@ __global__ void __launch_bounds__(kLocThreads) k_loc_comp(FactorView fv, const D
   }
 }
 
+// ================================================================================================================
+// The persistent loop: ALL linearisations of an mb_icp_run (or the one of an mb_factor_linearize) in ONE cooperative
+// launch, one 512-thread block per SM, grid-wide barriers instead of kernel boundaries.  A block is four GROUPS of
+// 128 threads; a group works on a tile of the voxel-ordered scan exactly like a block of k_linearize (named barriers
+// instead of __syncthreads).  One linearisation:
+//   A   per tile: transform + data-association gate (:276-287) and, in the device-resident loop, the folded
+//       localizability pass of the previous linearisation.  A tile in which no point re-associates is finished on
+//       the spot (C).  Otherwise its re-associating points are appended to a global queue (one reservation per tile,
+//       so the queue keeps the voxel order tile by tile) and the tile is deferred.
+//       -> block partial -> grid barrier #1 (it also publishes the queue length)
+//   B   only when the queue is not empty: the queue is dealt out EVENLY over all warps of the device — restricted
+//       k-NN (:294), distance gates (:296-302), plane fit (:176-229); results go to the points' state.  An iteration
+//       that re-associates 13 % of the points, all of them in a few far-away tiles, keeps every SM busy with a few
+//       queries per warp instead of a few blocks with full warps (a warp's search time grows with the number of
+//       different queries it carries: 7 us for two, 50 us for thirty-two).  -> grid barrier #2
+//   C'  the deferred tiles: residual, s-check, Huber, Jacobian, localizability vectors (:319-355), reduction
+//       (:364-366, 396-403).  -> block partial -> grid barrier #3
+//   D   EVERY block sums the block partials in block order (bitwise identical everywhere), exchanges the packet with
+//       the other ranks through the peer mailboxes (block 0 stores, every block reads its own rank's mailbox), and
+//       runs the finalize roles on its own copy of the factor's DevState in shared memory: the next linearisation
+//       starts without another barrier.  Block 0 writes the trace.
+// A fully cached linearisation costs ONE grid barrier.  After the last linearisation: the component-localizability
+// pass (:434-457) over the block's own tiles, one more barrier, and block 0 hands the result to the device-side
+// DevState, the mailboxes and the polling host.
+struct LoopCtl {
+  unsigned long long bar;  // grid barrier arrivals: monotonic, a multiple of the grid size between launches
+  unsigned q_count[2];     // queue length by linearisation parity
+};
+
+struct LoopArgs {
+  int iters, do_step, reg_4_dof, linearize_count0, has_pose, pad;
+  PoseArg pose;  // has_pose: pose / gravity of the host-facing call
+  mb_icp_trace* trace;
+  HostOut ho;
+};
+
+constexpr int kLoopThreads = 512, kLoopWarps = kLoopThreads / 32, kLoopGroups = kLoopThreads / kLinThreads;
+#if defined(MB_LOOP_TIMING)  // development: SM clock of block 0 at the phase boundaries of every linearisation
+__device__ long long g_loop_t[64][12];
+#define MB_LOOP_T(it, slot) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (it) < 64) g_loop_t[it][slot] = clock64(); } while (0)
+#else
+#define MB_LOOP_T(it, slot) do { } while (0)
+#endif
+constexpr uint8_t kFresh = 0x80;  // status bit: written by phase B, consumed by phase C'
+
+template <int ROWS>
+struct LoopShared {
+  uint32_t pk[kLoopGroups][ROWS * kLinThreads];  // phase B: knn_thread's s_pk; phases A / C: [warp][32][7] doubles
+  uint32_t blk[kLoopGroups][24 * kLinThreads];
+  double red[kLoopWarps][kPack];
+  double tmp[kLoopThreads];
+  double packed[kXchgDoubles];
+  DevState ds;
+  unsigned long long bar_next;
+  int warp_need[kLoopGroups][kLinWarps];
+  unsigned qbase[kLoopGroups];
+  uint16_t tab[kTabEntries];
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void group_sync(int grp) {
+  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kLinThreads) : "memory");
+}
+__device__ __forceinline__ d3 ld3cg(const double* base, size_t ld, size_t i) {
+  return mk3(__ldcg(base + i), __ldcg(base + ld + i), __ldcg(base + 2 * ld + i));
+}
+// All blocks of the (cooperative, fully resident) grid.  `next` = this block's count of arrivals the barrier has to
+// reach, kept in shared memory; one arrival and one polling thread per block.
+__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long* next, unsigned n_blocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long target = *next + n_blocks;
+    *next = target;
+    __threadfence();
+    atomicAdd(bar, 1ull);
+    while (ld_acquire_gpu(bar) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int K, int ROWS>
+__global__ void __launch_bounds__(kLoopThreads, 1)
+    k_icp_loop(MapView mv, FactorView fv, DevState* ds_g, LoopArgs la, const PeerTable* __restrict__ peer) {
+  extern __shared__ __align__(16) unsigned char s_loop_raw[];
+  LoopShared<ROWS>& S = *reinterpret_cast<LoopShared<ROWS>*>(s_loop_raw);
+  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5, grp = tid >> 7, gt = tid & (kLinThreads - 1), gw = wib & (kLinWarps - 1);
+  const unsigned n_blocks = gridDim.x;
+  LoopCtl* const ctl = fv.ctl;
+  if (tid == 0) S.bar_next = (ld_acquire_gpu(&ctl->bar) / n_blocks) * n_blocks;  // nobody passes barrier #1 before this block arrives
+  fill_scan_table(mv, S.tab);
+  {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(ds_g);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(&S.ds);
+    for (int w = tid; w < (int)(sizeof(DevState) / 8); w += kLoopThreads) dst[w] = src[w];
+  }
+  __syncthreads();
+  if (la.has_pose && tid < 16) reinterpret_cast<double*>(&S.ds)[tid] = la.pose.v[tid];  // pose (12), gravity (3), lambda lead DevState
+  const unsigned long long xseq0 = peer ? *peer->xseq : 0ull;
+  double(*s_row)[7] = reinterpret_cast<double(*)[7]>(S.pk[grp]) + gw * 32;
+  static_assert(sizeof(uint32_t) * ROWS * kLinThreads >= sizeof(double) * 7 * kLinThreads, "s_row fits");
+  const int pr = kTriRow[lane], pc = kTriCol[lane];
+  const int k = fv.k;
+  const bool forced = (fv.flags & 1u) != 0;
+  const double inv_sigma = 1.0 / fv.sigma;
+  const int tile_pts = fv.tile;
+  const size_t n_tiles = (fv.n + tile_pts - 1) / tile_pts;
+  const size_t vg = (size_t)blockIdx.x * kLoopGroups + grp, n_vg = (size_t)n_blocks * kLoopGroups;
+  __syncthreads();
+
+  for (int it = 0; it < la.iters; ++it) {
+    const int par = it & 1;
+    MB_LOOP_T(it, 0);
+    const uint32_t stamp = (uint32_t)(la.linearize_count0 + it + 1);
+    if (blockIdx.x == 0 && tid == 0) ctl->q_count[par ^ 1] = 0u;  // the next linearisation's counter: idle during this one
+    m33 R;
+#pragma unroll
+    for (int a = 0; a < 9; ++a) R.m[a] = S.ds.pose[a];
+    const d3 T = mk3(S.ds.pose[9], S.ds.pose[10], S.ds.pose[11]);
+    const double* const Vt = S.ds.lin.eigvec_trans;  // of the previous linearisation (folded pass)
+    const double* const Vr = S.ds.lin.eigvec_rot;
+    double acc = 0.0, lacc = 0.0;
+    int cnt = 0;
+
+    // C: residual, Jacobian, accumulation of point i.  st carries kFresh when phase B has just fitted its plane.
+    auto finish = [&](size_t i, bool act, const d3& ps, const d3& pt, uint8_t st) {
+      double row[7] = {0, 0, 0, 0, 0, 0, 0};
+      if (act) {
+        const bool fresh = (st & kFresh) != 0;
+        st &= (uint8_t)~kFresh;
+        if (fresh ? st == MB_UNPROCESSED : st > MB_CORRES_PLANE_INVALID) {
+          const d3 mean = ld3cg(fv.mean, fv.ld, i), normal = ld3cg(fv.normal, fv.ld, i);
+          double e = dot3(normal, sub3(mean, pt));
+          const double s_chk = 1 - 0.9 * fabs(e) / __ldg(fv.rroot + i);
+          if (s_chk < 0.9) {
+            st = MB_MAX_ERROR;
+          } else {
+            double sqrt_w = 1.0;
+            if (fv.use_huber) {
+              const double we = e / fv.sigma;
+              if (fabs(we) > fv.kh) sqrt_w = sqrt(fv.kh / fabs(we));
+            }
+            const double scale = sqrt_w == 1.0 ? inv_sigma : sqrt_w / fv.sigma;
+            e *= scale;
+            const d3 ns = mul33Tv(R, normal);
+            const d3 jr = cross3(ns, ps);
+            const double z = sqnorm3(jr);
+            st3(fv.loc_rot, fv.ld, i, z > 0 ? div3(jr, sqrt(z)) : jr);
+            st3(fv.loc_trans, fv.ld, i, mk3(-ns.x, -ns.y, -ns.z));
+            row[0] = jr.x * scale;
+            row[1] = jr.y * scale;
+            row[2] = jr.z * scale;
+            row[3] = -ns.x * scale;
+            row[4] = -ns.y * scale;
+            row[5] = -ns.z * scale;
+            row[6] = e;
+            st = MB_VALID;
+          }
+        }
+        fv.status[i] = st;
+      }
+      // [J e]^T [J e] over the warp's 32 points: lane a sums its entry over the rows in point order.
+      if (__ballot_sync(kFull, act && st == MB_VALID)) {
+#pragma unroll
+        for (int a = 0; a < 7; ++a) s_row[lane][a] = row[a];
+        __syncwarp();
+#pragma unroll 8
+        for (int p = 0; p < 32; ++p) acc += s_row[p][pr] * s_row[p][pc];
+        __syncwarp();
+      }
+#pragma unroll
+      for (int s = 0; s < 9; ++s) {
+        const int c = __popc(__ballot_sync(kFull, act && st == s));
+        if (lane == s) cnt += c;
+      }
+    };
+    auto write_partials = [&]() {
+      if (lane < 28) S.red[wib][lane] = acc;
+      if (lane >= 30) S.red[wib][lane + 8] = S.red[wib][lane + 16] = 0.0;  // pad entries 38, 39, 46, 47
+      if (lane < 10) S.red[wib][kPackCnt + lane] = (double)cnt;
+      if (lane < 6) S.red[wib][kPackLoc + lane] = lacc;
+      __syncthreads();
+      if (tid < kPack) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kLoopWarps; ++w) v += S.red[w][tid];
+        __stcg(fv.partials + (size_t)blockIdx.x * kPack + tid, v);
+      }
+    };
+
+    // ---- A (+ C for the tiles that keep every association) -----------------------------------------------------
+    for (size_t tile = vg; tile < n_tiles; tile += n_vg) {
+      const size_t i = tile * tile_pts + gt;
+      const bool act = gt < tile_pts && i < fv.n;
+      d3 ps = mk3(0, 0, 0), pt = mk3(0, 0, 0);
+      uint8_t st = MB_UNPROCESSED;
+      bool need = false;
+      if (act) {
+        const float4 s = __ldg(fv.src + i);
+        ps = mk3((double)s.x, (double)s.y, (double)s.z);
+        pt = add3(mul33v(R, ps), T);
+        st = __ldcg(fv.status + i);
+        const d3 da = ld3cg(fv.p_da, fv.ld, i);
+        need = forced || sqnorm3(sub3(pt, da)) >= fv.da_gate_sq;
+      }
+      if (fv.fold_loc) {  // this point's share of the PREVIOUS linearisation's component localizabilities (:434-457)
+        double v[6] = {0, 0, 0, 0, 0, 0};
+        if (act && st == MB_VALID) {
+          const d3 lt = ld3cg(fv.loc_trans, fv.ld, i), lr = ld3cg(fv.loc_rot, fv.ld, i);
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {  // column a of V: (V^T loc)_a, in mul33Tv's order of operations
+            const double tc = fabs(Vt[a] * lt.x + (Vt[3 + a] * lt.y + Vt[6 + a] * lt.z));
+            const double rc = fabs(Vr[a] * lr.x + (Vr[3 + a] * lr.y + Vr[6 + a] * lr.z));
+            v[a] = tc >= 0.5 ? tc : 0.0;
+            v[3 + a] = rc >= 0.5 ? rc : 0.0;
+          }
+        }
+        if (__ballot_sync(kFull, act && st == MB_VALID)) {
+#pragma unroll
+          for (int a = 0; a < 6; ++a) s_row[lane][a] = v[a];
+          __syncwarp();
+          if (lane < 6) {
+#pragma unroll 8
+            for (int p = 0; p < 32; ++p) lacc += s_row[p][lane];
+          }
+          __syncwarp();
+        }
+      }
+      const unsigned mask = __ballot_sync(kFull, need);
+      if (lane == 0) S.warp_need[grp][gw] = __popc(mask);
+      group_sync(grp);
+      int base = 0, n_need = 0;
+#pragma unroll
+      for (int w = 0; w < kLinWarps; ++w) {
+        if (w < gw) base += S.warp_need[grp][w];
+        n_need += S.warp_need[grp][w];
+      }
+      if (n_need == 0) {
+        finish(i, act, ps, pt, st);
+      } else {
+        if (gt == 0) {
+          S.qbase[grp] = atomicAdd(&ctl->q_count[par], (unsigned)n_need);
+          fv.tile_stamp[tile] = stamp;
+        }
+        group_sync(grp);
+        if (need) {
+          fv.queue[S.qbase[grp] + (unsigned)(base + __popc(mask & ((1u << lane) - 1)))] = (uint32_t)i;
+          st3(fv.p_da, fv.ld, i, pt);
+        }
+        if (lane == 9) cnt += __popc(mask);
+      }
+      group_sync(grp);  // warp_need / qbase are rewritten by the next tile
+    }
+    MB_LOOP_T(it, 1);
+    write_partials();
+    MB_LOOP_T(it, 2);
+    grid_barrier(&ctl->bar, &S.bar_next, n_blocks);
+    MB_LOOP_T(it, 3);
+    const unsigned q = __ldcg(&ctl->q_count[par]);
+    if (q) {
+      // ---- B: the queue, dealt out evenly over every warp of the device ----------------------------------------
+      const unsigned W = n_blocks * kLoopWarps;
+      const unsigned rounds = (q + 32u * W - 1u) / (32u * W);
+      const unsigned per = min(32u, max(1u, (q + W * rounds - 1u) / (W * rounds)));
+      const unsigned n_tasks = (q + per - 1u) / per;
+      for (unsigned task = blockIdx.x * kLoopWarps + wib; task < n_tasks; task += W) {
+        const unsigned qi = task * per + lane;
+        const bool on = (unsigned)lane < per && qi < q;
+        const size_t i = on ? (size_t)__ldcg(fv.queue + qi) : 0;
+        const float4 s = __ldg(fv.src + i);
+        const d3 pt = add3(mul33v(R, mk3((double)s.x, (double)s.y, (double)s.z)), T);
+        double bd[K];
+        uint32_t bs[K];
+        uint32_t* s_pk = S.pk[grp] + gt;
+        knn_thread<K>(mv, S.tab, s_pk, S.blk[grp] + gt, kLinThreads, pt.x, pt.y, pt.z, k, on, bd, bs);
+        if (on) {
+          float4 nb[K];
+          uint64_t g[K];
+          const int found = knn_resolve_all<K, true>(mv, s_pk, kLinThreads, bs, k, g, nb);
+          double dk = 0.0;
+#pragma unroll
+          for (int j = 0; j < K; ++j) {
+            if (j < k) {
+              if (j == k - 1) dk = bd[j];
+              // indices are only meaningful when all k exist (the reference discards partial results)
+              if (fv.knn_idx) fv.knn_idx[i * k + j] = found == k ? g[j] : ~0ull;
+            }
+          }
+          uint8_t rs = MB_UNPROCESSED;
+          if (found != k) {
+            rs = MB_INSUFFICIENT_CORRES_POINTS;
+          } else if (dk > fv.max_corr_sq) {
+            rs = MB_CORRES_MAX_DIST;
+          } else {
+            bool normal_set;
+            d3 mean = mk3(0, 0, 0), normal = mk3(0, 0, 0);
+            rs = fit_plane<K>(nb, k, T, fv.pvd, mean, normal, normal_set);
+            st3(fv.mean, fv.ld, i, mean);
+            if (normal_set) st3(fv.normal, fv.ld, i, normal);
+          }
+          fv.status[i] = (uint8_t)(rs | kFresh);
+        }
+        __syncwarp();
+      }
+      MB_LOOP_T(it, 4);
+      grid_barrier(&ctl->bar, &S.bar_next, n_blocks);
+      MB_LOOP_T(it, 5);
+      // ---- C': the deferred tiles --------------------------------------------------------------------------------
+      for (size_t tile = vg; tile < n_tiles; tile += n_vg) {
+        if (__ldcg(fv.tile_stamp + tile) != stamp) continue;  // uniform over the group
+        const size_t i = tile * tile_pts + gt;
+        const bool act = gt < tile_pts && i < fv.n;
+        d3 ps = mk3(0, 0, 0), pt = mk3(0, 0, 0);
+        uint8_t st = MB_UNPROCESSED;
+        if (act) {
+          const float4 s = __ldg(fv.src + i);
+          ps = mk3((double)s.x, (double)s.y, (double)s.z);
+          pt = add3(mul33v(R, ps), T);
+          st = __ldcg(fv.status + i);
+        }
+        finish(i, act, ps, pt, st);
+      }
+      __syncthreads();  // S.red: the first write_partials' readers are long done, but keep the phases apart
+      MB_LOOP_T(it, 6);
+      write_partials();
+      grid_barrier(&ctl->bar, &S.bar_next, n_blocks);
+      MB_LOOP_T(it, 7);
+    }
+    // ---- D: packet, exchange, finalize — in every block ---------------------------------------------------------
+    block_sum_rows(fv.partials, (int)n_blocks, kPack, S.tmp, S.packed, kLoopThreads);
+    __syncthreads();
+    MB_LOOP_T(it, 8);
+    if (peer) {
+      const int world = peer->world, rank = peer->rank;
+      const unsigned long long seq = xseq0 + 1ull + (unsigned long long)it;
+      const size_t pbase = (size_t)((seq & 1ull) * kMaxRanks);
+      if (blockIdx.x == 0) {
+        const size_t slot = pbase + (unsigned)rank;
+        for (int x = tid; x < world * kPack; x += kLoopThreads) {
+          const int dst = x / kPack, e = x - dst * kPack;
+          peer->mbox[dst][slot * kXchgDoubles + e] = S.packed[e];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < world) st_release_sys(peer->flag[tid] + slot, seq);
+      }
+      if (tid < world) {
+        const unsigned long long* fl = peer->flag[rank] + pbase + tid;
+        while (ld_acquire_sys(fl) != seq) {
+        }
+        __threadfence_system();
+      }
+      __syncthreads();
+      if (tid < kPack) {
+        const double* mb = peer->mbox[rank] + pbase * kXchgDoubles + tid;
+        double v = 0.0;
+        for (int r = 0; r < world; ++r) v += __ldcg(mb + (size_t)r * kXchgDoubles);
+        S.packed[tid] = v;
+      }
+      __syncthreads();
+    }
+    {
+      FinArgs fa;
+      fa.reg_4_dof = la.reg_4_dof;
+      fa.linearize_count = la.linearize_count0 + it + 1;
+      fa.do_step = la.do_step;
+      fa.iter = it;
+      fa.trace = blockIdx.x == 0 ? la.trace : nullptr;
+      // warp 0, lane 0: projection + packing + solve + retract; warp 1, lanes 0..3: the four eigen roles in lock step
+      const int role = wib == 0 ? (lane == 0 ? 4 : -1) : (wib == 1 && lane < 4 ? lane : -1);
+      if (role >= 0) finalize_role(S.packed, &S.ds, &S.ds, fa, role);
+    }
+    __syncthreads();
+    MB_LOOP_T(it, 9);
+  }
+
+  // ---- after the last linearisation: its component localizabilities (:434-457), results out ------------------------
+  if (la.iters > 0) {
+    double a6[6] = {0, 0, 0, 0, 0, 0};
+    const double* const Vt = S.ds.lin.eigvec_trans;
+    const double* const Vr = S.ds.lin.eigvec_rot;
+    for (size_t tile = vg; tile < n_tiles; tile += n_vg) {
+      const size_t i = tile * tile_pts + gt;
+      if (gt < tile_pts && i < fv.n && __ldcg(fv.status + i) == MB_VALID) {
+        const d3 lt = ld3cg(fv.loc_trans, fv.ld, i), lr = ld3cg(fv.loc_rot, fv.ld, i);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const double tc = fabs(Vt[a] * lt.x + (Vt[3 + a] * lt.y + Vt[6 + a] * lt.z));
+          const double rc = fabs(Vr[a] * lr.x + (Vr[3 + a] * lr.y + Vr[6 + a] * lr.z));
+          a6[a] += tc >= 0.5 ? tc : 0.0;
+          a6[3 + a] += rc >= 0.5 ? rc : 0.0;
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      double v = a6[a];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+      if (lane == 0) S.red[wib][a] = v;
+    }
+    if (lane == 0) S.red[wib][6] = S.red[wib][7] = 0.0;
+    __syncthreads();
+    if (tid < 8) {
+      double v = 0.0;
+      for (int w = 0; w < kLoopWarps; ++w) v += S.red[w][tid];
+      __stcg(fv.partials2 + (size_t)blockIdx.x * 8 + tid, v);
+    }
+    grid_barrier(&ctl->bar, &S.bar_next, n_blocks);
+    if (blockIdx.x != 0) return;
+    if (tid < 2) ctl->q_count[tid] = 0u;  // every block has read its last queue length
+    double* const loc = S.packed + kPack;  // [8]
+    block_sum_rows(fv.partials2, (int)n_blocks, 8, S.tmp, loc, kLoopThreads);
+    __syncthreads();
+    if (peer) {
+      // the six sums of every rank, through the same mailboxes as the packets (doubles 48..53 of the last exchange's slot)
+      const int world = peer->world, rank = peer->rank;
+      const unsigned long long seq = xseq0 + (unsigned long long)la.iters;
+      const size_t pbase = (size_t)((seq & 1ull) * kMaxRanks);
+      if (tid < world * 6) {
+        const int dst = tid / 6, e = tid - dst * 6;
+        peer->mbox[dst][(pbase + (unsigned)rank) * kXchgDoubles + kPack + e] = loc[e];
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (tid < world) {
+        st_release_sys(peer->lflag[tid] + pbase + (unsigned)rank, seq);
+        const unsigned long long* fl = peer->lflag[rank] + pbase + tid;
+        while (ld_acquire_sys(fl) != seq) {
+        }
+        __threadfence_system();
+      }
+      __syncthreads();
+      double v = 0.0;
+      if (tid < 6)
+        for (int r = 0; r < world; ++r) v += __ldcg(peer->mbox[rank] + (pbase + (unsigned)r) * kXchgDoubles + kPack + tid);
+      __syncthreads();
+      if (tid < 6) loc[tid] = v;
+      if (tid == 0) *peer->xseq = seq;
+      __syncthreads();
+    }
+    // device-side copies: DevState (pose, last linearisation), packet, component localizabilities
+    {
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(ds_g);
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&S.ds);
+      for (int w = tid; w < (int)(sizeof(DevState) / 8); w += kLoopThreads) dst[w] = src[w];
+      if (tid < kPack) fv.packed[tid] = S.packed[tid];
+      if (tid < 8) fv.loc_out[tid] = tid < 6 ? loc[tid] : 0.0;
+    }
+    if (la.ho.out) {  // hand the finished linearisation to the polling host
+      constexpr int kWords = (int)(sizeof(mb_linearization) / 8);
+      const unsigned long long* lin = reinterpret_cast<const unsigned long long*>(&S.ds.lin);
+      for (int w = tid; w < kWords; w += kLoopThreads) la.ho.out[w] = lin[w];
+      if (tid < 6) la.ho.out[kWords + tid] = (unsigned long long)__double_as_longlong(loc[tid]);
+      __threadfence_system();
+      __syncthreads();
+      if (tid == 0) *la.ho.flag = la.ho.seq;
+    }
+  }
+}
+
 // device scan records -> float4 source points of the factor (xyz only), zero padded to ld
 __global__ void k_pack_src(const unsigned char* __restrict__ data, size_t stride, size_t begin, size_t n, size_t ld,
                            float4* __restrict__ src) {
@@ -923,6 +1393,12 @@ struct mb_factor {
   double* packed = nullptr;  // kPack + 8 (loc_out)
   unsigned* tickets = nullptr;  // [0] final, [1] loc, [2..] groups
   DevState* ds = nullptr;
+  // persistent loop (k_icp_loop): control words, re-association queue, per-tile stamps
+  LoopCtl* ctl = nullptr;
+  uint32_t* queue = nullptr;
+  uint32_t* tile_stamp = nullptr;
+  size_t n_tiles = 0;
+  int loop_grid = 0;
   mb_icp_trace* d_trace = nullptr;
   int trace_cap = 0;
   int grid = 0, grid2 = 0, n_groups = 0;
@@ -975,6 +1451,9 @@ struct mb_factor {
     v.partials2 = partials2;
     v.ticket2 = tickets + 1;
     v.loc_out = packed + kPack;
+    v.ctl = ctl;
+    v.queue = queue;
+    v.tile_stamp = tile_stamp;
     return v;
   }
 };
@@ -987,6 +1466,7 @@ int reset_state(mb_factor* f) {
     // status, the five vector blocks and the index block are contiguous: one memset for the zeros
     MB_CUDA(cudaMemsetAsync(f->vecs, 0, 15 * f->ld * sizeof(double) + f->ld, st));
     MB_CUDA(cudaMemsetAsync(f->knn_idx, 0xff, f->n * f->cfg.num_corres_points * sizeof(uint64_t), st));
+    MB_CUDA(cudaMemsetAsync(f->tile_stamp, 0, f->n_tiles * sizeof(uint32_t), st));  // stamps count from 1 again
   }
   f->linearize_count = 0;
   f->sorted = false;  // the next first linearisation re-sorts under its own pose (all state is zero again)
@@ -1086,6 +1566,58 @@ int enqueue_last_loc_comp(mb_factor* f) {
   return MB_OK;
 }
 
+// development switch (MB_LOOP=0): the per-linearisation kernels instead of the persistent loop, for A/B timing
+bool use_loop(const mb_ctx* c) {
+  static const int sw = [] {
+    const char* e = getenv("MB_LOOP");
+    return e ? atoi(e) : 1;
+  }();
+  return sw != 0 && (c->world == 1 || c->d_peer != nullptr);
+}
+
+// One cooperative launch of the persistent loop: `iters` linearisations (each followed by the harness GN step when
+// do_step), starting from the pose in DevState or, host-facing call, in `pose_arg`.
+int enqueue_loop(mb_factor* f, int iters, int do_step, mb_icp_trace* d_trace, const PoseArg* pose_arg, const HostOut* host_out) {
+  mb_ctx* c = f->ctx;
+  cudaStream_t st = c->stream;
+  if (iters <= 0) return MB_OK;
+  if (f->linearize_count == 0) MB_TRY(enqueue_sort(f, pose_arg));  // first linearisation since construction / reset
+  MapView mv = f->map->view();
+  FactorView fv = f->view();
+  fv.fold_loc = do_step ? 1 : 0;
+  LoopArgs la;
+  std::memset(&la, 0, sizeof(la));
+  la.iters = iters;
+  la.do_step = do_step;
+  la.reg_4_dof = (int)f->cfg.reg_4_dof;
+  la.linearize_count0 = f->linearize_count;
+  la.has_pose = pose_arg ? 1 : 0;
+  if (pose_arg) la.pose = *pose_arg;
+  la.trace = d_trace;
+  if (host_out) la.ho = *host_out;
+  const PeerTable* peer = c->world > 1 ? c->d_peer : nullptr;
+  DevState* ds = f->ds;
+  void* args[] = {&mv, &fv, &ds, &la, &peer};
+  const void* kern;
+  size_t smem;
+  if (f->lin_small) {
+    kern = (const void*)k_icp_loop<5, 19>;
+    smem = sizeof(LoopShared<19>);
+  } else {
+    kern = (const void*)k_icp_loop<MB_MAX_K, 27>;
+    smem = sizeof(LoopShared<27>);
+  }
+  static bool opted_in = false;
+  if (!opted_in) {
+    MB_CUDA(cudaFuncSetAttribute((const void*)k_icp_loop<5, 19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LoopShared<19>)));
+    MB_CUDA(cudaFuncSetAttribute((const void*)k_icp_loop<MB_MAX_K, 27>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LoopShared<27>)));
+    opted_in = true;
+  }
+  MB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(f->loop_grid), dim3(kLoopThreads), args, smem, st));
+  ++c->launches;
+  return MB_OK;
+}
+
 void drop_graph(mb_factor* f) {
   if (f->graph) cudaGraphExecDestroy(f->graph);
   f->graph = nullptr;
@@ -1129,6 +1661,8 @@ static int factor_init(mb_factor* f, mb_ctx* ctx, mb_map* map, const void* pts, 
       break;
     }
   const size_t n_tiles = (f->n + f->tile_points - 1) / f->tile_points;
+  f->n_tiles = n_tiles;
+  f->loop_grid = ctx->sm_count;
   f->grid = (int)std::max<size_t>(1, std::min<size_t>(n_tiles, capacity));
   f->n_groups = (f->grid + kGroup - 1) / kGroup;
   f->grid2 = (int)std::max<size_t>(1, std::min<size_t>((f->n + kLocThreads - 1) / kLocThreads, (size_t)ctx->sm_count * 4));
@@ -1147,12 +1681,15 @@ static int factor_init(mb_factor* f, mb_ctx* ctx, mb_map* map, const void* pts, 
   const size_t o_rroot = take(f->ld * sizeof(double));
   const size_t o_vecs = take(15 * f->ld * sizeof(double) + f->ld);  // status follows the vectors directly
   const size_t o_idx = take(f->ld * k * sizeof(uint64_t));
-  const size_t o_par = take((size_t)f->grid * kPack * sizeof(double));
+  const size_t o_queue = take(f->ld * sizeof(uint32_t));
+  const size_t o_par = take((size_t)std::max(f->grid, f->loop_grid) * kPack * sizeof(double));
   const size_t o_gpar = take((size_t)f->n_groups * kPack * sizeof(double));
-  const size_t o_par2 = take((size_t)f->grid2 * 8 * sizeof(double));
+  const size_t o_par2 = take((size_t)std::max(f->grid2, f->loop_grid) * 8 * sizeof(double));
   const size_t o_packed = take((kPack + 8) * sizeof(double));
   const size_t o_tick = take((2 + (size_t)f->n_groups) * sizeof(unsigned));  // final, loc, groups...
   const size_t o_ds = take(sizeof(DevState));
+  const size_t o_ctl = take(sizeof(LoopCtl));
+  const size_t o_stamp = take(std::max<size_t>(n_tiles, 1) * sizeof(uint32_t));
   f->block_bytes = off;
   int rc = dev_alloc(ctx, &f->block, f->block_bytes);
   if (rc != MB_OK) {
@@ -1172,6 +1709,9 @@ static int factor_init(mb_factor* f, mb_ctx* ctx, mb_map* map, const void* pts, 
   f->packed = (double*)(base + o_packed);
   f->tickets = (unsigned*)(base + o_tick);
   f->ds = (DevState*)(base + o_ds);
+  f->ctl = (LoopCtl*)(base + o_ctl);
+  f->queue = (uint32_t*)(base + o_queue);
+  f->tile_stamp = (uint32_t*)(base + o_stamp);
 
   bool staged = true;  // the context's pinned staging buffer was used: wait for the copy before returning
   bool copied_from_caller = false;
@@ -1329,6 +1869,12 @@ MB_API int mb_debug_time_finalize(mb_factor* f, unsigned role_mask, int reps, fl
   return MB_OK;
 }
 
+#if defined(MB_LOOP_TIMING)
+MB_API int mb_debug_loop_times(long long* out /* 64 x 12 */) {
+  return cudaMemcpyFromSymbol(out, g_loop_t, sizeof(long long) * 64 * 12) == cudaSuccess ? MB_OK : MB_ERR_CUDA;
+}
+#endif
+
 int mb_factor_release(mb_factor* f) {
   if (!f) return MB_OK;
   cudaSetDevice(f->ctx->device);
@@ -1381,7 +1927,13 @@ int mb_factor_linearize(mb_factor* f, const double R[9], const double t[3], cons
     ho.flag = (volatile unsigned*)((char*)f->ctx->pin_small + 2048);
     ho.seq = ++f->ctx->host_seq;
     if (ho.seq == 0) ho.seq = ++f->ctx->host_seq;
-    MB_TRY(enqueue_linearize(f, 0, 0, nullptr, f->linearize_count, &pa, &ho));
+    if (use_loop(f->ctx)) {
+      --f->linearize_count;
+      MB_TRY(enqueue_loop(f, 1, 0, nullptr, &pa, &ho));
+      ++f->linearize_count;
+    } else {
+      MB_TRY(enqueue_linearize(f, 0, 0, nullptr, f->linearize_count, &pa, &ho));
+    }
     // Poll the completion flag: busy for the first ~100 us (a call normally ends well inside that), then yielding the
     // core between polls; the stream is queried now and then so that a failed launch ends the wait with its error, and
     // a kernel that never finishes ends it after kPollTimeoutS instead of hanging the caller (mimosa's node has three
@@ -1496,7 +2048,10 @@ int mb_icp_run(mb_factor* f, double R[9], double t[3], int iters, double lambda,
   hin[15] = lambda;
   MB_CUDA(cudaMemcpyAsync(f->ds->pose, hin, 16 * sizeof(double), cudaMemcpyHostToDevice, st));
   const bool use_graph = (f->flags & 2u) != 0 && iters > 0;
-  if (use_graph) {
+  if (use_loop(f->ctx)) {
+    MB_TRY(enqueue_loop(f, iters, 1, f->d_trace, nullptr, nullptr));
+    f->linearize_count += iters;
+  } else if (use_graph) {
     // The captured sequence bakes the iteration index and linearize_count into k_finalize's arguments.
     if (!f->graph || f->graph_iters != iters || f->graph_count0 != f->linearize_count) {
       drop_graph(f);
