@@ -726,6 +726,11 @@ def main():
     t60 = min(timed_run(60) for _ in range(3))
     log(f"[rank {rank}] warm 20-iter run {t20 * 1e3:.1f} us, 60-iter run {t60 * 1e3:.1f} us -> "
         f"{(t60 - t20) * 1e3 / 40:.2f} us per cached iteration")
+    if os.environ.get("MB_BENCH_PHASES"):  # development: library built with -DMB_LOOP_TIMING
+        timed_run(20)  # (every rank: the loop exchanges packets)
+        if rank == 0:
+            import loop_phases
+            loop_phases.print_table(ctx.lib, 20)
 
     total_ms = float(np.sum(step_ms))
     e2e_total = float(np.sum(e2e_secs))

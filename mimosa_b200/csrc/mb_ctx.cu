@@ -299,6 +299,7 @@ int mb_comm_ipc_open(mb_ctx* c, const void* handles) {
     t.mbox[r] = (double*)base;
     t.flag[r] = (unsigned long long*)((char*)base + kXchgMboxBytes);
     t.lflag[r] = (unsigned long long*)((char*)base + kXchgMboxBytes + kXchgFlagBytes);
+    t.ll[r] = (unsigned long long*)((char*)base + kXchgLlOffset);
   }
   t.xseq = (unsigned long long*)((char*)c->xchg_block + kXchgMboxBytes + 2 * kXchgFlagBytes);
   if (!c->d_peer) MB_CUDA(cudaMalloc((void**)&c->d_peer, sizeof(PeerTable)));

@@ -785,8 +785,9 @@ __global__ void __launch_bounds__(kLocThreads) k_loc_comp(FactorView fv, const D
 // pass (:434-457) over the block's own tiles, one more barrier, and block 0 hands the result to the device-side
 // DevState, the mailboxes and the polling host.
 struct LoopCtl {
-  unsigned long long bar;  // grid barrier arrivals: monotonic, a multiple of the grid size between launches
-  unsigned q_count[2];     // queue length by linearisation parity
+  unsigned long long bar;    // grid barrier arrivals: monotonic, a multiple of the grid size between launches
+  unsigned long long xflag;  // several ranks: number of the last exchange whose summed packet block 0 has published
+  unsigned q_count[2];       // queue length by linearisation parity
 };
 
 struct LoopArgs {
@@ -796,14 +797,21 @@ struct LoopArgs {
   HostOut ho;
 };
 
-constexpr int kLoopThreads = 512, kLoopWarps = kLoopThreads / 32, kLoopGroups = kLoopThreads / kLinThreads;
+#ifndef MB_LOOP_THREADS
+#define MB_LOOP_THREADS 512
+#endif
+constexpr int kLoopThreads = MB_LOOP_THREADS, kLoopWarps = kLoopThreads / 32, kLoopGroups = kLoopThreads / kLinThreads;
 #if defined(MB_LOOP_TIMING)  // development: SM clock of block 0 at the phase boundaries of every linearisation
 __device__ long long g_loop_t[64][12];
 #define MB_LOOP_T(it, slot) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (it) < 64) g_loop_t[it][slot] = clock64(); } while (0)
+__device__ long long g_loop_f[64][12];
+#define MB_LOOP_F(it, slot) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (it) < 64) g_loop_f[it][slot] = clock64(); } while (0)
 #else
+#define MB_LOOP_F(it, slot) do { } while (0)
 #define MB_LOOP_T(it, slot) do { } while (0)
 #endif
 constexpr uint8_t kFresh = 0x80;  // status bit: written by phase B, consumed by phase C'
+constexpr int kPpt = 2;            // points per thread and tile in phases A / C (tiles of up to kPpt * 128 points)
 
 template <int ROWS>
 struct LoopShared {
@@ -823,6 +831,51 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long
   unsigned long long v;
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Flag-in-data words of the peer mailbox (mb_internal.cuh): one 8-byte store / load each, system scope, no ordering
+// needed — a word carries its own exchange number.
+__device__ __forceinline__ void ll_store(unsigned long long* p, uint32_t data, uint32_t flag) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(((unsigned long long)flag << 32) | data) : "memory");
+}
+__device__ __forceinline__ uint32_t ll_wait(const unsigned long long* p, uint32_t flag) {
+  unsigned long long v;
+  do {
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  } while ((uint32_t)(v >> 32) != flag);
+  return (uint32_t)v;
+}
+// This rank's `count` doubles src[0..count) into entries first.. of every rank's mailbox slot (all threads of the block).
+__device__ __forceinline__ void ll_send(const PeerTable* peer, unsigned long long seq, const double* src, int first, int count) {
+  const int world = peer->world;
+  const size_t slot = (size_t)((seq & 1ull) * kMaxRanks + (unsigned)peer->rank) * (2 * kXchgDoubles);
+  for (int x = threadIdx.x; x < world * count * 2; x += blockDim.x) {
+    const int dst = x / (count * 2), w = x - dst * (count * 2);
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(src[w >> 1]);
+    ll_store(peer->ll[dst] + slot + 2 * first + w, (uint32_t)(bits >> (32 * (w & 1))), (uint32_t)seq);
+  }
+}
+// Wait for every rank's `count` doubles of exchange `seq` in this rank's mailbox and add them in rank order into
+// dst[0..count) (shared memory; s_words: world * count * 2 words of scratch).  All threads of the block.
+__device__ __forceinline__ void ll_gather(const PeerTable* peer, unsigned long long seq, int first, int count, uint32_t* s_words, double* dst) {
+  const int world = peer->world;
+  const unsigned long long* base = peer->ll[peer->rank] + (size_t)((seq & 1ull) * kMaxRanks) * (2 * kXchgDoubles);
+  for (int x = threadIdx.x; x < world * count * 2; x += blockDim.x) {
+    const int r = x / (count * 2), w = x - r * (count * 2);
+    s_words[x] = ll_wait(base + (size_t)r * (2 * kXchgDoubles) + 2 * first + w, (uint32_t)seq);
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < count) {
+    double v = 0.0;
+    for (int r = 0; r < world; ++r) {
+      const uint32_t lo = s_words[(r * count + threadIdx.x) * 2], hi = s_words[(r * count + threadIdx.x) * 2 + 1];
+      v += __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+    }
+    dst[threadIdx.x] = v;
+  }
+  __syncthreads();
 }
 __device__ __forceinline__ void group_sync(int grp) {
   asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kLinThreads) : "memory");
@@ -874,6 +927,18 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
   const size_t n_tiles = (fv.n + tile_pts - 1) / tile_pts;
   const size_t vg = (size_t)blockIdx.x * kLoopGroups + grp, n_vg = (size_t)n_blocks * kLoopGroups;
   __syncthreads();
+  // A thread's points of the most recent linearisation: localizability vectors and "Valid", kept in SHARED memory
+  // for the component-localizability sums (:434-457) that need that linearisation's eigenvectors — taken in the
+  // next linearisation's phase A (device-resident loop) or after the last one.  They live in the group's block-probe
+  // scratch, which only phase B uses (written in C / C', read before the next B), and in the tail of S.pk behind
+  // s_row.  Only when a group owns a single tile; otherwise those passes read the points' state back from memory.
+  // (Keeping them in registers was built and measured: 416 B of spills and every phase 15-30 % slower.)
+  const bool one_tile = n_tiles <= n_vg;
+  double* const k_loc = reinterpret_cast<double*>(S.blk[grp]) + gt;  // [(c * kPpt + u) * 128], c < 3 rot, c >= 3 trans
+  uint8_t* const k_valid = reinterpret_cast<uint8_t*>(S.pk[grp]) + sizeof(double) * 7 * kLinThreads + gt;  // [u * 128]
+  static_assert(sizeof(uint32_t) * 24 * kLinThreads >= sizeof(double) * 6 * kPpt * kLinThreads, "kept vectors fit S.blk");
+  static_assert(sizeof(uint32_t) * ROWS * kLinThreads >= sizeof(double) * 7 * kLinThreads + kPpt * kLinThreads, "kept flags fit S.pk");
+  bool kept = false;  // uniform over the group: the scratch holds its tile's vectors (phase B overwrites the scratch)
 
   for (int it = 0; it < la.iters; ++it) {
     const int par = it & 1;
@@ -889,56 +954,97 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     double acc = 0.0, lacc = 0.0;
     int cnt = 0;
 
-    // C: residual, Jacobian, accumulation of point i.  st carries kFresh when phase B has just fitted its plane.
-    auto finish = [&](size_t i, bool act, const d3& ps, const d3& pt, uint8_t st) {
-      double row[7] = {0, 0, 0, 0, 0, 0, 0};
-      if (act) {
-        const bool fresh = (st & kFresh) != 0;
-        st &= (uint8_t)~kFresh;
-        if (fresh ? st == MB_UNPROCESSED : st > MB_CORRES_PLANE_INVALID) {
-          const d3 mean = ld3cg(fv.mean, fv.ld, i), normal = ld3cg(fv.normal, fv.ld, i);
-          double e = dot3(normal, sub3(mean, pt));
-          const double s_chk = 1 - 0.9 * fabs(e) / __ldg(fv.rroot + i);
-          if (s_chk < 0.9) {
-            st = MB_MAX_ERROR;
-          } else {
-            double sqrt_w = 1.0;
-            if (fv.use_huber) {
-              const double we = e / fv.sigma;
-              if (fabs(we) > fv.kh) sqrt_w = sqrt(fv.kh / fabs(we));
-            }
-            const double scale = sqrt_w == 1.0 ? inv_sigma : sqrt_w / fv.sigma;
-            e *= scale;
-            const d3 ns = mul33Tv(R, normal);
-            const d3 jr = cross3(ns, ps);
-            const double z = sqnorm3(jr);
-            st3(fv.loc_rot, fv.ld, i, z > 0 ? div3(jr, sqrt(z)) : jr);
-            st3(fv.loc_trans, fv.ld, i, mk3(-ns.x, -ns.y, -ns.z));
-            row[0] = jr.x * scale;
-            row[1] = jr.y * scale;
-            row[2] = jr.z * scale;
-            row[3] = -ns.x * scale;
-            row[4] = -ns.y * scale;
-            row[5] = -ns.z * scale;
-            row[6] = e;
-            st = MB_VALID;
-          }
+    // C: residual, Jacobian, accumulation of a thread's kPpt points (independent chains, interleaved by the compiler).
+    // st carries kFresh when phase B has just fitted the point's plane.
+    auto finish = [&](const size_t (&i)[kPpt], const bool (&act)[kPpt], const d3 (&ps)[kPpt], const d3 (&pt)[kPpt], uint8_t (&st)[kPpt]) {
+      double row[kPpt][7];
+      bool go[kPpt];
+      d3 mean[kPpt], normal[kPpt];
+      double rr[kPpt];
+#pragma unroll
+      for (int u = 0; u < kPpt; ++u) {
+#pragma unroll
+        for (int a = 0; a < 7; ++a) row[u][a] = 0.0;
+        const bool fresh = (st[u] & kFresh) != 0;
+        st[u] &= (uint8_t)~kFresh;
+        go[u] = act[u] && (fresh ? st[u] == MB_UNPROCESSED : st[u] > MB_CORRES_PLANE_INVALID);
+        mean[u] = normal[u] = mk3(0, 0, 0);
+        rr[u] = 1.0;
+        if (go[u]) {
+          mean[u] = ld3cg(fv.mean, fv.ld, i[u]);
+          normal[u] = ld3cg(fv.normal, fv.ld, i[u]);
+          rr[u] = __ldg(fv.rroot + i[u]);
         }
-        fv.status[i] = st;
       }
-      // [J e]^T [J e] over the warp's 32 points: lane a sums its entry over the rows in point order.
-      if (__ballot_sync(kFull, act && st == MB_VALID)) {
+      MB_LOOP_F(it, 4);
+      // branch-free per point (selects instead of branches), so that the two points' fp64 chains interleave
+      d3 lrot[kPpt], ltrans[kPpt];
+      bool valid[kPpt];
 #pragma unroll
-        for (int a = 0; a < 7; ++a) s_row[lane][a] = row[a];
-        __syncwarp();
+      for (int u = 0; u < kPpt; ++u) {
+        // (a skipped point computes on harmless non-zero stand-ins: a zero numerator would send the whole warp through
+        // the division's slow path)
+        double e = go[u] ? dot3(normal[u], sub3(mean[u], pt[u])) : 1.0;
+        const double s_chk = 1 - 0.9 * fabs(e) / rr[u];
+        valid[u] = go[u] && !(s_chk < 0.9);
+        double scale = inv_sigma;
+        if (fv.use_huber) {  // uniform
+          const double we = e / fv.sigma;
+          if (fabs(we) > fv.kh) scale = sqrt(fv.kh / fabs(we)) / fv.sigma;  // rare: beyond the Huber threshold
+        }
+        e *= scale;
+        const d3 ns = mul33Tv(R, normal[u]);
+        const d3 jr = go[u] ? cross3(ns, ps[u]) : mk3(1.0, 1.0, 1.0);
+        const double z = sqnorm3(jr);
+        const double zr = z > 0 ? sqrt(z) : 1.0;
+        const d3 jn = div3(jr, zr);
+        lrot[u] = z > 0 ? jn : jr;
+        ltrans[u] = mk3(-ns.x, -ns.y, -ns.z);
+        row[u][0] = valid[u] ? jr.x * scale : 0.0;
+        row[u][1] = valid[u] ? jr.y * scale : 0.0;
+        row[u][2] = valid[u] ? jr.z * scale : 0.0;
+        row[u][3] = valid[u] ? -ns.x * scale : 0.0;
+        row[u][4] = valid[u] ? -ns.y * scale : 0.0;
+        row[u][5] = valid[u] ? -ns.z * scale : 0.0;
+        row[u][6] = valid[u] ? e : 0.0;
+        if (go[u]) st[u] = valid[u] ? MB_VALID : MB_MAX_ERROR;
+      }
+#pragma unroll
+      for (int u = 0; u < kPpt; ++u) {
+        if (valid[u]) {
+          st3(fv.loc_rot, fv.ld, i[u], lrot[u]);
+          st3(fv.loc_trans, fv.ld, i[u], ltrans[u]);
+        }
+        if (act[u]) fv.status[i[u]] = st[u];
+        if (one_tile) {
+          kept = true;
+          k_loc[(0 * kPpt + u) * kLinThreads] = lrot[u].x;
+          k_loc[(1 * kPpt + u) * kLinThreads] = lrot[u].y;
+          k_loc[(2 * kPpt + u) * kLinThreads] = lrot[u].z;
+          k_loc[(3 * kPpt + u) * kLinThreads] = ltrans[u].x;
+          k_loc[(4 * kPpt + u) * kLinThreads] = ltrans[u].y;
+          k_loc[(5 * kPpt + u) * kLinThreads] = ltrans[u].z;
+          k_valid[u * kLinThreads] = valid[u] ? 1 : 0;
+        }
+      }
+      MB_LOOP_F(it, 5);
+      // [J e]^T [J e] over the warp's points: lane a sums its entry over the rows in point order.
+#pragma unroll
+      for (int u = 0; u < kPpt; ++u) {
+        if (u == 1) MB_LOOP_F(it, 6);
+        if (__ballot_sync(kFull, act[u] && st[u] == MB_VALID)) {
+#pragma unroll
+          for (int a = 0; a < 7; ++a) s_row[lane][a] = row[u][a];
+          __syncwarp();
 #pragma unroll 8
-        for (int p = 0; p < 32; ++p) acc += s_row[p][pr] * s_row[p][pc];
-        __syncwarp();
-      }
+          for (int p = 0; p < 32; ++p) acc += s_row[p][pr] * s_row[p][pc];
+          __syncwarp();
+        }
 #pragma unroll
-      for (int s = 0; s < 9; ++s) {
-        const int c = __popc(__ballot_sync(kFull, act && st == s));
-        if (lane == s) cnt += c;
+        for (int s = 0; s < 9; ++s) {
+          const int c = __popc(__ballot_sync(kFull, act[u] && st[u] == s));
+          if (lane == s) cnt += c;
+        }
       }
     };
     auto write_partials = [&]() {
@@ -956,45 +1062,81 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     };
 
     // ---- A (+ C for the tiles that keep every association) -----------------------------------------------------
+    // Thread gt of the group owns points gt and gt + 128 of the tile (the second only in 256-point tiles).
     for (size_t tile = vg; tile < n_tiles; tile += n_vg) {
-      const size_t i = tile * tile_pts + gt;
-      const bool act = gt < tile_pts && i < fv.n;
-      d3 ps = mk3(0, 0, 0), pt = mk3(0, 0, 0);
-      uint8_t st = MB_UNPROCESSED;
-      bool need = false;
-      if (act) {
-        const float4 s = __ldg(fv.src + i);
-        ps = mk3((double)s.x, (double)s.y, (double)s.z);
-        pt = add3(mul33v(R, ps), T);
-        st = __ldcg(fv.status + i);
-        const d3 da = ld3cg(fv.p_da, fv.ld, i);
-        need = forced || sqnorm3(sub3(pt, da)) >= fv.da_gate_sq;
-      }
-      if (fv.fold_loc) {  // this point's share of the PREVIOUS linearisation's component localizabilities (:434-457)
-        double v[6] = {0, 0, 0, 0, 0, 0};
-        if (act && st == MB_VALID) {
-          const d3 lt = ld3cg(fv.loc_trans, fv.ld, i), lr = ld3cg(fv.loc_rot, fv.ld, i);
+      MB_LOOP_F(it, 0);
+      size_t i[kPpt];
+      bool act[kPpt], need[kPpt];
+      d3 ps[kPpt], pt[kPpt];
+      uint8_t st[kPpt];
 #pragma unroll
-          for (int a = 0; a < 3; ++a) {  // column a of V: (V^T loc)_a, in mul33Tv's order of operations
-            const double tc = fabs(Vt[a] * lt.x + (Vt[3 + a] * lt.y + Vt[6 + a] * lt.z));
-            const double rc = fabs(Vr[a] * lr.x + (Vr[3 + a] * lr.y + Vr[6 + a] * lr.z));
-            v[a] = tc >= 0.5 ? tc : 0.0;
-            v[3 + a] = rc >= 0.5 ? rc : 0.0;
+      for (int u = 0; u < kPpt; ++u) {
+        i[u] = tile * tile_pts + u * kLinThreads + gt;
+        act[u] = u * kLinThreads + gt < tile_pts && i[u] < fv.n;
+        ps[u] = pt[u] = mk3(0, 0, 0);
+        st[u] = MB_UNPROCESSED;
+        need[u] = false;
+        if (act[u]) {
+          const float4 s = __ldg(fv.src + i[u]);
+          ps[u] = mk3((double)s.x, (double)s.y, (double)s.z);
+          pt[u] = add3(mul33v(R, ps[u]), T);
+          st[u] = __ldcg(fv.status + i[u]);
+          const d3 da = ld3cg(fv.p_da, fv.ld, i[u]);
+          need[u] = forced || sqnorm3(sub3(pt[u], da)) >= fv.da_gate_sq;
+        }
+      }
+      MB_LOOP_F(it, 1);
+      // The points' share of the PREVIOUS linearisation's component localizabilities (:434-457).  (The first
+      // linearisation of a launch has no predecessor whose sums anyone reads.)
+      if (fv.fold_loc && it > 0) {
+        double v[kPpt][6];
+        bool was_valid[kPpt];
+#pragma unroll
+        for (int u = 0; u < kPpt; ++u) {
+#pragma unroll
+          for (int a = 0; a < 6; ++a) v[u][a] = 0.0;
+          was_valid[u] = kept ? k_valid[u * kLinThreads] != 0 : (act[u] && st[u] == MB_VALID);
+          if (was_valid[u]) {
+            d3 lt, lr;
+            if (kept) {
+              lr = mk3(k_loc[(0 * kPpt + u) * kLinThreads], k_loc[(1 * kPpt + u) * kLinThreads], k_loc[(2 * kPpt + u) * kLinThreads]);
+              lt = mk3(k_loc[(3 * kPpt + u) * kLinThreads], k_loc[(4 * kPpt + u) * kLinThreads], k_loc[(5 * kPpt + u) * kLinThreads]);
+            } else {
+              lt = ld3cg(fv.loc_trans, fv.ld, i[u]);
+              lr = ld3cg(fv.loc_rot, fv.ld, i[u]);
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {  // column a of V: (V^T loc)_a, in mul33Tv's order of operations
+              const double tc = fabs(Vt[a] * lt.x + (Vt[3 + a] * lt.y + Vt[6 + a] * lt.z));
+              const double rc = fabs(Vr[a] * lr.x + (Vr[3 + a] * lr.y + Vr[6 + a] * lr.z));
+              v[u][a] = tc >= 0.5 ? tc : 0.0;
+              v[u][3 + a] = rc >= 0.5 ? rc : 0.0;
+            }
           }
         }
-        if (__ballot_sync(kFull, act && st == MB_VALID)) {
 #pragma unroll
-          for (int a = 0; a < 6; ++a) s_row[lane][a] = v[a];
-          __syncwarp();
-          if (lane < 6) {
+        for (int u = 0; u < kPpt; ++u) {
+          if (__ballot_sync(kFull, was_valid[u])) {
+#pragma unroll
+            for (int a = 0; a < 6; ++a) s_row[lane][a] = v[u][a];
+            __syncwarp();
+            if (lane < 6) {
 #pragma unroll 8
-            for (int p = 0; p < 32; ++p) lacc += s_row[p][lane];
+              for (int p = 0; p < 32; ++p) lacc += s_row[p][lane];
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
-      const unsigned mask = __ballot_sync(kFull, need);
-      if (lane == 0) S.warp_need[grp][gw] = __popc(mask);
+      MB_LOOP_F(it, 2);
+      unsigned mask[kPpt];
+      int warp_need = 0;
+#pragma unroll
+      for (int u = 0; u < kPpt; ++u) {
+        mask[u] = __ballot_sync(kFull, need[u]);
+        warp_need += __popc(mask[u]);
+      }
+      if (lane == 0) S.warp_need[grp][gw] = warp_need;
       group_sync(grp);
       int base = 0, n_need = 0;
 #pragma unroll
@@ -1002,19 +1144,25 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
         if (w < gw) base += S.warp_need[grp][w];
         n_need += S.warp_need[grp][w];
       }
+      MB_LOOP_F(it, 3);
       if (n_need == 0) {
         finish(i, act, ps, pt, st);
+        MB_LOOP_F(it, 7);
       } else {
         if (gt == 0) {
           S.qbase[grp] = atomicAdd(&ctl->q_count[par], (unsigned)n_need);
           fv.tile_stamp[tile] = stamp;
         }
         group_sync(grp);
-        if (need) {
-          fv.queue[S.qbase[grp] + (unsigned)(base + __popc(mask & ((1u << lane) - 1)))] = (uint32_t)i;
-          st3(fv.p_da, fv.ld, i, pt);
+#pragma unroll
+        for (int u = 0; u < kPpt; ++u) {
+          if (need[u]) {
+            fv.queue[S.qbase[grp] + (unsigned)(base + __popc(mask[u] & ((1u << lane) - 1)))] = (uint32_t)i[u];
+            st3(fv.p_da, fv.ld, i[u], pt[u]);
+          }
+          base += __popc(mask[u]);
         }
-        if (lane == 9) cnt += __popc(mask);
+        if (lane == 9) cnt += warp_need;
       }
       group_sync(grp);  // warp_need / qbase are rewritten by the next tile
     }
@@ -1026,6 +1174,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     const unsigned q = __ldcg(&ctl->q_count[par]);
     if (q) {
       // ---- B: the queue, dealt out evenly over every warp of the device ----------------------------------------
+      kept = false;  // the search scratch is about to be overwritten
       const unsigned W = n_blocks * kLoopWarps;
       const unsigned rounds = (q + 32u * W - 1u) / (32u * W);
       const unsigned per = min(32u, max(1u, (q + W * rounds - 1u) / (W * rounds)));
@@ -1075,15 +1224,22 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
       // ---- C': the deferred tiles --------------------------------------------------------------------------------
       for (size_t tile = vg; tile < n_tiles; tile += n_vg) {
         if (__ldcg(fv.tile_stamp + tile) != stamp) continue;  // uniform over the group
-        const size_t i = tile * tile_pts + gt;
-        const bool act = gt < tile_pts && i < fv.n;
-        d3 ps = mk3(0, 0, 0), pt = mk3(0, 0, 0);
-        uint8_t st = MB_UNPROCESSED;
-        if (act) {
-          const float4 s = __ldg(fv.src + i);
-          ps = mk3((double)s.x, (double)s.y, (double)s.z);
-          pt = add3(mul33v(R, ps), T);
-          st = __ldcg(fv.status + i);
+        size_t i[kPpt];
+        bool act[kPpt];
+        d3 ps[kPpt], pt[kPpt];
+        uint8_t st[kPpt];
+#pragma unroll
+        for (int u = 0; u < kPpt; ++u) {
+          i[u] = tile * tile_pts + u * kLinThreads + gt;
+          act[u] = u * kLinThreads + gt < tile_pts && i[u] < fv.n;
+          ps[u] = pt[u] = mk3(0, 0, 0);
+          st[u] = MB_UNPROCESSED;
+          if (act[u]) {
+            const float4 s = __ldg(fv.src + i[u]);
+            ps[u] = mk3((double)s.x, (double)s.y, (double)s.z);
+            pt[u] = add3(mul33v(R, ps[u]), T);
+            st[u] = __ldcg(fv.status + i[u]);
+          }
         }
         finish(i, act, ps, pt, st);
       }
@@ -1094,38 +1250,38 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
       MB_LOOP_T(it, 7);
     }
     // ---- D: packet, exchange, finalize — in every block ---------------------------------------------------------
-    block_sum_rows(fv.partials, (int)n_blocks, kPack, S.tmp, S.packed, kLoopThreads);
-    __syncthreads();
-    MB_LOOP_T(it, 8);
-    if (peer) {
-      const int world = peer->world, rank = peer->rank;
+    if (!peer) {
+      block_sum_rows(fv.partials, (int)n_blocks, kPack, S.tmp, S.packed, kLoopThreads);
+      __syncthreads();
+      MB_LOOP_T(it, 8);
+    } else {
+      // Several ranks: block 0 alone talks to the peers — its packet goes straight into every rank's mailbox (peer
+      // stores over NVLink, flag-in-data words: no fence, no separate flag), it waits for the other ranks' words in
+      // this rank's mailbox, adds the packets in rank order (bit-identical on every rank) and publishes the sum to the
+      // other blocks of this GPU through fv.packed and a gpu-scope flag.  Measured per exchange at N = 2: every block
+      // polling mailbox flags at system scope 9-14 us, block 0 alone with fence + flags 7-8 us.
       const unsigned long long seq = xseq0 + 1ull + (unsigned long long)it;
-      const size_t pbase = (size_t)((seq & 1ull) * kMaxRanks);
       if (blockIdx.x == 0) {
-        const size_t slot = pbase + (unsigned)rank;
-        for (int x = tid; x < world * kPack; x += kLoopThreads) {
-          const int dst = x / kPack, e = x - dst * kPack;
-          peer->mbox[dst][slot * kXchgDoubles + e] = S.packed[e];
-        }
-        __threadfence_system();
+        block_sum_rows(fv.partials, (int)n_blocks, kPack, S.tmp, S.packed, kLoopThreads);
         __syncthreads();
-        if (tid < world) st_release_sys(peer->flag[tid] + slot, seq);
-      }
-      if (tid < world) {
-        const unsigned long long* fl = peer->flag[rank] + pbase + tid;
-        while (ld_acquire_sys(fl) != seq) {
+        MB_LOOP_T(it, 8);
+        ll_send(peer, seq, S.packed, 0, kPack);
+        ll_gather(peer, seq, 0, kPack, reinterpret_cast<uint32_t*>(S.tmp), S.packed);  // (includes this rank's own packet)
+        if (tid < kPack) __stcg(fv.packed + tid, S.packed[tid]);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release_gpu(&ctl->xflag, seq);
+      } else {
+        if (tid == 0) {
+          while (ld_acquire_gpu(&ctl->xflag) < seq) {
+          }
         }
-        __threadfence_system();
+        __syncthreads();
+        if (tid < kPack) S.packed[tid] = __ldcg(fv.packed + tid);
+        __syncthreads();
       }
-      __syncthreads();
-      if (tid < kPack) {
-        const double* mb = peer->mbox[rank] + pbase * kXchgDoubles + tid;
-        double v = 0.0;
-        for (int r = 0; r < world; ++r) v += __ldcg(mb + (size_t)r * kXchgDoubles);
-        S.packed[tid] = v;
-      }
-      __syncthreads();
     }
+    MB_LOOP_T(it, 10);
     {
       FinArgs fa;
       fa.reg_4_dof = la.reg_4_dof;
@@ -1146,16 +1302,36 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     double a6[6] = {0, 0, 0, 0, 0, 0};
     const double* const Vt = S.ds.lin.eigvec_trans;
     const double* const Vr = S.ds.lin.eigvec_rot;
-    for (size_t tile = vg; tile < n_tiles; tile += n_vg) {
-      const size_t i = tile * tile_pts + gt;
-      if (gt < tile_pts && i < fv.n && __ldcg(fv.status + i) == MB_VALID) {
-        const d3 lt = ld3cg(fv.loc_trans, fv.ld, i), lr = ld3cg(fv.loc_rot, fv.ld, i);
+    if (kept) {  // the thread's own points, from the group's scratch
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          const double tc = fabs(Vt[a] * lt.x + (Vt[3 + a] * lt.y + Vt[6 + a] * lt.z));
-          const double rc = fabs(Vr[a] * lr.x + (Vr[3 + a] * lr.y + Vr[6 + a] * lr.z));
-          a6[a] += tc >= 0.5 ? tc : 0.0;
-          a6[3 + a] += rc >= 0.5 ? rc : 0.0;
+      for (int u = 0; u < kPpt; ++u) {
+        if (k_valid[u * kLinThreads]) {
+          const d3 lr = mk3(k_loc[(0 * kPpt + u) * kLinThreads], k_loc[(1 * kPpt + u) * kLinThreads], k_loc[(2 * kPpt + u) * kLinThreads]);
+          const d3 lt = mk3(k_loc[(3 * kPpt + u) * kLinThreads], k_loc[(4 * kPpt + u) * kLinThreads], k_loc[(5 * kPpt + u) * kLinThreads]);
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            const double tc = fabs(Vt[a] * lt.x + (Vt[3 + a] * lt.y + Vt[6 + a] * lt.z));
+            const double rc = fabs(Vr[a] * lr.x + (Vr[3 + a] * lr.y + Vr[6 + a] * lr.z));
+            a6[a] += tc >= 0.5 ? tc : 0.0;
+            a6[3 + a] += rc >= 0.5 ? rc : 0.0;
+          }
+        }
+      }
+    } else {
+      for (size_t tile = vg; tile < n_tiles; tile += n_vg) {
+#pragma unroll
+        for (int u = 0; u < kPpt; ++u) {
+          const size_t i = tile * tile_pts + u * kLinThreads + gt;
+          if (u * kLinThreads + gt < tile_pts && i < fv.n && __ldcg(fv.status + i) == MB_VALID) {
+            const d3 lt = ld3cg(fv.loc_trans, fv.ld, i), lr = ld3cg(fv.loc_rot, fv.ld, i);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+              const double tc = fabs(Vt[a] * lt.x + (Vt[3 + a] * lt.y + Vt[6 + a] * lt.z));
+              const double rc = fabs(Vr[a] * lr.x + (Vr[3 + a] * lr.y + Vr[6 + a] * lr.z));
+              a6[a] += tc >= 0.5 ? tc : 0.0;
+              a6[3 + a] += rc >= 0.5 ? rc : 0.0;
+            }
+          }
         }
       }
     }
@@ -1180,29 +1356,10 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     block_sum_rows(fv.partials2, (int)n_blocks, 8, S.tmp, loc, kLoopThreads);
     __syncthreads();
     if (peer) {
-      // the six sums of every rank, through the same mailboxes as the packets (doubles 48..53 of the last exchange's slot)
-      const int world = peer->world, rank = peer->rank;
+      // the six sums of every rank, through the same mailbox slot as the last packet (entries 48..53)
       const unsigned long long seq = xseq0 + (unsigned long long)la.iters;
-      const size_t pbase = (size_t)((seq & 1ull) * kMaxRanks);
-      if (tid < world * 6) {
-        const int dst = tid / 6, e = tid - dst * 6;
-        peer->mbox[dst][(pbase + (unsigned)rank) * kXchgDoubles + kPack + e] = loc[e];
-      }
-      __threadfence_system();
-      __syncthreads();
-      if (tid < world) {
-        st_release_sys(peer->lflag[tid] + pbase + (unsigned)rank, seq);
-        const unsigned long long* fl = peer->lflag[rank] + pbase + tid;
-        while (ld_acquire_sys(fl) != seq) {
-        }
-        __threadfence_system();
-      }
-      __syncthreads();
-      double v = 0.0;
-      if (tid < 6)
-        for (int r = 0; r < world; ++r) v += __ldcg(peer->mbox[rank] + (pbase + (unsigned)r) * kXchgDoubles + kPack + tid);
-      __syncthreads();
-      if (tid < 6) loc[tid] = v;
+      ll_send(peer, seq, loc, kPack, 6);
+      ll_gather(peer, seq, kPack, 6, reinterpret_cast<uint32_t*>(S.tmp), loc);
       if (tid == 0) *peer->xseq = seq;
       __syncthreads();
     }
@@ -1403,6 +1560,7 @@ struct mb_factor {
   int trace_cap = 0;
   int grid = 0, grid2 = 0, n_groups = 0;
   int tile_points = 128;  // points per block tile of k_linearize
+  int loop_tile = 256;    // points per group tile of k_icp_loop
   // k_linearize launch shape: kernel variant (k == 5 and <= 19 neighbour voxels, or generic), staging pool per warp
   bool lin_small = true;
   // voxel order (see k_group_sort): the caller's points, sorted position -> caller's index
@@ -1585,6 +1743,7 @@ int enqueue_loop(mb_factor* f, int iters, int do_step, mb_icp_trace* d_trace, co
   MapView mv = f->map->view();
   FactorView fv = f->view();
   fv.fold_loc = do_step ? 1 : 0;
+  fv.tile = f->loop_tile;
   LoopArgs la;
   std::memset(&la, 0, sizeof(la));
   la.iters = iters;
@@ -1661,7 +1820,14 @@ static int factor_init(mb_factor* f, mb_ctx* ctx, mb_map* map, const void* pts, 
       break;
     }
   const size_t n_tiles = (f->n + f->tile_points - 1) / f->tile_points;
-  f->n_tiles = n_tiles;
+  // k_icp_loop: groups of 128 threads, two points per thread in a full tile; again the smallest tile that still covers
+  // the shard in one round of the device's groups
+  {
+    const size_t groups = (size_t)ctx->sm_count * kLoopGroups;
+    const size_t per_group = (f->n + groups - 1) / groups;
+    f->loop_tile = (int)std::min<size_t>(kPpt * kLinThreads, std::max<size_t>(32, (per_group + 31) / 32 * 32));
+  }
+  f->n_tiles = std::max(n_tiles, (f->n + f->loop_tile - 1) / f->loop_tile);
   f->loop_grid = ctx->sm_count;
   f->grid = (int)std::max<size_t>(1, std::min<size_t>(n_tiles, capacity));
   f->n_groups = (f->grid + kGroup - 1) / kGroup;
@@ -1845,7 +2011,8 @@ MB_API int mb_debug_time_finalize(mb_factor* f, unsigned role_mask, int reps, fl
   HostOut no_out;
   no_out.out = nullptr, no_out.flag = nullptr, no_out.seq = 0;
   FinArgs fa;
-  fa.reg_4_dof = (int)f->cfg.reg_4_dof, fa.linearize_count = 0, fa.do_step = 0, fa.iter = 0, fa.trace = nullptr;
+  fa.reg_4_dof = (int)f->cfg.reg_4_dof, fa.linearize_count = 0, fa.do_step = (role_mask & 128u) ? 1 : 0, fa.iter = 0, fa.trace = nullptr;
+  role_mask &= 127u;  // bit 7: with the harness GN step (solve + retract) in role 4
   auto one = [&]() {
     if (role_mask == 32u) {
       if (f->lin_small)
@@ -1872,6 +2039,9 @@ MB_API int mb_debug_time_finalize(mb_factor* f, unsigned role_mask, int reps, fl
 #if defined(MB_LOOP_TIMING)
 MB_API int mb_debug_loop_times(long long* out /* 64 x 12 */) {
   return cudaMemcpyFromSymbol(out, g_loop_t, sizeof(long long) * 64 * 12) == cudaSuccess ? MB_OK : MB_ERR_CUDA;
+}
+MB_API int mb_debug_loop_fine(long long* out /* 64 x 12 */) {
+  return cudaMemcpyFromSymbol(out, g_loop_f, sizeof(long long) * 64 * 12) == cudaSuccess ? MB_OK : MB_ERR_CUDA;
 }
 #endif
 

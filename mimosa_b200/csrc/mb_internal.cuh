@@ -65,16 +65,23 @@ namespace mb {
 // n + 1 while a slow one still reads exchange n; it cannot reach n + 2 before every rank has consumed n.
 constexpr int kMaxRanks = 8;
 constexpr int kXchgDoubles = 56;  // >= the 48-double packet + the six component localizabilities of k_loc_comp
+// The persistent loop (k_icp_loop) uses a flag-in-data mailbox instead: every double travels as two 8-byte words
+// {32 data bits, 32-bit exchange number}, each written by ONE 8-byte store — a word is either absent or complete, so
+// the receiver needs neither a fence on the sender's side nor a separate flag (the protocol of NCCL's LL transport):
+//   ll       u64   [2 parity][kMaxRanks source][2 * kXchgDoubles]
 struct PeerTable {
   int world, rank;
   double* mbox[kMaxRanks];
   unsigned long long* flag[kMaxRanks];
   unsigned long long* lflag[kMaxRanks];
+  unsigned long long* ll[kMaxRanks];
   unsigned long long* xseq;
 };
 constexpr size_t kXchgMboxBytes = 2 * kMaxRanks * kXchgDoubles * sizeof(double);
 constexpr size_t kXchgFlagBytes = 2 * kMaxRanks * sizeof(unsigned long long);
-constexpr size_t kXchgBlockBytes = 8192;
+constexpr size_t kXchgLlOffset = 8192;
+constexpr size_t kXchgLlBytes = 2 * kMaxRanks * 2 * kXchgDoubles * sizeof(unsigned long long);
+constexpr size_t kXchgBlockBytes = kXchgLlOffset + kXchgLlBytes;
 }  // namespace mb
 
 // ---- handles ----------------------------------------------------------------------------------------

@@ -95,7 +95,8 @@ def test_peer_memory_exchange_two_gpus(tmp_path, ctx, oracle):
         port = 29600 + (os.getpid() % 1500) + int(use_peer)
         mp.spawn(_worker, args=(2, port, use_peer, out), nprocs=2, join=True)
         got[use_peer] = np.load(out)
-    assert np.array_equal(got[True], got[False]), "peer-memory sum (rank order) and NCCL sum differ"
+    # (the two paths run different kernels with different, each fixed, summation trees inside a rank)
+    assert np.allclose(got[True], got[False], rtol=1e-9, atol=1e-9 * np.abs(got[False]).max()), "peer-memory and NCCL paths differ"
     n_lin = 36 + 6 + 1 + 6 + 9
     lin2, comps2 = got[True][12:12 + n_lin], got[True][12 + n_lin:].reshape(ITERS, 6)
     got = {k: v[:12] for k, v in got.items()}

@@ -14,7 +14,7 @@ f = ICPFactor(ctx, m, scan, hornbill_config())
 f.linearize(R, t)
 fn = ctx.lib.mb_debug_time_finalize
 fn.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.POINTER(C.c_float)]
-for mask, name in [(0, "none (launch only)"), (1, "role0 eig Hrr"), (2, "role1 eig Htt"), (4, "role2 Schur rr"), (8, "role3 Schur tt"), (16, "role4 pack/solve"), (31, "all"), (32, "k_linearize cached"), (33, "k_linearize cached + fused finalize"), (64, "k_loc_comp")]:
+for mask, name in [(0, "none (launch only)"), (1, "role0 eig Hrr"), (2, "role1 eig Htt"), (4, "role2 Schur rr"), (8, "role3 Schur tt"), (16, "role4 pack"), (144, "role4 pack+solve+retract"), (31, "all"), (159, "all + step")]:
     us = C.c_float()
     assert fn(f.h, mask, 200, C.byref(us)) == 0
     print(f"mask {mask:2d} {name:22s} {us.value:7.2f} us/launch", flush=True)
