@@ -171,14 +171,21 @@ __device__ __forceinline__ void block_sum_rows(const double* rows, int count, in
   if (part < parts) {
     double v = 0.0;
     int b = part;
-    for (; b + 7 * parts < count; b += 8 * parts) {
-      double x[8];
+    for (; b + 15 * parts < count; b += 16 * parts) {  // 16 rows in flight: one L2 round trip for up to 16 * parts rows
+      double x[16];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) x[u] = __ldcg(rows + (size_t)(b + u * parts) * width + a);
+      for (int u = 0; u < 16; ++u) x[u] = __ldcg(rows + (size_t)(b + u * parts) * width + a);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v += x[u];
+      for (int u = 0; u < 16; ++u) v += x[u];
     }
-    for (; b < count; b += parts) v += __ldcg(rows + (size_t)b * width + a);
+    {
+      double x[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) x[u] = b + u * parts < count ? __ldcg(rows + (size_t)(b + u * parts) * width + a) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+        if (b + u * parts < count) v += x[u];
+    }
     s_tmp[part * width + a] = v;
   }
   __syncthreads();
@@ -214,6 +221,18 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
+#if defined(MB_LOOP_TIMING)  // development: SM clock of block 0 at the phase boundaries of every linearisation
+__device__ long long g_loop_t[64][12];
+#define MB_LOOP_T(it, slot) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (it) < 64) g_loop_t[it][slot] = clock64(); } while (0)
+__device__ long long g_loop_f[64][12];
+#define MB_LOOP_F(it, slot) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (it) < 64) g_loop_f[it][slot] = clock64(); } while (0)
+#define MB_FIN_STORE(it, slot) g_loop_f[it][slot] = clock64()
+#else
+#define MB_LOOP_F(it, slot) do { } while (0)
+#define MB_FIN_STORE(it, slot) (void)0
+#define MB_LOOP_T(it, slot) do { } while (0)
+#endif
+#define MB_FIN_T(it, slot) do { if (blockIdx.x == 0 && (it) < 64) MB_FIN_STORE(it, slot); } while (0)
 // What follows the reduction of one linearisation (arguments of the finalize roles).
 struct FinArgs {
   int reg_4_dof, linearize_count, do_step, iter;
@@ -248,6 +267,7 @@ __device__ __noinline__ void finalize_role(const double* packed, const DevState*
       Htr.m[3 * r + c] = H[6 * (r + 3) + c];
       Htt.m[3 * r + c] = H[6 * (r + 3) + 3 + c];
     }
+  if (role == 4) MB_FIN_T(fa.iter, 8);
   if (role < 4) {
     // The four eigen roles run as four LANES of one warp: the same instruction stream for all of them (one trip
     // through the instruction cache instead of four), selected inputs and outputs.  Lanes 2 / 3 first form their Schur
@@ -267,6 +287,7 @@ __device__ __noinline__ void finalize_role(const double* packed, const DevState*
     double* const vec_out = role == 0 ? L.eigvec_rot : role == 1 ? L.eigvec_trans : role == 2 ? L.degen_eigvec_rot : L.degen_eigvec_trans;
     for (int a = 0; a < 3; ++a) loc_out[a] = role == 2 ? loc[a] * 57.29578 : loc[a];  // RAD2DEG (PCL's macro), :428
     for (int a = 0; a < 9; ++a) vec_out[a] = V.m[a];
+    if (role == 0) MB_FIN_T(fa.iter, 11);
   } else {
     double b[6];
 #pragma unroll
@@ -308,9 +329,11 @@ __device__ __noinline__ void finalize_role(const double* packed, const DevState*
     for (int a = 0; a < 9; ++a) L.counts[a] = (int64_t)packed[kPackCnt + a];
     L.linearize_count = fa.linearize_count;
     L.n_searched = (int32_t)packed[kPackSearched];
+    MB_FIN_T(fa.iter, 9);
     if (fa.do_step) {
       double delta[6] = {0, 0, 0, 0, 0, 0};
       const bool ok = solve6_ldlt(H, in->lambda, g, delta);
+      MB_FIN_T(fa.iter, 10);
       if (ok) {
         se3_retract(R, T, delta);
 #pragma unroll
@@ -801,15 +824,7 @@ struct LoopArgs {
 #define MB_LOOP_THREADS 512
 #endif
 constexpr int kLoopThreads = MB_LOOP_THREADS, kLoopWarps = kLoopThreads / 32, kLoopGroups = kLoopThreads / kLinThreads;
-#if defined(MB_LOOP_TIMING)  // development: SM clock of block 0 at the phase boundaries of every linearisation
-__device__ long long g_loop_t[64][12];
-#define MB_LOOP_T(it, slot) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (it) < 64) g_loop_t[it][slot] = clock64(); } while (0)
-__device__ long long g_loop_f[64][12];
-#define MB_LOOP_F(it, slot) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (it) < 64) g_loop_f[it][slot] = clock64(); } while (0)
-#else
-#define MB_LOOP_F(it, slot) do { } while (0)
-#define MB_LOOP_T(it, slot) do { } while (0)
-#endif
+
 constexpr uint8_t kFresh = 0x80;  // status bit: written by phase B, consumed by phase C'
 constexpr int kPpt = 2;            // points per thread and tile in phases A / C (tiles of up to kPpt * 128 points)
 
@@ -923,6 +938,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
   const int k = fv.k;
   const bool forced = (fv.flags & 1u) != 0;
   const double inv_sigma = 1.0 / fv.sigma;
+  const double kh_sigma_lo = fv.kh * fv.sigma * 0.9999999;  // |e| at or below this: |e / sigma| <= k for certain
   const int tile_pts = fv.tile;
   const size_t n_tiles = (fv.n + tile_pts - 1) / tile_pts;
   const size_t vg = (size_t)blockIdx.x * kLoopGroups + grp, n_vg = (size_t)n_blocks * kLoopGroups;
@@ -985,12 +1001,20 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
         // (a skipped point computes on harmless non-zero stand-ins: a zero numerator would send the whole warp through
         // the division's slow path)
         double e = go[u] ? dot3(normal[u], sub3(mean[u], pt[u])) : 1.0;
-        const double s_chk = 1 - 0.9 * fabs(e) / rr[u];
-        valid[u] = go[u] && !(s_chk < 0.9);
+        // s-check (:323-326): 1 - 0.9 |e| / rr < 0.9.  With x = 0.9 |e| the outcome is certain without the division
+        // unless x / rr lies within 1e-7 of 0.1 (the quotient's rounding moves it by 1e-17): only then is it formed.
+        const double x9 = 0.9 * fabs(e);
+        bool max_err = x9 > rr[u] * 0.1000001;
+        if (!max_err && !(x9 < rr[u] * 0.0999999)) max_err = 1 - x9 / rr[u] < 0.9;
+        valid[u] = go[u] && !max_err;
+        // Huber (:330-336): |e / sigma| > k decides; the quotient itself is only needed beyond the threshold.
         double scale = inv_sigma;
         if (fv.use_huber) {  // uniform
-          const double we = e / fv.sigma;
-          if (fabs(we) > fv.kh) scale = sqrt(fv.kh / fabs(we)) / fv.sigma;  // rare: beyond the Huber threshold
+          const double ae = fabs(e);
+          if (ae > kh_sigma_lo) {  // rare: at or beyond the threshold (exact test inside)
+            const double we = e / fv.sigma;
+            if (fabs(we) > fv.kh) scale = sqrt(fv.kh / fabs(we)) / fv.sigma;
+          }
         }
         e *= scale;
         const d3 ns = mul33Tv(R, normal[u]);

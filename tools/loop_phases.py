@@ -50,11 +50,12 @@ def print_fine(lib, n_it=20):
     assert lib.mb_debug_loop_fine(buf) == 0
     t = np.array(buf, dtype=np.int64).reshape(64, 12)[:n_it]
     mhz = 1965.0
-    print("it | loads+gate  fold  ballot+sync  C:loads  C:math+stores  acc0  acc1+counts   (us, block 0 thread 0)", file=sys.stderr)
+    print("it | loads+gate  fold  ballot+sync  C:loads  C:math+stores  acc0  acc1+counts | fin: pack  solve  (eig role 0 done after)", file=sys.stderr)
     for it in range(n_it):
         r = t[it]
         d = [(r[k + 1] - r[k]) / mhz for k in range(7)]
-        print(f"{it:2d} | " + "  ".join(f"{x:6.2f}" for x in d), file=sys.stderr)
+        fin = [(r[9] - r[8]) / mhz, (r[10] - r[9]) / mhz, (r[11] - r[8]) / mhz]
+        print(f"{it:2d} | " + "  ".join(f"{x:6.2f}" for x in d) + " | " + "  ".join(f"{x:6.2f}" for x in fin), file=sys.stderr)
 
 
 if __name__ == "__main__":
