@@ -342,6 +342,9 @@ def run_stream(n_scans_arg, ctx, mg, cfg, synth, cpu_scans=0, coords_counts_pts=
     gate = KeyframeGate(1.0, 10.0, 10, np.eye(3))  # hornbill: map_keyframe_trans_thresh 1, rot 10 deg, 10 forced clouds
     n_warm = 4 if n_scans > 8 else 0
     cur = mg
+    import gc
+    gc.collect()
+    gc.disable()  # a generation-2 collection inside the loop is a ~100 ms stall of the HOST clock this config is timed with
     for s, (rec, R_true, t_true) in enumerate(scans):
         ctx.sync()
         t0 = time.perf_counter()
@@ -383,6 +386,7 @@ def run_stream(n_scans_arg, ctx, mg, cfg, synth, cpu_scans=0, coords_counts_pts=
         if os.environ.get("MB_BENCH_STREAM_VERBOSE"):
             log(f"  scan {s:3d} key={int(is_key)} ms: deskew {1e3 * (t1 - t0):6.2f} preprocess {1e3 * (t2 - t1):6.2f} get_factors {1e3 * (t3 - t2):7.2f} "
                 f"updates {1e3 * (t4 - t3):6.2f} update_map {1e3 * (t5 - t4):7.2f}  total {1e3 * (t5 - t0):7.2f}")
+    gc.enable()
     warm = per_scan[n_warm:]
     line = {"metric": "stream_scans_per_sec", "value": len(warm) / float(np.sum(warm)), "unit": "scans/s",
             "config": {"workload": "C5: 131072-pt scans at 10 Hz vs rolling 10M-pt map; per scan deskew + T_B_L + downsample + "

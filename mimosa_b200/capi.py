@@ -123,6 +123,7 @@ SIGNATURES = {
     "mb_timer_begin": (C.c_int, [_P]),
     "mb_timer_end": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "mb_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "mb_set_resident_window": (C.c_int, [_P, C.c_uint]),
     "mb_flush_l2": (C.c_int, [_P, _SZ]),
     "mb_flush_l2_read": (C.c_int, [_P, _SZ]),
     "mb_host_register": (C.c_int, [_P, C.c_size_t]),

@@ -29,8 +29,20 @@ int pinned_reserve(mb_ctx* c, size_t bytes) {
   return MB_OK;
 }
 
-int dev_alloc(mb_ctx* c, void** p, size_t bytes) {
+// Size classes of the pool: multiples of 256 B up to 4 KiB, above that eight classes per power of two (a block is at
+// most 12.5 % larger than asked).  A streaming pipeline asks for a slightly different size every scan (the
+// down-sampled cloud has 21 8xx points, never the same number twice): with exact-size reuse every scan missed the pool,
+// paid a cudaMalloc, and — once the pool was full — a cudaFree of tens of milliseconds.
+static size_t size_class(size_t bytes) {
   bytes = std::max<size_t>((bytes + 255) & ~(size_t)255, 256);
+  if (bytes <= 4096) return bytes;
+  const int lg = 63 - __builtin_clzll((unsigned long long)bytes);
+  const size_t step = (size_t)1 << (lg - 3);
+  return (bytes + step - 1) & ~(step - 1);
+}
+
+int dev_alloc(mb_ctx* c, void** p, size_t bytes) {
+  bytes = size_class(bytes);
   for (size_t i = 0; i < c->pool.size(); ++i)
     if (c->pool[i].bytes == bytes) {
       *p = c->pool[i].p;
@@ -54,7 +66,7 @@ int dev_alloc(mb_ctx* c, void** p, size_t bytes) {
 
 void dev_free(mb_ctx* c, void* p, size_t bytes) {
   if (!p) return;
-  bytes = std::max<size_t>((bytes + 255) & ~(size_t)255, 256);
+  bytes = size_class(bytes);
   // Limits sized for a 180 GB device: a streaming pipeline alternates two 10 M-point maps, their search mirrors and the
   // per-scan factor / scan blocks (~3 GB); when a limit is hit the OLDEST cached block makes room (a cudaFree in the
   // per-scan path costs tens of milliseconds: it was the 99 ms outlier of round 1's streaming numbers).
@@ -139,12 +151,14 @@ int mb_init(int device, mb_ctx** out) {
   MB_CUDA(cudaEventCreate(&c->ev1));
   MB_CUDA(cudaMallocHost(&c->pin_small, 4096));
   std::memset(c->pin_small, 0, 4096);
+  if (const char* e = getenv("MB_RESIDENT_US")) c->srv_window_us = (unsigned)std::max(0, atoi(e));
   *out = c;
   return MB_OK;
 }
 
 int mb_shutdown(mb_ctx* c) {
   if (!c) return MB_OK;
+  server_stop(c);
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->comm) ncclCommDestroy(c->comm);
@@ -165,6 +179,7 @@ int mb_shutdown(mb_ctx* c) {
 
 int mb_sync(mb_ctx* c) {
   MB_REQUIRE(c, "null ctx");
+  server_stop(c);
   MB_CUDA(cudaSetDevice(c->device));
   MB_CUDA(cudaStreamSynchronize(c->stream));
   return MB_OK;
@@ -172,6 +187,7 @@ int mb_sync(mb_ctx* c) {
 
 int mb_timer_begin(mb_ctx* c) {
   MB_REQUIRE(c, "null ctx");
+  server_stop(c);
   MB_CUDA(cudaSetDevice(c->device));
   MB_CUDA(cudaEventRecord(c->ev0, c->stream));
   return MB_OK;
@@ -179,10 +195,19 @@ int mb_timer_begin(mb_ctx* c) {
 
 int mb_timer_end(mb_ctx* c, float* ms) {
   MB_REQUIRE(c && ms, "null argument");
+  server_stop(c);
   MB_CUDA(cudaSetDevice(c->device));
   MB_CUDA(cudaEventRecord(c->ev1, c->stream));
   MB_CUDA(cudaEventSynchronize(c->ev1));
   MB_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return MB_OK;
+}
+
+int mb_set_resident_window(mb_ctx* c, unsigned microseconds) {
+  MB_REQUIRE(c, "null ctx");
+  MB_REQUIRE(microseconds <= 1000000u, "window above one second");
+  server_stop(c);
+  c->srv_window_us = microseconds;
   return MB_OK;
 }
 

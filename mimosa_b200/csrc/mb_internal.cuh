@@ -102,6 +102,14 @@ struct mb_ctx {
   size_t pinned_bytes = 0;
   void* pin_small = nullptr;  // 4 KiB page-locked (device-mapped) block for poses in / normal equations out / flag
   unsigned host_seq = 0;      // sequence number of the last host-polled completion (mb_factor_linearize)
+  // Resident linearisation kernel (mb_factor.cu, k_icp_loop in serve mode): after a host-facing linearisation the
+  // kernel stays on the device for a short window and takes the next pose from the mapped block below instead of a
+  // new launch.  srv_req numbers every host-facing request of this context; srv_live / srv_factor: a kernel that may
+  // still be resident and the factor it serves.
+  unsigned long long srv_req = 0;
+  bool srv_live = false;
+  struct mb_factor* srv_factor = nullptr;
+  unsigned srv_window_us = 30;  // MB_RESIDENT_US (0: every call is a launch)
   // Size-keyed cache of released device blocks: a factor is created and destroyed for every scan with the
   // same sizes, and cudaMalloc/cudaFree would otherwise dominate the per-scan host cost.
   struct Block {
@@ -114,6 +122,22 @@ struct mb_ctx {
 };
 
 namespace mb {
+// Words of the context's mapped block the resident kernel and the host talk through (byte offsets into pin_small;
+// all monotonic request numbers, so nothing ever has to be reset):
+constexpr size_t kSrvRec = 3072;   // the request record (host -> device), 4 lines of 64 bytes = 32 words of 8 bytes:
+                                   //   lines 0..2: 7 payload words each — the 16 doubles [pose 12 | gravity 3 | lambda]
+                                   //   at word i + i / 7 — and the REQUEST NUMBER in word 7 / 15 / 23, written last;
+                                   //   word 24: the kernel serving requests <= this number must leave
+constexpr size_t kSrvExit = 2128;  // u64: the first request number a departed kernel did NOT serve (device -> host)
+constexpr size_t kSrvResp = 2136;  // u64: number of the last request whose result sits at offset 256 (device -> host)
+// Ask a resident kernel to leave (it would on its own once its window closes): everything enqueued on the context's
+// stream afterwards then starts without that delay.
+inline void server_stop(mb_ctx* c) {
+  if (c->srv_live) {
+    __atomic_store_n((unsigned long long*)((char*)c->pin_small + kSrvRec) + 24, c->srv_req, __ATOMIC_RELEASE);
+    c->srv_live = false;
+  }
+}
 // Grow-only page-locked staging buffer of the context (synchronises the stream when it has to grow).
 int pinned_reserve(mb_ctx* c, size_t bytes);
 // Pooled device allocations (exact-size reuse).  dev_free never synchronises: the caller guarantees that no

@@ -113,6 +113,10 @@ class Context:
         check(self.lib.mb_timer_end(self.h, C.byref(ms)))
         return float(ms.value)
 
+    def set_resident_window(self, microseconds: int):
+        """How long the linearisation kernel stays resident after a host-facing call (0: every call launches)."""
+        check(self.lib.mb_set_resident_window(self.h, int(microseconds)))
+
     def launch_count(self) -> int:
         v = C.c_uint64()
         check(self.lib.mb_launch_count(self.h, C.byref(v)))
