@@ -198,6 +198,11 @@ MB_API int mb_comm_init(mb_ctx* ctx, int rank, int world, const void* id128);
  * mailbox and the post-reduction kernel sums the mailbox in rank order — no collective call on that path. */
 MB_API int mb_comm_ipc_handle(mb_ctx* ctx, void* handle64);
 MB_API int mb_comm_ipc_open(mb_ctx* ctx, const void* handles /* world x 64 bytes */);
+/* Device-side barrier of all ranks on the context's stream (after mb_comm_ipc_open): a one-block kernel that exchanges
+ * a word through the peer mailboxes, so that what every rank enqueues next starts within a few microseconds of the
+ * others.  bench.py puts it in front of each timed step: a host-side barrier alone releases eight processes hundreds of
+ * microseconds apart, and the early ranks would count that wait inside their first in-kernel exchange. */
+MB_API int mb_comm_barrier(mb_ctx* ctx);
 
 /* ---- map: mimosa::lidar::IncrementalVoxelMapPCL over gtsam_points::iVox ------------------------------
  * mb_map_create   <- IncrementalVoxelMapPCL(leaf) + set_lru_horizon + set_neighbor_voxel_mode +

@@ -132,6 +132,7 @@ SIGNATURES = {
     "mb_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "mb_comm_ipc_handle": (C.c_int, [_P, _P]),
     "mb_comm_ipc_open": (C.c_int, [_P, _P]),
+    "mb_comm_barrier": (C.c_int, [_P]),
     "mb_map_create": (C.c_int, [_P, C.c_float, C.c_float, C.c_int, C.c_int, C.c_uint64, C.POINTER(_P)]),
     "mb_map_release": (C.c_int, [_P]),
     "mb_map_insert": (C.c_int, [_P, _P, _SZ, _SZ]),

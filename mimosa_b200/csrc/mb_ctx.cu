@@ -321,12 +321,9 @@ int mb_comm_ipc_open(mb_ctx* c, const void* handles) {
       if (!c->xchg_peer[r]) MB_CUDA(cudaIpcOpenMemHandle(&c->xchg_peer[r], h, cudaIpcMemLazyEnablePeerAccess));
       base = c->xchg_peer[r];
     }
-    t.mbox[r] = (double*)base;
-    t.flag[r] = (unsigned long long*)((char*)base + kXchgMboxBytes);
-    t.lflag[r] = (unsigned long long*)((char*)base + kXchgMboxBytes + kXchgFlagBytes);
-    t.ll[r] = (unsigned long long*)((char*)base + kXchgLlOffset);
+    t.ll[r] = (unsigned long long*)base;
   }
-  t.xseq = (unsigned long long*)((char*)c->xchg_block + kXchgMboxBytes + 2 * kXchgFlagBytes);
+  t.xseq = (unsigned long long*)((char*)c->xchg_block + kXchgLlBytes);
   if (!c->d_peer) MB_CUDA(cudaMalloc((void**)&c->d_peer, sizeof(PeerTable)));
   MB_CUDA(cudaMemcpy(c->d_peer, &t, sizeof(t), cudaMemcpyHostToDevice));
   return MB_OK;

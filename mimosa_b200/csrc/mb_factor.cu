@@ -84,14 +84,6 @@ struct PoseArg {
   double v[16];  // R (9), t (3), gravity (3), lambda
 };
 
-// Where the last block of k_loc_comp leaves the finished linearisation for the host (mapped page-locked
-// memory; out == nullptr: nothing is written).  The host polls `flag` for `seq` instead of synchronising the stream.
-struct HostOut {
-  unsigned long long* out;  // sizeof(mb_linearization) / 8 words, then the six component localizabilities
-  volatile unsigned* flag;
-  unsigned seq;
-};
-
 struct DevState {        // small device-resident block per factor
   double pose[12];       // R row-major (9), t (3)
   double gravity[3];
@@ -209,18 +201,6 @@ __device__ __forceinline__ void localizability(const m33& JtJ, double loc[3], m3
 #ifndef MB_LIN_BLOCKS
 #define MB_LIN_BLOCKS 4  // measured: 4 x 128 threads at 128 registers beat 5 x 96 and 3 x 156
 #endif
-// PoseT = PoseArg: host-facing single call (pose in the kernel parameters); PoseT = NoPose: device-resident loop.
-struct NoPose {};
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
 #if defined(MB_LOOP_TIMING)  // development: SM clock of block 0 at the phase boundaries of every linearisation
 __device__ long long g_loop_t[64][12];
 #define MB_LOOP_T(it, slot) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (it) < 64) g_loop_t[it][slot] = clock64(); } while (0)
@@ -372,43 +352,12 @@ __device__ __noinline__ void finalize_role(const double* packed, const DevState*
   }
 }
 
-// Several ranks: wait for every rank's packet of this exchange in this rank's mailbox and add them in rank order
-// (identical on every rank).  Called by all threads of a block with >= kPack threads; s_packed receives the sum.
-__device__ __forceinline__ void peer_gather(const PeerTable* __restrict__ peer, double* s_packed, double* packed_out) {
-  const int world = peer->world, rank = peer->rank;
-  const unsigned long long seq = *peer->xseq + 1ull;
-  const size_t base = (size_t)((seq & 1ull) * kMaxRanks);
-  if ((int)threadIdx.x < world) {
-    const unsigned long long* fl = peer->flag[rank] + base + threadIdx.x;
-    while (ld_acquire_sys(fl) != seq) {
-    }
-    __threadfence_system();
-  }
-  __syncthreads();
-  if (threadIdx.x < kPack) {
-    const double* mb = peer->mbox[rank] + base * kXchgDoubles + threadIdx.x;
-    double v = 0.0;
-    for (int r = 0; r < world; ++r) v += __ldcg(mb + (size_t)r * kXchgDoubles);
-    s_packed[threadIdx.x] = v;
-    packed_out[threadIdx.x] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) *peer->xseq = seq;
-}
-
 // What follows the reduction, in its own small kernel (two warps: the solve, and the four eigen roles as four lanes of
 // the other).  Running the roles inside k_linearize's last block was built and measured (profiles/r2_experiments.md):
 // under k_linearize's register cap the same chain takes 10-13 us instead of 4-6.
-__global__ void __launch_bounds__(64) k_finalize(const double* packed_in, DevState* ds, FinArgs fa, unsigned role_mask,
-                                                 const PeerTable* __restrict__ peer, double* packed_out) {
-  __shared__ double s_packed[kXchgDoubles];
+__global__ void __launch_bounds__(64) k_finalize(const double* packed, DevState* ds, FinArgs fa, unsigned role_mask) {
   pdl_launch_dependents();
   pdl_wait();
-  const double* packed = packed_in;
-  if (peer) {
-    peer_gather(peer, s_packed, packed_out);
-    packed = s_packed;
-  }
   // warp 0, lane 0: projection + packing + solve + retract; warp 1, lanes 0..3: the four eigen roles in lock step
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int role = warp == 0 ? (lane == 0 ? 4 : -1) : (lane < 4 ? lane : -1);
@@ -421,9 +370,8 @@ __global__ void __launch_bounds__(64) k_finalize(const double* packed_in, DevSta
 // measured in round 2 and lost (profiles/r2_experiments.md): one warp per 32-point tile with the neighbourhood
 // resolved once per voxel group and staged through the bulk-copy engine, and a three-phase form with grid barriers
 // and pulled, compacted search passes.
-template <int K, typename PoseT, int ROWS>
-__global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
-    k_linearize(MapView mv, FactorView fv, DevState* ds, PoseT pa, const PeerTable* __restrict__ peer) {
+template <int K, int ROWS>
+__global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS) k_linearize(MapView mv, FactorView fv, DevState* ds) {
   double* pose_dev = ds->pose;
   __shared__ uint16_t s_tab[kTabEntries];
   // s_pk (phase B: probed neighbour words, [n_off][thread]; cooperative search: the per-thread candidate stacks,
@@ -452,17 +400,9 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
   // k_finalize wrote and overwrite per-point state the previous k_loc_comp may still be reading
   pdl_wait();
   m33 R;
-  d3 T;
-  if constexpr (std::is_same<PoseT, PoseArg>::value) {
-    if (blockIdx.x == 0 && tid < 16) pose_dev[tid] = pa.v[tid];  // k_finalize reads pose / gravity / lambda there
 #pragma unroll
-    for (int a = 0; a < 9; ++a) R.m[a] = pa.v[a];
-    T = mk3(pa.v[9], pa.v[10], pa.v[11]);
-  } else {
-#pragma unroll
-    for (int a = 0; a < 9; ++a) R.m[a] = pose_dev[a];
-    T = mk3(pose_dev[9], pose_dev[10], pose_dev[11]);
-  }
+  for (int a = 0; a < 9; ++a) R.m[a] = pose_dev[a];
+  const d3 T = mk3(pose_dev[9], pose_dev[10], pose_dev[11]);
   const int k = fv.k;
   const bool forced = (fv.flags & 1u) != 0;
   const double inv_sigma = 1.0 / fv.sigma;  // = sqrt_w / sigma for the points Huber leaves alone (sqrt_w == 1)
@@ -678,28 +618,11 @@ __global__ void __launch_bounds__(kLinThreads, MB_LIN_BLOCKS)
   __threadfence();
   block_sum_rows(fv.gpartials, n_groups, kPack, s_tmp, fv.packed, kLinThreads);
   if (tid == 0) *fv.ticket = 0u;
-  if (peer) {
-    // Several ranks: this rank's packet goes straight into every rank's mailbox (peer stores over NVLink),
-    // then the flags are raised — k_finalize on each rank sums the mailbox in rank order (mb_internal.cuh).
-    __syncthreads();  // the packet written by this block's first kPack threads is visible to all of them
-    const int world = peer->world, rank = peer->rank;
-    const unsigned long long seq = *peer->xseq + 1ull;
-    const size_t slot = (size_t)((seq & 1ull) * kMaxRanks + (unsigned)rank);
-    for (int x = tid; x < world * kPack; x += kLinThreads) {
-      const int dst = x / kPack, e = x - dst * kPack;
-      peer->mbox[dst][slot * kXchgDoubles + e] = fv.packed[e];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < world) st_release_sys(peer->flag[tid] + slot, seq);
-  }
 }
 
 // Component localizabilities (geometric_factor.hpp:434-457): sum over Valid points of |loc_i^T V| with
 // entries below 0.5 zeroed.
-template <bool kHostOut>
-__global__ void __launch_bounds__(kLocThreads) k_loc_comp(FactorView fv, const DevState* __restrict__ ds, HostOut ho,
-                                                          const PeerTable* __restrict__ peer) {
+__global__ void __launch_bounds__(kLocThreads) k_loc_comp(FactorView fv, const DevState* __restrict__ ds) {
   __shared__ double s_red[kLocThreads / 32][8];
   __shared__ double s_tmp[(kLocThreads / 8) * 8];
   __shared__ bool s_last;
@@ -744,43 +667,6 @@ __global__ void __launch_bounds__(kLocThreads) k_loc_comp(FactorView fv, const D
   __threadfence();
   block_sum_rows(fv.partials2, (int)gridDim.x, 8, s_tmp, fv.loc_out, kLocThreads);
   if (threadIdx.x == 0) *fv.ticket2 = 0u;
-  if (peer) {
-    // Several ranks, sums wanted by the caller: the six partial sums travel through the same mailboxes as the
-    // packet (doubles 40..45 of this exchange's slot, their own flags) and are added in rank order right here.
-    __syncthreads();
-    const int world = peer->world, rank = peer->rank;
-    const unsigned long long seq = *peer->xseq;  // k_finalize has already counted this exchange
-    const size_t par = (size_t)((seq & 1ull) * kMaxRanks);
-    if ((int)threadIdx.x < world * 6) {
-      const int dst = threadIdx.x / 6, e = threadIdx.x - dst * 6;
-      peer->mbox[dst][(par + (unsigned)rank) * kXchgDoubles + kPack + e] = fv.loc_out[e];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < world) {
-      st_release_sys(peer->lflag[threadIdx.x] + par + (unsigned)rank, seq);
-      const unsigned long long* fl = peer->lflag[rank] + par + threadIdx.x;
-      while (ld_acquire_sys(fl) != seq) {
-      }
-      __threadfence_system();
-    }
-    __syncthreads();
-    if (threadIdx.x < 6) {
-      double v = 0.0;
-      for (int r = 0; r < world; ++r) v += __ldcg(peer->mbox[rank] + (par + (unsigned)r) * kXchgDoubles + kPack + threadIdx.x);
-      fv.loc_out[threadIdx.x] = v;
-    }
-  }
-  if (kHostOut) {  // hand the finished linearisation to the polling host
-    __syncthreads();
-    constexpr int kWords = (int)(sizeof(mb_linearization) / 8);
-    const unsigned long long* lin = reinterpret_cast<const unsigned long long*>(&ds->lin);
-    for (int w = threadIdx.x; w < kWords; w += kLocThreads) ho.out[w] = lin[w];
-    if (threadIdx.x < 6) ho.out[kWords + threadIdx.x] = (unsigned long long)__double_as_longlong(fv.loc_out[threadIdx.x]);
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) *ho.flag = ho.seq;
-  }
 }
 
 // ================================================================================================================
@@ -899,6 +785,17 @@ __device__ __forceinline__ void ll_gather(const PeerTable* peer, unsigned long l
     dst[threadIdx.x] = v;
   }
   __syncthreads();
+}
+// Device-side barrier of all ranks: one exchange of a single word (entry kXchgDoubles - 1 of the mailbox slot).
+__global__ void __launch_bounds__(64) k_rank_barrier(const PeerTable* __restrict__ peer) {
+  __shared__ double s_one[1];
+  __shared__ uint32_t s_words[2 * kMaxRanks];
+  const unsigned long long seq = *peer->xseq + 1ull;
+  if (threadIdx.x == 0) s_one[0] = 1.0;
+  __syncthreads();
+  ll_send(peer, seq, s_one, kXchgDoubles - 1, 1);
+  ll_gather(peer, seq, kXchgDoubles - 1, 1, s_words, s_one);
+  if (threadIdx.x == 0) *peer->xseq = seq;
 }
 __device__ __forceinline__ void group_sync(int grp) {
   asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kLinThreads) : "memory");
@@ -1541,23 +1438,13 @@ __global__ void k_pack_src(const unsigned char* __restrict__ data, size_t stride
 // hashes collide merely interleave.  All per-point state lives in sorted order; `perm` (sorted position -> index in
 // the caller's scan) brings it back to reference order in mb_factor_download_state (geometric_factor.hpp:79-84: the
 // reference's arrays are indexed like the source cloud).  The result is a deterministic function of scan and pose.
-// development (MB_LIN_SORT=0): the caller's order, for A/B measurements of what the voxel order buys
-__global__ void k_copy_src(const float4* __restrict__ src_raw, size_t n, float4* __restrict__ src, double* __restrict__ rroot) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float4 p = src_raw[i];
-  src[i] = p;
-  rroot[i] = sqrt(sqrt(sqnorm3(mk3((double)p.x, (double)p.y, (double)p.z))));
-}
-
 constexpr int kGsThreads = 1024, kGsWarps = kGsThreads / 32;
 constexpr int kGsRows = 4;                          // rows of 32 points per warp
 constexpr int kGsChunk = kGsThreads * kGsRows;      // points per block
 constexpr int kGsBins = 2048;
 constexpr size_t kGsSmem = (size_t)kGsWarps * kGsBins * sizeof(uint16_t) + kGsBins * sizeof(uint32_t) + 64 * sizeof(uint32_t);
-template <typename PoseT>
 __global__ void __launch_bounds__(kGsThreads, 1)
-    k_group_sort(const float4* __restrict__ src_raw, size_t n, const DevState* __restrict__ ds, PoseT pa, double inv_leaf,
+    k_group_sort(const float4* __restrict__ src_raw, size_t n, const DevState* __restrict__ ds, PoseArg pa, int has_pose, double inv_leaf,
                  float4* __restrict__ src, uint32_t* __restrict__ perm, double* __restrict__ rroot) {
   extern __shared__ __align__(16) unsigned char s_gs[];
   uint16_t* hist = reinterpret_cast<uint16_t*>(s_gs);                                   // [warp][bin]
@@ -1566,16 +1453,9 @@ __global__ void __launch_bounds__(kGsThreads, 1)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int x = tid; x < kGsWarps * kGsBins / 2; x += kGsThreads) reinterpret_cast<uint32_t*>(hist)[x] = 0u;
   m33 R;
-  d3 T;
-  if constexpr (std::is_same<PoseT, PoseArg>::value) {
 #pragma unroll
-    for (int a = 0; a < 9; ++a) R.m[a] = pa.v[a];
-    T = mk3(pa.v[9], pa.v[10], pa.v[11]);
-  } else {
-#pragma unroll
-    for (int a = 0; a < 9; ++a) R.m[a] = ds->pose[a];
-    T = mk3(ds->pose[9], ds->pose[10], ds->pose[11]);
-  }
+  for (int a = 0; a < 9; ++a) R.m[a] = has_pose ? pa.v[a] : ds->pose[a];
+  const d3 T = has_pose ? mk3(pa.v[9], pa.v[10], pa.v[11]) : mk3(ds->pose[9], ds->pose[10], ds->pose[11]);
   __syncthreads();
   const size_t chunk0 = (size_t)blockIdx.x * kGsChunk;
   uint16_t* const my_hist = hist + (size_t)warp * kGsBins;
@@ -1770,43 +1650,33 @@ int enqueue_sort(mb_factor* f, const PoseArg* pose_arg) {
   if (f->n == 0) return MB_OK;
   mb_ctx* c = f->ctx;
   cudaStream_t st = c->stream;
-  if (const char* e = getenv("MB_LIN_SORT")) {
-    if (atoi(e) == 0) {
-      k_copy_src<<<(unsigned)((f->n + 255) / 256), 256, 0, st>>>(f->src_raw, f->n, f->src, f->rroot);
-      ++c->launches;
-      f->sorted = false;
-      return MB_OK;
-    }
-  }
   static bool opted_in = false;
   if (!opted_in) {
-    MB_CUDA(cudaFuncSetAttribute(k_group_sort<PoseArg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGsSmem));
-    MB_CUDA(cudaFuncSetAttribute(k_group_sort<NoPose>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGsSmem));
+    MB_CUDA(cudaFuncSetAttribute(k_group_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGsSmem));
     opted_in = true;
   }
   const unsigned blocks = (unsigned)((f->n + kGsChunk - 1) / kGsChunk);
-  if (pose_arg)
-    k_group_sort<PoseArg><<<blocks, kGsThreads, kGsSmem, st>>>(f->src_raw, f->n, f->ds, *pose_arg, f->map->inv_leaf, f->src, f->perm, f->rroot);
-  else
-    k_group_sort<NoPose><<<blocks, kGsThreads, kGsSmem, st>>>(f->src_raw, f->n, f->ds, NoPose{}, f->map->inv_leaf, f->src, f->perm, f->rroot);
+  PoseArg pa;
+  std::memset(&pa, 0, sizeof(pa));
+  if (pose_arg) pa = *pose_arg;
+  k_group_sort<<<blocks, kGsThreads, kGsSmem, st>>>(f->src_raw, f->n, f->ds, pa, pose_arg ? 1 : 0, f->map->inv_leaf, f->src, f->perm, f->rroot);
   ++c->launches;
   f->sorted = true;
   MB_CUDA(cudaGetLastError());
   return MB_OK;
 }
 
-// Enqueue one linearisation (+ optional GN step) on the context stream.
-int enqueue_linearize(mb_factor* f, int do_step, int iter, mb_icp_trace* d_trace, int linearize_count,
-                      const PoseArg* pose_arg = nullptr, const HostOut* host_out = nullptr) {
+// Several ranks WITHOUT the peer-memory exchange: one linearisation (+ optional GN step) as separate kernels on the
+// context stream, the 48-double packet all-reduced with NCCL between them (north_star's "single NCCL allreduce of the
+// 6x6 normal equations per ICP iteration").
+int enqueue_linearize(mb_factor* f, int do_step, int iter, mb_icp_trace* d_trace, int linearize_count) {
   mb_ctx* c = f->ctx;
   cudaStream_t st = c->stream;
-  if (linearize_count == 1) MB_TRY(enqueue_sort(f, pose_arg));  // first linearisation since construction / reset
+  if (linearize_count == 1) MB_TRY(enqueue_sort(f, nullptr));  // first linearisation since construction / reset
   FactorView fv = f->view();
   // Device-resident loop: the localizability pass of this linearisation is folded into the NEXT k_linearize (and
   // mb_icp_run launches k_loc_comp once, after the last iteration); the host-facing single call runs it right away.
   fv.fold_loc = do_step ? 1 : 0;
-  const PeerTable* peer = c->world > 1 ? c->d_peer : nullptr;  // nullptr: single rank, or NCCL all-reduce
-  const bool nccl = c->world > 1 && !peer;
   FinArgs fa;
   fa.reg_4_dof = (int)f->cfg.reg_4_dof;
   fa.linearize_count = linearize_count;
@@ -1814,32 +1684,18 @@ int enqueue_linearize(mb_factor* f, int do_step, int iter, mb_icp_trace* d_trace
   fa.iter = iter;
   fa.trace = d_trace;
   const dim3 grid(f->grid), block(kLinThreads);
-  if (pose_arg) {
-    if (f->lin_small)  // the specialised kernel: k = 5 and at most 19 neighbour voxels
-      MB_CUDA(launch_pdl(k_linearize<5, PoseArg, 19>, grid, block, st, f->map->view(), fv, f->ds, *pose_arg, peer));
-    else
-      MB_CUDA(launch_pdl(k_linearize<MB_MAX_K, PoseArg, 27>, grid, block, st, f->map->view(), fv, f->ds, *pose_arg, peer));
-  } else {
-    if (f->lin_small)
-      MB_CUDA(launch_pdl(k_linearize<5, NoPose, 19>, grid, block, st, f->map->view(), fv, f->ds, NoPose{}, peer));
-    else
-      MB_CUDA(launch_pdl(k_linearize<MB_MAX_K, NoPose, 27>, grid, block, st, f->map->view(), fv, f->ds, NoPose{}, peer));
-  }
-  if (nccl) MB_NCCL(ncclAllReduce(f->packed, f->packed, kPack, ncclDouble, ncclSum, c->comm, st));
-  MB_CUDA(launch_pdl(k_finalize, dim3(1), dim3(64), st, (const double*)f->packed, f->ds, fa, 31u, peer, f->packed));
+  if (f->lin_small)  // the specialised kernel: k = 5 and at most 19 neighbour voxels
+    MB_CUDA(launch_pdl(k_linearize<5, 19>, grid, block, st, f->map->view(), fv, f->ds));
+  else
+    MB_CUDA(launch_pdl(k_linearize<MB_MAX_K, 27>, grid, block, st, f->map->view(), fv, f->ds));
+  MB_NCCL(ncclAllReduce(f->packed, f->packed, kPack, ncclDouble, ncclSum, c->comm, st));
+  MB_CUDA(launch_pdl(k_finalize, dim3(1), dim3(64), st, (const double*)f->packed, f->ds, fa, 31u));
   c->launches += 2;
-  if (host_out) {
-    MB_CUDA(launch_pdl(k_loc_comp<true>, dim3(f->grid2), dim3(kLocThreads), st, fv, (const DevState*)f->ds, *host_out, peer));
+  if (!do_step) {
+    MB_CUDA(launch_pdl(k_loc_comp, dim3(f->grid2), dim3(kLocThreads), st, fv, (const DevState*)f->ds));
     ++c->launches;
-  } else if (!do_step) {
-    HostOut none;
-    none.out = nullptr, none.flag = nullptr, none.seq = 0;
-    MB_CUDA(launch_pdl(k_loc_comp<false>, dim3(f->grid2), dim3(kLocThreads), st, fv, (const DevState*)f->ds, none, peer));
-    ++c->launches;
+    MB_NCCL(ncclAllReduce(f->packed + kPack, f->packed + kPack, 6, ncclDouble, ncclSum, c->comm, st));
   }
-  // The cross-rank sum of the six component localizabilities is only needed when they are handed out
-  // (mb_factor_linearize): through the peer mailboxes inside k_loc_comp, or with NCCL as the fallback.
-  if (nccl && !do_step) MB_NCCL(ncclAllReduce(f->packed + kPack, f->packed + kPack, 6, ncclDouble, ncclSum, c->comm, st));
   MB_CUDA(cudaGetLastError());
   return MB_OK;
 }
@@ -1847,13 +1703,8 @@ int enqueue_linearize(mb_factor* f, int do_step, int iter, mb_icp_trace* d_trace
 // The localizability pass of the loop's LAST linearisation (the earlier ones were folded into their successors).
 int enqueue_last_loc_comp(mb_factor* f) {
   mb_ctx* c = f->ctx;
-  HostOut none;
-  none.out = nullptr, none.flag = nullptr, none.seq = 0;
-  // several ranks: the six sums cover every rank's shard, like the folded sums of the earlier iterations
-  const PeerTable* peer = c->world > 1 ? c->d_peer : nullptr;
-  MB_CUDA(launch_pdl(k_loc_comp<false>, dim3(f->grid2), dim3(kLocThreads), c->stream, f->view(), (const DevState*)f->ds, none, peer));
-  if (c->world > 1 && !peer)
-    MB_NCCL(ncclAllReduce(f->packed + kPack, f->packed + kPack, 6, ncclDouble, ncclSum, c->comm, c->stream));
+  MB_CUDA(launch_pdl(k_loc_comp, dim3(f->grid2), dim3(kLocThreads), c->stream, f->view(), (const DevState*)f->ds));
+  MB_NCCL(ncclAllReduce(f->packed + kPack, f->packed + kPack, 6, ncclDouble, ncclSum, c->comm, c->stream));
   ++c->launches;
   return MB_OK;
 }
@@ -1940,9 +1791,9 @@ static int factor_init(mb_factor* f, mb_ctx* ctx, mb_map* map, const void* pts, 
   f->lin_small = k == 5 && map->n_off <= 19;
   int per_sm = MB_LIN_BLOCKS;
   if (f->lin_small)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<5, NoPose, 19>, kLinThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<5, 19>, kLinThreads, 0);
   else
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<MB_MAX_K, NoPose, 27>, kLinThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize<MB_MAX_K, 27>, kLinThreads, 0);
   per_sm = std::max(per_sm, 1);
   // Points per tile: the smallest of 32 / 64 / 128 whose tiles still fit the device in one round.  A full scan on one
   // GPU needs 128 (and two rounds); a shard of a scan on 4 or 8 GPUs gets 64 or 32, which spreads its points over all
@@ -2122,6 +1973,18 @@ static int factor_create_impl(mb_ctx* ctx, mb_map* map, const void* pts, const m
 
 extern "C" {
 
+int mb_comm_barrier(mb_ctx* c) {
+  MB_REQUIRE(c, "null ctx");
+  if (c->world <= 1) return MB_OK;
+  MB_REQUIRE(c->d_peer, "mb_comm_barrier needs the peer-memory exchange (mb_comm_ipc_open)");
+  server_stop(c);
+  MB_CUDA(cudaSetDevice(c->device));
+  k_rank_barrier<<<1, 64, 0, c->stream>>>(c->d_peer);
+  ++c->launches;
+  MB_CUDA(cudaGetLastError());
+  return MB_OK;
+}
+
 int mb_factor_create(mb_ctx* ctx, mb_map* map, const void* pts, size_t n, size_t stride_bytes,
                      const mb_icp_config* cfg, size_t shard_begin, size_t shard_end, mb_factor** out) {
   return factor_create_impl(ctx, map, pts, nullptr, n, stride_bytes, cfg, shard_begin, shard_end, out);
@@ -2135,32 +1998,16 @@ int mb_factor_create_from_scan(mb_ctx* ctx, mb_map* map, mb_scan* scan, const mb
 }
 
 // Timing diagnostic (not part of the documented ABI): average device time of k_finalize restricted to the roles
-// in `role_mask`, `reps` back-to-back launches on the factor's last reduced packet.
+// in `role_mask` (bit 7: with the harness GN step in role 4), `reps` back-to-back launches on the factor's last packet.
 MB_API int mb_debug_time_finalize(mb_factor* f, unsigned role_mask, int reps, float* us_per_launch) {
   MB_REQUIRE(f && us_per_launch && reps > 0, "bad argument");
+  server_stop(f->ctx);
   MB_CUDA(cudaSetDevice(f->ctx->device));
   cudaStream_t st = f->ctx->stream;
-  const FactorView fv = f->view();
-  // role_mask < 32: k_finalize with those roles; 32: k_linearize at the current pose (fully cached after one call);
-  // 64: k_loc_comp.  Back to back.
-  const NoPose no_pose{};
-  HostOut no_out;
-  no_out.out = nullptr, no_out.flag = nullptr, no_out.seq = 0;
   FinArgs fa;
   fa.reg_4_dof = (int)f->cfg.reg_4_dof, fa.linearize_count = 0, fa.do_step = (role_mask & 128u) ? 1 : 0, fa.iter = 0, fa.trace = nullptr;
-  role_mask &= 127u;  // bit 7: with the harness GN step (solve + retract) in role 4
-  auto one = [&]() {
-    if (role_mask == 32u) {
-      if (f->lin_small)
-        k_linearize<5, NoPose, 19><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds, no_pose, nullptr);
-      else
-        k_linearize<MB_MAX_K, NoPose, 27><<<f->grid, kLinThreads, 0, st>>>(f->map->view(), fv, f->ds, no_pose, nullptr);
-    } else if (role_mask == 64u) {
-      k_loc_comp<false><<<f->grid2, kLocThreads, 0, st>>>(fv, f->ds, no_out, nullptr);
-    } else {
-      k_finalize<<<1, 64, 0, st>>>(f->packed, f->ds, fa, role_mask, nullptr, f->packed);
-    }
-  };
+  role_mask &= 127u;
+  auto one = [&]() { k_finalize<<<1, 64, 0, st>>>(f->packed, f->ds, fa, role_mask); };
   for (int w = 0; w < 3; ++w) one();
   MB_CUDA(cudaEventRecord(f->ctx->ev0, st));
   for (int r = 0; r < reps; ++r) one();

@@ -53,35 +53,26 @@ void set_error(const char* fmt, ...);
 namespace mb {
 // ---- peer-memory exchange of the per-iteration packet (single node, NVLink / NVSwitch) -----------------
 // Every rank owns one small cudaMalloc'd block, exported to the other ranks with cudaIpcGetMemHandle:
-//   mailbox  double[2 parity][kMaxRanks source][kXchgDoubles]   the packets of all ranks for one exchange
-//   flags    u64   [2 parity][kMaxRanks source]                 exchange number the packet belongs to
-//   lflags   u64   [2 parity][kMaxRanks source]                 same, for the six component localizabilities that
-//                                                               k_loc_comp's last block puts into doubles 48..53
-//   xseq     u64                                                number of exchanges this rank has completed
-// The last block of k_linearize STORES its packet straight into every rank's mailbox (peer stores over NVLink)
-// and then raises the flags (release, system scope); k_finalize polls its OWN flags (local memory), adds the
-// packets in rank order — bit-identical on every rank — and proceeds.  No collective call, no extra kernel,
-// and the transfer overlaps the tail of the reduction.  Two parities: a fast rank may already write exchange
-// n + 1 while a slow one still reads exchange n; it cannot reach n + 2 before every rank has consumed n.
+//   ll     u64 [2 parity][kMaxRanks source][2 * kXchgDoubles]   the packets of all ranks for one exchange
+//   xseq   u64                                                  number of exchanges this rank has completed
+// A packet is kXchgDoubles doubles: the 48-double reduction packet of a linearisation, the six component
+// localizabilities of the last one (entries 48..53), one word for the ranks' device-side barrier (entry 55).  Every
+// double travels as two 8-byte words {32 data bits, 32-bit exchange number}, each written by ONE 8-byte store — a
+// word is either absent or complete, so the receiver needs neither a fence on the sender's side nor a separate flag
+// (the protocol of NCCL's LL transport).  Block 0 of k_icp_loop STORES its packet straight into every rank's block
+// (peer stores over NVLink), waits for all ranks' words in its own block (local memory), adds the packets in rank
+// order — bit-identical on every rank — and publishes the sum to the other blocks of its GPU.  No collective call,
+// no extra kernel.  Two parities: a fast rank may already write exchange n + 1 while a slow one still reads
+// exchange n; it cannot reach n + 2 before every rank has consumed n.
 constexpr int kMaxRanks = 8;
-constexpr int kXchgDoubles = 56;  // >= the 48-double packet + the six component localizabilities of k_loc_comp
-// The persistent loop (k_icp_loop) uses a flag-in-data mailbox instead: every double travels as two 8-byte words
-// {32 data bits, 32-bit exchange number}, each written by ONE 8-byte store — a word is either absent or complete, so
-// the receiver needs neither a fence on the sender's side nor a separate flag (the protocol of NCCL's LL transport):
-//   ll       u64   [2 parity][kMaxRanks source][2 * kXchgDoubles]
+constexpr int kXchgDoubles = 56;
 struct PeerTable {
   int world, rank;
-  double* mbox[kMaxRanks];
-  unsigned long long* flag[kMaxRanks];
-  unsigned long long* lflag[kMaxRanks];
   unsigned long long* ll[kMaxRanks];
   unsigned long long* xseq;
 };
-constexpr size_t kXchgMboxBytes = 2 * kMaxRanks * kXchgDoubles * sizeof(double);
-constexpr size_t kXchgFlagBytes = 2 * kMaxRanks * sizeof(unsigned long long);
-constexpr size_t kXchgLlOffset = 8192;
 constexpr size_t kXchgLlBytes = 2 * kMaxRanks * 2 * kXchgDoubles * sizeof(unsigned long long);
-constexpr size_t kXchgBlockBytes = kXchgLlOffset + kXchgLlBytes;
+constexpr size_t kXchgBlockBytes = kXchgLlBytes + 256;
 }  // namespace mb
 
 // ---- handles ----------------------------------------------------------------------------------------

@@ -154,6 +154,10 @@ class Context:
         buf = C.create_string_buffer(handles, len(handles))
         check(self.lib.mb_comm_ipc_open(self.h, buf))
 
+    def comm_barrier(self):
+        """Device-side barrier of all ranks on the context's stream (peer mailboxes)."""
+        check(self.lib.mb_comm_barrier(self.h))
+
     def downsample(self, xyz: np.ndarray, leaf: float, cap: int, min_dist: float) -> np.ndarray:
         """Geometric::downsample (geometric.cpp:55-126): indices of the kept points, reference order."""
         pts = np.ascontiguousarray(xyz, dtype=np.float32)
