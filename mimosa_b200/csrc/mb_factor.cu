@@ -1306,6 +1306,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
       const unsigned long long* lin = reinterpret_cast<const unsigned long long*>(&S.ds.lin);
       for (int w = tid; w < kWords; w += kLoopThreads) out[w] = lin[w];
       if (tid < 6) out[kWords + tid] = (unsigned long long)__double_as_longlong(loc[tid]);
+      if (tid >= 32 && tid < 44) out[kWords + 6 + (tid - 32)] = (unsigned long long)__double_as_longlong(S.ds.pose[tid - 32]);  // (mb_icp_run)
       __threadfence_system();
       __syncthreads();
       if (tid == 0) *reinterpret_cast<volatile unsigned long long*>(la.mapped + kSrvResp) = la.req0 + (unsigned long long)(it0 / la.iters);
@@ -1723,7 +1724,9 @@ int enqueue_loop(mb_factor* f, int iters, int do_step, mb_icp_trace* d_trace, co
   if (f->linearize_count == 0) MB_TRY(enqueue_sort(f, pose_arg));  // first linearisation since construction / reset
   MapView mv = f->map->view();
   FactorView fv = f->view();
-  fv.fold_loc = do_step ? 1 : 0;
+  // The component localizabilities of the linearisations BEFORE the last one only ever reach the caller through the
+  // trace: without a trace that pass is not run (the last linearisation's come out of the final pass either way).
+  fv.fold_loc = do_step && d_trace ? 1 : 0;
   fv.tile = f->loop_tile;
   LoopArgs la;
   std::memset(&la, 0, sizeof(la));
@@ -2068,7 +2071,7 @@ int mb_factor_linearize(mb_factor* f, const double R[9], const double t[3], cons
   // request / response numbers at kSrv* (mb_internal.cuh)
   double* hin = (double*)c->pin_small;
   char* hout = (char*)c->pin_small + 256;
-  static_assert(256 + sizeof(mb_linearization) + 6 * sizeof(double) <= 2048, "pin_small too small");
+  static_assert(256 + sizeof(mb_linearization) + 18 * sizeof(double) <= 2048, "pin_small too small");
   static_assert(sizeof(mb_linearization) % 8 == 0, "mb_linearization is copied as 8-byte words");
   if (use_loop(c)) {
     // Single GPU, or several with the peer-memory exchange set up.  No copy operation and no stream synchronisation on
@@ -2226,6 +2229,30 @@ int mb_icp_run(mb_factor* f, double R[9], double t[3], int iters, double lambda,
     MB_TRY(dev_alloc(f->ctx, (void**)&f->d_trace, (size_t)iters * sizeof(mb_icp_trace)));
     f->trace_cap = iters;
   }
+  if (use_loop(f->ctx)) {
+    // One launch, no copy operations: the start pose travels in the kernel parameters and block 0 leaves the final
+    // pose and the last linearisation's component localizabilities in the context's mapped block.
+    if (iters == 0) return MB_OK;
+    PoseArg pa;
+    std::memcpy(pa.v, R, 9 * sizeof(double));
+    std::memcpy(pa.v + 9, t, 3 * sizeof(double));
+    pa.v[12] = 0.0, pa.v[13] = 0.0, pa.v[14] = -1.0, pa.v[15] = lambda;
+    const unsigned long long n = ++f->ctx->srv_req;
+    MB_TRY(enqueue_loop(f, iters, 1, trace ? f->d_trace : nullptr, &pa, n, false));
+    f->linearize_count += iters;
+    if (trace) MB_CUDA(cudaMemcpyAsync(trace, f->d_trace, (size_t)iters * sizeof(mb_icp_trace), cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    const double* res = (const double*)((const char*)f->ctx->pin_small + 256 + sizeof(mb_linearization));  // loc (6), pose (12)
+    if (trace) {
+      for (int a = 0; a < 3; ++a) {
+        trace[iters - 1].loc_trans_comp[a] = res[a];
+        trace[iters - 1].loc_rot_comp[a] = res[3 + a];
+      }
+    }
+    std::memcpy(R, res + 6, 9 * sizeof(double));
+    std::memcpy(t, res + 15, 3 * sizeof(double));
+    return MB_OK;
+  }
   double* hin = (double*)f->ctx->pin_small;
   std::memcpy(hin, R, 9 * sizeof(double));
   std::memcpy(hin + 9, t, 3 * sizeof(double));
@@ -2235,10 +2262,7 @@ int mb_icp_run(mb_factor* f, double R[9], double t[3], int iters, double lambda,
   hin[15] = lambda;
   MB_CUDA(cudaMemcpyAsync(f->ds->pose, hin, 16 * sizeof(double), cudaMemcpyHostToDevice, st));
   const bool use_graph = (f->flags & 2u) != 0 && iters > 0;
-  if (use_loop(f->ctx)) {
-    MB_TRY(enqueue_loop(f, iters, 1, f->d_trace, nullptr, 0, false));
-    f->linearize_count += iters;
-  } else if (use_graph) {
+  if (use_graph) {
     // The captured sequence bakes the iteration index and linearize_count into k_finalize's arguments.
     if (!f->graph || f->graph_iters != iters || f->graph_count0 != f->linearize_count) {
       drop_graph(f);
