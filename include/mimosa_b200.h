@@ -191,11 +191,13 @@ MB_API int mb_host_unregister(void* p);
  * (torch.distributed / MPI / anything) and every rank calls mb_comm_init. */
 MB_API int mb_comm_unique_id(void* id128);
 MB_API int mb_comm_init(mb_ctx* ctx, int rank, int world, const void* id128);
-/* Optional, single node: exchange the per-iteration packet through peer memory (NVLink / NVSwitch) instead of an
- * NCCL all-reduce.  After mb_comm_init every rank calls mb_comm_ipc_handle (64-byte CUDA IPC handle of its
- * mailbox), the caller all-gathers the handles in rank order, and every rank calls mb_comm_ipc_open with all
- * `world` handles.  From then on the last block of the linearisation kernel stores its packet into every rank's
- * mailbox and the post-reduction kernel sums the mailbox in rank order — no collective call on that path. */
+/* Single node: exchange the per-iteration packet through peer memory (NVLink / NVSwitch) inside the persistent ICP
+ * kernel instead of an NCCL all-reduce between kernels.  After mb_comm_init every rank calls mb_comm_ipc_handle
+ * (64-byte CUDA IPC handle of its mailbox), the caller all-gathers the handles in rank order, and every rank calls
+ * mb_comm_ipc_open with all `world` handles.  From then on block 0 of the loop kernel stores its packet into every
+ * rank's mailbox (flag-in-data words: no fence, no flag), sums the mailbox in rank order and publishes the sum to the
+ * other blocks — no collective call on that path.  Without this set-up the library runs one kernel chain per
+ * linearisation with ncclAllReduce in between. */
 MB_API int mb_comm_ipc_handle(mb_ctx* ctx, void* handle64);
 MB_API int mb_comm_ipc_open(mb_ctx* ctx, const void* handles /* world x 64 bytes */);
 /* Device-side barrier of all ranks on the context's stream (after mb_comm_ipc_open): a one-block kernel that exchanges

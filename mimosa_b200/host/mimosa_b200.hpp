@@ -89,6 +89,8 @@ class Context {
   Context& operator=(const Context&) = delete;
   mb_ctx* get() const { return ctx_; }
   void sync() const { check(mb_sync(ctx_)); }
+  // How long the linearisation kernel stays resident after ICPFactorB200::linearize (0: every call launches).
+  void set_resident_window(unsigned microseconds) const { check(mb_set_resident_window(ctx_, microseconds)); }
 
   // Geometric::downsample (geometric.cpp:55-126): indices of the kept points in the reference's output order.
   std::vector<uint32_t> downsample(const Point* pts, size_t n, float leaf, size_t cap, float min_dist) const {
