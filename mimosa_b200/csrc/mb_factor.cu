@@ -698,6 +698,7 @@ struct LoopCtl {
   unsigned long long xflag;  // several ranks: number of the last exchange whose summed packet block 0 has published
   unsigned long long sflag;  // resident kernel: 2 * request number (+ 1: leave) block 0 has published to the other blocks
   unsigned q_count[2];       // queue length by linearisation parity
+  unsigned q_next[2];        // second and later rounds of phase B: tasks handed out so far
 };
 
 struct LoopArgs {
@@ -873,7 +874,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     const int par = it & 1;
     MB_LOOP_T(it, 0);
     const uint32_t stamp = (uint32_t)(la.linearize_count0 + it + 1);
-    if (blockIdx.x == 0 && tid == 0) ctl->q_count[par ^ 1] = 0u;  // the next linearisation's counter: idle during this one
+    if (blockIdx.x == 0 && tid == 0) ctl->q_count[par ^ 1] = ctl->q_next[par ^ 1] = 0u;  // the next linearisation's counters: idle during this one
     m33 R;
 #pragma unroll
     for (int a = 0; a < 9; ++a) R.m[a] = S.ds.pose[a];
@@ -1112,11 +1113,16 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     if (q) {
       // ---- B: the queue, dealt out evenly over every warp of the device ----------------------------------------
       kept = false;  // the search scratch is about to be overwritten
+      // Tasks of `per` consecutive queue entries, dealt out over the SMs first (task t -> warp t / n_blocks of block
+      // t % n_blocks).  A short queue is spread thin — one query per warp runs 27 us, thirty-two 42 us — and once the
+      // queue exceeds a round of the device the tasks are full warps: a pass executes almost the same instructions for
+      // 14 queries as for 28 (measured: tasks of half the length made a full phase B 40 % slower).
       const unsigned W = n_blocks * kLoopWarps;
-      const unsigned rounds = (q + 32u * W - 1u) / (32u * W);
-      const unsigned per = min(32u, max(1u, (q + W * rounds - 1u) / (W * rounds)));
+      const unsigned per = min(32u, max(1u, (q + W - 1u) / W));
       const unsigned n_tasks = (q + per - 1u) / per;
-      for (unsigned task = blockIdx.x * kLoopWarps + wib; task < n_tasks; task += W) {
+      // A warp's first task is its own number; the tasks beyond the first round are PULLED (a warp whose first task was
+      // cheap takes more of them: a task's cost varies 2x with the voxels its queries fall into).
+      for (unsigned task = (unsigned)wib * n_blocks + blockIdx.x; task < n_tasks;) {
         const unsigned qi = task * per + lane;
         const bool on = (unsigned)lane < per && qi < q;
         const size_t i = on ? (size_t)__ldcg(fv.queue + qi) : 0;
@@ -1154,6 +1160,9 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
           fv.status[i] = (uint8_t)(rs | kFresh);
         }
         __syncwarp();
+        unsigned nxt = 0;
+        if (lane == 0) nxt = W + atomicAdd(&ctl->q_next[par], 1u);
+        task = __shfl_sync(kFull, nxt, 0);
       }
       MB_LOOP_T(it, 4);
       grid_barrier(&ctl->bar, &S.bar_next, n_blocks);
@@ -1288,7 +1297,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     }
     grid_barrier(&ctl->bar, &S.bar_next, n_blocks);
     if (blockIdx.x == 0) {
-    if (tid < 2) ctl->q_count[tid] = 0u;  // every block has read its last queue length
+    if (tid < 2) ctl->q_count[tid] = ctl->q_next[tid] = 0u;  // every block has read its last queue length
     double* const loc = S.packed + kPack;  // [8]
     block_sum_rows(fv.partials2, (int)n_blocks, 8, S.tmp, loc, kLoopThreads);
     __syncthreads();
