@@ -697,6 +697,7 @@ struct LoopCtl {
   unsigned long long bar;    // grid barrier arrivals: monotonic, a multiple of the grid size between launches
   unsigned long long xflag;  // several ranks: number of the last exchange whose summed packet block 0 has published
   unsigned long long sflag;  // resident kernel: 2 * request number (+ 1: leave) block 0 has published to the other blocks
+  unsigned long long epass;  // final passes (component localizabilities) this factor has completed
   unsigned q_count[2];       // queue length by linearisation parity
   unsigned q_next[2];        // second and later rounds of phase B: tasks handed out so far
 };
@@ -845,6 +846,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
   __syncthreads();
   if (la.has_pose && tid < 16) reinterpret_cast<double*>(&S.ds)[tid] = la.pose.v[tid];  // pose (12), gravity (3), lambda lead DevState
   const unsigned long long xseq0 = peer ? *peer->xseq : 0ull;
+  const unsigned long long epass0 = __ldcg(&ctl->epass);  // (block 0 advances it only after every block's first final pass)
   double(*s_row)[7] = reinterpret_cast<double(*)[7]>(S.pk[grp]) + gw * 32;
   static_assert(sizeof(uint32_t) * ROWS * kLinThreads >= sizeof(double) * 7 * kLinThreads, "s_row fits");
   const int pr = kTriRow[lane], pc = kTriCol[lane];
@@ -1288,18 +1290,56 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
       if (lane == 0) S.red[wib][a] = v;
     }
-    if (lane == 0) S.red[wib][6] = S.red[wib][7] = 0.0;
     __syncthreads();
-    if (tid < 8) {
+    // Block sums -> block 0, WITHOUT a grid barrier: every block leaves its six sums as flag-in-data words (two 8-byte
+    // words {32 data bits, pass number} per double, as in the peer mailbox) and goes on — to the next request, or home;
+    // block 0 waits for all blocks' words and adds them in block order.
+    const unsigned long long pass = epass0 + (unsigned long long)(it0 / la.iters) + 1ull;
+    unsigned long long* const ll2 = reinterpret_cast<unsigned long long*>(fv.partials2);
+    if (tid < 12) {
       double v = 0.0;
-      for (int w = 0; w < kLoopWarps; ++w) v += S.red[w][tid];
-      __stcg(fv.partials2 + (size_t)blockIdx.x * 8 + tid, v);
+      for (int w = 0; w < kLoopWarps; ++w) v += S.red[w][tid >> 1];
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+      const unsigned long long word = ((pass & 0xffffffffull) << 32) | ((bits >> (32 * (tid & 1))) & 0xffffffffull);
+      asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(ll2 + (size_t)blockIdx.x * 16 + tid), "l"(word) : "memory");
     }
-    grid_barrier(&ctl->bar, &S.bar_next, n_blocks);
     if (blockIdx.x == 0) {
-    if (tid < 2) ctl->q_count[tid] = ctl->q_next[tid] = 0u;  // every block has read its last queue length
+    __syncthreads();  // S.red is re-used for the gathered words
+    uint32_t* const s_words = reinterpret_cast<uint32_t*>(&S.red[0][0]);  // n_blocks * 12 words (S.red and S.tmp are adjacent)
+    static_assert(sizeof(S.red) + sizeof(S.tmp) >= 160 * 12 * sizeof(uint32_t), "gathered words fit");
+    for (int x = tid; x < (int)n_blocks * 12; x += kLoopThreads) {
+      const unsigned long long* src = ll2 + (size_t)(x / 12) * 16 + (x % 12);
+      unsigned long long w;
+      do {
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+      } while ((uint32_t)(w >> 32) != (uint32_t)pass);
+      s_words[x] = (uint32_t)w;
+    }
+    __syncthreads();
     double* const loc = S.packed + kPack;  // [8]
-    block_sum_rows(fv.partials2, (int)n_blocks, 8, S.tmp, loc, kLoopThreads);
+    {
+      // component e: eight chains over consecutive blocks, then the chains in order (a fixed order: bitwise repeatable)
+      __shared__ double s_chain[6][8];
+      const int per_chain = ((int)n_blocks + 7) / 8;
+      if (tid < 48) {
+        const int e = tid >> 3, c = tid & 7;
+        double v = 0.0;
+        for (int b = c * per_chain; b < min((c + 1) * per_chain, (int)n_blocks); ++b) {
+          const uint32_t lo = s_words[b * 12 + 2 * e], hi = s_words[b * 12 + 2 * e + 1];
+          v += __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+        }
+        s_chain[e][c] = v;
+      }
+      __syncthreads();
+      if (tid < 8) {
+        double v = 0.0;
+        if (tid < 6)
+          for (int c = 0; c < 8; ++c) v += s_chain[tid][c];
+        loc[tid] = v;
+      }
+      if (tid == 0) ctl->epass = pass;
+      if (tid < 2) ctl->q_count[tid] = ctl->q_next[tid] = 0u;  // every block has finished its last linearisation
+    }
     __syncthreads();
     if (peer) {
       // the six sums of every rank, through the same mailbox slot as the last packet (entries 48..53)
@@ -1309,16 +1349,20 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
       if (tid == 0) *peer->xseq = seq;
       __syncthreads();
     }
-    if (la.mapped) {  // hand the finished linearisation to the polling host
-      unsigned long long* const out = reinterpret_cast<unsigned long long*>(la.mapped + 256);
+    if (la.mapped) {
+      // Hand the finished linearisation to the polling host: flag-in-data words (mb_internal.cuh: kSrvOut), one store
+      // per word, no fence, no separate flag (with a fence and a flag the hand-over alone was ~3 us longer).
+      unsigned long long* const out = reinterpret_cast<unsigned long long*>(la.mapped + kSrvOut);
       constexpr int kWords = (int)(sizeof(mb_linearization) / 8);
       const unsigned long long* lin = reinterpret_cast<const unsigned long long*>(&S.ds.lin);
-      for (int w = tid; w < kWords; w += kLoopThreads) out[w] = lin[w];
-      if (tid < 6) out[kWords + tid] = (unsigned long long)__double_as_longlong(loc[tid]);
-      if (tid >= 32 && tid < 44) out[kWords + 6 + (tid - 32)] = (unsigned long long)__double_as_longlong(S.ds.pose[tid - 32]);  // (mb_icp_run)
-      __threadfence_system();
-      __syncthreads();
-      if (tid == 0) *reinterpret_cast<volatile unsigned long long*>(la.mapped + kSrvResp) = la.req0 + (unsigned long long)(it0 / la.iters);
+      const uint32_t req = (uint32_t)(la.req0 + (unsigned long long)(it0 / la.iters));
+      for (int x = tid; x < 2 * (int)kSrvOutDoubles; x += kLoopThreads) {
+        const int d = x >> 1;
+        const unsigned long long bits = d < kWords       ? lin[d]
+                                        : d < kWords + 6 ? (unsigned long long)__double_as_longlong(loc[d - kWords])
+                                                         : (unsigned long long)__double_as_longlong(S.ds.pose[d - kWords - 6]);
+        ll_store(out + x, (uint32_t)(bits >> (32 * (x & 1))), req);
+      }
 #if defined(MB_LOOP_TIMING)
       if (tid == 0) {
         unsigned long long g0;
@@ -1848,7 +1892,7 @@ static int factor_init(mb_factor* f, mb_ctx* ctx, mb_map* map, const void* pts, 
   const size_t o_queue = take(f->ld * sizeof(uint32_t));
   const size_t o_par = take((size_t)std::max(f->grid, f->loop_grid) * kPack * sizeof(double));
   const size_t o_gpar = take((size_t)f->n_groups * kPack * sizeof(double));
-  const size_t o_par2 = take((size_t)std::max(f->grid2, f->loop_grid) * 8 * sizeof(double));
+  const size_t o_par2 = take((size_t)std::max(f->grid2, f->loop_grid) * 16 * sizeof(double));  // (k_icp_loop: 12 flag-in-data words per block)
   const size_t o_packed = take((kPack + 8) * sizeof(double));
   const size_t o_tick = take((2 + (size_t)f->n_groups) * sizeof(unsigned));  // final, loc, groups...
   const size_t o_ds = take(sizeof(DevState));
@@ -1930,8 +1974,9 @@ static int factor_init(mb_factor* f, mb_ctx* ctx, mb_map* map, const void* pts, 
     for (size_t z = f->n; z < f->ld; ++z) h[z] = make_float4(0.f, 0.f, 0.f, 0.f);
     MB_CUDA(cudaMemcpyAsync(f->src_raw, h, f->ld * sizeof(float4), cudaMemcpyHostToDevice, st));
   }
-  // everything from `packed` to the end of the block (packet, tickets, DevState) starts at zero
-  MB_CUDA(cudaMemsetAsync(base + o_packed, 0, f->block_bytes - o_packed, st));
+  // everything from `partials2` to the end of the block (flag-in-data block sums, packet, tickets, DevState, loop control
+  // words, tile stamps) starts at zero
+  MB_CUDA(cudaMemsetAsync(base + o_par2, 0, f->block_bytes - o_par2, st));
   MB_TRY(reset_state(f));
   if (staged) MB_CUDA(cudaStreamSynchronize(st));  // the pinned staging buffer is free again
   // Like the reference's constructor (geometric_factor.hpp:125 copies the cloud), the caller's buffer has been
@@ -2079,8 +2124,9 @@ int mb_factor_linearize(mb_factor* f, const double R[9], const double t[3], cons
   // page-locked, device-mapped block: [pose 12 | gravity 3 | lambda] in at 0, [mb_linearization | loc 6] out at 256,
   // request / response numbers at kSrv* (mb_internal.cuh)
   double* hin = (double*)c->pin_small;
-  char* hout = (char*)c->pin_small + 256;
-  static_assert(256 + sizeof(mb_linearization) + 18 * sizeof(double) <= 2048, "pin_small too small");
+  char* hout = (char*)c->pin_small + 256;  // (NCCL mode: plain copies land here)
+  char local_out[sizeof(mb_linearization) + 6 * sizeof(double)];
+  const char* result = hout;
   static_assert(sizeof(mb_linearization) % 8 == 0, "mb_linearization is copied as 8-byte words");
   if (use_loop(c)) {
     // Single GPU, or several with the peer-memory exchange set up.  No copy operation and no stream synchronisation on
@@ -2089,8 +2135,8 @@ int mb_factor_linearize(mb_factor* f, const double R[9], const double t[3], cons
     // window afterwards (srv_window_us) and a call that arrives inside it only POSTS its pose to the mapped block — no
     // launch (measured: 41 us per cached call with a launch each, of which the device works 26).
     const unsigned long long n = ++c->srv_req;
-    auto* resp = (const unsigned long long*)((const char*)c->pin_small + kSrvResp);
     auto* gone = (const unsigned long long*)((const char*)c->pin_small + kSrvExit);
+    unsigned long long res[kSrvOutDoubles];
     // Poll for request n's result: busy for the first ~100 us (a call normally ends well inside that), then yielding
     // the core between polls; the stream is queried now and then so that a failed launch ends the wait with its error,
     // and a kernel that never answers ends it after kPollTimeoutS instead of hanging the caller (mimosa's node has
@@ -2102,11 +2148,11 @@ int mb_factor_linearize(mb_factor* f, const double R[9], const double t[3], cons
       unsigned spins = 0;
       bool yielding = false;
       for (;;) {
-        if (__atomic_load_n(resp, __ATOMIC_ACQUIRE) == n) return 1;
-        if (posted && __atomic_load_n(gone, __ATOMIC_ACQUIRE) >= n) return __atomic_load_n(resp, __ATOMIC_ACQUIRE) == n ? 1 : 0;
+        if (read_result(c, n, res)) return 1;
+        if (posted && __atomic_load_n(gone, __ATOMIC_ACQUIRE) >= n) return read_result(c, n, res) ? 1 : 0;
         if ((++spins & 0x3ffu) == 0) {
           const cudaError_t q = cudaStreamQuery(st);
-          if (q == cudaSuccess) return __atomic_load_n(resp, __ATOMIC_ACQUIRE) == n ? 1 : 0;
+          if (q == cudaSuccess) return read_result(c, n, res) ? 1 : 0;
           if (q != cudaErrorNotReady) {
             set_error("mb_factor_linearize: %s", cudaGetErrorString(q));
             return -1;
@@ -2158,6 +2204,8 @@ int mb_factor_linearize(mb_factor* f, const double R[9], const double t[3], cons
       }
     }
     ++f->linearize_count;
+    std::memcpy(local_out, res, sizeof(local_out));
+    result = local_out;
   } else {
     ++f->linearize_count;
     std::memcpy(hin, R, 9 * sizeof(double));
@@ -2170,8 +2218,8 @@ int mb_factor_linearize(mb_factor* f, const double R[9], const double t[3], cons
                             cudaMemcpyDeviceToHost, st));
     MB_CUDA(cudaStreamSynchronize(st));
   }
-  std::memcpy(out, hout, sizeof(mb_linearization));
-  const double* loc = (const double*)(hout + sizeof(mb_linearization));
+  std::memcpy(out, result, sizeof(mb_linearization));
+  const double* loc = (const double*)(result + sizeof(mb_linearization));
   for (int a = 0; a < 3; ++a) {
     out->loc_trans_comp[a] = loc[a];
     out->loc_rot_comp[a] = loc[3 + a];
@@ -2251,7 +2299,12 @@ int mb_icp_run(mb_factor* f, double R[9], double t[3], int iters, double lambda,
     f->linearize_count += iters;
     if (trace) MB_CUDA(cudaMemcpyAsync(trace, f->d_trace, (size_t)iters * sizeof(mb_icp_trace), cudaMemcpyDeviceToHost, st));
     MB_CUDA(cudaStreamSynchronize(st));
-    const double* res = (const double*)((const char*)f->ctx->pin_small + 256 + sizeof(mb_linearization));  // loc (6), pose (12)
+    unsigned long long words[kSrvOutDoubles];
+    if (!read_result(f->ctx, n, words)) {
+      set_error("mb_icp_run: the kernel ended without handing over its result");
+      return MB_ERR_CUDA;
+    }
+    const double* res = (const double*)(words + sizeof(mb_linearization) / 8);  // loc (6), pose (12)
     if (trace) {
       for (int a = 0; a < 3; ++a) {
         trace[iters - 1].loc_trans_comp[a] = res[a];

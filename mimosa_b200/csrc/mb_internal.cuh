@@ -91,7 +91,7 @@ struct mb_ctx {
   size_t flush_bytes = 0;
   void* pinned = nullptr;  // page-locked staging for host <-> device copies of scans
   size_t pinned_bytes = 0;
-  void* pin_small = nullptr;  // 4 KiB page-locked (device-mapped) block for poses in / normal equations out / flag
+  void* pin_small = nullptr;  // 4 KiB page-locked (device-mapped) block for poses in / normal equations out
   unsigned host_seq = 0;      // sequence number of the last host-polled completion (mb_factor_linearize)
   // Resident linearisation kernel (mb_factor.cu, k_icp_loop in serve mode): after a host-facing linearisation the
   // kernel stays on the device for a short window and takes the next pose from the mapped block below instead of a
@@ -119,8 +119,26 @@ constexpr size_t kSrvRec = 3072;   // the request record (host -> device), 4 lin
                                    //   lines 0..2: 7 payload words each — the 16 doubles [pose 12 | gravity 3 | lambda]
                                    //   at word i + i / 7 — and the REQUEST NUMBER in word 7 / 15 / 23, written last;
                                    //   word 24: the kernel serving requests <= this number must leave
-constexpr size_t kSrvExit = 2128;  // u64: the first request number a departed kernel did NOT serve (device -> host)
-constexpr size_t kSrvResp = 2136;  // u64: number of the last request whose result sits at offset 256 (device -> host)
+constexpr size_t kSrvOut = 256;    // the result (device -> host): kSrvOutDoubles doubles [mb_linearization | component
+                                   //   localizabilities 6 | pose 12] as flag-in-data words — each double is two 8-byte
+                                   //   words {32 data bits, low 32 bits of the REQUEST NUMBER}, every word written by one
+                                   //   store: no fence and no separate flag on the device, the host accepts the result
+                                   //   when every word shows its request's number
+constexpr size_t kSrvOutDoubles = sizeof(mb_linearization) / 8 + 6 + 12;
+constexpr size_t kSrvExit = 2560;  // u64: the first request number a departed kernel did NOT serve (device -> host)
+static_assert(kSrvOut + 2 * 8 * kSrvOutDoubles <= kSrvExit, "result words overlap the control words");
+// The result of request n, if all of it has arrived.
+inline bool read_result(const mb_ctx* c, unsigned long long n, unsigned long long* res /* kSrvOutDoubles */) {
+  const unsigned long long* w = (const unsigned long long*)((const char*)c->pin_small + kSrvOut);
+  const unsigned flag = (unsigned)n;
+  if ((unsigned)(__atomic_load_n(w + 2 * kSrvOutDoubles - 1, __ATOMIC_ACQUIRE) >> 32) != flag) return false;
+  for (size_t d = 0; d < kSrvOutDoubles; ++d) {
+    const unsigned long long lo = __atomic_load_n(w + 2 * d, __ATOMIC_RELAXED), hi = __atomic_load_n(w + 2 * d + 1, __ATOMIC_RELAXED);
+    if ((unsigned)(lo >> 32) != flag || (unsigned)(hi >> 32) != flag) return false;
+    res[d] = (hi << 32) | (lo & 0xffffffffull);
+  }
+  return true;
+}
 // Ask a resident kernel to leave (it would on its own once its window closes): everything enqueued on the context's
 // stream afterwards then starts without that delay.
 inline void server_stop(mb_ctx* c) {
