@@ -769,7 +769,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_total / args.steps,
                 "what": "C++ caller over the C ABI (host/e2e_caller.cpp): mb_factor_create(host scan) + 20 x [mb_factor_linearize("
-                        "host pose) -> host H,g,f + mb_gn_step on the host], host clock; single GPU: the linearisation kernel stays "
+                        "host pose) -> host H,g,f + mb_gn_step on the host], host clock; the linearisation kernel stays "
                         "resident for 30 us after a call (mb_set_resident_window) and a call inside that window posts its pose "
                         "through mapped memory instead of launching", "final_pose_err_m": e2e_pose_err},
         "gpu_launches": int(launches),

@@ -166,7 +166,7 @@ MB_API int mb_timer_begin(mb_ctx* ctx);
 MB_API int mb_timer_end(mb_ctx* ctx, float* ms);
 /* Number of kernel launches this context has issued since creation (bench.py's gpu_launches). */
 MB_API int mb_launch_count(mb_ctx* ctx, uint64_t* out);
-/* Residency window of the linearisation kernel (single GPU).  ICPFactor::linearize is called several times in a row on
+/* Residency window of the linearisation kernel.  ICPFactor::linearize is called several times in a row on
  * one factor (ISAM2's update and its additional iterations, mimosa/src/graph/manager.cpp:585-588; the reference has
  * no analogue of a launch).  After mb_factor_linearize has handed over its result the kernel stays on the device for
  * `microseconds` and a call on the same factor that arrives inside the window only posts its pose through mapped

@@ -704,7 +704,7 @@ struct LoopCtl {
 
 struct LoopArgs {
   int iters, do_step, reg_4_dof, linearize_count0, has_pose;
-  // serve (host-facing call, single rank): after the result of request req0 has been handed over the kernel stays
+  // serve (host-facing call): after the result of request req0 has been handed over the kernel stays
   // resident for window_ns, taking the poses of requests req0 + 1, req0 + 2, ... from the context's mapped block
   // (mb_internal.cuh: kSrv*) — one linearisation each — until the window passes without a request or the host asks
   // it to leave.
@@ -2131,7 +2131,7 @@ int mb_factor_linearize(mb_factor* f, const double R[9], const double t[3], cons
   if (use_loop(c)) {
     // Single GPU, or several with the peer-memory exchange set up.  No copy operation and no stream synchronisation on
     // this path: the pose travels in the kernel parameters, block 0 writes the result straight into mapped host memory
-    // and then the number of the request, which the host polls.  Single GPU: the kernel stays resident for a short
+    // as flag-in-data words the host polls.  The kernel stays resident for a short
     // window afterwards (srv_window_us) and a call that arrives inside it only POSTS its pose to the mapped block — no
     // launch (measured: 41 us per cached call with a launch each, of which the device works 26).
     const unsigned long long n = ++c->srv_req;
@@ -2194,7 +2194,7 @@ int mb_factor_linearize(mb_factor* f, const double R[9], const double t[3], cons
       std::memcpy(pa.v + 9, t, 3 * sizeof(double));
       std::memcpy(pa.v + 12, gravity_unit, 3 * sizeof(double));
       pa.v[15] = 0.0;
-      const bool serve = c->world == 1 && c->srv_window_us > 0;
+      const bool serve = c->srv_window_us > 0;  // (several ranks: every rank's caller posts to its own rank's kernel)
       MB_TRY(enqueue_loop(f, 1, 0, nullptr, &pa, n, serve));
       c->srv_live = serve;
       c->srv_factor = f;
