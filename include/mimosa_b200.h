@@ -170,7 +170,7 @@ MB_API int mb_launch_count(mb_ctx* ctx, uint64_t* out);
  * one factor (ISAM2's update and its additional iterations, mimosa/src/graph/manager.cpp:585-588; the reference has
  * no analogue of a launch).  After mb_factor_linearize has handed over its result the kernel stays on the device for
  * `microseconds` and a call on the same factor that arrives inside the window only posts its pose through mapped
- * memory instead of launching (41 -> 27 us per call measured); anything else enqueued on the context meanwhile simply
+ * memory instead of launching (41 -> 30 us per call measured); anything else enqueued on the context meanwhile simply
  * waits for the window to close, and every other mb_factor_ / mb_sync / mb_timer_ call closes it at once.  0 turns it off.
  * Default 30, or the environment variable MB_RESIDENT_US at mb_init. */
 MB_API int mb_set_resident_window(mb_ctx* ctx, unsigned microseconds);
