@@ -6,7 +6,7 @@ registered against a ~10 M-point hashed voxel map, 20 Gauss-Newton iterations pe
 (mimosa/config/hornbill/params.yaml:86-102).  One "step" = one scan = 20 ICP iterations (each = one
 ICPFactor::linearize + 6x6 solve + SE(3) retract, data-association cache semantics on, as in the reference).
 
-  value     device-resident loop (mb_icp_run, CUDA graph), scan + map already in HBM; per-step CUDA-event times
+  value     device-resident loop (mb_icp_run: one persistent kernel per scan), scan + map already in HBM; per-step CUDA-event times
   configs   (N = 1 only) BASELINE.json's other configurations as sub-objects, each with its own CPU-oracle baseline:
             C2 (2 M-point map), C3 (Airy-style scan, deskewed on the device), C5 (10 Hz stream, scans/s end to end)
   e2e       the reference-facing call sequence with HOST buffers: ICPFactor(scan) [H2D], then 20 x
@@ -546,7 +546,7 @@ def run_other_configs(ctx, mg, cfg, synth, coords_counts_pts, steps, warmup, wit
     c3 = {"workload": "C3: 65280-pt Airy-style scan vs 10M-pt map, deskewed on the device inside the step, 20 ICP iters/scan",
           "value": ITERS / (float(np.mean(ms3)) * 1e-3), "unit": UNIT, "ms_per_step": float(np.mean(ms3)), "scan_points": int(n3),
           "final_pose_err_m": float(np.abs(np.asarray(t) - t3).max()),
-          "note": "the step also creates the factor from the device scan (no CUDA graph: the factor is new every scan)"}
+          "note": "the step also creates the factor from the device scan (the factor is new every scan)"}
     if with_cpu:
         mo = orc.IVoxRef(**HORNBILL_MAP)
         mo.load_raw(coords, counts, None, pts, lru_counter)

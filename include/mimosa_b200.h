@@ -267,7 +267,8 @@ MB_API int mb_icp_run(mb_factor* f, double R[9], double t[3], int iters, double 
 MB_API int mb_gn_step(const double H[36], const double g[6], double lambda, double R[9], double t[3], double delta[6],
                       int* solve_ok);
 /* Debug/ablation switches: bit0 = disable the data-association cache ("forced" search every call);
- * bit1 = run mb_icp_run as one captured CUDA graph. */
+ * bit1 = replay mb_icp_run as one captured CUDA graph (only the NCCL all-reduce mode launches several kernels per
+ * iteration; otherwise the whole loop is one kernel and the bit has no effect). */
 MB_API int mb_factor_set_flags(mb_factor* f, uint32_t flags);
 
 /* ---- scan preparation and map update: the steps either side of the factor in the LiDAR callback ---------
