@@ -728,6 +728,8 @@ template <int ROWS>
 struct LoopShared {
   uint32_t pk[kLoopGroups][ROWS * kLinThreads];  // phase B: knn_thread's s_pk; phases A / C: [warp][32][7] doubles
   uint32_t blk[kLoopGroups][24 * kLinThreads];
+  double rows[kLoopWarps][kPpt][32][8];  // phases A / C: the whitened [J (6), e, 0] rows of a warp's points, both slots
+  double cmat[kLoopWarps][8][8];         // a warp's accumulated [J e]^T [J e] (tensor-core fragment -> packed entries)
   double red[kLoopWarps][kPack];
   double tmp[kLoopThreads];
   double packed[kXchgDoubles];
@@ -847,8 +849,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
   if (la.has_pose && tid < 16) reinterpret_cast<double*>(&S.ds)[tid] = la.pose.v[tid];  // pose (12), gravity (3), lambda lead DevState
   const unsigned long long xseq0 = peer ? *peer->xseq : 0ull;
   const unsigned long long epass0 = __ldcg(&ctl->epass);  // (block 0 advances it only after every block's first final pass)
-  double(*s_row)[7] = reinterpret_cast<double(*)[7]>(S.pk[grp]) + gw * 32;
-  static_assert(sizeof(uint32_t) * ROWS * kLinThreads >= sizeof(double) * 7 * kLinThreads, "s_row fits");
+  double(*s_row)[8] = S.rows[wib][0];
   const int pr = kTriRow[lane], pc = kTriCol[lane];
   const int k = fv.k;
   const bool forced = (fv.flags & 1u) != 0;
@@ -861,14 +862,14 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
   // A thread's points of the most recent linearisation: localizability vectors and "Valid", kept in SHARED memory
   // for the component-localizability sums (:434-457) that need that linearisation's eigenvectors — taken in the
   // next linearisation's phase A (device-resident loop) or after the last one.  They live in the group's block-probe
-  // scratch, which only phase B uses (written in C / C', read before the next B), and in the tail of S.pk behind
-  // s_row.  Only when a group owns a single tile; otherwise those passes read the points' state back from memory.
+  // scratch, which only phase B uses (written in C / C', read before the next B), and in the head of S.pk.  Only
+  // when a group owns a single tile; otherwise those passes read the points' state back from memory.
   // (Keeping them in registers was built and measured: 416 B of spills and every phase 15-30 % slower.)
   const bool one_tile = n_tiles <= n_vg;
   double* const k_loc = reinterpret_cast<double*>(S.blk[grp]) + gt;  // [(c * kPpt + u) * 128], c < 3 rot, c >= 3 trans
-  uint8_t* const k_valid = reinterpret_cast<uint8_t*>(S.pk[grp]) + sizeof(double) * 7 * kLinThreads + gt;  // [u * 128]
+  uint8_t* const k_valid = reinterpret_cast<uint8_t*>(S.pk[grp]) + gt;  // [u * 128]
   static_assert(sizeof(uint32_t) * 24 * kLinThreads >= sizeof(double) * 6 * kPpt * kLinThreads, "kept vectors fit S.blk");
-  static_assert(sizeof(uint32_t) * ROWS * kLinThreads >= sizeof(double) * 7 * kLinThreads + kPpt * kLinThreads, "kept flags fit S.pk");
+  static_assert(sizeof(uint32_t) * ROWS * kLinThreads >= kPpt * kLinThreads, "kept flags fit S.pk");
   bool kept = false;  // uniform over the group: the scratch holds its tile's vectors (phase B overwrites the scratch)
 
   for (int it0 = 0;; it0 += la.iters) {  // one pass; serve mode: one pass per request
@@ -883,7 +884,12 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     const d3 T = mk3(S.ds.pose[9], S.ds.pose[10], S.ds.pose[11]);
     const double* const Vt = S.ds.lin.eigvec_trans;  // of the previous linearisation (folded pass)
     const double* const Vr = S.ds.lin.eigvec_rot;
-    double acc = 0.0, lacc = 0.0;
+    // [J e]^T [J e] accumulates on the FP64 tensor core: with M = the 8 x 32 matrix of a warp's rows (row 7 zero) the
+    // sum is M M^T, eight mma.m8n8k4 per 32 points, and because the product is symmetric the A and B fragments of a
+    // lane are the SAME element — M[lane >> 2][4 kk + (lane & 3)] — so a lane needs one shared-memory load per four
+    // points.  (Lane a summing entry a over the rows in a scalar loop pulled 64 doubles per lane and slot through
+    // shared memory: 1.8 us of a 6.5 us phase, bandwidth bound.)  c0 / c1 = C[lane >> 2][2 (lane & 3) + {0, 1}].
+    double c0 = 0.0, c1 = 0.0, lacc = 0.0;
     int cnt = 0;
 
     // C: residual, Jacobian, accumulation of a thread's kPpt points (independent chains, interleaved by the compiler).
@@ -968,16 +974,21 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
         }
       }
       MB_LOOP_F(it, 5);
-      // [J e]^T [J e] over the warp's points: lane a sums its entry over the rows in point order.
+      // rows -> shared memory -> tensor-core fragments
 #pragma unroll
       for (int u = 0; u < kPpt; ++u) {
         if (u == 1) MB_LOOP_F(it, 6);
-        if (__ballot_sync(kFull, act[u] && st[u] == MB_VALID)) {
+        if (__ballot_sync(kFull, act[u] && st[u] == MB_VALID)) {  // (rows of points that are not Valid are zero)
+          double(*r)[8] = S.rows[wib][u];
 #pragma unroll
-          for (int a = 0; a < 7; ++a) s_row[lane][a] = row[u][a];
+          for (int a = 0; a < 7; ++a) r[lane][a] = row[u][a];
+          r[lane][7] = 0.0;
           __syncwarp();
-#pragma unroll 8
-          for (int p = 0; p < 32; ++p) acc += s_row[p][pr] * s_row[p][pc];
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const double m = r[4 * kk + (lane & 3)][lane >> 2];
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(m), "d"(m));
+          }
           __syncwarp();
         }
 #pragma unroll
@@ -988,7 +999,10 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
       }
     };
     auto write_partials = [&]() {
-      if (lane < 28) S.red[wib][lane] = acc;
+      S.cmat[wib][lane >> 2][2 * (lane & 3)] = c0;
+      S.cmat[wib][lane >> 2][2 * (lane & 3) + 1] = c1;
+      __syncwarp();
+      if (lane < 28) S.red[wib][lane] = S.cmat[wib][pr][pc];
       if (lane >= 30) S.red[wib][lane + 8] = S.red[wib][lane + 16] = 0.0;  // pad entries 38, 39, 46, 47
       if (lane < 10) S.red[wib][kPackCnt + lane] = (double)cnt;
       if (lane < 6) S.red[wib][kPackLoc + lane] = lacc;
