@@ -16,7 +16,7 @@ for f in funcs[1:]:
             lines = [l for l in body.splitlines() if re.match(r"\s+/\*[0-9a-f]{4,6}\*/", l)]
             ops = collections.Counter(re.sub(r"^(@!?U?P\d+\s+)?", "", l.split("*/", 1)[1].strip()).split(" ")[0].split(".")[0].rstrip(";") for l in lines)
             head = "# %s: %d SASS instructions; most frequent opcodes: %s\n" % (name, len(lines), ", ".join("%s %d" % kv for kv in ops.most_common(14)))
-            special = {k: v for k, v in ops.items() if k in ("UBLKCP", "UTMALDG", "SYNCS", "UTCMMA", "HMMA", "DMMA", "ACQBULK", "PREEXIT", "BAR", "ATOMG", "REDG", "MATCH", "REDUX")}
+            special = {k: v for k, v in ops.items() if k in ("DMMA", "UBLKCP", "UTMALDG", "SYNCS", "UTCMMA", "HMMA", "DMMA", "ACQBULK", "PREEXIT", "BAR", "ATOMG", "REDG", "MATCH", "REDUX")}
             head += "# barrier / atomic / bulk-copy / tensor opcodes present: %s\n" % (special or "none")
             gzip.open(out, "wt").write(head + body)
             print(out, head.strip())
